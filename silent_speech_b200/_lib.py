@@ -1,0 +1,85 @@
+"""ctypes binding of libssb.so (the C ABI declared in include/ssb.h).
+
+There is NO fallback: if the shared library is missing it is built with nvcc, and if that
+is impossible the import of any kernel-backed function raises.  Nothing in this package
+computes the hot path on the CPU.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libssb.so")
+
+c_i64 = ctypes.c_int64
+c_i32 = ctypes.c_int32
+c_f32 = ctypes.c_float
+c_u64 = ctypes.c_uint64
+c_ptr = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/ssb.h one to one (tests check the symbol list)
+_SIGNATURES = {
+    "ssb_version": (ctypes.c_int, []),
+    "ssb_last_error": (ctypes.c_char_p, []),
+    "ssb_device_sm_count": (ctypes.c_int, []),
+    "ssb_dtw_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i64]),
+    "ssb_dtw_align_batch": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr,
+                                           c_ptr, c_i64, c_ptr]),
+    "ssb_dtw_time_warp_batch": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                               c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+}
+
+_lock = threading.Lock()
+_lib = None
+
+
+class SSBError(RuntimeError):
+    """A libssb entry point returned a non-zero status."""
+
+    def __init__(self, code, message):
+        super().__init__(f"libssb error {code}: {message}")
+        self.code = code
+
+
+def signatures():
+    return dict(_SIGNATURES)
+
+
+def load():
+    """Load (building first if stale/missing) libssb.so and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH) or os.environ.get("SSB_REBUILD") == "1":
+            from . import build as _build  # needs nvcc; raises loudly when impossible
+            _build.build()
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().ssb_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc != 0:
+        raise SSBError(rc, last_error())
+
+
+def current_stream():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise SSBError(-1, f"{name} must live on a CUDA device; libssb has no CPU path")
+    return t

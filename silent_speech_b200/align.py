@@ -1,0 +1,109 @@
+"""Drop-in mirror of the reference's align.py (align.py:5-34) on the B200 DTW kernels.
+
+Same names, same argument meaning, same return types:
+  time_warp(costs) -> np.ndarray              (align.py:5-14)
+  align_from_distances(distance_matrix, debug=False) -> list[int]   (align.py:16-34)
+plus the batched device-side entry points the reference lacks
+  align_batch(cost) / time_warp_batch(cost)   torch CUDA tensors, no host round trip.
+
+All arithmetic runs in csrc/dtw.cu through the C ABI (ssb_dtw_*); there is no CPU path.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.SSBError(-3, "align: a CUDA device is required (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _prepare(cost):
+    """-> (tensor, npairs, pair_stride, N, M, stride_i, stride_j) for the C ABI."""
+    _lib.require_cuda(cost, "cost")
+    if cost.dtype != torch.float32:
+        raise TypeError("DTW kernels compute in fp32 (the dtype the reference feeds them, "
+                        "transduction_model.py:126); got %s" % cost.dtype)
+    t = cost.unsqueeze(0) if cost.dim() == 2 else cost
+    if t.dim() != 3:
+        raise ValueError("cost must be (N, M) or (P, N, M)")
+    P, N, M = t.shape
+    sp, si, sj = t.stride()
+    ok = (si == 1 or sj == 1) and N > 1 and M > 1 and (P <= 1 or sp >= N * M)
+    if not ok:  # degenerate vectors or exotic views: one contiguous copy
+        t = t.contiguous()
+        sp, si, sj = N * M, M, 1
+    return t, P, sp, N, M, si, sj
+
+
+def align_batch(cost, return_dtw=False):
+    """DTW-align a batch of cost matrices on the GPU.
+
+    cost: CUDA fp32 tensor (P, N, M) or (N, M), any view with one unit stride among the last
+    two dims (e.g. `costs.transpose(-1, -2)` exactly as transduction_model.py:126 builds it).
+    Returns int32 CUDA tensor (P, N): path[p, i] = matched column for row i
+    (semantics of align.py:16-34), and optionally the accumulated-cost matrices.
+    """
+    lib = _lib.load()
+    t, P, sp, N, M, si, sj = _prepare(cost)
+    path = torch.empty((P, N), dtype=torch.int32, device=t.device)
+    if P == 0:
+        return (path, torch.empty_like(t)) if return_dtw else path
+    ws_bytes = lib.ssb_dtw_workspace_bytes(P, N, M, si, sj)
+    if ws_bytes < 0:
+        raise _lib.SSBError(ws_bytes, _lib.last_error())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        if return_dtw:
+            dtw = torch.empty_strided(t.shape, t.stride(), dtype=torch.float32, device=t.device)
+            _lib.check(lib.ssb_dtw_time_warp_batch(t.data_ptr(), P, sp, N, M, si, sj,
+                                                   dtw.data_ptr(), path.data_ptr(), ws.data_ptr(),
+                                                   ws_bytes, _lib.current_stream()))
+            return path, dtw
+        _lib.check(lib.ssb_dtw_align_batch(t.data_ptr(), P, sp, N, M, si, sj, path.data_ptr(),
+                                           ws.data_ptr(), ws_bytes, _lib.current_stream()))
+    return path
+
+
+def _to_device(a):
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D cost matrix")
+    if a.dtype != np.float32:
+        raise TypeError("DTW kernels compute in fp32; got %s" % a.dtype)
+    dev = _device()
+    if a.flags.c_contiguous or a.size == 0:
+        return torch.from_numpy(a).to(dev, non_blocking=False)
+    if a.flags.f_contiguous:  # the reference's costs.T view: ship the underlying C block
+        return torch.from_numpy(a.T).to(dev, non_blocking=False).t()
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+
+
+def time_warp(costs):
+    """Accumulated-cost matrix, as align.py:5-14 returns it (numpy in, numpy out)."""
+    t = _to_device(costs)
+    _, dtw = align_batch(t, return_dtw=True)
+    out = dtw[0].cpu().numpy() if dtw.dim() == 3 else dtw.cpu().numpy()
+    return out
+
+
+def align_from_distances(distance_matrix, debug=False):
+    """For each row of the (N, M) matrix, the matched column under monotonic alignment.
+
+    Mirrors align.py:16-34: numpy matrix in, Python list of N ints out; `debug=True`
+    additionally plots the path when matplotlib is importable.
+    """
+    t = _to_device(distance_matrix)
+    path = align_batch(t)[0].cpu().tolist()
+    if debug:
+        try:
+            import matplotlib.pyplot as plt
+            visual = np.zeros(np.asarray(distance_matrix).shape, dtype=np.float32)
+            visual[range(len(path)), path] = 1
+            plt.matshow(visual)
+            plt.show()
+        except ImportError:
+            pass
+    return path

@@ -1,0 +1,338 @@
+// Batched DTW alignment for sm_100a: register-resident wavefront fill + 2-bit direction
+// codes + backtrace.  Replaces align.py:5-14 (time_warp) and align.py:16-34
+// (align_from_distances) of the reference.
+//
+// Layout vocabulary.  A cost matrix has a contiguous "strip" axis y (extent Ny) and a
+// strided "sweep" axis x (extent Nx, `pitch` elements apart).  The reference hands DTW
+// an F-ordered view (costs.T, transduction_model.py:126), so there y == DTW row i and
+// x == DTW column j (Y_IS_I); for a C-ordered matrix y == j and x == i.  The recurrence is
+// symmetric under that swap, only the tie-break order changes, so one kernel serves both.
+//
+// Work decomposition.  One warp owns one (pair) at a time and walks it in bands of
+// BAND = 32 lanes x R strip-rows.  Inside a band lane l owns strip rows [y0, y0+R) and, at
+// step s, computes sweep column x = s - l (a systolic skew of one column per lane): the
+// value of the row above comes from lane l-1 by one shuffle per step, the diagonal is the
+// previous shuffle result, the left neighbour is the lane's own register.  Each cell does
+// exactly one fp32 add (cost + min3), so the result is bit-identical to the reference's
+// sequential loop.  The band's bottom row is parked in shared memory (Nx floats, updated in
+// place 31 columns behind the read position) and feeds lane 0 of the next band.
+//
+// HBM traffic.  Cost tiles stream global->shared with cp.async: at step s lane l = 8g+q
+// copies ITS OWN 16 B (its R=4 rows) of column s-8g+PF, so every group of 8 lanes fetches
+// one full 128 B line, each lane only ever reads shared memory it filled itself (no
+// cross-lane visibility hazards), and the per-lane ring is RING=32 columns deep
+// (PF=24 columns of prefetch + 8 of intra-group skew): 16 KB of shared memory per warp.
+// Cost is read exactly once: 4 B/cell algorithmic, plus 0.29 B/cell of direction codes
+// written in the skewed (step-major) order so that every 16 steps a warp stores one
+// coalesced 512 B row of packed codes.
+#include "ssb_common.cuh"
+#include <math_constants.h>
+
+namespace {
+
+constexpr int R = 4;            // strip rows per lane
+constexpr int BAND = 32 * R;    // strip rows per band
+constexpr int RING = 32;        // ring depth (columns), power of two
+constexpr int PF = 24;          // prefetch distance (columns); RING - PF >= 8
+constexpr int RING_BYTES = RING * 32 * 16;
+static_assert(PF % 4 == 0 && RING - PF >= 8, "ring geometry");
+
+struct DtwParams {
+  const float* cost;
+  float* dtw_out;  // nullable
+  uint32_t* dirs;
+  int64_t pair_stride;
+  int64_t pitch;
+  int64_t dirs_pair_words;
+  int Ny, Nx, nbands, nsw, npairs;
+};
+
+template <bool Y_IS_I, bool VEC, bool WRITE_DTW>
+__global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
+  unsigned char* wbase = smem + (size_t)warp * (RING_BYTES + bnd_bytes);
+  const float4* ring = reinterpret_cast<const float4*>(wbase);
+  float* bnd = reinterpret_cast<float*>(wbase + RING_BYTES);
+  const uint32_t ring_u32 = ssb::smem_u32(wbase);
+  const int g8 = lane & ~7;
+  const float INF = CUDART_INF_F;
+
+  for (int pair = blockIdx.x * warps_per_cta + warp; pair < p.npairs;
+       pair += gridDim.x * warps_per_cta) {
+    const float* cost = p.cost + (int64_t)pair * p.pair_stride;
+    float* dout = WRITE_DTW ? p.dtw_out + (int64_t)pair * p.pair_stride : nullptr;
+    uint4* dirs = reinterpret_cast<uint4*>(p.dirs + (int64_t)pair * p.dirs_pair_words);
+
+    for (int band = 0; band < p.nbands; ++band) {
+      const int y0 = band * BAND + lane * R;
+      const bool row0 = (y0 == 0);
+      const int rows_valid = min(max(p.Ny - y0, 0), R);
+      const bool last_band = (band + 1 == p.nbands);
+
+      float v[R];
+      uint32_t pk[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        v[r] = INF;  // column x = 0 of the DTW table
+        pk[r] = 0u;
+      }
+      if (row0) v[0] = 0.f;  // dtw[0,0]
+      if (WRITE_DTW) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r < rows_valid) dout[y0 + r] = v[r];
+      }
+      float up_in = INF, diag_in = INF;
+
+      auto issue = [&](int s) {
+        const int xl = s - g8 + PF;
+        if (xl >= 1 && xl < p.Nx && rows_valid > 0) {
+          const uint32_t dst = ring_u32 + ((((xl & (RING - 1)) << 5) + lane) << 4);
+          const float* src = cost + (int64_t)xl * p.pitch + y0;
+          if (VEC) {
+            ssb::cp_async_16(dst, src, rows_valid * 4);
+          } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if (r < rows_valid) ssb::cp_async_4(dst + 4 * r, src + r, 4);
+          }
+        }
+      };
+
+      // prologue: the loads that steps s < 0 would have issued (6 groups of 4 steps)
+#pragma unroll 1
+      for (int gi = 0; gi < PF / 4; ++gi) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) issue(-PF + 4 * gi + u);
+        ssb::cp_async_commit();
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < p.nsw; ++c) {
+#pragma unroll
+        for (int quad = 0; quad < 4; ++quad) {
+          // columns consumed in steps 4k..4k+3 were issued in group <= k-PF/4
+          ssb::cp_async_wait<PF / 4 - 1>();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int s = c * 16 + quad * 4 + u;
+            issue(s);
+            const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
+            float bval = INF;
+            if (band > 0 && lane == 0 && s >= 1 && s < p.Nx) bval = bnd[s];
+            diag_in = up_in;
+            up_in = (lane == 0) ? bval : t;
+            const int x = s - lane;
+            if (x >= 1 && x < p.Nx) {
+              const float4 c4 = ring[((x & (RING - 1)) << 5) + lane];
+              float cc[R] = {c4.x, c4.y, c4.z, c4.w};
+              if (row0) cc[0] = INF;  // dtw[0, x>=1] = +inf
+              float upc = up_in, upp = diag_in;
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const float old = v[r];
+                // reference order (align.py:13,26): up=(i-1,j), left=(i,j-1), diag; first wins
+                const float first = Y_IS_I ? upc : old;
+                const float second = Y_IS_I ? old : upc;
+                const bool p1 = second < first;
+                const float m1 = p1 ? second : first;
+                const bool p2 = upp < m1;
+                const float m = p2 ? upp : m1;
+                const uint32_t code = p2 ? 2u : (p1 ? 1u : 0u);
+                const float nv = cc[r] + m;
+                pk[r] = pk[r] * 4u + code;
+                upp = old;
+                upc = nv;
+                v[r] = nv;
+              }
+              if (WRITE_DTW) {
+                float* o = dout + (int64_t)x * p.pitch + y0;
+                if (VEC && rows_valid == R) {
+                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int r = 0; r < R; ++r)
+                    if (r < rows_valid) o[r] = v[r];
+                }
+              }
+              if (lane == 31 && !last_band) bnd[x] = v[R - 1];
+            } else {
+#pragma unroll
+              for (int r = 0; r < R; ++r) pk[r] <<= 2;
+            }
+          }
+          ssb::cp_async_commit();
+        }
+        dirs[((int64_t)band * p.nsw + c) * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      ssb::cp_async_wait<0>();
+      __syncwarp();  // bnd[] written by lane 31 is read by lane 0 in the next band
+    }
+  }
+}
+
+// One thread per pair walks the path from (N-1, M-1) (align.py:19-26).
+template <bool Y_IS_I>
+__global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t dirs_pair_words,
+                                     int nsw, int N, int M, int npairs,
+                                     int32_t* __restrict__ path) {
+  const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pair >= npairs) return;
+  const uint32_t* d = dirs + (int64_t)pair * dirs_pair_words;
+  int32_t* out = path + (int64_t)pair * N;
+  int i = N - 1, j = M - 1;
+  int64_t cur_idx = -1;
+  uint32_t cur_word = 0;
+  while (i > 0 && j > 0) {
+    out[i] = j;
+    const int x = Y_IS_I ? j : i, y = Y_IS_I ? i : j;
+    const int band = y / BAND, l = (y % BAND) / R, r = y % R, s = x + l;
+    const int64_t idx = (((int64_t)band * nsw + (s >> 4)) * 32 + l) * 4 + r;
+    if (idx != cur_idx) {
+      cur_word = __ldg(d + idx);
+      cur_idx = idx;
+    }
+    const uint32_t code = (cur_word >> (2 * (15 - (s & 15)))) & 3u;
+    if (code != 1u) --i;  // up or diagonal
+    if (code != 0u) --j;  // left or diagonal
+  }
+}
+
+struct Geometry {
+  bool y_is_i;
+  int Ny, Nx, nbands, nsw;
+  int64_t pitch, dirs_pair_words;
+};
+
+int make_geometry(int64_t N, int64_t M, int64_t stride_i, int64_t stride_j, Geometry* g) {
+  SSB_REQUIRE(N >= 1 && M >= 1, "dtw: N=%lld M=%lld must be >= 1", (long long)N, (long long)M);
+  SSB_REQUIRE(N < (1 << 24) && M < (1 << 24), "dtw: dimension too large");
+  SSB_REQUIRE(stride_i == 1 || stride_j == 1,
+              "dtw: one of stride_i/stride_j must be 1 (got %lld, %lld)", (long long)stride_i,
+              (long long)stride_j);
+  SSB_REQUIRE(!(stride_i == 1 && stride_j == 1) || N == 1 || M == 1,
+              "dtw: both strides are 1 but the matrix is not a vector");
+  g->y_is_i = (stride_i == 1) && (stride_j != 1 || M == 1);
+  g->Ny = (int)(g->y_is_i ? N : M);
+  g->Nx = (int)(g->y_is_i ? M : N);
+  g->pitch = g->y_is_i ? stride_j : stride_i;
+  SSB_REQUIRE(g->Nx == 1 || g->pitch >= g->Ny, "dtw: pitch %lld < contiguous extent %d",
+              (long long)g->pitch, g->Ny);
+  g->nbands = (g->Ny + BAND - 1) / BAND;
+  g->nsw = (g->Nx + 30) / 16 + 1;
+  g->dirs_pair_words = (int64_t)g->nbands * g->nsw * BAND;
+  return SSB_OK;
+}
+
+template <bool Y_IS_I, bool VEC, bool WRITE_DTW>
+int launch_fill(const DtwParams& p, cudaStream_t st) {
+  auto kern = dtw_fill_kernel<Y_IS_I, VEC, WRITE_DTW>;
+  const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
+  const int per_warp = RING_BYTES + bnd_bytes;
+  int warps = 4;
+  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+  SSB_REQUIRE(warps * per_warp <= 227 * 1024, "dtw: sweep extent %d too large for shared memory",
+              p.Nx);
+  if (p.npairs < 4 * ssb::num_sms()) warps = 1;  // few pairs: spread one warp per CTA
+  const int smem = warps * per_warp;
+  SSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+  if (occ < 1) occ = 1;
+  const int64_t want = ((int64_t)p.npairs + warps - 1) / warps;
+  const int64_t cap = (int64_t)ssb::num_sms() * occ;
+  const int grid = (int)(want < cap ? want : cap);
+  kern<<<grid, warps * 32, smem, st>>>(p);
+  SSB_LAUNCH_CHECK("dtw_fill_kernel");
+  return SSB_OK;
+}
+
+int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64_t M,
+        int64_t stride_i, int64_t stride_j, float* dtw, int32_t* path, void* workspace,
+        int64_t workspace_bytes, void* stream) {
+  Geometry g;
+  if (int rc = make_geometry(N, M, stride_i, stride_j, &g)) return rc;
+  SSB_REQUIRE(npairs >= 0 && npairs < (1LL << 31), "dtw: bad npairs %lld", (long long)npairs);
+  if (npairs == 0) return SSB_OK;
+  SSB_REQUIRE(cost && path && workspace, "dtw: null pointer");
+  const int64_t need = npairs * g.dirs_pair_words * 4;
+  if (workspace_bytes < need) {
+    ssb::set_error("dtw: workspace %lld B < required %lld B", (long long)workspace_bytes,
+                   (long long)need);
+    return SSB_ERR_WORKSPACE;
+  }
+  SSB_REQUIRE(((uintptr_t)workspace & 15) == 0, "dtw: workspace must be 16 B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  DtwParams p;
+  p.cost = cost;
+  p.dtw_out = dtw;
+  p.dirs = (uint32_t*)workspace;
+  p.pair_stride = pair_stride;
+  p.pitch = g.pitch;
+  p.dirs_pair_words = g.dirs_pair_words;
+  p.Ny = g.Ny;
+  p.Nx = g.Nx;
+  p.nbands = g.nbands;
+  p.nsw = g.nsw;
+  p.npairs = (int)npairs;
+  const bool vec = (g.pitch % 4 == 0) && (pair_stride % 4 == 0) && (((uintptr_t)cost & 15) == 0) &&
+                   (!dtw || ((uintptr_t)dtw & 15) == 0);
+
+  SSB_CUDA(cudaMemsetAsync(path, 0, (size_t)npairs * N * sizeof(int32_t), st));
+  int rc;
+#define SSB_DTW_DISPATCH(YI, V)                                            \
+  rc = dtw ? launch_fill<YI, V, true>(p, st) : launch_fill<YI, V, false>(p, st)
+  if (g.y_is_i) {
+    if (vec) SSB_DTW_DISPATCH(true, true); else SSB_DTW_DISPATCH(true, false);
+  } else {
+    if (vec) SSB_DTW_DISPATCH(false, true); else SSB_DTW_DISPATCH(false, false);
+  }
+#undef SSB_DTW_DISPATCH
+  if (rc) return rc;
+
+  const int threads = 64;
+  const int grid = (int)((npairs + threads - 1) / threads);
+  if (g.y_is_i)
+    dtw_backtrace_kernel<true><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nsw, (int)N,
+                                                         (int)M, (int)npairs, path);
+  else
+    dtw_backtrace_kernel<false><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nsw,
+                                                          (int)N, (int)M, (int)npairs, path);
+  SSB_LAUNCH_CHECK("dtw_backtrace_kernel");
+  return SSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ssb_dtw_workspace_bytes(int64_t npairs, int64_t N, int64_t M, int64_t stride_i,
+                                int64_t stride_j) {
+  Geometry g;
+  if (make_geometry(N, M, stride_i, stride_j, &g)) return SSB_ERR_ARG;
+  if (npairs < 0) return SSB_ERR_ARG;
+  const int64_t b = npairs * g.dirs_pair_words * 4;
+  return b > 16 ? b : 16;
+}
+
+int ssb_dtw_align_batch(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N,
+                        int64_t M, int64_t stride_i, int64_t stride_j, int32_t* path,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  return run(cost, npairs, pair_stride, N, M, stride_i, stride_j, nullptr, path, workspace,
+             workspace_bytes, stream);
+}
+
+int ssb_dtw_time_warp_batch(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N,
+                            int64_t M, int64_t stride_i, int64_t stride_j, float* dtw,
+                            int32_t* path, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  SSB_REQUIRE(dtw != nullptr, "dtw: null dtw output");
+  return run(cost, npairs, pair_stride, N, M, stride_i, stride_j, dtw, path, workspace,
+             workspace_bytes, stream);
+}
+
+}  // extern "C"

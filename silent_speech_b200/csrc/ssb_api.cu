@@ -1,0 +1,53 @@
+// Library-level entry points: version, error string, device query.
+#include "ssb_common.cuh"
+#include <string.h>
+
+namespace ssb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  // clear the sticky-free error state so the next call starts clean
+  (void)cudaGetLastError();
+  return (int)e;
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cached_dev = dev;
+    cached = n;
+  }
+  return cached;
+}
+
+}  // namespace ssb
+
+extern "C" {
+
+int ssb_version(void) { return 100; }  // 0.1.0
+
+const char* ssb_last_error(void) { return ssb::g_err; }
+
+int ssb_device_sm_count(void) {
+  int n = ssb::num_sms();
+  if (n <= 0) {
+    ssb::set_error("no CUDA device available");
+    return SSB_ERR_UNSUPPORTED;
+  }
+  return n;
+}
+
+}  // extern "C"

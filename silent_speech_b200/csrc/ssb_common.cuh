@@ -1,0 +1,94 @@
+// Shared device/host helpers for the libssb kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/ssb.h"
+
+namespace ssb {
+
+// ---- error plumbing (thread-local message, C return codes) -----------------
+void set_error(const char* fmt, ...);
+int  cuda_fail(cudaError_t e, const char* what);
+
+#define SSB_REQUIRE(cond, ...)                      \
+  do {                                              \
+    if (!(cond)) {                                  \
+      ::ssb::set_error(__VA_ARGS__);                \
+      return SSB_ERR_ARG;                           \
+    }                                               \
+  } while (0)
+
+#define SSB_CUDA(call)                                              \
+  do {                                                              \
+    cudaError_t e__ = (call);                                       \
+    if (e__ != cudaSuccess) return ::ssb::cuda_fail(e__, #call);    \
+  } while (0)
+
+#define SSB_LAUNCH_CHECK(name)                                      \
+  do {                                                              \
+    cudaError_t e__ = cudaGetLastError();                           \
+    if (e__ != cudaSuccess) return ::ssb::cuda_fail(e__, name);     \
+  } while (0)
+
+int num_sms();
+
+// ---- small device helpers ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011). One call = 4 x 32 random bits.
+// Used for every dropout site so forward and backward regenerate identical masks from
+// (seed, site offset, element index) without storing them.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// keep-mask for 4 consecutive elements starting at element index 4*idx4 of dropout site `site`.
+// Element e is kept iff its 32 random bits >= thresh, thresh = round(p * 2^32).
+__device__ __forceinline__ uint4 dropout_bits4(uint64_t seed, uint32_t site, uint64_t idx4) {
+  uint4 ctr = make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, 0x5353425Fu);
+  uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  return philox4x32_10(ctr, key);
+}
+
+}  // namespace ssb
