@@ -68,6 +68,24 @@ SSB_API int ssb_dtw_time_warp_batch(const float* cost, int64_t npairs, int64_t p
                             int32_t* path, void* workspace, int64_t workspace_bytes,
                             void* stream);
 
+/* ---- log-mel spectrogram ---------------------------------------------------
+ * Replaces data_utils.py:39-62 (`mel_spectrogram`, center=False) together with
+ * data_utils.py:29-34 (`dynamic_range_compression_torch` / `spectral_normalize_torch`).
+ *
+ * y: (B, S) fp32 clips, rows `y_stride` apart.  The (n_fft-hop)/2 reflect padding of
+ * data_utils.py:51 is applied inside the kernel.  mel_basis: dense (num_mels, n_fft/2+1)
+ * fp32 filterbank exactly as the reference holds it (data_utils.py:47-48); tap_begin/tap_end:
+ * int32[num_mels], the half-open range of non-zero bins of each filter (host-computed).
+ * out: (B, num_mels, frames) fp32, frames = ssb_mel_num_frames(S, n_fft, hop);
+ * out = log(max(mel_basis @ sqrt(re^2+im^2+1e-9), clip_val)).
+ * Built for n_fft == win == 1024 (the reference's only configuration, data_utils.py:79).
+ */
+SSB_API int64_t ssb_mel_num_frames(int64_t S, int n_fft, int hop);
+SSB_API int ssb_mel_fwd(const float* y, int64_t B, int64_t S, int64_t y_stride, int n_fft, int hop,
+                        int win, const float* mel_basis, const int32_t* tap_begin,
+                        const int32_t* tap_end, int num_mels, float clip_val, float* out,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,10 @@ _SIGNATURES = {
                                            c_ptr, c_i64, c_ptr]),
     "ssb_dtw_time_warp_batch": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                                c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ssb_mel_num_frames": (c_i64, [c_i64, ctypes.c_int, ctypes.c_int]),
+    "ssb_mel_fwd": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_f32, c_ptr,
+                                   c_ptr]),
 }
 
 _lock = threading.Lock()

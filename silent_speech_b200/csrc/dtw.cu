@@ -27,6 +27,7 @@
 // coalesced 512 B row of packed codes.
 #include "ssb_common.cuh"
 #include <math_constants.h>
+#include <type_traits>
 
 namespace {
 
@@ -35,6 +36,8 @@ constexpr int BAND = 32 * R;    // strip rows per band
 constexpr int RING = 32;        // ring depth (columns), power of two
 constexpr int PF = 24;          // prefetch distance (columns); RING - PF >= 8
 constexpr int RING_BYTES = RING * 32 * 16;
+constexpr int RING_MASK = (RING - 1) << 9;  // byte offset of a column inside the ring
+constexpr int CH = 16;          // steps per chunk == 2-bit codes per direction word
 static_assert(PF % 4 == 0 && RING - PF >= 8, "ring geometry");
 
 struct DtwParams {
@@ -44,8 +47,15 @@ struct DtwParams {
   int64_t pair_stride;
   int64_t pitch;
   int64_t dirs_pair_words;
-  int Ny, Nx, nbands, nsw, npairs;
+  int Ny, Nx, nbands, nch, npairs;
 };
+
+// Direction codes: 2 raw predicate bits per cell: bit0 = "second candidate (i,j-1) < first
+// (i-1,j)", bit1 = "diagonal < min(first, second)".  The backtrace resolves them in the
+// first-wins order of Python's min() (align.py:26): bit1 -> diagonal, else bit0 -> left, else up.
+// One word packs the 16 steps of a chunk for one strip row (earliest step in the top bits);
+// words are stored step-major:  dirs[(band*nch + chunk)*32 + lane]  (uint4 = the lane's 4 rows)
+// so that every chunk ends with one coalesced 512 B store per warp.
 
 template <bool Y_IS_I, bool VEC, bool WRITE_DTW>
 __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
@@ -54,11 +64,16 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
   const int warps_per_cta = blockDim.x >> 5;
   const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
   unsigned char* wbase = smem + (size_t)warp * (RING_BYTES + bnd_bytes);
-  const float4* ring = reinterpret_cast<const float4*>(wbase);
+  const unsigned char* ring_lane = wbase + lane * 16;  // this lane's 16 B slot of every column
   float* bnd = reinterpret_cast<float*>(wbase + RING_BYTES);
-  const uint32_t ring_u32 = ssb::smem_u32(wbase);
+  const uint32_t ring_u32 = ssb::smem_u32(wbase) + lane * 16;
   const int g8 = lane & ~7;
   const float INF = CUDART_INF_F;
+  const int Nx = p.Nx;
+  const int64_t pitch = p.pitch;
+  // chunks in which every lane is inside [1, Nx) and every prefetch is in range
+  const int steady_lo = 32 / CH;
+  const int steady_hi = (Nx - CH - PF) / CH;  // inclusive; may be < steady_lo
 
   for (int pair = blockIdx.x * warps_per_cta + warp; pair < p.npairs;
        pair += gridDim.x * warps_per_cta) {
@@ -70,7 +85,10 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
       const int y0 = band * BAND + lane * R;
       const bool row0 = (y0 == 0);
       const int rows_valid = min(max(p.Ny - y0, 0), R);
-      const bool last_band = (band + 1 == p.nbands);
+      const int y0_ld = rows_valid > 0 ? y0 : 0;  // keep the address legal for idle lanes
+      const int ld_bytes = rows_valid * 4;
+      const bool rd_bnd = (band > 0) && (lane == 0);
+      const bool wr_bnd = (band + 1 < p.nbands) && (lane == 31);
 
       float v[R];
       uint32_t pk[R];
@@ -87,86 +105,135 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
       }
       float up_in = INF, diag_in = INF;
 
-      auto issue = [&](int s) {
-        const int xl = s - g8 + PF;
-        if (xl >= 1 && xl < p.Nx && rows_valid > 0) {
-          const uint32_t dst = ring_u32 + ((((xl & (RING - 1)) << 5) + lane) << 4);
-          const float* src = cost + (int64_t)xl * p.pitch + y0;
-          if (VEC) {
-            ssb::cp_async_16(dst, src, rows_valid * 4);
+      auto prefetch = [&](uint32_t dst, const float* src) {
+        if (VEC) {
+          ssb::cp_async_16(dst, src, ld_bytes);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (r < rows_valid) ssb::cp_async_4(dst + 4 * r, src + r, 4);
+        }
+      };
+
+      auto cells = [&](const float4 c4, int x) {
+        float cc[R] = {c4.x, c4.y, c4.z, c4.w};
+        if (row0) cc[0] = INF;  // dtw[0, x>=1] = +inf
+        float upc = up_in, upp = diag_in;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float old = v[r];
+          // reference order (align.py:13,26): up=(i-1,j), left=(i,j-1), diag; first wins
+          const float first = Y_IS_I ? upc : old;
+          const float second = Y_IS_I ? old : upc;
+          float nv;
+          // Inline PTX pins the shape ptxas emits per cell: FSETP FSEL FSETP FSEL FADD SEL SEL
+          // IMAD.  (Left to itself it rewrites the packing into 4 LOP3 bit-inserts per cell, or
+          // parks the predicates with P2R and replays them at the end of the chunk.)
+          asm("{\n\t"
+              ".reg .pred p1, p2;\n\t"
+              ".reg .f32 m1, m;\n\t"
+              ".reg .u32 c;\n\t"
+              "setp.lt.f32 p1, %3, %2;\n\t"
+              "selp.f32 m1, %3, %2, p1;\n\t"
+              "selp.u32 c, 1, 0, p1;\n\t"
+              "setp.lt.f32 p2, %4, m1;\n\t"
+              "selp.f32 m, %4, m1, p2;\n\t"
+              "selp.u32 c, 2, c, p2;\n\t"
+              "add.rn.f32 %0, %5, m;\n\t"
+              "mad.lo.u32 %1, %1, 4, c;\n\t"
+              "}"
+              : "=f"(nv), "+r"(pk[r])
+              : "f"(first), "f"(second), "f"(upp), "f"(cc[r]));
+          upp = old;
+          upc = nv;
+          v[r] = nv;
+        }
+        if (WRITE_DTW) {
+          float* o = dout + (int64_t)x * pitch + y0;
+          if (VEC && rows_valid == R) {
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
           } else {
 #pragma unroll
             for (int r = 0; r < R; ++r)
-              if (r < rows_valid) ssb::cp_async_4(dst + 4 * r, src + r, 4);
+              if (r < rows_valid) o[r] = v[r];
           }
         }
       };
 
-      // prologue: the loads that steps s < 0 would have issued (6 groups of 4 steps)
+      // ---- general step: every range predicate evaluated (head / tail chunks) ---------
+      auto step_general = [&](int s) {
+        const int xl = s - g8 + PF;
+        if (xl >= 1 && xl < Nx)
+          prefetch(ring_u32 + ((xl << 9) & RING_MASK), cost + ((int64_t)xl * pitch + y0_ld));
+        const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
+        float bval = INF;
+        if (rd_bnd && s >= 1 && s < Nx) bval = bnd[s];
+        diag_in = up_in;
+        up_in = (lane == 0) ? bval : t;
+        const int x = s - lane;
+        if (x >= 1 && x < Nx) {
+          cells(*reinterpret_cast<const float4*>(ring_lane + ((x << 9) & RING_MASK)), x);
+          if (wr_bnd) bnd[x] = v[R - 1];
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; ++r) pk[r] <<= 2;
+        }
+      };
+
+      // prologue: the loads that steps s < 0 would have issued (PF/4 groups of 4 steps)
 #pragma unroll 1
       for (int gi = 0; gi < PF / 4; ++gi) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) issue(-PF + 4 * gi + u);
+        for (int u = 0; u < 4; ++u) {
+          const int xl = 4 * gi + u - g8;
+          if (xl >= 1 && xl < Nx)
+            prefetch(ring_u32 + ((xl << 9) & RING_MASK), cost + ((int64_t)xl * pitch + y0_ld));
+        }
         ssb::cp_async_commit();
       }
 
 #pragma unroll 1
-      for (int c = 0; c < p.nsw; ++c) {
+      for (int c = 0; c < p.nch; ++c) {
+        const int s0 = c * CH;
+        if (c >= steady_lo && c <= steady_hi) {
+          // ---- steady chunk: no range checks, running addresses --------------------
+          const float* src = cost + ((int64_t)(s0 - g8 + PF) * pitch + y0_ld);
+          uint32_t wr_off = (uint32_t)((s0 - g8 + PF) << 9) & RING_MASK;
+          uint32_t rd_off = (uint32_t)((s0 - lane) << 9) & RING_MASK;
+          const float* bnd_rd = bnd + s0;         // lane 0 reads  bnd[s]
+          float* bnd_wr = bnd + (s0 - lane);      // lane 31 writes bnd[x]
 #pragma unroll
-        for (int quad = 0; quad < 4; ++quad) {
-          // columns consumed in steps 4k..4k+3 were issued in group <= k-PF/4
-          ssb::cp_async_wait<PF / 4 - 1>();
+          for (int quad = 0; quad < CH / 4; ++quad) {
+            // columns consumed in steps 4k..4k+3 were issued in group <= k - PF/4
+            ssb::cp_async_wait<PF / 4 - 1>();
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int s = c * 16 + quad * 4 + u;
-            issue(s);
-            const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
-            float bval = INF;
-            if (band > 0 && lane == 0 && s >= 1 && s < p.Nx) bval = bnd[s];
-            diag_in = up_in;
-            up_in = (lane == 0) ? bval : t;
-            const int x = s - lane;
-            if (x >= 1 && x < p.Nx) {
-              const float4 c4 = ring[((x & (RING - 1)) << 5) + lane];
-              float cc[R] = {c4.x, c4.y, c4.z, c4.w};
-              if (row0) cc[0] = INF;  // dtw[0, x>=1] = +inf
-              float upc = up_in, upp = diag_in;
-#pragma unroll
-              for (int r = 0; r < R; ++r) {
-                const float old = v[r];
-                // reference order (align.py:13,26): up=(i-1,j), left=(i,j-1), diag; first wins
-                const float first = Y_IS_I ? upc : old;
-                const float second = Y_IS_I ? old : upc;
-                const bool p1 = second < first;
-                const float m1 = p1 ? second : first;
-                const bool p2 = upp < m1;
-                const float m = p2 ? upp : m1;
-                const uint32_t code = p2 ? 2u : (p1 ? 1u : 0u);
-                const float nv = cc[r] + m;
-                pk[r] = pk[r] * 4u + code;
-                upp = old;
-                upc = nv;
-                v[r] = nv;
-              }
-              if (WRITE_DTW) {
-                float* o = dout + (int64_t)x * p.pitch + y0;
-                if (VEC && rows_valid == R) {
-                  *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                  for (int r = 0; r < R; ++r)
-                    if (r < rows_valid) o[r] = v[r];
-                }
-              }
-              if (lane == 31 && !last_band) bnd[x] = v[R - 1];
-            } else {
-#pragma unroll
-              for (int r = 0; r < R; ++r) pk[r] <<= 2;
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const int u = quad * 4 + u4;
+              prefetch(ring_u32 + wr_off, src);
+              src += pitch;
+              wr_off = (wr_off + 512u) & RING_MASK;
+              const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
+              float bval = INF;
+              if (rd_bnd) bval = bnd_rd[u];
+              diag_in = up_in;
+              up_in = (lane == 0) ? bval : t;
+              const float4 c4 = *reinterpret_cast<const float4*>(ring_lane + rd_off);
+              rd_off = (rd_off + 512u) & RING_MASK;
+              cells(c4, s0 + u - lane);
+              if (wr_bnd) bnd_wr[u] = v[R - 1];
             }
+            ssb::cp_async_commit();
           }
-          ssb::cp_async_commit();
+        } else {
+#pragma unroll
+          for (int quad = 0; quad < CH / 4; ++quad) {
+            ssb::cp_async_wait<PF / 4 - 1>();
+#pragma unroll
+            for (int u4 = 0; u4 < 4; ++u4) step_general(s0 + quad * 4 + u4);
+            ssb::cp_async_commit();
+          }
         }
-        dirs[((int64_t)band * p.nsw + c) * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dirs[((int64_t)band * p.nch + c) * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       ssb::cp_async_wait<0>();
       __syncwarp();  // bnd[] written by lane 31 is read by lane 0 in the next band
@@ -177,7 +244,7 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
 // One thread per pair walks the path from (N-1, M-1) (align.py:19-26).
 template <bool Y_IS_I>
 __global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t dirs_pair_words,
-                                     int nsw, int N, int M, int npairs,
+                                     int nch, int N, int M, int npairs,
                                      int32_t* __restrict__ path) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= npairs) return;
@@ -190,20 +257,21 @@ __global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t 
     out[i] = j;
     const int x = Y_IS_I ? j : i, y = Y_IS_I ? i : j;
     const int band = y / BAND, l = (y % BAND) / R, r = y % R, s = x + l;
-    const int64_t idx = (((int64_t)band * nsw + (s >> 4)) * 32 + l) * 4 + r;
+    const int64_t idx = (((int64_t)band * nch + (s / CH)) * 32 + l) * 4 + r;
     if (idx != cur_idx) {
       cur_word = __ldg(d + idx);
       cur_idx = idx;
     }
-    const uint32_t code = (cur_word >> (2 * (15 - (s & 15)))) & 3u;
-    if (code != 1u) --i;  // up or diagonal
-    if (code != 0u) --j;  // left or diagonal
+    const uint32_t code = (cur_word >> (2 * (CH - 1 - (s % CH)))) & 3u;
+    const bool diag = (code & 2u) != 0u, left = (code & 1u) != 0u;
+    if (diag || !left) --i;  // up or diagonal
+    if (diag || left) --j;   // left or diagonal
   }
 }
 
 struct Geometry {
   bool y_is_i;
-  int Ny, Nx, nbands, nsw;
+  int Ny, Nx, nbands, nch;
   int64_t pitch, dirs_pair_words;
 };
 
@@ -222,8 +290,8 @@ int make_geometry(int64_t N, int64_t M, int64_t stride_i, int64_t stride_j, Geom
   SSB_REQUIRE(g->Nx == 1 || g->pitch >= g->Ny, "dtw: pitch %lld < contiguous extent %d",
               (long long)g->pitch, g->Ny);
   g->nbands = (g->Ny + BAND - 1) / BAND;
-  g->nsw = (g->Nx + 30) / 16 + 1;
-  g->dirs_pair_words = (int64_t)g->nbands * g->nsw * BAND;
+  g->nch = (g->Nx + 30) / CH + 1;  // steps 0 .. Nx-1+31
+  g->dirs_pair_words = (int64_t)g->nbands * g->nch * BAND;
   return SSB_OK;
 }
 
@@ -277,7 +345,7 @@ int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64
   p.Ny = g.Ny;
   p.Nx = g.Nx;
   p.nbands = g.nbands;
-  p.nsw = g.nsw;
+  p.nch = g.nch;
   p.npairs = (int)npairs;
   const bool vec = (g.pitch % 4 == 0) && (pair_stride % 4 == 0) && (((uintptr_t)cost & 15) == 0) &&
                    (!dtw || ((uintptr_t)dtw & 15) == 0);
@@ -297,10 +365,10 @@ int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64
   const int threads = 64;
   const int grid = (int)((npairs + threads - 1) / threads);
   if (g.y_is_i)
-    dtw_backtrace_kernel<true><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nsw, (int)N,
+    dtw_backtrace_kernel<true><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nch, (int)N,
                                                          (int)M, (int)npairs, path);
   else
-    dtw_backtrace_kernel<false><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nsw,
+    dtw_backtrace_kernel<false><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nch,
                                                           (int)N, (int)M, (int)npairs, path);
   SSB_LAUNCH_CHECK("dtw_backtrace_kernel");
   return SSB_OK;
