@@ -86,6 +86,110 @@ SSB_API int ssb_mel_fwd(const float* y, int64_t B, int64_t S, int64_t y_stride, 
                         const int32_t* tap_end, int num_mels, float clip_val, float* out,
                         void* stream);
 
+/* ---- dense contractions with gathered operands ------------------------------
+ * Replaces nn.Linear (architecture.py:51,55,59; transformer.py:32,34), the three
+ * nn.Conv1d shapes of ResBlock (architecture.py:18,20,24: k3/p1 stride 1|2, k1 stride 2),
+ * the four einsum projections of MultiHeadAttention (transformer.py:96-98,111), the
+ * relative-position einsum (transformer.py:249-253) and all of their gradients.
+ *
+ * A(m,k) is gathered from a channels-last tensor:  m -> (b = m / rows_per_batch,
+ * t = m % rows_per_batch),  k -> (tap = k / C, c = k % C),  source row
+ * ts = t*s_t + tap*s_tap + off  (zero outside [0, L_src)),  element
+ * base[b*batch_stride + ts*ld + c].   A plain row-major matrix is rows_per_batch = M,
+ * C = K, L_src = M, s_t = 1, s_tap = 0, off = 0.
+ * Output row m goes to  out.base[b*batch_stride + (t*d_t + d_off)*ld + n].
+ * Weights are always in "GEMM layout" W[k, n] (n contiguous).
+ */
+typedef struct {
+  const float* base;
+  int64_t batch_stride;
+  int32_t rows_per_batch, C, L_src, ld, s_t, s_tap, off;
+} ssb_gather_t;
+
+typedef struct {
+  float* base;
+  int64_t batch_stride;
+  int32_t rows_per_batch, ld, d_t, d_off;
+} ssb_scatter_t;
+
+typedef struct {
+  ssb_scatter_t out;
+  const float* bias;      /* [N] added before relu, or NULL */
+  const float* mask_src;  /* plain (M, N), ld == N: result *= (mask_src > 0) * mask_scale, or NULL */
+  float mask_scale;
+  int32_t relu;           /* max(x, 0) */
+  int32_t accumulate;     /* out += result */
+  float drop_p;           /* inverted dropout after relu; 0 disables */
+  uint64_t seed;          /* Philox key */
+  uint32_t site;          /* Philox stream id of this dropout site */
+} ssb_epilogue_t;
+
+/* C[m,n] = epi( sum_k A(m,k) * W[k*ldw + n] ) */
+SSB_API int ssb_gemm_nn(const ssb_gather_t* A, const float* W, int64_t ldw,
+                        const ssb_epilogue_t* epi, int64_t M, int64_t N, int64_t K, void* stream);
+/* C[m,j] = epi( sum_k A(m,k) * W[(tapK*N + j)*ldw + k % Cb] ),  tapK = tap{0,1,2}[k / Cb]
+ * (data gradients: W is read transposed, tap blocks optionally permuted) */
+SSB_API int ssb_gemm_nt(const ssb_gather_t* A, const float* W, int64_t ldw, int64_t Cb, int tap0,
+                        int tap1, int tap2, const ssb_epilogue_t* epi, int64_t M, int64_t N,
+                        int64_t K, void* stream);
+/* dW[k*lddw + n] (+)= sum_m A(m,k) * G[m*ldg + n]   (weight gradients; split over m) */
+SSB_API int ssb_gemm_tn(const ssb_gather_t* A, const float* G, int64_t ldg, float* dW,
+                        int64_t lddw, int accumulate, int64_t M, int64_t N, int64_t K,
+                        void* stream);
+
+/* ---- per-channel reductions, BatchNorm1d, residual+dropout+LayerNorm -----------
+ * All tensors (rows, C) fp32, C contiguous and a multiple of 4.
+ */
+SSB_API int64_t ssb_col_partials_bytes(int64_t rows, int64_t C);
+/* out[c] (+)= sum_r x[r,c]   (bias gradients) */
+SSB_API int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumulate,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+/* nn.BatchNorm1d statistics (architecture.py:19,21,25).  training != 0: batch mean / biased var
+ * over rows, running stats updated in place (momentum, unbiased var); else running stats.
+ * Produces mean, rstd and the fused affine  scale = gamma*rstd, shift = beta - mean*scale. */
+SSB_API int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* gamma,
+                         const float* beta, float* running_mean, float* running_var,
+                         float momentum, float eps, int training, float* mean, float* rstd,
+                         float* scale, float* shift, void* workspace, int64_t workspace_bytes,
+                         void* stream);
+/* y = [relu]( x*scale + shift [+ x2*scale2 + shift2] )   (architecture.py:32-40) */
+SSB_API int ssb_bn_apply(const float* x, const float* scale, const float* shift, const float* x2,
+                         const float* scale2, const float* shift2, int relu, int64_t rows,
+                         int64_t C, float* y, void* stream);
+/* BatchNorm backward through an optional ReLU mask (dz = dy * (mask_src > 0)).
+ * workspace >= ssb_col_partials_bytes(rows, C) + 8*C bytes. */
+SSB_API int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const float* mean,
+                       const float* rstd, const float* gamma, int training, int64_t rows,
+                       int64_t C, float* dx, float* dgamma, float* dbeta, void* workspace,
+                       int64_t workspace_bytes, void* stream);
+/* z = res + dropout(branch); y = LayerNorm(z)*gamma + beta   (transformer.py:55-56,58-59) */
+SSB_API int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const float* gamma,
+                                   const float* beta, int64_t rows, int64_t D, float eps,
+                                   float drop_p, uint64_t seed, uint32_t site, float* z_out,
+                                   float* y, float* mean, float* rstd, void* stream);
+SSB_API int64_t ssb_add_dropout_ln_bwd_workspace_bytes(int64_t rows, int64_t D);
+SSB_API int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean,
+                                   const float* rstd, const float* gamma, int64_t rows, int64_t D,
+                                   float drop_p, uint64_t seed, uint32_t site, float* d_res,
+                                   float* d_branch, float* dgamma, float* dbeta, void* workspace,
+                                   int64_t workspace_bytes, void* stream);
+
+/* ---- banded relative-position attention ------------------------------------------
+ * Replaces transformer.py:99-110 (logits, softmax, dropout, PV) with the relative-position
+ * logits of transformer.py:162-297 folded in (closed form: band |k-q| <= W exact, W <= 99).
+ * qkv: (B*T, 3*H*dh) [q|k|v]; R, P, dS: (B*T, H, RW) band tensors indexed by r = k-q+W
+ * (RW % 4 == 0, RW >= 2W+1; padding columns are written as 0); O, dO: (B*T, H*dh).
+ * P receives the pre-dropout probabilities (may be NULL for inference).
+ * Backward writes dS (for the positional dQ GEMM) and all of dqkv (content part of dq).
+ */
+SSB_API int ssb_band_attn_fwd(const float* qkv, const float* R, int64_t B, int64_t T, int64_t H,
+                              int64_t dh, int64_t W, int64_t RW, float drop_p, uint64_t seed,
+                              uint32_t site, float* P, float* O, void* stream);
+SSB_API int ssb_band_attn_bwd(const float* qkv, const float* P, const float* dO, int64_t B,
+                              int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW,
+                              float drop_p, uint64_t seed, uint32_t site, float* dS, float* dqkv,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

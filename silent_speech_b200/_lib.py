@@ -17,6 +17,32 @@ c_f32 = ctypes.c_float
 c_u64 = ctypes.c_uint64
 c_ptr = ctypes.c_void_p
 
+c_int = ctypes.c_int
+c_u32 = ctypes.c_uint32
+
+
+class Gather(ctypes.Structure):
+    """ssb_gather_t"""
+    _fields_ = [("base", c_ptr), ("batch_stride", c_i64), ("rows_per_batch", c_i32), ("C", c_i32),
+                ("L_src", c_i32), ("ld", c_i32), ("s_t", c_i32), ("s_tap", c_i32), ("off", c_i32)]
+
+
+class Scatter(ctypes.Structure):
+    """ssb_scatter_t"""
+    _fields_ = [("base", c_ptr), ("batch_stride", c_i64), ("rows_per_batch", c_i32), ("ld", c_i32),
+                ("d_t", c_i32), ("d_off", c_i32)]
+
+
+class Epilogue(ctypes.Structure):
+    """ssb_epilogue_t"""
+    _fields_ = [("out", Scatter), ("bias", c_ptr), ("mask_src", c_ptr), ("mask_scale", c_f32),
+                ("relu", c_i32), ("accumulate", c_i32), ("drop_p", c_f32), ("seed", c_u64),
+                ("site", c_u32)]
+
+
+_PG = ctypes.POINTER(Gather)
+_PE = ctypes.POINTER(Epilogue)
+
 # name -> (restype, argtypes); mirrors include/ssb.h one to one (tests check the symbol list)
 _SIGNATURES = {
     "ssb_version": (ctypes.c_int, []),
@@ -31,6 +57,28 @@ _SIGNATURES = {
     "ssb_mel_fwd": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_f32, c_ptr,
                                    c_ptr]),
+    "ssb_gemm_nn": (c_int, [_PG, c_ptr, c_i64, _PE, c_i64, c_i64, c_i64, c_ptr]),
+    "ssb_gemm_nt": (c_int, [_PG, c_ptr, c_i64, c_i64, c_int, c_int, c_int, _PE, c_i64, c_i64,
+                            c_i64, c_ptr]),
+    "ssb_gemm_tn": (c_int, [_PG, c_ptr, c_i64, c_ptr, c_i64, c_int, c_i64, c_i64, c_i64, c_ptr]),
+    "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
+    "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
+    "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,
+                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ssb_bn_apply": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr,
+                             c_ptr]),
+    "ssb_bn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr,
+                           c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ssb_add_dropout_ln_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_f32,
+                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ssb_add_dropout_ln_bwd_workspace_bytes": (c_i64, [c_i64, c_i64]),
+    "ssb_add_dropout_ln_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32,
+                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
+                                       c_ptr]),
+    "ssb_band_attn_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
+                                  c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
+    "ssb_band_attn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                  c_f32, c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
 }
 
 _lock = threading.Lock()

@@ -1,0 +1,122 @@
+"""Mirror of the reference's architecture.py on the B200 kernels.
+
+`Model(num_features, num_outs, num_aux_outs=None)` with `forward(x_feat, x_raw, session_ids)`
+keeps the reference's signature, flags, parameter / buffer names and shapes
+(architecture.py:10-12, 14-84; state_dict contract in SURVEY.md §8b), so the reference's
+transduction_model.py / recognition_model.py run unchanged against it and its checkpoints load.
+
+Data flow (channels-last, no NCL transposes): x_raw (B, L, 8) -> 3 x ResBlock as gathered
+GEMMs + fused BatchNorm/ReLU/residual kernels -> (B*T, D) tokens -> w_raw_in -> N encoder
+layers (transformer.py mirror) -> output heads.
+"""
+import random
+
+import torch
+from torch import nn
+from absl import flags
+
+from . import functional as F_
+from .transformer import TransformerEncoder, TransformerEncoderLayer
+
+FLAGS = flags.FLAGS
+for _define, _name, _default, _help in (
+        (flags.DEFINE_integer, 'model_size', 768, 'number of hidden dimensions'),
+        (flags.DEFINE_integer, 'num_layers', 6, 'number of layers'),
+        (flags.DEFINE_float, 'dropout', .2, 'dropout')):
+    try:
+        _define(_name, _default, _help)
+    except flags.DuplicateFlagError:   # the reference's own architecture.py is also imported
+        pass
+
+
+def _conv_weight(conv):
+    """nn.Conv1d weight (Cout, Cin, k) -> GEMM layout (k*Cin, Cout), row = tap*Cin + ci."""
+    w = conv.weight
+    return w.permute(2, 1, 0).reshape(w.shape[2] * w.shape[1], w.shape[0]).contiguous()
+
+
+class ResBlock(nn.Module):
+    """architecture.py:14-40.  Submodules exist for their parameters/buffers (checkpoint
+    contract); forward runs the fused channels-last kernels."""
+
+    def __init__(self, num_ins, num_outs, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv1d(num_ins, num_outs, 3, padding=1, stride=stride)
+        self.bn1 = nn.BatchNorm1d(num_outs)
+        self.conv2 = nn.Conv1d(num_outs, num_outs, 3, padding=1)
+        self.bn2 = nn.BatchNorm1d(num_outs)
+        if stride != 1 or num_ins != num_outs:
+            self.residual_path = nn.Conv1d(num_ins, num_outs, 1, stride=stride)
+            self.res_norm = nn.BatchNorm1d(num_outs)
+        else:
+            self.residual_path = None
+        self.stride = stride
+
+    def _bn_args(self, bn):
+        if self.training:
+            bn.num_batches_tracked += 1
+        return bn.weight, bn.bias, bn.running_mean, bn.running_var
+
+    def forward_cl(self, x):
+        """x: (B, L, Cin) channels-last -> (B, Lout, Cout)."""
+        if self.residual_path is None:
+            raise NotImplementedError("identity residual is never instantiated by the reference "
+                                      "(architecture.py:46-50) and is not built")
+        tr = self.training
+        c1 = F_.conv1d_cl(x, _conv_weight(self.conv1), self.conv1.bias, 3, self.stride)
+        h1 = F_.bn_act(c1, *self._bn_args(self.bn1), training=tr, relu=True,
+                       momentum=self.bn1.momentum, eps=self.bn1.eps)
+        c2 = F_.conv1d_cl(h1, _conv_weight(self.conv2), self.conv2.bias, 3, 1)
+        cr = F_.conv1d_cl(x, _conv_weight(self.residual_path), self.residual_path.bias, 1,
+                          self.stride)
+        ga, ba, rma, rva = self._bn_args(self.bn2)
+        gb, bb, rmb, rvb = self._bn_args(self.res_norm)
+        return F_.bn_act(c2, ga, ba, rma, rva, tr, True, cr, gb, bb, rmb, rvb,
+                         momentum=self.bn2.momentum, eps=self.bn2.eps)
+
+    def forward(self, x):
+        """x: (B, Cin, L) as in the reference -> (B, Cout, Lout)."""
+        return self.forward_cl(x.transpose(1, 2).contiguous()).transpose(1, 2)
+
+
+class Model(nn.Module):
+    def __init__(self, num_features, num_outs, num_aux_outs=None):
+        super().__init__()
+        model_size = FLAGS['model_size'].value
+        num_layers = FLAGS['num_layers'].value
+        dropout = FLAGS['dropout'].value
+        self.conv_blocks = nn.Sequential(
+            ResBlock(8, model_size, 2),
+            ResBlock(model_size, model_size, 2),
+            ResBlock(model_size, model_size, 2),
+        )
+        self.w_raw_in = nn.Linear(model_size, model_size)
+        encoder_layer = TransformerEncoderLayer(d_model=model_size, nhead=8,
+                                                relative_positional=True,
+                                                relative_positional_distance=100,
+                                                dim_feedforward=3072, dropout=dropout)
+        self.transformer = TransformerEncoder(encoder_layer, num_layers)
+        self.w_out = nn.Linear(model_size, num_outs)
+        self.has_aux_out = num_aux_outs is not None
+        if self.has_aux_out:
+            self.w_aux = nn.Linear(model_size, num_aux_outs)
+
+    def forward(self, x_feat, x_raw, session_ids):
+        # x_raw is (batch, time, electrode); x_feat and session_ids are ignored, as in the
+        # reference (architecture.py:61)
+        if self.training:
+            r = random.randrange(8)           # architecture.py:64-68, mutates the caller's tensor
+            if r > 0:
+                x_raw[:, :-r, :] = x_raw[:, r:, :].clone()
+                x_raw[:, -r:, :] = 0
+        x = x_raw.to(torch.float32).contiguous()
+        for blk in self.conv_blocks:
+            x = blk.forward_cl(x)
+        B, T, D = x.shape
+        x2 = F_.linear(x.view(B * T, D), self.w_raw_in.weight.t().contiguous(), self.w_raw_in.bias)
+        x2 = self.transformer.forward_tokens(x2, B, T)
+        out = F_.linear(x2, self.w_out.weight.t().contiguous(), self.w_out.bias).view(B, T, -1)
+        if self.has_aux_out:
+            aux = F_.linear(x2, self.w_aux.weight.t().contiguous(), self.w_aux.bias).view(B, T, -1)
+            return out, aux
+        return out

@@ -1,0 +1,386 @@
+// fp32 CUDA-core GEMM family with gathered operands (sm_100a).
+//
+// One tile engine (128x128x16, 256 threads, 8x8 register micro-tiles, double-buffered shared
+// memory) serves every dense contraction of the model that is not (yet) on the tcgen05 path:
+//   NN  C[m,n]  = epi( sum_k A(m,k) * W[k,n] )          forward of Linear / Conv1d
+//   NT  C[m,j]  = epi( sum_k A(m,k) * W[row(j,k), col(k)] )   data gradient (W read transposed)
+//   TN  C[k,n] += sum_m A(m,k) * G[m,n]                  weight gradient (split over m)
+// A is never materialised: A(m,k) is gathered on the fly from a channels-last activation
+// tensor (B, L, C) with  m -> (b, t),  k -> (tap, c),  source row  t*s_t + tap*s_tap + off,
+// rows outside [0, L) read as zero.  That one rule expresses nn.Linear (taps = 1), the k3/p1
+// convolutions with stride 1 or 2, the k1/s2 residual convolution and all of their data
+// gradients (architecture.py:18-24) without im2col buffers or padded copies.
+// Output rows go through the same (b, t) -> b*batch_stride + (t*d_t + d_off)*ld map, which
+// lets the stride-2 data gradients write the even / odd input rows directly.
+#include "ssb_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256, PAD = 4;
+
+struct Gather {          // A(m, k)
+  const float* base;
+  int64_t batch_stride;  // elements between batch items of the source
+  int rows_per_batch;    // m -> b = m / rows_per_batch, t = m % rows_per_batch
+  int C;                 // channels per tap (k -> tap = k / C, c = k % C)
+  int L_src;             // valid source rows per batch item
+  int ld;                // elements between consecutive source rows
+  int s_t, s_tap, off;   // source row = t*s_t + tap*s_tap + off
+};
+
+struct Scatter {         // C(m, n) destination
+  float* base;
+  int64_t batch_stride;
+  int rows_per_batch;
+  int ld;
+  int d_t, d_off;        // dest row = t*d_t + d_off
+};
+
+struct WeightNT {        // B(n', k') = W[(tapmap[k'/Cb]*Nn + n') * ld + k' % Cb]
+  const float* base;
+  int ld, Cb, Nn;
+  int tapmap[3];
+};
+
+struct Epilogue {
+  Scatter out;
+  const float* bias;       // [N] or null
+  const float* mask_src;   // plain (M, N) row-major, ld = N: keep where mask_src > 0
+  float mask_scale;
+  int relu;
+  int accumulate;          // C += result
+  float drop_p;            // dropout applied after relu (0 = off)
+  float drop_scale;
+  uint32_t drop_thresh;
+  uint64_t seed;
+  uint32_t site;
+};
+
+__device__ __forceinline__ const float* gather_ptr(const Gather& g, int m, int k, bool& valid) {
+  const int b = m / g.rows_per_batch;
+  const int t = m - b * g.rows_per_batch;
+  const int tap = k / g.C;
+  const int c = k - tap * g.C;
+  const int ts = t * g.s_t + tap * g.s_tap + g.off;
+  valid = (unsigned)ts < (unsigned)g.L_src;
+  return g.base + (int64_t)b * g.batch_stride + (int64_t)ts * g.ld + c;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+// ---------------------------------------------------------------------------------------
+// MODE 0: NN   (B = W[k, n], n contiguous)
+// MODE 1: NT   (B = WeightNT, k contiguous)
+// MODE 2: TN   (reduction over m; A gathered, B = G[m, n]); output plain (K, N)
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(THREADS)
+gemm_kernel(const Gather ga, const float* __restrict__ Bplain, int ldb, const WeightNT wnt,
+            const Epilogue ep, int M, int N, int K, int red_per_split) {
+  // "o" = output index of the operand (m for A, n for B; for TN: k for A, n for B)
+  // "r" = reduction index (k for NN/NT; m for TN)
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+
+  const int tid = threadIdx.x;
+  const int o0a = blockIdx.y * BM;   // A-side output origin (m, or k for TN)
+  const int o0b = blockIdx.x * BN;   // B-side output origin (n)
+  const int OA = (MODE == 2) ? K : M;   // extent of A-side output index
+  const int RED = (MODE == 2) ? M : K;  // reduction extent
+  const int red_begin = blockIdx.z * red_per_split;
+  const int red_end = min(RED, red_begin + red_per_split);
+
+  // --- per-thread load coordinates -------------------------------------------------
+  // RED-contiguous operand tiles: o = tid % 128, r4 = (tid / 128) * 4 (+8 second half)
+  // OUT-contiguous operand tiles: o4 = (tid % 32) * 4, r = tid / 32 (+8 second half)
+  const int rc_o = tid & 127, rc_r4 = (tid >> 7) << 2;
+  const int oc_o4 = (tid & 31) << 2, oc_r = tid >> 5;
+
+  float4 ra[2], rb[2];
+
+  auto load_tiles = [&](int r0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // ---- A ----
+      if (MODE != 2) {  // A(m, k): k contiguous
+        const int m = o0a + rc_o, k = r0 + rc_r4 + 8 * h;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < M && k < red_end) {
+          bool ok;
+          const float* p = gather_ptr(ga, m, k, ok);
+          if (ok) v = ldg4(p);
+        }
+        ra[h] = v;
+      } else {          // TN: tile rows are m (reduction), columns are k (contiguous)
+        const int m = r0 + oc_r + 8 * h, k = o0a + oc_o4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < red_end && k < K) {
+          bool ok;
+          const float* p = gather_ptr(ga, m, k, ok);
+          if (ok) v = ldg4(p);
+        }
+        ra[h] = v;
+      }
+      // ---- B ----
+      if (MODE == 0) {  // W[k, n], n contiguous
+        const int k = r0 + oc_r + 8 * h, n = o0b + oc_o4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < red_end && n < N) v = ldg4(Bplain + (int64_t)k * ldb + n);
+        rb[h] = v;
+      } else if (MODE == 1) {  // B(n', k'), k' contiguous inside a tap block
+        const int n = o0b + rc_o, k = r0 + rc_r4 + 8 * h;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < N && k < red_end) {
+          const int tap = k / wnt.Cb, c = k - tap * wnt.Cb;
+          v = ldg4(wnt.base + ((int64_t)wnt.tapmap[tap] * wnt.Nn + n) * wnt.ld + c);
+        }
+        rb[h] = v;
+      } else {  // TN: G[m, n]
+        const int m = r0 + oc_r + 8 * h, n = o0b + oc_o4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < red_end && n < N) v = ldg4(Bplain + (int64_t)m * ldb + n);
+        rb[h] = v;
+      }
+    }
+  };
+
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (MODE != 2) {
+        const int r = rc_r4 + 8 * h;
+        As[buf][r + 0][rc_o] = ra[h].x;
+        As[buf][r + 1][rc_o] = ra[h].y;
+        As[buf][r + 2][rc_o] = ra[h].z;
+        As[buf][r + 3][rc_o] = ra[h].w;
+      } else {
+        *reinterpret_cast<float4*>(&As[buf][oc_r + 8 * h][oc_o4]) = ra[h];
+      }
+      if (MODE == 1) {
+        const int r = rc_r4 + 8 * h;
+        Bs[buf][r + 0][rc_o] = rb[h].x;
+        Bs[buf][r + 1][rc_o] = rb[h].y;
+        Bs[buf][r + 2][rc_o] = rb[h].z;
+        Bs[buf][r + 3][rc_o] = rb[h].w;
+      } else {
+        *reinterpret_cast<float4*>(&Bs[buf][oc_r + 8 * h][oc_o4]) = rb[h];
+      }
+    }
+  };
+
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int ntiles = (red_end > red_begin) ? (red_end - red_begin + BK - 1) / BK : 0;
+  if (ntiles > 0) {
+    load_tiles(red_begin);
+    store_tiles(0);
+  }
+  __syncthreads();
+  for (int tIdx = 0; tIdx < ntiles; ++tIdx) {
+    const int buf = tIdx & 1;
+    if (tIdx + 1 < ntiles) load_tiles(red_begin + (tIdx + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (tIdx + 1 < ntiles) store_tiles(buf ^ 1);
+    __syncthreads();
+  }
+
+  // --- epilogue -----------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int oa = o0a + ((i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (oa >= OA) continue;
+    float* row;
+    if (MODE == 2) {
+      row = ep.out.base + (int64_t)oa * ep.out.ld;
+    } else {
+      const int b = oa / ep.out.rows_per_batch, t = oa - b * ep.out.rows_per_batch;
+      row = ep.out.base + (int64_t)b * ep.out.batch_stride +
+            (int64_t)(t * ep.out.d_t + ep.out.d_off) * ep.out.ld;
+    }
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = o0b + jh * 64 + tx * 4;
+      if (n >= N) continue;
+      float4 v = make_float4(acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2],
+                             acc[i][jh * 4 + 3]);
+      if (MODE == 2) {
+        if (gridDim.z > 1) {
+          atomicAdd(row + n + 0, v.x);
+          atomicAdd(row + n + 1, v.y);
+          atomicAdd(row + n + 2, v.z);
+          atomicAdd(row + n + 3, v.w);
+        } else {
+          if (ep.accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(row + n);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *reinterpret_cast<float4*>(row + n) = v;
+        }
+        continue;
+      }
+      if (ep.bias) {
+        const float4 bv = ldg4(ep.bias + n);
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      }
+      if (ep.relu) {
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+      }
+      if (ep.drop_p > 0.f) {
+        const uint64_t e = (uint64_t)oa * (uint64_t)N + (uint64_t)n;  // n % 4 == 0
+        const uint4 rnd = ssb::dropout_bits4(ep.seed, ep.site, e >> 2);
+        v.x = rnd.x >= ep.drop_thresh ? v.x * ep.drop_scale : 0.f;
+        v.y = rnd.y >= ep.drop_thresh ? v.y * ep.drop_scale : 0.f;
+        v.z = rnd.z >= ep.drop_thresh ? v.z * ep.drop_scale : 0.f;
+        v.w = rnd.w >= ep.drop_thresh ? v.w * ep.drop_scale : 0.f;
+      }
+      if (ep.mask_src) {
+        const float4 mk = ldg4(ep.mask_src + (int64_t)oa * N + n);
+        v.x = mk.x > 0.f ? v.x * ep.mask_scale : 0.f;
+        v.y = mk.y > 0.f ? v.y * ep.mask_scale : 0.f;
+        v.z = mk.z > 0.f ? v.z * ep.mask_scale : 0.f;
+        v.w = mk.w > 0.f ? v.w * ep.mask_scale : 0.f;
+      }
+      if (ep.accumulate) {
+        const float4 o = *reinterpret_cast<const float4*>(row + n);
+        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+      }
+      *reinterpret_cast<float4*>(row + n) = v;
+    }
+  }
+}
+
+int check_gather(const ssb_gather_t* g, int64_t M, int64_t K) {
+  SSB_REQUIRE(g && g->base, "gemm: null A");
+  SSB_REQUIRE(g->rows_per_batch > 0 && g->C > 0 && g->L_src > 0 && g->ld >= g->C,
+              "gemm: bad gather geometry");
+  SSB_REQUIRE(g->C % 4 == 0 && g->ld % 4 == 0 && g->batch_stride % 4 == 0 &&
+                  ((uintptr_t)g->base & 15) == 0,
+              "gemm: A must be 16 B aligned with channel counts divisible by 4");
+  SSB_REQUIRE(K % 4 == 0 && K <= (int64_t)3 * g->C, "gemm: K=%lld incompatible with C=%d",
+              (long long)K, g->C);
+  SSB_REQUIRE(M < (1LL << 31) && K < (1LL << 31), "gemm: dimension too large");
+  return SSB_OK;
+}
+
+Gather to_gather(const ssb_gather_t* g) {
+  Gather r;
+  r.base = g->base; r.batch_stride = g->batch_stride; r.rows_per_batch = g->rows_per_batch;
+  r.C = g->C; r.L_src = g->L_src; r.ld = g->ld; r.s_t = g->s_t; r.s_tap = g->s_tap; r.off = g->off;
+  return r;
+}
+
+int fill_epilogue(const ssb_epilogue_t* e, int64_t M, int64_t N, Epilogue* out) {
+  SSB_REQUIRE(e && e->out.base, "gemm: null output");
+  SSB_REQUIRE(e->out.rows_per_batch > 0 && e->out.ld >= N && e->out.ld % 4 == 0 &&
+                  e->out.batch_stride % 4 == 0 && ((uintptr_t)e->out.base & 15) == 0,
+              "gemm: bad output geometry / alignment");
+  SSB_REQUIRE(N % 4 == 0, "gemm: N=%lld must be a multiple of 4", (long long)N);
+  SSB_REQUIRE(e->drop_p >= 0.f && e->drop_p < 1.f, "gemm: bad dropout p");
+  out->out.base = e->out.base; out->out.batch_stride = e->out.batch_stride;
+  out->out.rows_per_batch = e->out.rows_per_batch; out->out.ld = e->out.ld;
+  out->out.d_t = e->out.d_t; out->out.d_off = e->out.d_off;
+  out->bias = e->bias; out->mask_src = e->mask_src; out->mask_scale = e->mask_scale;
+  out->relu = e->relu; out->accumulate = e->accumulate;
+  out->drop_p = e->drop_p;
+  out->drop_scale = e->drop_p > 0.f ? 1.f / (1.f - e->drop_p) : 1.f;
+  const double th = (double)e->drop_p * 4294967296.0;
+  out->drop_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
+  out->seed = e->seed; out->site = e->site;
+  return SSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ssb_gemm_nn(const ssb_gather_t* A, const float* W, int64_t ldw, const ssb_epilogue_t* epi,
+                int64_t M, int64_t N, int64_t K, void* stream) {
+  if (M == 0 || N == 0) return SSB_OK;
+  if (int rc = check_gather(A, M, K)) return rc;
+  SSB_REQUIRE(W && ldw >= N && ldw % 4 == 0 && ((uintptr_t)W & 15) == 0, "gemm_nn: bad W");
+  Epilogue ep;
+  if (int rc = fill_epilogue(epi, M, N, &ep)) return rc;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
+  SSB_REQUIRE(grid.y <= 65535, "gemm_nn: M too large for grid.y");
+  WeightNT dummy = {};
+  gemm_kernel<0><<<grid, THREADS, 0, (cudaStream_t)stream>>>(to_gather(A), W, (int)ldw, dummy, ep,
+                                                             (int)M, (int)N, (int)K, (int)K);
+  SSB_LAUNCH_CHECK("gemm_nn");
+  return SSB_OK;
+}
+
+int ssb_gemm_nt(const ssb_gather_t* A, const float* W, int64_t ldw, int64_t Cb, int tap0, int tap1,
+                int tap2, const ssb_epilogue_t* epi, int64_t M, int64_t N, int64_t K,
+                void* stream) {
+  if (M == 0 || N == 0) return SSB_OK;
+  if (int rc = check_gather(A, M, K)) return rc;
+  SSB_REQUIRE(W && ldw >= Cb && ldw % 4 == 0 && Cb % 4 == 0 && ((uintptr_t)W & 15) == 0 &&
+                  K % Cb == 0 && K / Cb <= 3,
+              "gemm_nt: bad W geometry");
+  Epilogue ep;
+  if (int rc = fill_epilogue(epi, M, N, &ep)) return rc;
+  WeightNT w;
+  w.base = W; w.ld = (int)ldw; w.Cb = (int)Cb; w.Nn = (int)N;
+  w.tapmap[0] = tap0; w.tapmap[1] = tap1; w.tapmap[2] = tap2;
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
+  SSB_REQUIRE(grid.y <= 65535, "gemm_nt: M too large for grid.y");
+  gemm_kernel<1><<<grid, THREADS, 0, (cudaStream_t)stream>>>(to_gather(A), nullptr, 0, w, ep,
+                                                             (int)M, (int)N, (int)K, (int)K);
+  SSB_LAUNCH_CHECK("gemm_nt");
+  return SSB_OK;
+}
+
+int ssb_gemm_tn(const ssb_gather_t* A, const float* G, int64_t ldg, float* dW, int64_t lddw,
+                int accumulate, int64_t M, int64_t N, int64_t K, void* stream) {
+  if (K == 0 || N == 0) return SSB_OK;
+  if (int rc = check_gather(A, M, K)) return rc;
+  SSB_REQUIRE(G && dW && ldg >= N && lddw >= N && ldg % 4 == 0 && lddw % 4 == 0 && N % 4 == 0 &&
+                  ((uintptr_t)G & 15) == 0 && ((uintptr_t)dW & 15) == 0,
+              "gemm_tn: bad G / dW geometry");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tiles = (int)(((N + BN - 1) / BN) * ((K + BM - 1) / BM));
+  int splits = 1;
+  const int sms = ssb::num_sms();
+  if (M > 4 * BK) {
+    splits = (2 * sms + tiles - 1) / tiles;
+    const int64_t max_splits = (M + 8 * BK - 1) / (8 * BK);
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 1024) splits = 1024;
+  }
+  int64_t per = (M + splits - 1) / splits;
+  per = ((per + BK - 1) / BK) * BK;
+  splits = (int)((M + per - 1) / per);
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !accumulate)
+    SSB_CUDA(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)N * 4, (size_t)K, st));
+  Epilogue ep = {};
+  ep.out.base = dW; ep.out.ld = (int)lddw; ep.out.rows_per_batch = 1; ep.accumulate = accumulate;
+  WeightNT dummy = {};
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((K + BM - 1) / BM), (unsigned)splits);
+  gemm_kernel<2><<<grid, THREADS, 0, st>>>(to_gather(A), G, (int)ldg, dummy, ep, (int)M, (int)N,
+                                           (int)K, (int)per);
+  SSB_LAUNCH_CHECK("gemm_tn");
+  return SSB_OK;
+}
+
+}  // extern "C"

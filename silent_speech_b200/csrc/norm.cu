@@ -1,0 +1,544 @@
+// Normalisation / reduction kernels of the transduction model (sm_100a), channels-last.
+//
+//   column statistics + BatchNorm1d (training and eval) forward/backward   architecture.py:19-25,32-40
+//   residual add + dropout + LayerNorm forward/backward                    transformer.py:55-59
+//   column sums (bias gradients)
+//
+// All tensors are (rows, C) fp32 with C contiguous; per-channel quantities are column
+// reductions.  Reductions are two-stage and deterministic: a grid of CTAs writes fp32
+// partials per row chunk, a finalize kernel adds them in fp64 in a fixed order.
+#include "ssb_common.cuh"
+
+namespace {
+
+constexpr int RCH = 256;  // rows per partial chunk
+
+// ---- column partial sums -------------------------------------------------------------
+// MODE 0: sum(x), sum(x^2)                       (BatchNorm batch statistics)
+// MODE 1: sum(x)                                  (bias gradient)
+// MODE 2: sum(dz), sum(dz * xhat)   dz = dy * (mask_src > 0 if mask_src)   (BatchNorm backward)
+// block = 32 column-lanes (float4 each -> 128 columns) x 8 row-lanes
+template <int MODE>
+__global__ void __launch_bounds__(256)
+col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                    const float* __restrict__ mask_src, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, int64_t rows, int C, int ld,
+                    float* __restrict__ partials /* [nchunks][2][C] */) {
+  __shared__ float4 red[2][8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cl) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * RCH;
+  const int64_t r1 = min(rows, r0 + RCH);
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+  if (c < C) {
+    float4 mu = s0, rs = s0;
+    if (MODE == 2) {
+      mu = *reinterpret_cast<const float4*>(mean + c);
+      rs = *reinterpret_cast<const float4*>(rstd + c);
+    }
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      if (MODE == 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+        s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+        s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y);
+        s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
+      } else if (MODE == 1) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+        s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+      } else {
+        float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * ld + c));
+        if (mask_src) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src + r * ld + c));
+          g.x = m.x > 0.f ? g.x : 0.f; g.y = m.y > 0.f ? g.y : 0.f;
+          g.z = m.z > 0.f ? g.z : 0.f; g.w = m.w > 0.f ? g.w : 0.f;
+        }
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+        s0.x += g.x; s0.y += g.y; s0.z += g.z; s0.w += g.w;
+        s1.x = fmaf(g.x, (v.x - mu.x) * rs.x, s1.x); s1.y = fmaf(g.y, (v.y - mu.y) * rs.y, s1.y);
+        s1.z = fmaf(g.z, (v.z - mu.z) * rs.z, s1.z); s1.w = fmaf(g.w, (v.w - mu.w) * rs.w, s1.w);
+      }
+    }
+  }
+  red[0][rl][cl] = s0;
+  red[1][rl][cl] = s1;
+  __syncthreads();
+  if (rl < 2 && c < C) {
+    float4 a = red[rl][0][cl];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 b = red[rl][i][cl];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (rl == 0 || MODE != 1)
+      *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 2 + rl) * C + c) = a;
+  }
+}
+
+// ---- finalize kernels (one thread per channel, fp64 accumulation over chunks) ---------
+__global__ void colsum_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+                                       float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < nchunks; ++k) s += (double)partials[((int64_t)k * 2) * C + c];
+  out[c] = (accumulate ? out[c] : 0.f) + (float)s;
+}
+
+// training: batch statistics -> (mean, rstd, scale, shift) + running-stat update
+// (biased variance normalises, unbiased variance feeds running_var; nn.BatchNorm1d semantics)
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+                                   double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean,
+                                   float* running_var, float momentum, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < nchunks; ++k) {
+    s += (double)partials[((int64_t)k * 2) * C + c];
+    ss += (double)partials[((int64_t)k * 2 + 1) * C + c];
+  }
+  const double mu = s / count;
+  double var = ss / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float r = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
+  rstd[c] = r;
+  const float sc = gamma[c] * r;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mu * sc;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval: running statistics -> (mean, rstd, scale, shift)
+__global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean,
+                                      const float* __restrict__ running_var, float eps,
+                                      float* __restrict__ mean, float* __restrict__ rstd,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float r = 1.f / sqrtf(running_var[c] + eps);
+  mean[c] = running_mean[c];
+  rstd[c] = r;
+  scale[c] = gamma[c] * r;
+  shift[c] = beta[c] - running_mean[c] * gamma[c] * r;
+}
+
+// y = [relu]( x*scale + shift  [+ x2*scale2 + shift2] )
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                const float* __restrict__ shift, const float* __restrict__ x2,
+                const float* __restrict__ scale2, const float* __restrict__ shift2, int relu,
+                int64_t n4, int C4, float* __restrict__ y) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c);
+    const float4 sh = *reinterpret_cast<const float4*>(shift + c);
+    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z),
+                           fmaf(v.w, sc.w, sh.w));
+    if (x2) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(x2) + i);
+      const float4 sc2 = *reinterpret_cast<const float4*>(scale2 + c);
+      const float4 sh2 = *reinterpret_cast<const float4*>(shift2 + c);
+      o.x += fmaf(w.x, sc2.x, sh2.x); o.y += fmaf(w.y, sc2.y, sh2.y);
+      o.z += fmaf(w.z, sc2.z, sh2.z); o.w += fmaf(w.w, sc2.w, sh2.w);
+    }
+    if (relu) {
+      o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+    }
+    reinterpret_cast<float4*>(y)[i] = o;
+  }
+}
+
+// BatchNorm backward, finalize: sums -> dgamma, dbeta and the two per-channel means
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+                                       double count, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ m_dz,
+                                       float* __restrict__ m_dzx) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, sx = 0.0;
+  for (int k = 0; k < nchunks; ++k) {
+    s += (double)partials[((int64_t)k * 2) * C + c];
+    sx += (double)partials[((int64_t)k * 2 + 1) * C + c];
+  }
+  dbeta[c] = (float)s;
+  dgamma[c] = (float)sx;
+  m_dz[c] = (float)(s / count);
+  m_dzx[c] = (float)(sx / count);
+}
+
+// dx = gamma*rstd * (dz - mean(dz) - xhat*mean(dz*xhat));  eval mode: dx = gamma*rstd*dz
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask_src,
+                    const float* __restrict__ x, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ m_dz, const float* __restrict__ m_dzx, int64_t n4,
+                    int C4, float* __restrict__ dx) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    if (mask_src) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src) + i);
+      g.x = m.x > 0.f ? g.x : 0.f; g.y = m.y > 0.f ? g.y : 0.f;
+      g.z = m.z > 0.f ? g.z : 0.f; g.w = m.w > 0.f ? g.w : 0.f;
+    }
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
+    const float4 rs = *reinterpret_cast<const float4*>(rstd + c);
+    const float4 ga = *reinterpret_cast<const float4*>(gamma + c);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
+    if (m_dz) {
+      a = *reinterpret_cast<const float4*>(m_dz + c);
+      bq = *reinterpret_cast<const float4*>(m_dzx + c);
+    }
+    float4 o;
+    o.x = ga.x * rs.x * (g.x - a.x - (v.x - mu.x) * rs.x * bq.x);
+    o.y = ga.y * rs.y * (g.y - a.y - (v.y - mu.y) * rs.y * bq.y);
+    o.z = ga.z * rs.z * (g.z - a.z - (v.z - mu.z) * rs.z * bq.z);
+    o.w = ga.w * rs.w * (g.w - a.w - (v.w - mu.w) * rs.w * bq.w);
+    reinterpret_cast<float4*>(dx)[i] = o;
+  }
+}
+
+// ---- residual + dropout + LayerNorm ----------------------------------------------------
+// One warp per row; D <= 1024, D % 4 == 0.  z = res + dropout(branch); y = LN(z).
+constexpr int LN_MAXV = 8;  // float4 per lane
+
+__global__ void __launch_bounds__(256)
+add_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ branch,
+                  const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows,
+                  int D, float eps, float drop_p, float drop_scale, uint32_t drop_thresh,
+                  uint64_t seed, uint32_t site, float* __restrict__ z_out,
+                  float* __restrict__ y, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nv = D >> 2;
+  float4 z[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(res + row * D) + v);
+      float4 b = __ldg(reinterpret_cast<const float4*>(branch + row * D) + v);
+      if (drop_p > 0.f) {
+        const uint4 rnd = ssb::dropout_bits4(seed, site, (uint64_t)row * nv + v);
+        b.x = rnd.x >= drop_thresh ? b.x * drop_scale : 0.f;
+        b.y = rnd.y >= drop_thresh ? b.y * drop_scale : 0.f;
+        b.z = rnd.z >= drop_thresh ? b.z * drop_scale : 0.f;
+        b.w = rnd.w >= drop_thresh ? b.w * drop_scale : 0.f;
+      }
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      z[i] = a;
+      s += a.x + a.y + a.z + a.w;
+    }
+  }
+  s = ssb::warp_sum(s);
+  const float mu = s / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      const float dx = z[i].x - mu, dy = z[i].y - mu, dz = z[i].z - mu, dw = z[i].w - mu;
+      q += dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+  }
+  q = ssb::warp_sum(q);
+  const float rs = rsqrtf(q / (float)D + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + v * 4);
+      const float4 b = *reinterpret_cast<const float4*>(beta + v * 4);
+      float4 o;
+      o.x = (z[i].x - mu) * rs * g.x + b.x;
+      o.y = (z[i].y - mu) * rs * g.y + b.y;
+      o.z = (z[i].z - mu) * rs * g.z + b.z;
+      o.w = (z[i].w - mu) * rs * g.w + b.w;
+      reinterpret_cast<float4*>(y + row * D)[v] = o;
+      if (z_out) reinterpret_cast<float4*>(z_out + row * D)[v] = z[i];
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mu;
+    if (rstd_out) rstd_out[row] = rs;
+  }
+}
+
+// backward: d_res = dz, d_branch = dz * dropmask * scale; per-CTA partial dgamma/dbeta
+constexpr int LN_ROWS_PER_CTA = 64;
+
+__global__ void __launch_bounds__(256)
+add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
+                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ gamma, int64_t rows, int D, float drop_p,
+                  float drop_scale, uint32_t drop_thresh, uint64_t seed, uint32_t site,
+                  float* __restrict__ d_res, float* __restrict__ d_branch,
+                  float* __restrict__ partials /* [nblk][2][D] : dgamma, dbeta */) {
+  __shared__ float sm[2][1024];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = D >> 2;
+  for (int i = threadIdx.x; i < 2 * 1024; i += 256) (&sm[0][0])[i] = 0.f;
+  __syncthreads();
+  float4 dg[LN_MAXV], db[LN_MAXV], g4[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[i] = dg[i];
+    const int v = lane + i * 32;
+    g4[i] = v < nv ? *reinterpret_cast<const float4*>(gamma + v * 4) : dg[i];
+  }
+  const int64_t r0 = (int64_t)blockIdx.x * LN_ROWS_PER_CTA;
+  const int64_t r1 = min(rows, r0 + LN_ROWS_PER_CTA);
+  for (int64_t row = r0 + warp; row < r1; row += 8) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 gy[LN_MAXV], xh[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nv) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + row * D) + v);
+        const float4 zz = __ldg(reinterpret_cast<const float4*>(z + row * D) + v);
+        xh[i] = make_float4((zz.x - mu) * rs, (zz.y - mu) * rs, (zz.z - mu) * rs,
+                            (zz.w - mu) * rs);
+        gy[i] = make_float4(d.x * g4[i].x, d.y * g4[i].y, d.z * g4[i].z, d.w * g4[i].w);
+        s1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
+        s2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
+        dg[i].x = fmaf(d.x, xh[i].x, dg[i].x); dg[i].y = fmaf(d.y, xh[i].y, dg[i].y);
+        dg[i].z = fmaf(d.z, xh[i].z, dg[i].z); dg[i].w = fmaf(d.w, xh[i].w, dg[i].w);
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      }
+    }
+    s1 = ssb::warp_sum(s1) / (float)D;
+    s2 = ssb::warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < nv) {
+        float4 o;
+        o.x = rs * (gy[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (gy[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (gy[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (gy[i].w - s1 - xh[i].w * s2);
+        reinterpret_cast<float4*>(d_res + row * D)[v] = o;
+        if (drop_p > 0.f) {
+          const uint4 rnd = ssb::dropout_bits4(seed, site, (uint64_t)row * nv + v);
+          o.x = rnd.x >= drop_thresh ? o.x * drop_scale : 0.f;
+          o.y = rnd.y >= drop_thresh ? o.y * drop_scale : 0.f;
+          o.z = rnd.z >= drop_thresh ? o.z * drop_scale : 0.f;
+          o.w = rnd.w >= drop_thresh ? o.w * drop_scale : 0.f;
+        }
+        reinterpret_cast<float4*>(d_branch + row * D)[v] = o;
+      }
+    }
+  }
+  // cross-warp reduction of the per-lane column partials
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int v = lane + i * 32;
+    if (v < nv) {
+      atomicAdd(&sm[0][v * 4 + 0], dg[i].x); atomicAdd(&sm[0][v * 4 + 1], dg[i].y);
+      atomicAdd(&sm[0][v * 4 + 2], dg[i].z); atomicAdd(&sm[0][v * 4 + 3], dg[i].w);
+      atomicAdd(&sm[1][v * 4 + 0], db[i].x); atomicAdd(&sm[1][v * 4 + 1], db[i].y);
+      atomicAdd(&sm[1][v * 4 + 2], db[i].z); atomicAdd(&sm[1][v * 4 + 3], db[i].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    partials[((int64_t)blockIdx.x * 2 + 0) * D + c] = sm[0][c];
+    partials[((int64_t)blockIdx.x * 2 + 1) * D + c] = sm[1][c];
+  }
+}
+
+__global__ void ln_param_grad_finalize_kernel(const float* __restrict__ partials, int nblk, int D,
+                                              float* __restrict__ dgamma,
+                                              float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double a = 0.0, b = 0.0;
+  for (int k = 0; k < nblk; ++k) {
+    a += (double)partials[((int64_t)k * 2) * D + c];
+    b += (double)partials[((int64_t)k * 2 + 1) * D + c];
+  }
+  dgamma[c] = (float)a;
+  dbeta[c] = (float)b;
+}
+
+int check_rows_c(const void* p, int64_t rows, int64_t C, const char* what) {
+  SSB_REQUIRE(p != nullptr, "%s: null pointer", what);
+  SSB_REQUIRE(rows >= 1 && C >= 4 && C % 4 == 0 && C < (1 << 24), "%s: bad shape rows=%lld C=%lld",
+              what, (long long)rows, (long long)C);
+  SSB_REQUIRE(((uintptr_t)p & 15) == 0, "%s: pointer must be 16 B aligned", what);
+  return SSB_OK;
+}
+
+inline int nchunks_for(int64_t rows) { return (int)((rows + RCH - 1) / RCH); }
+
+inline uint32_t thresh_of(float p) {
+  const double th = (double)p * 4294967296.0;
+  return th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ssb_col_partials_bytes(int64_t rows, int64_t C) {
+  if (rows < 0 || C < 0) return SSB_ERR_ARG;
+  return (int64_t)nchunks_for(rows > 0 ? rows : 1) * 2 * C * 4;
+}
+
+int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumulate,
+               void* workspace, int64_t workspace_bytes, void* stream) {
+  if (int rc = check_rows_c(x, rows, C, "colsum")) return rc;
+  SSB_REQUIRE(out && workspace && workspace_bytes >= ssb_col_partials_bytes(rows, C),
+              "colsum: bad out/workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nch = nchunks_for(rows);
+  dim3 grid((unsigned)((C + 127) / 128), (unsigned)nch);
+  col_partials_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
+                                               (int)C, (float*)workspace);
+  SSB_LAUNCH_CHECK("col_partials<1>");
+  colsum_finalize_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>((const float*)workspace, nch,
+                                                                      (int)C, out, accumulate);
+  SSB_LAUNCH_CHECK("colsum_finalize");
+  return SSB_OK;
+}
+
+int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float momentum, float eps,
+                 int training, float* mean, float* rstd, float* scale, float* shift,
+                 void* workspace, int64_t workspace_bytes, void* stream) {
+  if (int rc = check_rows_c(x, rows, C, "bn_stats")) return rc;
+  SSB_REQUIRE(gamma && beta && mean && rstd && scale && shift, "bn_stats: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned cb = (unsigned)((C + 127) / 128);
+  if (!training) {
+    SSB_REQUIRE(running_mean && running_var, "bn_stats: eval mode needs running statistics");
+    bn_eval_affine_kernel<<<cb, 128, 0, st>>>((int)C, gamma, beta, running_mean, running_var, eps,
+                                              mean, rstd, scale, shift);
+    SSB_LAUNCH_CHECK("bn_eval_affine");
+    return SSB_OK;
+  }
+  SSB_REQUIRE(workspace && workspace_bytes >= ssb_col_partials_bytes(rows, C),
+              "bn_stats: workspace too small");
+  const int nch = nchunks_for(rows);
+  dim3 grid(cb, (unsigned)nch);
+  col_partials_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
+                                               (int)C, (float*)workspace);
+  SSB_LAUNCH_CHECK("col_partials<0>");
+  bn_finalize_kernel<<<cb, 128, 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, gamma,
+                                         beta, running_mean, running_var, momentum, eps, mean,
+                                         rstd, scale, shift);
+  SSB_LAUNCH_CHECK("bn_finalize");
+  return SSB_OK;
+}
+
+int ssb_bn_apply(const float* x, const float* scale, const float* shift, const float* x2,
+                 const float* scale2, const float* shift2, int relu, int64_t rows, int64_t C,
+                 float* y, void* stream) {
+  if (int rc = check_rows_c(x, rows, C, "bn_apply")) return rc;
+  SSB_REQUIRE(scale && shift && y && (!x2 || (scale2 && shift2)), "bn_apply: null pointer");
+  const int64_t n4 = rows * C / 4;
+  const int64_t blocks = (n4 + 255) / 256;
+  const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+  bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, x2, scale2, shift2, relu,
+                                                          n4, (int)(C / 4), y);
+  SSB_LAUNCH_CHECK("bn_apply");
+  return SSB_OK;
+}
+
+int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const float* mean,
+               const float* rstd, const float* gamma, int training, int64_t rows, int64_t C,
+               float* dx, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
+               void* stream) {
+  if (int rc = check_rows_c(x, rows, C, "bn_bwd")) return rc;
+  SSB_REQUIRE(dy && mean && rstd && gamma && dx && dgamma && dbeta, "bn_bwd: null pointer");
+  const int64_t need = ssb_col_partials_bytes(rows, C) + 2 * C * 4;
+  SSB_REQUIRE(workspace && workspace_bytes >= need, "bn_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nch = nchunks_for(rows);
+  const unsigned cb = (unsigned)((C + 127) / 128);
+  float* partials = (float*)workspace;
+  float* m_dz = partials + (int64_t)nch * 2 * C;
+  float* m_dzx = m_dz + C;
+  dim3 grid(cb, (unsigned)nch);
+  col_partials_kernel<2><<<grid, 256, 0, st>>>(x, dy, mask_src, mean, rstd, rows, (int)C, (int)C,
+                                               partials);
+  SSB_LAUNCH_CHECK("col_partials<2>");
+  bn_bwd_finalize_kernel<<<cb, 128, 0, st>>>(partials, nch, (int)C, (double)rows, dgamma, dbeta,
+                                             m_dz, m_dzx);
+  SSB_LAUNCH_CHECK("bn_bwd_finalize");
+  const int64_t n4 = rows * C / 4;
+  const int64_t blocks = (n4 + 255) / 256;
+  const int g2 = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+  bn_bwd_apply_kernel<<<g2, 256, 0, st>>>(dy, mask_src, x, mean, rstd, gamma,
+                                          training ? m_dz : nullptr, training ? m_dzx : nullptr,
+                                          n4, (int)(C / 4), dx);
+  SSB_LAUNCH_CHECK("bn_bwd_apply");
+  return SSB_OK;
+}
+
+int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const float* gamma,
+                           const float* beta, int64_t rows, int64_t D, float eps, float drop_p,
+                           uint64_t seed, uint32_t site, float* z_out, float* y, float* mean,
+                           float* rstd, void* stream) {
+  if (int rc = check_rows_c(res, rows, D, "add_dropout_ln_fwd")) return rc;
+  SSB_REQUIRE(D <= 1024, "add_dropout_ln_fwd: D=%lld > 1024 not built", (long long)D);
+  SSB_REQUIRE(branch && gamma && beta && y, "add_dropout_ln_fwd: null pointer");
+  SSB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "add_dropout_ln_fwd: bad p");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  add_ln_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      res, branch, gamma, beta, rows, (int)D, eps, drop_p, drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,
+      thresh_of(drop_p), seed, site, z_out, y, mean, rstd);
+  SSB_LAUNCH_CHECK("add_ln_fwd");
+  return SSB_OK;
+}
+
+int64_t ssb_add_dropout_ln_bwd_workspace_bytes(int64_t rows, int64_t D) {
+  if (rows < 0 || D < 0) return SSB_ERR_ARG;
+  const int64_t nblk = (rows + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA;
+  return (nblk > 0 ? nblk : 1) * 2 * D * 4;
+}
+
+int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
+                           const float* gamma, int64_t rows, int64_t D, float drop_p,
+                           uint64_t seed, uint32_t site, float* d_res, float* d_branch,
+                           float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
+  if (int rc = check_rows_c(dy, rows, D, "add_dropout_ln_bwd")) return rc;
+  SSB_REQUIRE(D <= 1024, "add_dropout_ln_bwd: D=%lld > 1024 not built", (long long)D);
+  SSB_REQUIRE(z && mean && rstd && gamma && d_res && d_branch && dgamma && dbeta,
+              "add_dropout_ln_bwd: null pointer");
+  SSB_REQUIRE(workspace && workspace_bytes >= ssb_add_dropout_ln_bwd_workspace_bytes(rows, D),
+              "add_dropout_ln_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nblk = (int)((rows + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA);
+  add_ln_bwd_kernel<<<nblk, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, (int)D, drop_p,
+                                          drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,
+                                          thresh_of(drop_p), seed, site, d_res, d_branch,
+                                          (float*)workspace);
+  SSB_LAUNCH_CHECK("add_ln_bwd");
+  ln_param_grad_finalize_kernel<<<(unsigned)((D + 127) / 128), 128, 0, st>>>(
+      (const float*)workspace, nblk, (int)D, dgamma, dbeta);
+  SSB_LAUNCH_CHECK("ln_param_grad_finalize");
+  return SSB_OK;
+}
+
+}  // extern "C"

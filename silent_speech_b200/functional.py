@@ -1,0 +1,439 @@
+"""torch.autograd bindings of the libssb model kernels (GEMM family, BatchNorm, band attention,
+add+dropout+LayerNorm).  Autograd lives here in Python; every forward/backward body is a
+sequence of C-ABI calls on raw device pointers (csrc/*.cu).  There is no CPU path: tensors
+must be CUDA fp32.
+
+Layout conventions (B200-first, not the reference's NCL / seq-first):
+  activations are channels-last / token-major: conv stack (B, L, C), transformer (B*T, D);
+  weights are handed to the kernels in "GEMM layout" W[k, n] (n contiguous); the model
+  derives them from the reference-shaped parameters with differentiable torch views.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, Gather, Scatter
+
+_f32 = torch.float32
+
+
+def _chk(t, name):
+    _lib.require_cuda(t, name)
+    if t.dtype != _f32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _stream():
+    return _lib.current_stream()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _gather_plain(ptr, M, K, ld):
+    return Gather(ptr, 0, M, K, M, ld, 1, 0, 0)
+
+
+def _scatter_plain(ptr, M, ld):
+    return Scatter(ptr, 0, M, ld, 1, 0)
+
+
+def _epi(out, bias=None, relu=0, accumulate=0, mask_src=None, mask_scale=1.0, drop_p=0.0, seed=0,
+         site=0):
+    return Epilogue(out, bias.data_ptr() if bias is not None else None,
+                    mask_src.data_ptr() if mask_src is not None else None, mask_scale, int(relu),
+                    int(accumulate), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site))
+
+
+# ------------------------------------------------------------------------------------------
+# raw (non-differentiable) wrappers
+# ------------------------------------------------------------------------------------------
+def gemm_nn(ga, W, epi, M, N, K):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_nn(ctypes.byref(ga), W.data_ptr(), W.stride(0), ctypes.byref(epi), M,
+                               N, K, _stream()))
+
+
+def gemm_nt(ga, W, Cb, tapmap, epi, M, N, K):
+    lib = _lib.load()
+    t = list(tapmap) + [0, 0, 0]
+    _lib.check(lib.ssb_gemm_nt(ctypes.byref(ga), W.data_ptr(), W.stride(0), Cb, t[0], t[1], t[2],
+                               ctypes.byref(epi), M, N, K, _stream()))
+
+
+def gemm_tn(ga, G, dW, M, N, K, accumulate=False):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_tn(ctypes.byref(ga), G.data_ptr(), G.stride(0), dW.data_ptr(),
+                               dW.stride(0), int(accumulate), M, N, K, _stream()))
+
+
+def colsum(x2d, out=None, accumulate=False):
+    lib = _lib.load()
+    rows, C = x2d.shape
+    if out is None:
+        out = torch.empty(C, dtype=_f32, device=x2d.device)
+    nb = lib.ssb_col_partials_bytes(rows, C)
+    ws = _ws(nb, x2d.device)
+    _lib.check(lib.ssb_colsum(x2d.data_ptr(), rows, C, out.data_ptr(), int(accumulate),
+                              ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# Linear:  y = x @ Wg + b     (x: (M, K), Wg: (K, N))
+# ------------------------------------------------------------------------------------------
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Wg, bias):
+        _chk(x, "x"), _chk(Wg, "Wg")
+        M, K = x.shape
+        N = Wg.shape[1]
+        y = torch.empty((M, N), dtype=_f32, device=x.device)
+        gemm_nn(_gather_plain(x.data_ptr(), M, K, K), Wg,
+                _epi(_scatter_plain(y.data_ptr(), M, N), bias=bias), M, N, K)
+        ctx.save_for_backward(x, Wg)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wg = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = Wg.shape[1]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm_nt(_gather_plain(dy.data_ptr(), M, N, N), Wg, N, (0,),
+                    _epi(_scatter_plain(dx.data_ptr(), M, K)), M, K, N)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(Wg)
+            gemm_tn(_gather_plain(x.data_ptr(), M, K, K), dy, dW, M, N, K)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy)
+        return dx, dW, db
+
+
+def linear(x2d, Wg, bias=None):
+    return _LinearFn.apply(x2d, Wg, bias)
+
+
+# ------------------------------------------------------------------------------------------
+# FFN:  y = dropout(relu(x @ W1 + b1)) @ W2 + b2          transformer.py:57
+# ------------------------------------------------------------------------------------------
+class _FFNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2, p, seed, site):
+        _chk(x, "x"), _chk(W1, "W1"), _chk(W2, "W2")
+        M, K = x.shape
+        F_ = W1.shape[1]
+        N = W2.shape[1]
+        h = torch.empty((M, F_), dtype=_f32, device=x.device)
+        gemm_nn(_gather_plain(x.data_ptr(), M, K, K), W1,
+                _epi(_scatter_plain(h.data_ptr(), M, F_), bias=b1, relu=1, drop_p=p, seed=seed,
+                     site=site), M, F_, K)
+        y = torch.empty((M, N), dtype=_f32, device=x.device)
+        gemm_nn(_gather_plain(h.data_ptr(), M, F_, F_), W2,
+                _epi(_scatter_plain(y.data_ptr(), M, N), bias=b2), M, N, F_)
+        ctx.save_for_backward(x, W1, W2, h)
+        ctx.p = p
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W1, W2, h = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        F_ = W1.shape[1]
+        N = W2.shape[1]
+        scale = 1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0
+        dW2 = torch.empty_like(W2)
+        gemm_tn(_gather_plain(h.data_ptr(), M, F_, F_), dy, dW2, M, N, F_)
+        db2 = colsum(dy)
+        # dh = (dy @ W2^T) * (h > 0) / (1 - p): relu and dropout masks both read off h
+        dh = torch.empty_like(h)
+        gemm_nt(_gather_plain(dy.data_ptr(), M, N, N), W2, N, (0,),
+                _epi(_scatter_plain(dh.data_ptr(), M, F_), mask_src=h, mask_scale=scale), M, F_, N)
+        dW1 = torch.empty_like(W1)
+        gemm_tn(_gather_plain(x.data_ptr(), M, K, K), dh, dW1, M, F_, K)
+        db1 = colsum(dh)
+        dx = torch.empty_like(x)
+        gemm_nt(_gather_plain(dh.data_ptr(), M, F_, F_), W1, F_, (0,),
+                _epi(_scatter_plain(dx.data_ptr(), M, K)), M, K, F_)
+        return dx, dW1, db1, dW2, db2, None, None, None
+
+
+def ffn(x2d, W1g, b1, W2g, b2, p=0.0, seed=0, site=0):
+    return _FFNFn.apply(x2d, W1g, b1, W2g, b2, float(p), int(seed), int(site))
+
+
+# ------------------------------------------------------------------------------------------
+# Conv1d, channels-last: x (B, L, Cin) -> (B, Lout, Cout); kernel 3 pad 1 (stride 1|2) or
+# kernel 1 pad 0 stride 2.  Wg: (ksize*Cin, Cout), row = tap*Cin + ci.   architecture.py:18-24
+# ------------------------------------------------------------------------------------------
+def _conv_gather(x, L, Cin, Lout, ksize, stride):
+    off = -1 if ksize == 3 else 0
+    return Gather(x.data_ptr(), L * Cin, Lout, Cin, L, Cin, stride, 1, off)
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Wg, bias, ksize, stride):
+        _chk(x, "x"), _chk(Wg, "Wg")
+        B, L, Cin = x.shape
+        Cout = Wg.shape[1]
+        assert Wg.shape[0] == ksize * Cin and ksize in (1, 3) and stride in (1, 2)
+        Lout = (L - 1) // stride + 1
+        y = torch.empty((B, Lout, Cout), dtype=_f32, device=x.device)
+        M = B * Lout
+        gemm_nn(_conv_gather(x, L, Cin, Lout, ksize, stride), Wg,
+                _epi(_scatter_plain(y.data_ptr(), M, Cout), bias=bias), M, Cout, ksize * Cin)
+        ctx.save_for_backward(x, Wg)
+        ctx.cfg = (ksize, stride, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wg = ctx.saved_tensors
+        ksize, stride, has_bias = ctx.cfg
+        dy = dy.contiguous()
+        B, L, Cin = x.shape
+        _, Lout, Cout = dy.shape
+        M = B * Lout
+        dy2 = dy.view(M, Cout)
+        dx = dW = db = None
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(Wg)
+            gemm_tn(_conv_gather(x, L, Cin, Lout, ksize, stride), dy2, dW, M, Cout, ksize * Cin)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        if ctx.needs_input_grad[0]:
+            dyp = dy.data_ptr()
+            if ksize == 3 and stride == 1:
+                dx = torch.empty_like(x)
+                ga = Gather(dyp, Lout * Cout, L, Cout, Lout, Cout, 1, 1, -1)
+                gemm_nt(ga, Wg, Cout, (2, 1, 0), _epi(_scatter_plain(dx.data_ptr(), B * L, Cin)),
+                        B * L, Cin, 3 * Cout)
+            elif ksize == 3 and stride == 2:
+                dx = torch.empty_like(x)
+                ne, no = (L + 1) // 2, L // 2
+                # even input rows u = 2t: dx[2t] = dy[t] . W_tap1^T
+                ga = Gather(dyp, Lout * Cout, ne, Cout, Lout, Cout, 1, 0, 0)
+                out = Scatter(dx.data_ptr(), L * Cin, ne, Cin, 2, 0)
+                gemm_nt(ga, Wg, Cout, (1,), _epi(out), B * ne, Cin, Cout)
+                if no > 0:  # odd rows u = 2t+1: dx = dy[t] . W_tap2^T + dy[t+1] . W_tap0^T
+                    ga = Gather(dyp, Lout * Cout, no, Cout, Lout, Cout, 1, 1, 0)
+                    out = Scatter(dx.data_ptr(), L * Cin, no, Cin, 2, 1)
+                    gemm_nt(ga, Wg, Cout, (2, 0), _epi(out), B * no, Cin, 2 * Cout)
+            elif ksize == 1 and stride == 2:
+                dx = torch.zeros_like(x)
+                ne = (L + 1) // 2
+                ga = Gather(dyp, Lout * Cout, ne, Cout, Lout, Cout, 1, 0, 0)
+                out = Scatter(dx.data_ptr(), L * Cin, ne, Cin, 2, 0)
+                gemm_nt(ga, Wg, Cout, (0,), _epi(out), B * ne, Cin, Cout)
+            else:
+                raise NotImplementedError("conv backward for this (ksize, stride)")
+        return dx, dW, db, None, None
+
+
+def conv1d_cl(x, Wg, bias, ksize, stride):
+    return _ConvFn.apply(x, Wg, bias, ksize, stride)
+
+
+# ------------------------------------------------------------------------------------------
+# BatchNorm1d (+ optional second normalised branch) (+ ReLU), channels-last (rows, C)
+# ------------------------------------------------------------------------------------------
+def _bn_stats(x2, gamma, beta, rm, rv, training, momentum, eps):
+    lib = _lib.load()
+    rows, C = x2.shape
+    dev = x2.device
+    buf = torch.empty((4, C), dtype=_f32, device=dev)  # mean, rstd, scale, shift
+    ws = _ws(lib.ssb_col_partials_bytes(rows, C), dev)
+    _lib.check(lib.ssb_bn_stats(x2.data_ptr(), rows, C, gamma.data_ptr(), beta.data_ptr(),
+                                rm.data_ptr() if rm is not None else None,
+                                rv.data_ptr() if rv is not None else None, momentum, eps,
+                                int(training), buf[0].data_ptr(), buf[1].data_ptr(),
+                                buf[2].data_ptr(), buf[3].data_ptr(), ws.data_ptr(), ws.numel(),
+                                _stream()))
+    return buf
+
+
+def _bn_bwd(dy2, mask_src, x2, stats, gamma, training):
+    lib = _lib.load()
+    rows, C = x2.shape
+    dev = x2.device
+    dx = torch.empty_like(x2)
+    dg = torch.empty(C, dtype=_f32, device=dev)
+    db = torch.empty(C, dtype=_f32, device=dev)
+    ws = _ws(lib.ssb_col_partials_bytes(rows, C) + 8 * C, dev)
+    _lib.check(lib.ssb_bn_bwd(dy2.data_ptr(), mask_src.data_ptr() if mask_src is not None else None,
+                              x2.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                              gamma.data_ptr(), int(training), rows, C, dx.data_ptr(),
+                              dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return dx, dg, db
+
+
+class _BNActFn(torch.autograd.Function):
+    """y = [relu]( BN_a(xa) [+ BN_b(xb)] );  running stats updated in place when training."""
+
+    @staticmethod
+    def forward(ctx, xa, ga, ba, rma, rva, xb, gb, bb, rmb, rvb, training, relu, momentum, eps):
+        lib = _lib.load()
+        _chk(xa, "xa")
+        shape = xa.shape
+        C = shape[-1]
+        xa2 = xa.view(-1, C)
+        rows = xa2.shape[0]
+        sa = _bn_stats(xa2, ga, ba, rma, rva, training, momentum, eps)
+        sb = None
+        xb2 = None
+        if xb is not None:
+            _chk(xb, "xb")
+            xb2 = xb.view(-1, C)
+            sb = _bn_stats(xb2, gb, bb, rmb, rvb, training, momentum, eps)
+        y = torch.empty_like(xa)
+        _lib.check(lib.ssb_bn_apply(xa2.data_ptr(), sa[2].data_ptr(), sa[3].data_ptr(),
+                                    xb2.data_ptr() if xb2 is not None else None,
+                                    sb[2].data_ptr() if sb is not None else None,
+                                    sb[3].data_ptr() if sb is not None else None, int(relu), rows,
+                                    C, y.data_ptr(), _stream()))
+        ctx.training, ctx.relu, ctx.two = training, relu, xb is not None
+        if ctx.two:
+            ctx.save_for_backward(xa, ga, sa, y, xb, gb, sb)
+        else:
+            ctx.save_for_backward(xa, ga, sa, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        if ctx.two:
+            xa, ga, sa, y, xb, gb, sb = ctx.saved_tensors
+        else:
+            xa, ga, sa, y = ctx.saved_tensors
+        C = xa.shape[-1]
+        dy2 = dy.view(-1, C)
+        mask = y.view(-1, C) if ctx.relu else None
+        dxa, dga, dba = _bn_bwd(dy2, mask, xa.view(-1, C), sa, ga, ctx.training)
+        dxb = dgb = dbb = None
+        if ctx.two:
+            dxb, dgb, dbb = _bn_bwd(dy2, mask, xb.view(-1, C), sb, gb, ctx.training)
+            dxb = dxb.view_as(xb)
+        return (dxa.view_as(xa), dga, dba, None, None, dxb, dgb, dbb, None, None, None, None, None,
+                None)
+
+
+def bn_act(xa, ga, ba, rma, rva, training, relu, xb=None, gb=None, bb=None, rmb=None, rvb=None,
+           momentum=0.1, eps=1e-5):
+    return _BNActFn.apply(xa, ga, ba, rma, rva, xb, gb, bb, rmb, rvb, bool(training), bool(relu),
+                          float(momentum), float(eps))
+
+
+# ------------------------------------------------------------------------------------------
+# z = res + dropout(branch); y = LayerNorm(z)          transformer.py:55-56, 58-59
+# ------------------------------------------------------------------------------------------
+class _AddDropLNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, res, branch, gamma, beta, p, seed, site, eps):
+        lib = _lib.load()
+        _chk(res, "res"), _chk(branch, "branch")
+        rows, D = res.shape
+        dev = res.device
+        need_bwd = any(ctx.needs_input_grad[:4])
+        y = torch.empty_like(res)
+        z = torch.empty_like(res) if need_bwd else None
+        stat = torch.empty((2, rows), dtype=_f32, device=dev) if need_bwd else None
+        _lib.check(lib.ssb_add_dropout_ln_fwd(
+            res.data_ptr(), branch.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, D, eps, p,
+            seed & 0xFFFFFFFFFFFFFFFF, site, z.data_ptr() if need_bwd else None, y.data_ptr(),
+            stat[0].data_ptr() if need_bwd else None, stat[1].data_ptr() if need_bwd else None,
+            _stream()))
+        if need_bwd:
+            ctx.save_for_backward(z, stat, gamma)
+        ctx.cfg = (p, seed, site)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        z, stat, gamma = ctx.saved_tensors
+        p, seed, site = ctx.cfg
+        dy = dy.contiguous()
+        rows, D = z.shape
+        dev = z.device
+        d_res = torch.empty_like(z)
+        d_branch = torch.empty_like(z)
+        dg = torch.empty(D, dtype=_f32, device=dev)
+        db = torch.empty(D, dtype=_f32, device=dev)
+        ws = _ws(lib.ssb_add_dropout_ln_bwd_workspace_bytes(rows, D), dev)
+        _lib.check(lib.ssb_add_dropout_ln_bwd(
+            dy.data_ptr(), z.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(), gamma.data_ptr(),
+            rows, D, p, seed & 0xFFFFFFFFFFFFFFFF, site, d_res.data_ptr(), d_branch.data_ptr(),
+            dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        return d_res, d_branch, dg, db, None, None, None, None
+
+
+def add_dropout_layernorm(res, branch, gamma, beta, p=0.0, seed=0, site=0, eps=1e-5):
+    return _AddDropLNFn.apply(res, branch, gamma, beta, float(p), int(seed), int(site), float(eps))
+
+
+# ------------------------------------------------------------------------------------------
+# banded relative-position attention            transformer.py:99-110, 162-297
+# qkv: (B*T, 3D) [q|k|v];  E: (H, RW, dh) relative-position table zero-padded to RW rows,
+# never differentiated.  Returns O: (B*T, D).
+# ------------------------------------------------------------------------------------------
+class _BandAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, E, B, T, H, dh, W, p, seed, site):
+        lib = _lib.load()
+        _chk(qkv, "qkv"), _chk(E, "E")
+        M, D3 = qkv.shape
+        D = H * dh
+        RW = E.shape[1]
+        assert M == B * T and D3 == 3 * D and E.shape == (H, RW, dh)
+        dev = qkv.device
+        need_bwd = ctx.needs_input_grad[0]
+        R = torch.empty((M, H, RW), dtype=_f32, device=dev)
+        for h in range(H):  # R[:, h, :] = q_h @ E_h^T
+            ga = Gather(qkv.data_ptr() + 4 * h * dh, 0, M, dh, M, D3, 1, 0, 0)
+            out = Scatter(R.data_ptr() + 4 * h * RW, 0, M, H * RW, 1, 0)
+            gemm_nt(ga, E[h], dh, (0,), _epi(out), M, RW, dh)
+        P = torch.empty((M, H, RW), dtype=_f32, device=dev) if need_bwd else None
+        O = torch.empty((M, D), dtype=_f32, device=dev)
+        _lib.check(lib.ssb_band_attn_fwd(qkv.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p,
+                                         seed & 0xFFFFFFFFFFFFFFFF, site,
+                                         P.data_ptr() if need_bwd else None, O.data_ptr(),
+                                         _stream()))
+        if need_bwd:
+            ctx.save_for_backward(qkv, E, P)
+        ctx.cfg = (B, T, H, dh, W, p, seed, site)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        lib = _lib.load()
+        qkv, E, P = ctx.saved_tensors
+        B, T, H, dh, W, p, seed, site = ctx.cfg
+        dO = dO.contiguous()
+        M, D3 = qkv.shape
+        RW = E.shape[1]
+        dS = torch.empty_like(P)
+        dqkv = torch.empty_like(qkv)
+        _lib.check(lib.ssb_band_attn_bwd(qkv.data_ptr(), P.data_ptr(), dO.data_ptr(), B, T, H, dh,
+                                         W, RW, p, seed & 0xFFFFFFFFFFFFFFFF, site, dS.data_ptr(),
+                                         dqkv.data_ptr(), _stream()))
+        for h in range(H):  # dq_h += dS_h @ E_h   (positional part; no gradient for E: F3)
+            ga = Gather(dS.data_ptr() + 4 * h * RW, 0, M, RW, M, H * RW, 1, 0, 0)
+            out = Scatter(dqkv.data_ptr() + 4 * h * dh, 0, M, D3, 1, 0)
+            gemm_nn(ga, E[h], _epi(out, accumulate=1), M, dh, RW)
+        return dqkv, None, None, None, None, None, None, None, None, None
+
+
+def band_attention(qkv, E_pad, B, T, H, dh, W, p=0.0, seed=0, site=0):
+    return _BandAttnFn.apply(qkv, E_pad, int(B), int(T), int(H), int(dh), int(W), float(p),
+                             int(seed), int(site))

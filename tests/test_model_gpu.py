@@ -1,0 +1,140 @@
+"""GPU parity of the full Model (silent_speech_b200.architecture) against the golden vectors
+produced by the executed reference and against the torch oracle: eval/train outputs, loss,
+every parameter gradient, BatchNorm running statistics, the in-place input shift, and
+`relative_positional.embeddings.grad is None`.
+North-star tolerance: 1e-3 relative fp32.  This fp32 path is asserted at 1e-4."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+from absl import flags
+
+from make_golden_model import CASES, grad_fingerprint, make_input, scalar_loss
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+def max_rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / (np.abs(b).max() + 1e-30)
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "model_golden.npz"))
+
+
+def build(D, NL, dropout=0.0):
+    from silent_speech_b200 import architecture as A
+    F = flags.FLAGS
+    if not F.is_parsed():
+        F(["test"])
+    F.model_size, F.num_layers, F.dropout = D, NL, dropout
+    m = A.Model(112, 80, 48)
+    sd = om.formula_state_dict(D, NL)
+    assert list(m.state_dict().keys()) == list(sd.keys())          # checkpoint contract
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_model_matches_reference_golden(golden, ci):
+    name, D, NL, B, L, pyseed = CASES[ci]
+    m = build(D, NL)
+    x = make_input(B, L, ci)
+
+    m.eval()
+    with torch.no_grad():
+        pred, aux = m(None, x.clone().cuda(), None)
+    assert pred.is_contiguous() and aux.is_contiguous()
+    for got, key in ((pred, "eval_pred"), (aux, "eval_aux")):
+        want = golden[f"{name}_{key}"]
+        assert rel_l2(got.cpu().numpy(), want) < TOL and max_rel(got.cpu().numpy(), want) < TOL, key
+
+    m.train()
+    random.seed(pyseed)
+    xt = x.clone().cuda()
+    pred, aux = m(None, xt, None)
+    loss = scalar_loss(pred.cpu(), aux.cpu())
+    loss.backward()
+    assert rel_l2(pred.detach().cpu().numpy(), golden[f"{name}_train_pred"]) < TOL
+    assert rel_l2(aux.detach().cpu().numpy(), golden[f"{name}_train_aux"]) < TOL
+    np.testing.assert_array_equal(xt[:, -9:, :].cpu().numpy(), golden[f"{name}_train_x_after"])
+    assert abs(loss.item() - float(golden[f"{name}_train_loss"])) < 1e-4 * max(1.0, abs(loss.item()))
+    grads = {k: p.grad.cpu() for k, p in m.named_parameters() if p.grad is not None}
+    fp = grad_fingerprint(grads)
+    n = 0
+    for key in golden.files:
+        if key.startswith(f"{name}_grad::"):
+            k = key.split("::", 1)[1]
+            want = golden[key]
+            # fingerprint = [L2 norm, sum, 4 samples]; compare norm tightly, samples vs the norm scale
+            assert abs(fp[k][0] - want[0]) <= 2e-4 * want[0] + 1e-9, (k, fp[k][0], want[0])
+            scale = want[0] / np.sqrt(max(grads[k].numel(), 1)) + 1e-12
+            assert np.abs(fp[k][2:] - want[2:]).max() < 1e-2 * scale + 1e-7, (k, fp[k], want)
+            n += 1
+    assert n >= 40
+    for k, p in m.named_parameters():
+        if k.endswith("relative_positional.embeddings"):
+            assert p.grad is None
+    sd = m.state_dict()
+    for k in sd:
+        if "running_" in k:
+            assert rel_l2(sd[k].cpu().numpy(), golden[f"{name}_buf::{k}"]) < 1e-5, k
+        if "num_batches" in k:
+            assert int(sd[k]) == int(golden[f"{name}_buf::{k}"])
+
+
+def test_full_gradients_vs_oracle_medium():
+    """Every gradient element (not just fingerprints) against the CPU oracle, D=64, T=150."""
+    D, NL, B, L = 64, 2, 2, 1200
+    m = build(D, NL)
+    m.train()
+    x = make_input(B, L, 7)
+    random.seed(5)
+    pred, aux = m(None, x.clone().cuda(), None)
+    scalar_loss(pred.cpu(), aux.cpu()).backward()
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+              else v.clone()) for k, v in om.formula_state_dict(D, NL).items()}
+    random.seed(5)
+    op, oa = om.model_forward(sd, x.clone(), training=True, dropout_p=0.0)
+    scalar_loss(op, oa).backward()
+    assert rel_l2(pred.detach().cpu().numpy(), op.detach().numpy()) < TOL
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:
+            assert p.grad is None, k
+            continue
+        r = rel_l2(p.grad.cpu().numpy(), sd[k].grad.numpy())
+        if r > worst[1]:
+            worst = (k, r)
+    assert worst[1] < 1e-3, worst
+
+
+def test_train_mode_dropout_runs_and_differs():
+    m = build(32, 1, dropout=0.2)
+    m.train()
+    x = make_input(2, 400, 3).cuda()
+    torch.manual_seed(0)
+    random.seed(0)
+    a, _ = m(None, x.clone(), None)
+    random.seed(0)
+    b, _ = m(None, x.clone(), None)
+    assert not torch.equal(a, b)                 # fresh dropout seed per forward
+    torch.manual_seed(0)
+    random.seed(0)
+    c, _ = m(None, x.clone(), None)
+    assert torch.equal(a, c)                     # torch.manual_seed controls it
+    a.sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
