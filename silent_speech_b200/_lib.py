@@ -81,8 +81,26 @@ _SIGNATURES = {
                                   c_f32, c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
 }
 
+# kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
+_KERNELS_PER_CALL = {
+    "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
+    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_bn_stats": 2, "ssb_bn_apply": 1,
+    "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
+    "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
+}
+launch_count = 0   # running total of libssb kernel launches issued by this process
+
 _lock = threading.Lock()
 _lib = None
+
+
+def _counted(fn, n):
+    def call(*args):
+        global launch_count
+        launch_count += n
+        return fn(*args)
+    call.__name__ = fn.__name__
+    return call
 
 
 class SSBError(RuntimeError):
@@ -113,6 +131,8 @@ def load():
             fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly
             fn.restype = res
             fn.argtypes = args
+            if name in _KERNELS_PER_CALL:
+                setattr(lib, name, _counted(fn, _KERNELS_PER_CALL[name]))
         _lib = lib
     return _lib
 

@@ -41,7 +41,7 @@ def build(D, NL, dropout=0.0):
     F.model_size, F.num_layers, F.dropout = D, NL, dropout
     m = A.Model(112, 80, 48)
     sd = om.formula_state_dict(D, NL)
-    assert list(m.state_dict().keys()) == list(sd.keys())          # checkpoint contract
+    assert sorted(m.state_dict().keys()) == sorted(sd.keys())      # checkpoint contract
     for k, v in m.state_dict().items():
         assert tuple(v.shape) == tuple(sd[k].shape), k
     m.load_state_dict(sd, strict=True)
