@@ -190,6 +190,33 @@ SSB_API int ssb_band_attn_bwd(const float* qkv, const float* P, const float* dO,
                               float drop_p, uint64_t seed, uint32_t site, float* dS, float* dqkv,
                               void* stream);
 
+/* ---- tcgen05 tensor-core GEMM with fp32-class accuracy (bf16 hi/lo split, 3 MMAs) -----
+ * Same contractions as ssb_gemm_{nn,nt,tn} for the large shapes, on 5th-gen tensor cores.
+ * Operands are "split planes": [2][...] bf16 with x = hi + lo, produced by ssb_split_bf16
+ * (n % 8 == 0).  An operand is a channels-last tensor (batches, L_src, C) per plane:
+ *   element (b, row, c) of plane p at  planes[p*plane_stride + b*batch_stride + row*ld + c]
+ * and is consumed through TMA as the im2col matrix  A(m=(b,t), k=(tap,c)) =
+ * x[b, t*s_t + tap*s_tap + off, c]  (rows outside [0, L_src) read as zero), t < rows_out,
+ * K = taps*C.  A plain (M, K) matrix is batches = 1, rows_out = L_src = M, C = ld = K.
+ */
+typedef struct {
+  const void* planes;       /* bf16 [2][...] */
+  int64_t plane_stride;     /* elements between the hi and lo planes */
+  int64_t batch_stride;     /* elements between batch items */
+  int32_t batches, rows_out, L_src, C, ld, s_t, s_tap, off;
+} ssb_tc_operand_t;
+
+SSB_API int ssb_split_bf16(const float* x, int64_t n, void* planes /* bf16 [2][n] */, void* stream);
+/* C[(b,t), n] = epi( sum_k A((b,t), k) * B[n, k] );  B planes: [2][N][K] bf16 (K contiguous).
+ * K % 64 == 0, C % 64 == 0.  epi->out.rows_per_batch must equal A->rows_out. */
+SSB_API int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N, int64_t K,
+                               const ssb_epilogue_t* epi, void* stream);
+/* dW[k, n] (+)= sum_(b,t) X((b,t), k) * G[(b,t), n];  G planes: [2][batches*rows_out][N] bf16.
+ * K % 128 == 0, X->C % 128 == 0, N % 8 == 0. */
+SSB_API int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_plane_stride,
+                              int64_t N, int64_t K, float* dW, int64_t lddw, int accumulate,
+                              void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,14 @@ class Epilogue(ctypes.Structure):
                 ("site", c_u32)]
 
 
+class TcOperand(ctypes.Structure):
+    """ssb_tc_operand_t"""
+    _fields_ = [("planes", c_ptr), ("plane_stride", c_i64), ("batch_stride", c_i64),
+                ("batches", c_i32), ("rows_out", c_i32), ("L_src", c_i32), ("C", c_i32),
+                ("ld", c_i32), ("s_t", c_i32), ("s_tap", c_i32), ("off", c_i32)]
+
+
+_PT = ctypes.POINTER(TcOperand)
 _PG = ctypes.POINTER(Gather)
 _PE = ctypes.POINTER(Epilogue)
 
@@ -61,6 +69,9 @@ _SIGNATURES = {
     "ssb_gemm_nt": (c_int, [_PG, c_ptr, c_i64, c_i64, c_int, c_int, c_int, _PE, c_i64, c_i64,
                             c_i64, c_ptr]),
     "ssb_gemm_tn": (c_int, [_PG, c_ptr, c_i64, c_ptr, c_i64, c_int, c_i64, c_i64, c_i64, c_ptr]),
+    "ssb_split_bf16": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
+    "ssb_gemm_tc_kmajor": (c_int, [_PT, c_ptr, c_i64, c_i64, _PE, c_ptr]),
+    "ssb_gemm_tc_wgrad": (c_int, [_PT, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int, c_ptr]),
     "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,

@@ -437,3 +437,41 @@ class _BandAttnFn(torch.autograd.Function):
 def band_attention(qkv, E_pad, B, T, H, dh, W, p=0.0, seed=0, site=0):
     return _BandAttnFn.apply(qkv, E_pad, int(B), int(T), int(H), int(dh), int(W), float(p),
                              int(seed), int(site))
+
+
+# ------------------------------------------------------------------------------------------
+# tcgen05 path: bf16 hi/lo split planes + tensor-core GEMMs (csrc/gemm_tc.cu)
+# ------------------------------------------------------------------------------------------
+from ._lib import TcOperand  # noqa: E402
+
+
+def split_planes(x):
+    """fp32 tensor -> bf16 tensor (2, *x.shape): plane 0 = hi = bf16(x), plane 1 = lo = bf16(x - hi)."""
+    lib = _lib.load()
+    _chk(x, "x")
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.ssb_split_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def tc_operand_plain(planes, M, K):
+    """(2, M, K) split planes as a plain row-major matrix operand."""
+    return TcOperand(planes.data_ptr(), M * K, M * K, 1, M, M, K, K, 1, 0, 0)
+
+
+def tc_operand_conv(planes, B, L, C, rows_out, stride, taps_step, off):
+    """(2, B, L, C) split planes as the im2col operand of a k3/k1 convolution."""
+    return TcOperand(planes.data_ptr(), B * L * C, L * C, B, rows_out, L, C, C, stride, taps_step,
+                     off)
+
+
+def gemm_tc_kmajor(opA, Bplanes, N, K, epi):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_tc_kmajor(ctypes.byref(opA), Bplanes.data_ptr(), N, K,
+                                      ctypes.byref(epi), _stream()))
+
+
+def gemm_tc_wgrad(opX, Gplanes, N, K, dW, accumulate=False):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_tc_wgrad(ctypes.byref(opX), Gplanes.data_ptr(), Gplanes[0].numel(), N,
+                                     K, dW.data_ptr(), dW.stride(0), int(accumulate), _stream()))

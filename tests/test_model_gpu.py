@@ -79,6 +79,13 @@ def test_model_matches_reference_golden(golden, ci):
         if key.startswith(f"{name}_grad::"):
             k = key.split("::", 1)[1]
             want = golden[key]
+            if k.startswith("conv_blocks") and k.endswith(("conv1.bias", "conv2.bias",
+                                                           "residual_path.bias")):
+                # a bias in front of a training-mode BatchNorm has an analytically ZERO gradient;
+                # the reference's value is rounding noise (1e-7) -- only require ours to be noise too
+                assert fp[k][0] < 1e-4, (k, fp[k][0])
+                n += 1
+                continue
             # fingerprint = [L2 norm, sum, 4 samples]; compare norm tightly, samples vs the norm scale
             assert abs(fp[k][0] - want[0]) <= 2e-4 * want[0] + 1e-9, (k, fp[k][0], want[0])
             scale = want[0] / np.sqrt(max(grads[k].numel(), 1)) + 1e-12
@@ -115,6 +122,10 @@ def test_full_gradients_vs_oracle_medium():
     for k, p in m.named_parameters():
         if sd[k].grad is None:
             assert p.grad is None, k
+            continue
+        if k.startswith("conv_blocks") and k.endswith(("conv1.bias", "conv2.bias",
+                                                       "residual_path.bias")):
+            assert p.grad.abs().max().item() < 1e-4      # analytically zero (BatchNorm follows)
             continue
         r = rel_l2(p.grad.cpu().numpy(), sd[k].grad.numpy())
         if r > worst[1]:
