@@ -13,7 +13,9 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import Epilogue, Gather, Scatter
+import os
+
+from ._lib import Epilogue, Gather, Scatter, TcOperand
 
 _f32 = torch.float32
 
@@ -85,6 +87,100 @@ def colsum(x2d, out=None, accumulate=False):
 
 
 # ------------------------------------------------------------------------------------------
+# tcgen05 path: bf16 hi/lo split planes + tensor-core GEMMs (csrc/gemm_tc.cu)
+# ------------------------------------------------------------------------------------------
+
+
+def split_planes(x):
+    """fp32 tensor -> bf16 tensor (2, *x.shape): plane 0 = hi = bf16(x), plane 1 = lo = bf16(x - hi)."""
+    lib = _lib.load()
+    _chk(x, "x")
+    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.ssb_split_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def tc_operand_plain(planes, M, K):
+    """(2, M, K) split planes as a plain row-major matrix operand."""
+    return TcOperand(planes.data_ptr(), M * K, M * K, 1, M, M, K, K, 1, 0, 0)
+
+
+def tc_operand_conv(planes, B, L, C, rows_out, stride, taps_step, off):
+    """(2, B, L, C) split planes as the im2col operand of a k3/k1 convolution."""
+    return TcOperand(planes.data_ptr(), B * L * C, L * C, B, rows_out, L, C, C, stride, taps_step,
+                     off)
+
+
+def gemm_tc_kmajor(opA, Bplanes, N, K, epi):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_tc_kmajor(ctypes.byref(opA), Bplanes.data_ptr(), N, K,
+                                      ctypes.byref(epi), _stream()))
+
+
+def gemm_tc_wgrad(opX, Gplanes, N, K, dW, accumulate=False):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_tc_wgrad(ctypes.byref(opX), Gplanes.data_ptr(), Gplanes[0].numel(), N,
+                                     K, dW.data_ptr(), dW.stride(0), int(accumulate), _stream()))
+
+
+# ------------------------------------------------------------------------------------------
+# engine selection: tcgen05 (gemm_tc.cu) when the shape meets its tiling constraints, the
+# CUDA-core engine (gemm_simt.cu) otherwise (thin first conv C=8, K=dh=96 positional GEMMs,
+# unit-test sized models).  SSB_GEMM=simt forces the CUDA-core engine (A/B testing).
+# ------------------------------------------------------------------------------------------
+def _tc_enabled():
+    return os.environ.get("SSB_GEMM", "tc") != "simt"
+
+
+def _tc_fwd_ok(M, N, K, C=None):
+    C = K if C is None else C
+    return _tc_enabled() and K % 64 == 0 and C % 64 == 0 and N % 4 == 0 and M >= 64
+
+
+def _tc_wgrad_ok(M, N, K, C=None):
+    C = K if C is None else C
+    return _tc_enabled() and K % 128 == 0 and C % 128 == 0 and N % 8 == 0 and M >= 64
+
+
+def mm_fwd(x, Wg, epi_kwargs, out, M, N, K, xp=None):
+    """out[M,N] = epi(x[M,K] @ Wg[K,N]).  Returns the split planes of x if they were made."""
+    scat = _scatter_plain(out.data_ptr(), M, N)
+    if _tc_fwd_ok(M, N, K):
+        if xp is None:
+            xp = split_planes(x)
+        wp = split_planes(Wg.t().contiguous())                    # [N][K], K contiguous
+        gemm_tc_kmajor(tc_operand_plain(xp, M, K), wp, N, K, _epi(scat, **epi_kwargs))
+        return xp
+    gemm_nn(_gather_plain(x.data_ptr(), M, K, K), Wg, _epi(scat, **epi_kwargs), M, N, K)
+    return None
+
+
+def mm_dgrad(dy, Wg, epi_kwargs, out, M, N, K, dyp=None):
+    """out[M,K] = epi(dy[M,N] @ Wg[K,N]^T)."""
+    scat = _scatter_plain(out.data_ptr(), M, K)
+    if _tc_fwd_ok(M, K, N):
+        if dyp is None:
+            dyp = split_planes(dy)
+        gemm_tc_kmajor(tc_operand_plain(dyp, M, N), split_planes(Wg), K, N, _epi(scat, **epi_kwargs))
+        return dyp
+    gemm_nt(_gather_plain(dy.data_ptr(), M, N, N), Wg, N, (0,), _epi(scat, **epi_kwargs), M, K, N)
+    return dyp
+
+
+def mm_wgrad(x, dy, dW, M, N, K, xp=None, dyp=None):
+    """dW[K,N] = x[M,K]^T @ dy[M,N]."""
+    if _tc_wgrad_ok(M, N, K):
+        if xp is None:
+            xp = split_planes(x)
+        if dyp is None:
+            dyp = split_planes(dy)
+        gemm_tc_wgrad(tc_operand_plain(xp, M, K), dyp, N, K, dW)
+        return dyp
+    gemm_tn(_gather_plain(x.data_ptr(), M, K, K), dy, dW, M, N, K)
+    return dyp
+
+
+# ------------------------------------------------------------------------------------------
 # Linear:  y = x @ Wg + b     (x: (M, K), Wg: (K, N))
 # ------------------------------------------------------------------------------------------
 class _LinearFn(torch.autograd.Function):
@@ -94,8 +190,7 @@ class _LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = Wg.shape[1]
         y = torch.empty((M, N), dtype=_f32, device=x.device)
-        gemm_nn(_gather_plain(x.data_ptr(), M, K, K), Wg,
-                _epi(_scatter_plain(y.data_ptr(), M, N), bias=bias), M, N, K)
+        mm_fwd(x, Wg, dict(bias=bias), y, M, N, K)
         ctx.save_for_backward(x, Wg)
         ctx.has_bias = bias is not None
         return y
@@ -107,13 +202,13 @@ class _LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = Wg.shape[1]
         dx = dW = db = None
+        dyp = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            gemm_nt(_gather_plain(dy.data_ptr(), M, N, N), Wg, N, (0,),
-                    _epi(_scatter_plain(dx.data_ptr(), M, K)), M, K, N)
+            dyp = mm_dgrad(dy, Wg, {}, dx, M, N, K)
         if ctx.needs_input_grad[1]:
             dW = torch.empty_like(Wg)
-            gemm_tn(_gather_plain(x.data_ptr(), M, K, K), dy, dW, M, N, K)
+            mm_wgrad(x, dy, dW, M, N, K, dyp=dyp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy)
         return dx, dW, db
@@ -134,12 +229,9 @@ class _FFNFn(torch.autograd.Function):
         F_ = W1.shape[1]
         N = W2.shape[1]
         h = torch.empty((M, F_), dtype=_f32, device=x.device)
-        gemm_nn(_gather_plain(x.data_ptr(), M, K, K), W1,
-                _epi(_scatter_plain(h.data_ptr(), M, F_), bias=b1, relu=1, drop_p=p, seed=seed,
-                     site=site), M, F_, K)
+        mm_fwd(x, W1, dict(bias=b1, relu=1, drop_p=p, seed=seed, site=site), h, M, F_, K)
         y = torch.empty((M, N), dtype=_f32, device=x.device)
-        gemm_nn(_gather_plain(h.data_ptr(), M, F_, F_), W2,
-                _epi(_scatter_plain(y.data_ptr(), M, N), bias=b2), M, N, F_)
+        mm_fwd(h, W2, dict(bias=b2), y, M, N, F_)
         ctx.save_for_backward(x, W1, W2, h)
         ctx.p = p
         return y
@@ -153,18 +245,16 @@ class _FFNFn(torch.autograd.Function):
         N = W2.shape[1]
         scale = 1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0
         dW2 = torch.empty_like(W2)
-        gemm_tn(_gather_plain(h.data_ptr(), M, F_, F_), dy, dW2, M, N, F_)
+        dyp = mm_wgrad(h, dy, dW2, M, N, F_)
         db2 = colsum(dy)
         # dh = (dy @ W2^T) * (h > 0) / (1 - p): relu and dropout masks both read off h
         dh = torch.empty_like(h)
-        gemm_nt(_gather_plain(dy.data_ptr(), M, N, N), W2, N, (0,),
-                _epi(_scatter_plain(dh.data_ptr(), M, F_), mask_src=h, mask_scale=scale), M, F_, N)
+        mm_dgrad(dy, W2, dict(mask_src=h, mask_scale=scale), dh, M, N, F_, dyp=dyp)
         dW1 = torch.empty_like(W1)
-        gemm_tn(_gather_plain(x.data_ptr(), M, K, K), dh, dW1, M, F_, K)
+        dhp = mm_wgrad(x, dh, dW1, M, F_, K)
         db1 = colsum(dh)
         dx = torch.empty_like(x)
-        gemm_nt(_gather_plain(dh.data_ptr(), M, F_, F_), W1, F_, (0,),
-                _epi(_scatter_plain(dx.data_ptr(), M, K)), M, K, F_)
+        mm_dgrad(dh, W1, {}, dx, M, F_, K, dyp=dhp)
         return dx, dW1, db1, dW2, db2, None, None, None
 
 
@@ -191,8 +281,16 @@ class _ConvFn(torch.autograd.Function):
         Lout = (L - 1) // stride + 1
         y = torch.empty((B, Lout, Cout), dtype=_f32, device=x.device)
         M = B * Lout
-        gemm_nn(_conv_gather(x, L, Cin, Lout, ksize, stride), Wg,
-                _epi(_scatter_plain(y.data_ptr(), M, Cout), bias=bias), M, Cout, ksize * Cin)
+        off = -1 if ksize == 3 else 0
+        if _tc_fwd_ok(M, Cout, ksize * Cin, Cin):
+            xp = split_planes(x)
+            wp = split_planes(Wg.t().contiguous())               # [Cout][(tap, ci)]
+            gemm_tc_kmajor(tc_operand_conv(xp, B, L, Cin, Lout, stride, 1, off), wp, Cout,
+                           ksize * Cin, _epi(Scatter(y.data_ptr(), Lout * Cout, Lout, Cout, 1, 0),
+                                             bias=bias))
+        else:
+            gemm_nn(_conv_gather(x, L, Cin, Lout, ksize, stride), Wg,
+                    _epi(_scatter_plain(y.data_ptr(), M, Cout), bias=bias), M, Cout, ksize * Cin)
         ctx.save_for_backward(x, Wg)
         ctx.cfg = (ksize, stride, bias is not None)
         return y
@@ -205,37 +303,53 @@ class _ConvFn(torch.autograd.Function):
         B, L, Cin = x.shape
         _, Lout, Cout = dy.shape
         M = B * Lout
+        K = ksize * Cin
         dy2 = dy.view(M, Cout)
+        off = -1 if ksize == 3 else 0
         dx = dW = db = None
+        dyp = None
         if ctx.needs_input_grad[1]:
             dW = torch.empty_like(Wg)
-            gemm_tn(_conv_gather(x, L, Cin, Lout, ksize, stride), dy2, dW, M, Cout, ksize * Cin)
+            if _tc_wgrad_ok(M, Cout, K, Cin):
+                dyp = split_planes(dy)
+                gemm_tc_wgrad(tc_operand_conv(split_planes(x), B, L, Cin, Lout, stride, 1, off),
+                              dyp, Cout, K, dW)
+            else:
+                gemm_tn(_conv_gather(x, L, Cin, Lout, ksize, stride), dy2, dW, M, Cout, K)
         if has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
         if ctx.needs_input_grad[0]:
-            dyp = dy.data_ptr()
+            dyptr = dy.data_ptr()
+            W3 = Wg.view(ksize, Cin, Cout)
+            use_tc = _tc_fwd_ok(B * L // max(stride, 1), Cin, Cout, Cout)
+            if use_tc and dyp is None:
+                dyp = split_planes(dy)
+
+            def run(rows, taps, tap_off, tapmap, d_t, d_off, dst, accumulate=0):
+                """dst rows (b, t*d_t + d_off) = sum_j dy[b, t + j + tap_off] . W_tapmap[j]^T"""
+                out = Scatter(dst.data_ptr(), L * Cin, rows, Cin, d_t, d_off)
+                if use_tc:
+                    Bd = torch.stack([W3[t] for t in tapmap], dim=1).reshape(Cin, taps * Cout)
+                    gemm_tc_kmajor(tc_operand_conv(dyp, B, Lout, Cout, rows, 1, 1, tap_off),
+                                   split_planes(Bd.contiguous()), Cin, taps * Cout,
+                                   _epi(out, accumulate=accumulate))
+                else:
+                    ga = Gather(dyptr, Lout * Cout, rows, Cout, Lout, Cout, 1, 1, tap_off)
+                    gemm_nt(ga, Wg, Cout, tapmap, _epi(out, accumulate=accumulate), B * rows, Cin,
+                            taps * Cout)
+
             if ksize == 3 and stride == 1:
                 dx = torch.empty_like(x)
-                ga = Gather(dyp, Lout * Cout, L, Cout, Lout, Cout, 1, 1, -1)
-                gemm_nt(ga, Wg, Cout, (2, 1, 0), _epi(_scatter_plain(dx.data_ptr(), B * L, Cin)),
-                        B * L, Cin, 3 * Cout)
+                run(L, 3, -1, (2, 1, 0), 1, 0, dx)
             elif ksize == 3 and stride == 2:
                 dx = torch.empty_like(x)
                 ne, no = (L + 1) // 2, L // 2
-                # even input rows u = 2t: dx[2t] = dy[t] . W_tap1^T
-                ga = Gather(dyp, Lout * Cout, ne, Cout, Lout, Cout, 1, 0, 0)
-                out = Scatter(dx.data_ptr(), L * Cin, ne, Cin, 2, 0)
-                gemm_nt(ga, Wg, Cout, (1,), _epi(out), B * ne, Cin, Cout)
-                if no > 0:  # odd rows u = 2t+1: dx = dy[t] . W_tap2^T + dy[t+1] . W_tap0^T
-                    ga = Gather(dyp, Lout * Cout, no, Cout, Lout, Cout, 1, 1, 0)
-                    out = Scatter(dx.data_ptr(), L * Cin, no, Cin, 2, 1)
-                    gemm_nt(ga, Wg, Cout, (2, 0), _epi(out), B * no, Cin, 2 * Cout)
+                run(ne, 1, 0, (1,), 2, 0, dx)            # even rows: dy[t] . W_1^T
+                if no > 0:
+                    run(no, 2, 0, (2, 0), 2, 1, dx)      # odd rows: dy[t] . W_2^T + dy[t+1] . W_0^T
             elif ksize == 1 and stride == 2:
                 dx = torch.zeros_like(x)
-                ne = (L + 1) // 2
-                ga = Gather(dyp, Lout * Cout, ne, Cout, Lout, Cout, 1, 0, 0)
-                out = Scatter(dx.data_ptr(), L * Cin, ne, Cin, 2, 0)
-                gemm_nt(ga, Wg, Cout, (0,), _epi(out), B * ne, Cin, Cout)
+                run((L + 1) // 2, 1, 0, (0,), 2, 0, dx)
             else:
                 raise NotImplementedError("conv backward for this (ksize, stride)")
         return dx, dW, db, None, None
@@ -438,40 +552,3 @@ def band_attention(qkv, E_pad, B, T, H, dh, W, p=0.0, seed=0, site=0):
     return _BandAttnFn.apply(qkv, E_pad, int(B), int(T), int(H), int(dh), int(W), float(p),
                              int(seed), int(site))
 
-
-# ------------------------------------------------------------------------------------------
-# tcgen05 path: bf16 hi/lo split planes + tensor-core GEMMs (csrc/gemm_tc.cu)
-# ------------------------------------------------------------------------------------------
-from ._lib import TcOperand  # noqa: E402
-
-
-def split_planes(x):
-    """fp32 tensor -> bf16 tensor (2, *x.shape): plane 0 = hi = bf16(x), plane 1 = lo = bf16(x - hi)."""
-    lib = _lib.load()
-    _chk(x, "x")
-    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.ssb_split_bf16(x.data_ptr(), x.numel(), out.data_ptr(), _stream()))
-    return out
-
-
-def tc_operand_plain(planes, M, K):
-    """(2, M, K) split planes as a plain row-major matrix operand."""
-    return TcOperand(planes.data_ptr(), M * K, M * K, 1, M, M, K, K, 1, 0, 0)
-
-
-def tc_operand_conv(planes, B, L, C, rows_out, stride, taps_step, off):
-    """(2, B, L, C) split planes as the im2col operand of a k3/k1 convolution."""
-    return TcOperand(planes.data_ptr(), B * L * C, L * C, B, rows_out, L, C, C, stride, taps_step,
-                     off)
-
-
-def gemm_tc_kmajor(opA, Bplanes, N, K, epi):
-    lib = _lib.load()
-    _lib.check(lib.ssb_gemm_tc_kmajor(ctypes.byref(opA), Bplanes.data_ptr(), N, K,
-                                      ctypes.byref(epi), _stream()))
-
-
-def gemm_tc_wgrad(opX, Gplanes, N, K, dW, accumulate=False):
-    lib = _lib.load()
-    _lib.check(lib.ssb_gemm_tc_wgrad(ctypes.byref(opX), Gplanes.data_ptr(), Gplanes[0].numel(), N,
-                                     K, dW.data_ptr(), dW.stride(0), int(accumulate), _stream()))

@@ -133,6 +133,37 @@ def test_full_gradients_vs_oracle_medium():
     assert worst[1] < 1e-3, worst
 
 
+def test_tensor_core_path_vs_oracle_d128():
+    """D=128 makes every large GEMM / conv eligible for the tcgen05 bf16x3 engine (channel
+    counts multiples of 128).  Outputs and ALL gradients vs the CPU fp32 oracle, T=150 (> band)."""
+    D, NL, B, L = 128, 2, 3, 1200
+    m = build(D, NL)
+    m.train()
+    x = make_input(B, L, 9)
+    random.seed(7)
+    pred, aux = m(None, x.clone().cuda(), None)
+    scalar_loss(pred.cpu(), aux.cpu()).backward()
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+              else v.clone()) for k, v in om.formula_state_dict(D, NL).items()}
+    random.seed(7)
+    op, oa = om.model_forward(sd, x.clone(), training=True, dropout_p=0.0)
+    scalar_loss(op, oa).backward()
+    assert rel_l2(pred.detach().cpu().numpy(), op.detach().numpy()) < TOL
+    assert max_rel(aux.detach().cpu().numpy(), oa.detach().numpy()) < TOL
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:
+            assert p.grad is None, k
+            continue
+        if k.startswith("conv_blocks") and k.endswith(("conv1.bias", "conv2.bias",
+                                                       "residual_path.bias")):
+            continue
+        r = rel_l2(p.grad.cpu().numpy(), sd[k].grad.numpy())
+        if r > worst[1]:
+            worst = (k, r)
+    assert worst[1] < 1e-3, worst
+
+
 def test_train_mode_dropout_runs_and_differs():
     m = build(32, 1, dropout=0.2)
     m.train()

@@ -42,6 +42,24 @@ def test_linear_fwd_bwd(M, K, N):
     close(b.grad, g.sum(0), what="db")
 
 
+def test_engines_agree_linear(monkeypatch):
+    """tcgen05 (bf16x3) and CUDA-core engines on the same problem: both within 2e-5 of fp64."""
+    M, K, N = 2048, 768, 1024
+    x, W, b = rnd(M, K, seed=1), rnd(K, N, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    ref = (x.double() @ W.double() + b.double())
+    outs = {}
+    for eng in ("tc", "simt"):
+        monkeypatch.setenv("SSB_GEMM", eng)
+        xg, Wg = x.clone().requires_grad_(True), W.clone().requires_grad_(True)
+        y = SF.linear(xg, Wg, b)
+        y.backward(torch.ones_like(y))
+        close(y, ref, what=eng + " y")
+        close(Wg.grad, x.double().t() @ torch.ones(M, N, device=dev, dtype=torch.float64), what=eng + " dW")
+        close(xg.grad, torch.ones(M, N, device=dev, dtype=torch.float64) @ W.double().t(), what=eng + " dx")
+        outs[eng] = y.detach()
+    assert not torch.equal(outs["tc"], outs["simt"])      # really two different engines
+
+
 def test_ffn_fwd_bwd_no_dropout():
     M, D, Fh = 777, 64, 3072
     x = rnd(M, D, seed=1).requires_grad_(True)
