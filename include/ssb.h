@@ -152,10 +152,11 @@ SSB_API int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* g
                          float momentum, float eps, int training, float* mean, float* rstd,
                          float* scale, float* shift, void* workspace, int64_t workspace_bytes,
                          void* stream);
-/* y = [relu]( x*scale + shift [+ x2*scale2 + shift2] )   (architecture.py:32-40) */
-SSB_API int ssb_bn_apply(const float* x, const float* scale, const float* shift, const float* x2,
-                         const float* scale2, const float* shift2, int relu, int64_t rows,
-                         int64_t C, float* y, void* stream);
+/* y = [relu]( (x-mean)*scale + beta [+ (x2-mean2)*scale2 + beta2] )   (architecture.py:32-40) */
+SSB_API int ssb_bn_apply(const float* x, const float* mean, const float* scale, const float* beta,
+                         const float* x2, const float* mean2, const float* scale2,
+                         const float* beta2, int relu, int64_t rows, int64_t C, float* y,
+                         void* stream);
 /* BatchNorm backward through an optional ReLU mask (dz = dy * (mask_src > 0)).
  * workspace >= ssb_col_partials_bytes(rows, C) + 8*C bytes. */
 SSB_API int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const float* mean,

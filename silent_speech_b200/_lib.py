@@ -76,8 +76,8 @@ _SIGNATURES = {
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
-    "ssb_bn_apply": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr,
-                             c_ptr]),
+    "ssb_bn_apply": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64,
+                             c_i64, c_ptr, c_ptr]),
     "ssb_bn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr,
                            c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_add_dropout_ln_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_f32,

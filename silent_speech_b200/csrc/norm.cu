@@ -14,7 +14,9 @@ namespace {
 constexpr int RCH = 256;  // rows per partial chunk
 
 // ---- column partial sums -------------------------------------------------------------
-// MODE 0: sum(x), sum(x^2)                       (BatchNorm batch statistics)
+// MODE 0: sum(x-k), sum((x-k)^2), k = x[0, c]     (BatchNorm batch statistics; the per-channel
+//         shift keeps var = E[(x-k)^2] - E[x-k]^2 free of catastrophic cancellation when a
+//         channel's |mean| >> std, matching the stable algorithm torch uses)
 // MODE 1: sum(x)                                  (bias gradient)
 // MODE 2: sum(dz), sum(dz * xhat)   dz = dy * (mask_src > 0 if mask_src)   (BatchNorm backward)
 // block = 32 column-lanes (float4 each -> 128 columns) x 8 row-lanes
@@ -36,9 +38,12 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
       mu = *reinterpret_cast<const float4*>(mean + c);
       rs = *reinterpret_cast<const float4*>(rstd + c);
     }
+    float4 kk = s0;
+    if (MODE == 0) kk = __ldg(reinterpret_cast<const float4*>(x + c));
     for (int64_t r = r0 + rl; r < r1; r += 8) {
       if (MODE == 0) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+        float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
+        v.x -= kk.x; v.y -= kk.y; v.z -= kk.z; v.w -= kk.w;
         s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
         s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y);
         s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
@@ -86,7 +91,8 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
 
 // training: batch statistics -> (mean, rstd, scale, shift) + running-stat update
 // (biased variance normalises, unbiased variance feeds running_var; nn.BatchNorm1d semantics)
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+__global__ void bn_finalize_kernel(const float* __restrict__ partials,
+                                   const float* __restrict__ x_row0, int nchunks, int C,
                                    double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* running_mean,
                                    float* running_var, float momentum, float eps,
@@ -99,8 +105,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchun
     s += (double)partials[((int64_t)k * 2) * C + c];
     ss += (double)partials[((int64_t)k * 2 + 1) * C + c];
   }
-  const double mu = s / count;
-  double var = ss / count - mu * mu;
+  const double ms = s / count;                   // mean of the shifted data
+  const double mu = (double)x_row0[c] + ms;
+  double var = ss / count - ms * ms;
   if (var < 0.0) var = 0.0;
   const float r = (float)(1.0 / sqrt(var + (double)eps));
   mean[c] = (float)mu;
@@ -131,26 +138,31 @@ __global__ void bn_eval_affine_kernel(int C, const float* __restrict__ gamma,
   shift[c] = beta[c] - running_mean[c] * gamma[c] * r;
 }
 
-// y = [relu]( x*scale + shift  [+ x2*scale2 + shift2] )
+// y = [relu]( (x-mean)*scale + beta  [+ (x2-mean2)*scale2 + beta2] ),  scale = gamma*rstd.
+// Subtracting the mean first (instead of folding it into a shift) avoids cancellation between
+// x*scale and mean*scale when |mean| >> std.
 __global__ void __launch_bounds__(256)
-bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                const float* __restrict__ shift, const float* __restrict__ x2,
-                const float* __restrict__ scale2, const float* __restrict__ shift2, int relu,
+bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                const float* __restrict__ scale, const float* __restrict__ beta,
+                const float* __restrict__ x2, const float* __restrict__ mean2,
+                const float* __restrict__ scale2, const float* __restrict__ beta2, int relu,
                 int64_t n4, int C4, float* __restrict__ y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const float4 mu = *reinterpret_cast<const float4*>(mean + c);
     const float4 sc = *reinterpret_cast<const float4*>(scale + c);
-    const float4 sh = *reinterpret_cast<const float4*>(shift + c);
-    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z),
-                           fmaf(v.w, sc.w, sh.w));
+    const float4 be = *reinterpret_cast<const float4*>(beta + c);
+    float4 o = make_float4(fmaf(v.x - mu.x, sc.x, be.x), fmaf(v.y - mu.y, sc.y, be.y),
+                           fmaf(v.z - mu.z, sc.z, be.z), fmaf(v.w - mu.w, sc.w, be.w));
     if (x2) {
       const float4 w = __ldg(reinterpret_cast<const float4*>(x2) + i);
+      const float4 mu2 = *reinterpret_cast<const float4*>(mean2 + c);
       const float4 sc2 = *reinterpret_cast<const float4*>(scale2 + c);
-      const float4 sh2 = *reinterpret_cast<const float4*>(shift2 + c);
-      o.x += fmaf(w.x, sc2.x, sh2.x); o.y += fmaf(w.y, sc2.y, sh2.y);
-      o.z += fmaf(w.z, sc2.z, sh2.z); o.w += fmaf(w.w, sc2.w, sh2.w);
+      const float4 be2 = *reinterpret_cast<const float4*>(beta2 + c);
+      o.x += fmaf(w.x - mu2.x, sc2.x, be2.x); o.y += fmaf(w.y - mu2.y, sc2.y, be2.y);
+      o.z += fmaf(w.z - mu2.z, sc2.z, be2.z); o.w += fmaf(w.w - mu2.w, sc2.w, be2.w);
     }
     if (relu) {
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
@@ -443,23 +455,24 @@ int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* gamma, co
   col_partials_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
                                                (int)C, (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials<0>");
-  bn_finalize_kernel<<<cb, 128, 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, gamma,
+  bn_finalize_kernel<<<cb, 128, 0, st>>>((const float*)workspace, x, nch, (int)C, (double)rows, gamma,
                                          beta, running_mean, running_var, momentum, eps, mean,
                                          rstd, scale, shift);
   SSB_LAUNCH_CHECK("bn_finalize");
   return SSB_OK;
 }
 
-int ssb_bn_apply(const float* x, const float* scale, const float* shift, const float* x2,
-                 const float* scale2, const float* shift2, int relu, int64_t rows, int64_t C,
-                 float* y, void* stream) {
+int ssb_bn_apply(const float* x, const float* mean, const float* scale, const float* beta,
+                 const float* x2, const float* mean2, const float* scale2, const float* beta2,
+                 int relu, int64_t rows, int64_t C, float* y, void* stream) {
   if (int rc = check_rows_c(x, rows, C, "bn_apply")) return rc;
-  SSB_REQUIRE(scale && shift && y && (!x2 || (scale2 && shift2)), "bn_apply: null pointer");
+  SSB_REQUIRE(mean && scale && beta && y && (!x2 || (mean2 && scale2 && beta2)),
+              "bn_apply: null pointer");
   const int64_t n4 = rows * C / 4;
   const int64_t blocks = (n4 + 255) / 256;
   const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
-  bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, scale, shift, x2, scale2, shift2, relu,
-                                                          n4, (int)(C / 4), y);
+  bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mean, scale, beta, x2, mean2, scale2,
+                                                          beta2, relu, n4, (int)(C / 4), y);
   SSB_LAUNCH_CHECK("bn_apply");
   return SSB_OK;
 }

@@ -411,10 +411,11 @@ class _BNActFn(torch.autograd.Function):
             xb2 = xb.view(-1, C)
             sb = _bn_stats(xb2, gb, bb, rmb, rvb, training, momentum, eps)
         y = torch.empty_like(xa)
-        _lib.check(lib.ssb_bn_apply(xa2.data_ptr(), sa[2].data_ptr(), sa[3].data_ptr(),
+        _lib.check(lib.ssb_bn_apply(xa2.data_ptr(), sa[0].data_ptr(), sa[2].data_ptr(), ba.data_ptr(),
                                     xb2.data_ptr() if xb2 is not None else None,
+                                    sb[0].data_ptr() if sb is not None else None,
                                     sb[2].data_ptr() if sb is not None else None,
-                                    sb[3].data_ptr() if sb is not None else None, int(relu), rows,
+                                    bb.data_ptr() if sb is not None else None, int(relu), rows,
                                     C, y.data_ptr(), _stream()))
         ctx.training, ctx.relu, ctx.two = training, relu, xb is not None
         if ctx.two:
