@@ -124,7 +124,59 @@ def t_perf():
     print(f"perf split {M}x{K}: {e0.elapsed_time(e1)/10*1e3:.1f} us")
 
 
+
+
+def t_ffn():
+    """FFN-like chain pieces with every epilogue variant, odd sizes; each vs fp64."""
+    import itertools
+    for (M, D, Fh) in [(777, 64, 3072), (75, 32, 3072), (450, 128, 3072), (1000, 256, 1024)]:
+        x, W1, b1 = rnd(M, D, seed=1), rnd(D, Fh, seed=2, scale=D ** -0.5), rnd(Fh, seed=3, scale=0.1)
+        W2, b2 = rnd(Fh, D, seed=4, scale=Fh ** -0.5), rnd(D, seed=5, scale=0.1)
+        dy = rnd(M, D, seed=6)
+        xd, W1d, b1d, W2d, b2d, dyd = (t.double() for t in (x, W1, b1, W2, b2, dy))
+        h_ref = torch.relu(xd @ W1d + b1d)
+        h = torch.empty(M, Fh, device=dev)
+        SF.mm_fwd(x, W1, dict(bias=b1, relu=1), h, M, Fh, D)
+        print(f"ffn M={M} D={D} F={Fh}: h {rel(h, h_ref):.2e}", end=" ")
+        y = torch.empty(M, D, device=dev)
+        SF.mm_fwd(h, W2, dict(bias=b2), y, M, D, Fh)
+        print(f"y {rel(y, h.double() @ W2d + b2d):.2e}", end=" ")
+        dW2 = torch.empty(Fh, D, device=dev)
+        SF.mm_wgrad(h, dy, dW2, M, D, Fh)
+        print(f"dW2 {rel(dW2, h.double().t() @ dyd):.2e}", end=" ")
+        dh = torch.empty(M, Fh, device=dev)
+        SF.mm_dgrad(dy, W2, dict(mask_src=h, mask_scale=1.25), dh, M, D, Fh)
+        dh_ref = (dyd @ W2d.t()) * (h.double() > 0) * 1.25
+        print(f"dh {rel(dh, dh_ref):.2e}", end=" ")
+        dW1 = torch.empty(D, Fh, device=dev)
+        SF.mm_wgrad(x, dh, dW1, M, Fh, D)
+        print(f"dW1 {rel(dW1, xd.t() @ dh.double()):.2e}", end=" ")
+        dx = torch.empty(M, D, device=dev)
+        SF.mm_dgrad(dh, W1, {}, dx, M, Fh, D)
+        print(f"dx {rel(dx, dh.double() @ W1d.t()):.2e}")
+
+
+def t_convgrad():
+    """conv data / weight gradients through the autograd function, tc vs fp64 F.conv1d"""
+    for (B, L, Cin, Cout, k, s) in [(2, 256, 64, 64, 3, 1), (3, 600, 128, 128, 3, 1),
+                                    (3, 600, 128, 128, 3, 2), (3, 601, 128, 128, 3, 2),
+                                    (3, 600, 128, 128, 1, 2), (2, 301, 64, 128, 1, 2),
+                                    (4, 1000, 768, 768, 3, 2), (4, 1000, 768, 768, 1, 2)]:
+        x = rnd(B, L, Cin, seed=1).requires_grad_(True)
+        w = rnd(Cout, Cin, k, seed=2, scale=(Cin * k) ** -0.5).requires_grad_(True)
+        b = rnd(Cout, seed=3, scale=0.1).requires_grad_(True)
+        Wg = w.permute(2, 1, 0).reshape(k * Cin, Cout).contiguous()
+        y = SF.conv1d_cl(x, Wg, b, k, s)
+        xr, wr, br = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+        yr = F.conv1d(xr.transpose(1, 2), wr, br, stride=s, padding=1 if k == 3 else 0).transpose(1, 2)
+        g = rnd(*y.shape, seed=4)
+        y.backward(g)
+        yr.backward(g.double())
+        print(f"convgrad B={B} L={L} Cin={Cin} Cout={Cout} k={k} s={s}: y {rel(y, yr):.2e} "
+              f"dx {rel(x.grad, xr.grad):.2e} dw {rel(w.grad, wr.grad):.2e} db {rel(b.grad, br.grad):.2e}")
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     {"split": t_split, "kmajor": t_kmajor, "wgrad": t_wgrad, "conv1": lambda: t_conv(1),
-     "conv2": lambda: t_conv(2), "perf": t_perf}[what]()
+     "conv2": lambda: t_conv(2), "perf": t_perf, "ffn": t_ffn, "convgrad": t_convgrad}[what]()
