@@ -60,7 +60,8 @@ def test_engines_agree_linear(monkeypatch):
     assert not torch.equal(outs["tc"], outs["simt"])      # really two different engines
 
 
-def test_ffn_fwd_bwd_no_dropout():
+def test_ffn_fwd_bwd_no_dropout(monkeypatch):
+    monkeypatch.setenv("SSB_GEMM", "simt")    # exact fp32: masks identical to torch's
     M, D, Fh = 777, 64, 3072
     x = rnd(M, D, seed=1).requires_grad_(True)
     W1 = rnd(D, Fh, seed=2, scale=D ** -0.5).requires_grad_(True)
@@ -76,6 +77,36 @@ def test_ffn_fwd_bwd_no_dropout():
     close(y, yr, what="y")
     for a, b, n in zip((x, W1, b1, W2, b2), xs, "x W1 b1 W2 b2".split()):
         close(a.grad, b.grad, what="d" + n)
+
+
+@pytest.mark.parametrize("M,D,Fh", [(777, 64, 3072), (450, 128, 3072), (1000, 768, 3072)])
+def test_ffn_tensor_core_engine_vs_fp64(M, D, Fh):
+    """tcgen05 bf16x3 engine: forward within 2e-5 of fp64; backward checked against fp64
+    formulas evaluated with OUR ReLU mask (gradients through a ReLU kink are only comparable
+    at identical masks: a 4e-6 forward perturbation flips ~1e-5 of them)."""
+    x = rnd(M, D, seed=1).requires_grad_(True)
+    W1 = rnd(D, Fh, seed=2, scale=D ** -0.5).requires_grad_(True)
+    b1 = rnd(Fh, seed=3, scale=0.1).requires_grad_(True)
+    W2 = rnd(Fh, D, seed=4, scale=Fh ** -0.5).requires_grad_(True)
+    b2 = rnd(D, seed=5, scale=0.1).requires_grad_(True)
+    y = SF.ffn(x, W1, b1, W2, b2, 0.0, 0, 0)
+    g = rnd(M, D, seed=6)
+    y.backward(g)
+    xd, W1d, b1d, W2d, b2d, gd = (t.detach().double() for t in (x, W1, b1, W2, b2, g))
+    z = xd @ W1d + b1d
+    close(y, torch.relu(z) @ W2d + b2d, what="y")
+    # recover our mask from an identical forward GEMM
+    h = torch.empty(M, Fh, device=dev)
+    SF.mm_fwd(x.detach(), W1.detach(), dict(bias=b1.detach(), relu=1), h, M, Fh, D)
+    mask = (h > 0).double()
+    assert (mask != (z > 0).double()).float().mean().item() < 1e-4     # only kink-adjacent flips
+    hd = h.double()
+    dh = (gd @ W2d.t()) * mask
+    close(W2.grad, hd.t() @ gd, tol=5e-5, what="dW2")
+    close(b2.grad, gd.sum(0), what="db2")
+    close(W1.grad, xd.t() @ dh, tol=5e-5, what="dW1")
+    close(b1.grad, dh.sum(0), tol=5e-5, what="db1")
+    close(x.grad, dh @ W1d.t(), tol=5e-5, what="dx")
 
 
 def test_ffn_dropout_statistics_and_consistency():
