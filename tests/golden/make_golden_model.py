@@ -18,7 +18,7 @@ from _reference_import import fix_transformer_shim, import_reference  # noqa: E4
 OUT = os.path.join(HERE, "model_golden.npz")
 
 # (name, model_size, num_layers, B, L, python-random seed used for the train-mode shift)
-CASES = [("short", 32, 2, 3, 200, 1), ("band", 32, 1, 2, 1000, 2), ("odd", 64, 1, 2, 1003, 3)]
+CASES = [("short", 32, 2, 3, 200, 1), ("band", 32, 1, 2, 1000, 2), ("odd", 32, 1, 2, 1003, 3)]
 
 
 def make_input(B, L, case_idx):

