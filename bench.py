@@ -237,6 +237,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 per rank; the CPU arm uses every host core it can
+    torch.set_num_threads(os.cpu_count() or 1)
     n_utt = 4
     sec = cpu_port_step_time(n_utt, max(1, min(args.steps, 2)), 1 if args.warmup else 0)
     value = (n_utt / BS) / sec
@@ -308,6 +310,7 @@ def run_ours(args):
         if rank == 0:
             line["dtw"] = side
     if rank == 0 and world == 1 and not args.no_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
         n_utt = 4
         sec = cpu_port_step_time(n_utt, 1, 0)
         line["cpu_baseline"] = {"value": (n_utt / BS) / sec, "unit": "steps/s",

@@ -9,11 +9,12 @@
 // cost of 3 bf16 MMAs = 1.5x a TF32 MMA.  Split planes take exactly the bytes of the fp32
 // tensor they replace (2 + 2 B per element).
 //
-// Kernel shape (one CTA per 128 x 256 output tile, 192 threads, warp-specialised):
+// Kernel shape (persistent: one CTA per SM walks 128 x 256 output tiles; 192 threads,
+// warp-specialised; two TMEM accumulators so the epilogue of a tile overlaps the next tile's MMAs):
 //   warp 0    TMA producer: per 64-deep k-block, the A_hi/A_lo (2 x 16 KB) and B_hi/B_lo
 //             (2 x 32 KB) tiles land in 128B-swizzled shared memory (2 stages x 96 KB),
 //             completion on an mbarrier (complete_tx).
-//   warp 1    TMEM allocator (256 fp32 columns) and single-thread MMA issuer: 4 x 3
+//   warp 1    TMEM allocator (2 x 256 fp32 columns) and single-thread MMA issuer: 4 x 3
 //             tcgen05.mma (M128 N256 K16) per k-block, tcgen05.commit releases the stage.
 //   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias / ReLU / dropout /
 //             mask / accumulate / split-K reduction, fp32 stores through the same
@@ -39,7 +40,7 @@ constexpr int STAGES = 2;
 constexpr int A_PLANE = BM * BK * 2;   // 16 KB
 constexpr int B_PLANE = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // 96 KB
-constexpr int TMEM_COLS = 256;
+constexpr int TMEM_COLS = 512;   // two 256-column fp32 accumulators
 constexpr int THREADS = 192;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -54,6 +55,7 @@ struct TcParams {
   int M_valid_total;                             // rows of C (K-major: batches*rows_per_batch; MN: features)
   int N;
   int mn_major;
+  int tiles_x, tiles_y, splits;                   // persistent tile list
   // epilogue
   float* out; int64_t out_batch_stride; int out_ld, out_dt, out_doff;
   const float* bias; const float* mask_src; float mask_scale;
@@ -136,31 +138,28 @@ __host__ __device__ constexpr uint32_t make_idesc(int mn_major) {
          ((uint32_t)(mn_major & 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: gridDim.x CTAs (one per SM) walk the tile list; the two 256-column TMEM
+// accumulators alternate so that the epilogue of tile i runs under the MMAs of tile i+1, and
+// the TMA ring keeps streaming across tile boundaries.
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ssb::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;   // full[S], empty[S], tmem_full, tmem_ptr
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES, tfull_bar = bars + 16 * STAGES;
-  const uint32_t tmem_ptr_smem = bars + 16 * STAGES + 8;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_ptr_smem = tempty_bar + 16;
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - ssb::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-
-  // tile coordinates
-  int batch = 0, row0 = 0, f0 = 0, kb_begin = 0, kb_end = p.num_kb;
-  if (!p.mn_major) {
-    batch = blockIdx.y / p.tiles_per_batch;
-    row0 = (blockIdx.y - batch * p.tiles_per_batch) * BM;
-  } else {
-    f0 = blockIdx.y * BM;
-    kb_begin = blockIdx.z * p.kb_per_split;
-    kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
-  }
-  const int nkb = max(kb_end - kb_begin, 0);
+  const int tiles_xy = p.tiles_x * p.tiles_y;
+  const int total_tiles = tiles_xy * p.splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -169,7 +168,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(tfull_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 4);   // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -184,39 +186,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_gen;
 
+  // tile -> coordinates (n fastest, so concurrently running CTAs share A rows and sweep B)
+  auto decode = [&](int tile, int& n0, int& batch, int& row0, int& f0, int& kb_begin, int& nkb) {
+    const int z = tile / tiles_xy;
+    const int rem = tile - z * tiles_xy;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    n0 = tx * BN;
+    batch = 0; row0 = 0; f0 = 0;
+    if (!p.mn_major) {
+      batch = ty / p.tiles_per_batch;
+      row0 = (ty - batch * p.tiles_per_batch) * BM;
+      kb_begin = 0;
+      nkb = p.num_kb;
+    } else {
+      f0 = ty * BM;
+      kb_begin = z * p.kb_per_split;
+      nkb = max(min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin, 0);
+    }
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int kb = kb_begin + i;
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(empty_bar + 8 * s, ph ^ 1u);
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
-        if (!p.mn_major) {
-          const int kk = kb * BK;
-          const int tap = kk / p.a_inner, c0 = kk - tap * p.a_inner;
-          const int d1 = row0 * p.a_row_step + tap * p.a_tap_step + p.a_off;
-          tma_load_4d(st, &mapA, full_bar + 8 * s, c0, d1, batch, 0);
-          tma_load_4d(st + A_PLANE, &mapA, full_bar + 8 * s, c0, d1, batch, 1);
-          tma_load_4d(st + 2 * A_PLANE, &mapB, full_bar + 8 * s, kk, n0, 0, 0);
-          tma_load_4d(st + 2 * A_PLANE + B_PLANE, &mapB, full_bar + 8 * s, kk, n0, 0, 1);
-        } else {
-          const int b = kb / p.chunks_per_batch;
-          const int t0 = (kb - b * p.chunks_per_batch) * BK;
-          const int tap = f0 / p.a_inner, c0 = f0 - tap * p.a_inner;
-          const int d1 = t0 * p.a_row_step + tap * p.a_tap_step + p.a_off;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n0, batch, row0, f0, kb_begin, nkb;
+        decode(tile, n0, batch, row0, f0, kb_begin, nkb);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int kb = kb_begin + i;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1u);
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+          if (!p.mn_major) {
+            const int kk = kb * BK;
+            const int tap = kk / p.a_inner, c0 = kk - tap * p.a_inner;
+            const int d1 = row0 * p.a_row_step + tap * p.a_tap_step + p.a_off;
+            tma_load_4d(st, &mapA, full_bar + 8 * s, c0, d1, batch, 0);
+            tma_load_4d(st + A_PLANE, &mapA, full_bar + 8 * s, c0, d1, batch, 1);
+            tma_load_4d(st + 2 * A_PLANE, &mapB, full_bar + 8 * s, kk, n0, 0, 0);
+            tma_load_4d(st + 2 * A_PLANE + B_PLANE, &mapB, full_bar + 8 * s, kk, n0, 0, 1);
+          } else {
+            const int b = kb / p.chunks_per_batch;
+            const int t0 = (kb - b * p.chunks_per_batch) * BK;
+            const int tap = f0 / p.a_inner, c0 = f0 - tap * p.a_inner;
+            const int d1 = t0 * p.a_row_step + tap * p.a_tap_step + p.a_off;
 #pragma unroll
-          for (int pl = 0; pl < 2; ++pl) {
+            for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-            for (int h = 0; h < BM / 64; ++h)
-              tma_load_4d(st + pl * A_PLANE + h * 8192, &mapA, full_bar + 8 * s, c0 + 64 * h, d1,
-                          b, pl);
+              for (int h = 0; h < BM / 64; ++h)
+                tma_load_4d(st + pl * A_PLANE + h * 8192, &mapA, full_bar + 8 * s, c0 + 64 * h,
+                            d1, b, pl);
 #pragma unroll
-            for (int h = 0; h < BN / 64; ++h)
-              tma_load_4d(st + 2 * A_PLANE + pl * B_PLANE + h * 8192, &mapB, full_bar + 8 * s,
-                          n0 + 64 * h, t0, b, pl);
+              for (int h = 0; h < BN / 64; ++h)
+                tma_load_4d(st + 2 * A_PLANE + pl * B_PLANE + h * 8192, &mapB, full_bar + 8 * s,
+                            n0 + 64 * h, t0, b, pl);
+            }
           }
         }
       }
@@ -225,116 +251,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.mn_major);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
-        mbar_wait(full_bar + 8 * s, ph);
+      uint32_t it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+        int n0, batch, row0, f0, kb_begin, nkb;
+        decode(tile, n0, batch, row0, f0, kb_begin, nkb);
+        const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+        mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);      // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-        const uint32_t a_hi = st, a_lo = st + A_PLANE, b_hi = st + 2 * A_PLANE,
-                       b_lo = st + 2 * A_PLANE + B_PLANE;
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const uint32_t a_hi = st, a_lo = st + A_PLANE, b_hi = st + 2 * A_PLANE,
+                         b_lo = st + 2 * A_PLANE + B_PLANE;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          uint64_t dah, dal, dbh, dbl;
-          if (!p.mn_major) {
-            // K-major, SW128: rows of 128 B, 8-row groups 1024 B apart; +32 B per K=16 step
-            const uint32_t off = k * 32;
-            dah = make_desc(a_hi + off, 16, 1024);
-            dal = make_desc(a_lo + off, 16, 1024);
-            dbh = make_desc(b_hi + off, 16, 1024);
-            dbl = make_desc(b_lo + off, 16, 1024);
-          } else {
-            // MN-major, SW128: 64-element MN groups 8 KB apart (LBO), 8-row K groups 1 KB
-            // apart (SBO); +2 KB per K=16 step
-            const uint32_t off = k * 2048;
-            dah = make_desc(a_hi + off, 8192, 1024);
-            dal = make_desc(a_lo + off, 8192, 1024);
-            dbh = make_desc(b_hi + off, 8192, 1024);
-            dbl = make_desc(b_lo + off, 8192, 1024);
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t dah, dal, dbh, dbl;
+            if (!p.mn_major) {
+              // K-major, SW128: rows of 128 B, 8-row groups 1024 B apart; +32 B per K=16 step
+              const uint32_t off = k * 32;
+              dah = make_desc(a_hi + off, 16, 1024);
+              dal = make_desc(a_lo + off, 16, 1024);
+              dbh = make_desc(b_hi + off, 16, 1024);
+              dbl = make_desc(b_lo + off, 16, 1024);
+            } else {
+              // MN-major, SW128: 64-element MN groups 8 KB apart (LBO), 8-row K groups 1 KB
+              // apart (SBO); +2 KB per K=16 step
+              const uint32_t off = k * 2048;
+              dah = make_desc(a_hi + off, 8192, 1024);
+              dal = make_desc(a_lo + off, 8192, 1024);
+              dbh = make_desc(b_hi + off, 8192, 1024);
+              dbl = make_desc(b_lo + off, 8192, 1024);
+            }
+            const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(tmem_d, dah, dbh, idesc, acc0);
+            umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+            umma_bf16(tmem_d, dal, dbh, idesc, 1u);
           }
-          const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
-          umma_bf16(tmem_base, dah, dbh, idesc, acc0);
-          umma_bf16(tmem_base, dah, dbl, idesc, 1u);
-          umma_bf16(tmem_base, dal, dbh, idesc, 1u);
+          umma_commit(empty_bar + 8 * s);   // frees this smem stage when the MMAs retire
         }
-        umma_commit(empty_bar + 8 * s);   // frees this smem stage when the MMAs retire
+        umma_commit(tfull_bar + 8 * acc);   // accumulator complete
       }
-      umma_commit(tfull_bar);             // accumulator complete
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int lg = warp & 3;              // TMEM lane group this warp may read
     const int r = lg * 32 + lane;         // row inside the tile == TMEM lane
-    mbar_wait(tfull_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    bool row_ok;
-    float* orow;
-    int64_t grow;   // global output row index (for mask / dropout addressing)
-    if (!p.mn_major) {
-      const int t = row0 + r;
-      row_ok = t < p.rows_per_batch;
-      grow = (int64_t)batch * p.rows_per_batch + t;
-      orow = p.out + (int64_t)batch * p.out_batch_stride +
-             (int64_t)(t * p.out_dt + p.out_doff) * p.out_ld;
-    } else {
-      const int f = f0 + r;
-      row_ok = f < p.M_valid_total;
-      grow = f;
-      orow = p.out + (int64_t)f * p.out_ld;
-    }
-    if (nkb == 0) row_ok = false;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!row_ok) continue;
-      const int nb = n0 + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = nb + j;
-        if (n >= p.N) break;
-        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        if (p.atomic) {
-          atomicAdd(orow + n + 0, o.x);
-          atomicAdd(orow + n + 1, o.y);
-          atomicAdd(orow + n + 2, o.z);
-          atomicAdd(orow + n + 3, o.w);
-          continue;
-        }
-        if (p.bias) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-          o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-        }
-        if (p.relu) {
-          o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-        }
-        if (p.drop_p > 0.f) {
-          const uint64_t e = (uint64_t)grow * (uint64_t)p.N + (uint64_t)n;
-          const uint4 rnd = ssb::dropout_bits4(p.seed, p.site, e >> 2);
-          o.x = rnd.x >= p.drop_thresh ? o.x * p.drop_scale : 0.f;
-          o.y = rnd.y >= p.drop_thresh ? o.y * p.drop_scale : 0.f;
-          o.z = rnd.z >= p.drop_thresh ? o.z * p.drop_scale : 0.f;
-          o.w = rnd.w >= p.drop_thresh ? o.w * p.drop_scale : 0.f;
-        }
-        if (p.mask_src) {
-          const float4 mk = __ldg(reinterpret_cast<const float4*>(p.mask_src + grow * p.N + n));
-          o.x = mk.x > 0.f ? o.x * p.mask_scale : 0.f;
-          o.y = mk.y > 0.f ? o.y * p.mask_scale : 0.f;
-          o.z = mk.z > 0.f ? o.z * p.mask_scale : 0.f;
-          o.w = mk.w > 0.f ? o.w * p.mask_scale : 0.f;
-        }
-        if (p.accumulate) {
-          const float4 old = *reinterpret_cast<const float4*>(orow + n);
-          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-        }
-        *reinterpret_cast<float4*>(orow + n) = o;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      int n0, batch, row0, f0, kb_begin, nkb;
+      decode(tile, n0, batch, row0, f0, kb_begin, nkb);
+      const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      mbar_wait(tfull_bar + 8 * acc, aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      bool row_ok;
+      float* orow;
+      int64_t grow;   // global output row index (for mask / dropout addressing)
+      if (!p.mn_major) {
+        const int t = row0 + r;
+        row_ok = t < p.rows_per_batch;
+        grow = (int64_t)batch * p.rows_per_batch + t;
+        orow = p.out + (int64_t)batch * p.out_batch_stride +
+               (int64_t)(t * p.out_dt + p.out_doff) * p.out_ld;
+      } else {
+        const int f = f0 + r;
+        row_ok = f < p.M_valid_total;
+        grow = f;
+        orow = p.out + (int64_t)f * p.out_ld;
       }
+      if (nkb == 0) row_ok = false;
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= p.N) break;    // warp-uniform: nothing to store in this column block
+        uint32_t v[32];
+        tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!row_ok) continue;
+        const int nb = n0 + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = nb + j;
+          if (n >= p.N) break;
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          if (p.atomic) {
+            atomicAdd(orow + n + 0, o.x);
+            atomicAdd(orow + n + 1, o.y);
+            atomicAdd(orow + n + 2, o.z);
+            atomicAdd(orow + n + 3, o.w);
+            continue;
+          }
+          if (p.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (p.relu) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+          }
+          if (p.drop_p > 0.f) {
+            const uint64_t e = (uint64_t)grow * (uint64_t)p.N + (uint64_t)n;
+            const uint4 rnd = ssb::dropout_bits4(p.seed, p.site, e >> 2);
+            o.x = rnd.x >= p.drop_thresh ? o.x * p.drop_scale : 0.f;
+            o.y = rnd.y >= p.drop_thresh ? o.y * p.drop_scale : 0.f;
+            o.z = rnd.z >= p.drop_thresh ? o.z * p.drop_scale : 0.f;
+            o.w = rnd.w >= p.drop_thresh ? o.w * p.drop_scale : 0.f;
+          }
+          if (p.mask_src) {
+            const float4 mk = __ldg(reinterpret_cast<const float4*>(p.mask_src + grow * p.N + n));
+            o.x = mk.x > 0.f ? o.x * p.mask_scale : 0.f;
+            o.y = mk.y > 0.f ? o.y * p.mask_scale : 0.f;
+            o.z = mk.z > 0.f ? o.z * p.mask_scale : 0.f;
+            o.w = mk.w > 0.f ? o.w * p.mask_scale : 0.f;
+          }
+          if (p.accumulate) {
+            const float4 old = *reinterpret_cast<const float4*>(orow + n);
+            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+          }
+          *reinterpret_cast<float4*>(orow + n) = o;
+        }
+      }
+      // hand the accumulator back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
 
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -413,7 +460,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, in
   return SSB_OK;
 }
 
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, dim3 grid,
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams p, dim3 tiles,
            cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -423,6 +470,12 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, 
                                   SMEM_BYTES));
     attr_set[dev] = true;
   }
+  p.tiles_x = (int)tiles.x;
+  p.tiles_y = (int)tiles.y;
+  p.splits = (int)tiles.z;
+  const int64_t total = (int64_t)tiles.x * tiles.y * tiles.z;
+  const int sms = ssb::num_sms();
+  const int grid = (int)(total < sms ? total : sms);
   gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
   SSB_LAUNCH_CHECK("gemm_tc_kernel");
   return SSB_OK;
@@ -490,7 +543,6 @@ int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N
   p.M_valid_total = A->batches * A->rows_out;
   p.mn_major = 0;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)(A->batches * p.tiles_per_batch), 1);
-  SSB_REQUIRE(grid.y <= 65535, "gemm_tc: too many M tiles");
   return launch(mapA, mapB, p, grid, (cudaStream_t)stream);
 }
 
