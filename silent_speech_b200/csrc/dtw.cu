@@ -241,7 +241,10 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
   }
 }
 
-// One thread per pair walks the path from (N-1, M-1) (align.py:19-26).
+// One thread per pair walks the path from (N-1, M-1) (align.py:19-26).  The walk is a chain of
+// ~N+M dependent loads; whenever it enters a new 32 B sector of direction words it prefetches
+// the two sectors it can move to next (previous rows of the same chunk, previous chunk of the
+// same rows) so that most sector changes hit L2/L1 instead of paying a DRAM round trip.
 template <bool Y_IS_I>
 __global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t dirs_pair_words,
                                      int nch, int N, int M, int npairs,
@@ -253,12 +256,18 @@ __global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t 
   int i = N - 1, j = M - 1;
   int64_t cur_idx = -1;
   uint32_t cur_word = 0;
+  int lowest = N;   // smallest row index assigned so far
   while (i > 0 && j > 0) {
     out[i] = j;
+    lowest = i;
     const int x = Y_IS_I ? j : i, y = Y_IS_I ? i : j;
     const int band = y / BAND, l = (y % BAND) / R, r = y % R, s = x + l;
     const int64_t idx = (((int64_t)band * nch + (s / CH)) * 32 + l) * 4 + r;
     if (idx != cur_idx) {
+      if ((idx >> 3) != (cur_idx >> 3)) {   // new 32 B sector
+        if (idx >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + idx - 8));
+        if (idx >= 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + idx - 128));
+      }
       cur_word = __ldg(d + idx);
       cur_idx = idx;
     }
@@ -267,6 +276,8 @@ __global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t 
     if (diag || !left) --i;  // up or diagonal
     if (diag || left) --j;   // left or diagonal
   }
+  // rows the walk never assigned keep the reference's initial value 0 (align.py:21)
+  for (int rr = lowest - 1; rr >= 0; --rr) out[rr] = 0;
 }
 
 struct Geometry {
@@ -350,7 +361,6 @@ int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64
   const bool vec = (g.pitch % 4 == 0) && (pair_stride % 4 == 0) && (((uintptr_t)cost & 15) == 0) &&
                    (!dtw || ((uintptr_t)dtw & 15) == 0);
 
-  SSB_CUDA(cudaMemsetAsync(path, 0, (size_t)npairs * N * sizeof(int32_t), st));
   int rc;
 #define SSB_DTW_DISPATCH(YI, V)                                            \
   rc = dtw ? launch_fill<YI, V, true>(p, st) : launch_fill<YI, V, false>(p, st)
