@@ -95,7 +95,7 @@ _SIGNATURES = {
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
 _KERNELS_PER_CALL = {
     "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
-    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_bn_stats": 2, "ssb_bn_apply": 1,
+    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
 }

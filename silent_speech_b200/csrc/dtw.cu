@@ -33,8 +33,8 @@ namespace {
 
 constexpr int R = 4;            // strip rows per lane
 constexpr int BAND = 32 * R;    // strip rows per band
-constexpr int RING = 32;        // ring depth (columns), power of two
-constexpr int PF = 24;          // prefetch distance (columns); RING - PF >= 8
+constexpr int RING = 16;        // ring depth (columns), power of two
+constexpr int PF = 8;           // prefetch distance (columns); RING - PF >= 8
 constexpr int RING_BYTES = RING * 32 * 16;
 constexpr int RING_MASK = (RING - 1) << 9;  // byte offset of a column inside the ring
 constexpr int CH = 16;          // steps per chunk == 2-bit codes per direction word

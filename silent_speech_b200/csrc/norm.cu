@@ -14,9 +14,9 @@ namespace {
 constexpr int RCH = 256;  // rows per partial chunk
 
 // ---- column partial sums -------------------------------------------------------------
-// MODE 0: sum(x-k), sum((x-k)^2), k = x[0, c]     (BatchNorm batch statistics; the per-channel
-//         shift keeps var = E[(x-k)^2] - E[x-k]^2 free of catastrophic cancellation when a
-//         channel's |mean| >> std, matching the stable algorithm torch uses)
+// MODE 0: sum((x-mean)^2)                         (BatchNorm variance, second pass: the two-pass
+//         form is immune to the cancellation of E[x^2]-mean^2 on near-constant channels, where
+//         a one-pass or shifted one-pass variance lost up to 1e-2 against torch's stable one)
 // MODE 1: sum(x)                                  (bias gradient)
 // MODE 2: sum(dz), sum(dz * xhat)   dz = dy * (mask_src > 0 if mask_src)   (BatchNorm backward)
 // block = 32 column-lanes (float4 each -> 128 columns) x 8 row-lanes
@@ -39,14 +39,13 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
       rs = *reinterpret_cast<const float4*>(rstd + c);
     }
     float4 kk = s0;
-    if (MODE == 0) kk = __ldg(reinterpret_cast<const float4*>(x + c));
+    if (MODE == 0) kk = *reinterpret_cast<const float4*>(mean + c);
     for (int64_t r = r0 + rl; r < r1; r += 8) {
       if (MODE == 0) {
         float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
         v.x -= kk.x; v.y -= kk.y; v.z -= kk.z; v.w -= kk.w;
-        s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
-        s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y);
-        s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
+        s0.x = fmaf(v.x, v.x, s0.x); s0.y = fmaf(v.y, v.y, s0.y);
+        s0.z = fmaf(v.z, v.z, s0.z); s0.w = fmaf(v.w, v.w, s0.w);
       } else if (MODE == 1) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
         s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
@@ -74,7 +73,7 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
       const float4 b = red[rl][i][cl];
       a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    if (rl == 0 || MODE != 1)
+    if (rl == 0 || MODE == 2)
       *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 2 + rl) * C + c) = a;
   }
 }
@@ -89,28 +88,31 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
   out[c] = (accumulate ? out[c] : 0.f) + (float)s;
 }
 
-// training: batch statistics -> (mean, rstd, scale, shift) + running-stat update
+// training, pass 1: mean[c] = sum(x) / count
+__global__ void bn_mean_kernel(const float* __restrict__ partials, int nchunks, int C, double count,
+                               float* __restrict__ mean) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < nchunks; ++k) s += (double)partials[((int64_t)k * 2) * C + c];
+  mean[c] = (float)(s / count);
+}
+
+// training, pass 2: centred sum of squares -> (rstd, scale, shift) + running-stat update
 // (biased variance normalises, unbiased variance feeds running_var; nn.BatchNorm1d semantics)
-__global__ void bn_finalize_kernel(const float* __restrict__ partials,
-                                   const float* __restrict__ x_row0, int nchunks, int C,
+__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
                                    double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* running_mean,
                                    float* running_var, float momentum, float eps,
-                                   float* __restrict__ mean, float* __restrict__ rstd,
+                                   const float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = 0; k < nchunks; ++k) {
-    s += (double)partials[((int64_t)k * 2) * C + c];
-    ss += (double)partials[((int64_t)k * 2 + 1) * C + c];
-  }
-  const double ms = s / count;                   // mean of the shifted data
-  const double mu = (double)x_row0[c] + ms;
-  double var = ss / count - ms * ms;
-  if (var < 0.0) var = 0.0;
+  double m2 = 0.0;
+  for (int k = 0; k < nchunks; ++k) m2 += (double)partials[((int64_t)k * 2) * C + c];
+  const double mu = (double)mean[c];
+  const double var = m2 / count;
   const float r = (float)(1.0 / sqrt(var + (double)eps));
-  mean[c] = (float)mu;
   rstd[c] = r;
   const float sc = gamma[c] * r;
   scale[c] = sc;
@@ -452,10 +454,15 @@ int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* gamma, co
               "bn_stats: workspace too small");
   const int nch = nchunks_for(rows);
   dim3 grid(cb, (unsigned)nch);
-  col_partials_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
+  col_partials_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
+                                               (int)C, (float*)workspace);
+  SSB_LAUNCH_CHECK("col_partials<1>");
+  bn_mean_kernel<<<cb, 128, 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, mean);
+  SSB_LAUNCH_CHECK("bn_mean");
+  col_partials_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, mean, nullptr, rows, (int)C,
                                                (int)C, (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials<0>");
-  bn_finalize_kernel<<<cb, 128, 0, st>>>((const float*)workspace, x, nch, (int)C, (double)rows, gamma,
+  bn_finalize_kernel<<<cb, 128, 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, gamma,
                                          beta, running_mean, running_var, momentum, eps, mean,
                                          rstd, scale, shift);
   SSB_LAUNCH_CHECK("bn_finalize");
