@@ -190,14 +190,16 @@ class _LinearFn(torch.autograd.Function):
         M, K = x.shape
         N = Wg.shape[1]
         y = torch.empty((M, N), dtype=_f32, device=x.device)
-        mm_fwd(x, Wg, dict(bias=bias), y, M, N, K)
-        ctx.save_for_backward(x, Wg)
+        xp = mm_fwd(x, Wg, dict(bias=bias), y, M, N, K)
+        # keep the split planes of x (same bytes as x) so backward does not split it again
+        keep_planes = xp is not None and ctx.needs_input_grad[1] and _tc_wgrad_ok(M, N, K)
+        ctx.save_for_backward(x, Wg, xp if keep_planes else None)
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, Wg = ctx.saved_tensors
+        x, Wg, xp = ctx.saved_tensors
         dy = dy.contiguous()
         M, K = x.shape
         N = Wg.shape[1]
@@ -208,7 +210,7 @@ class _LinearFn(torch.autograd.Function):
             dyp = mm_dgrad(dy, Wg, {}, dx, M, N, K)
         if ctx.needs_input_grad[1]:
             dW = torch.empty_like(Wg)
-            mm_wgrad(x, dy, dW, M, N, K, dyp=dyp)
+            mm_wgrad(x, dy, dW, M, N, K, xp=xp, dyp=dyp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy)
         return dx, dW, db
@@ -229,29 +231,30 @@ class _FFNFn(torch.autograd.Function):
         F_ = W1.shape[1]
         N = W2.shape[1]
         h = torch.empty((M, F_), dtype=_f32, device=x.device)
-        mm_fwd(x, W1, dict(bias=b1, relu=1, drop_p=p, seed=seed, site=site), h, M, F_, K)
+        xp = mm_fwd(x, W1, dict(bias=b1, relu=1, drop_p=p, seed=seed, site=site), h, M, F_, K)
         y = torch.empty((M, N), dtype=_f32, device=x.device)
-        mm_fwd(h, W2, dict(bias=b2), y, M, N, F_)
-        ctx.save_for_backward(x, W1, W2, h)
+        hp = mm_fwd(h, W2, dict(bias=b2), y, M, N, F_)
+        ctx.save_for_backward(x, W1, W2, h, xp if _tc_wgrad_ok(M, F_, K) else None,
+                              hp if _tc_wgrad_ok(M, N, F_) else None)
         ctx.p = p
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, W1, W2, h = ctx.saved_tensors
+        x, W1, W2, h, xp, hp = ctx.saved_tensors
         dy = dy.contiguous()
         M, K = x.shape
         F_ = W1.shape[1]
         N = W2.shape[1]
         scale = 1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0
         dW2 = torch.empty_like(W2)
-        dyp = mm_wgrad(h, dy, dW2, M, N, F_)
+        dyp = mm_wgrad(h, dy, dW2, M, N, F_, xp=hp)
         db2 = colsum(dy)
         # dh = (dy @ W2^T) * (h > 0) / (1 - p): relu and dropout masks both read off h
         dh = torch.empty_like(h)
         mm_dgrad(dy, W2, dict(mask_src=h, mask_scale=scale), dh, M, N, F_, dyp=dyp)
         dW1 = torch.empty_like(W1)
-        dhp = mm_wgrad(x, dh, dW1, M, F_, K)
+        dhp = mm_wgrad(x, dh, dW1, M, F_, K, xp=xp)
         db1 = colsum(dh)
         dx = torch.empty_like(x)
         mm_dgrad(dh, W1, {}, dx, M, F_, K, dyp=dhp)
@@ -282,6 +285,7 @@ class _ConvFn(torch.autograd.Function):
         y = torch.empty((B, Lout, Cout), dtype=_f32, device=x.device)
         M = B * Lout
         off = -1 if ksize == 3 else 0
+        xp = None
         if _tc_fwd_ok(M, Cout, ksize * Cin, Cin):
             xp = split_planes(x)
             wp = split_planes(Wg.t().contiguous())               # [Cout][(tap, ci)]
@@ -291,13 +295,14 @@ class _ConvFn(torch.autograd.Function):
         else:
             gemm_nn(_conv_gather(x, L, Cin, Lout, ksize, stride), Wg,
                     _epi(_scatter_plain(y.data_ptr(), M, Cout), bias=bias), M, Cout, ksize * Cin)
-        ctx.save_for_backward(x, Wg)
+        keep = xp is not None and ctx.needs_input_grad[1] and _tc_wgrad_ok(M, Cout, ksize * Cin, Cin)
+        ctx.save_for_backward(x, Wg, xp if keep else None)
         ctx.cfg = (ksize, stride, bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, Wg = ctx.saved_tensors
+        x, Wg, xp_saved = ctx.saved_tensors
         ksize, stride, has_bias = ctx.cfg
         dy = dy.contiguous()
         B, L, Cin = x.shape
@@ -312,8 +317,8 @@ class _ConvFn(torch.autograd.Function):
             dW = torch.empty_like(Wg)
             if _tc_wgrad_ok(M, Cout, K, Cin):
                 dyp = split_planes(dy)
-                gemm_tc_wgrad(tc_operand_conv(split_planes(x), B, L, Cin, Lout, stride, 1, off),
-                              dyp, Cout, K, dW)
+                xpl = xp_saved if xp_saved is not None else split_planes(x)
+                gemm_tc_wgrad(tc_operand_conv(xpl, B, L, Cin, Lout, stride, 1, off), dyp, Cout, K, dW)
             else:
                 gemm_tn(_conv_gather(x, L, Cin, Lout, ksize, stride), dy2, dW, M, Cout, K)
         if has_bias and ctx.needs_input_grad[2]:

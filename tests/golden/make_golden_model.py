@@ -17,8 +17,13 @@ from _reference_import import fix_transformer_shim, import_reference  # noqa: E4
 
 OUT = os.path.join(HERE, "model_golden.npz")
 
-# (name, model_size, num_layers, B, L, python-random seed used for the train-mode shift)
-CASES = [("short", 32, 2, 3, 200, 1), ("band", 32, 1, 2, 1000, 2), ("odd", 32, 1, 2, 1003, 3)]
+# (name, model_size, num_layers, B, L, python-random seed used for the train-mode shift, input id)
+# Input ids were picked so that no ReLU pre-activation of the fp64 oracle lies within 1e-5 of
+# zero (short 8.6e-5, band 4.2e-5, odd 1.2e-5): a gradient comparison across implementations
+# is only meaningful when no mask sits on the kink (one flipped mask moved a conv-block
+# gradient of the original "odd" input, margin 3e-6, by 10 %).
+CASES = [("short", 32, 2, 3, 200, 1, 0), ("band", 32, 1, 2, 1000, 2, 1),
+         ("odd", 32, 1, 2, 1003, 3, 11)]
 
 
 def make_input(B, L, case_idx):
@@ -56,7 +61,7 @@ def main():
     from oracle import model as om
 
     store = {"meta": np.array([",".join(map(str, c)) for c in CASES])}
-    for ci, (name, D, NL, B, L, pyseed) in enumerate(CASES):
+    for ci, (name, D, NL, B, L, pyseed, inp) in enumerate(CASES):
         FLAGS.model_size, FLAGS.num_layers, FLAGS.dropout = D, NL, 0.0
         ref = fix_transformer_shim(arch.Model(112, 80, 48))
         sd = om.formula_state_dict(D, NL)
@@ -64,7 +69,7 @@ def main():
 
         # ---- eval forward
         ref.eval()
-        x = make_input(B, L, ci)
+        x = make_input(B, L, inp)
         with torch.no_grad():
             pred, aux = ref(None, x.clone(), None)
         store[f"{name}_eval_pred"] = pred.numpy()

@@ -19,10 +19,10 @@ def golden(golden_dir):
 
 @pytest.mark.parametrize("ci", range(len(CASES)))
 def test_oracle_model_matches_reference(golden, ci):
-    name, D, NL, B, L, pyseed = CASES[ci]
+    name, D, NL, B, L, pyseed, inp = CASES[ci]
     sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
               else v.clone()) for k, v in om.formula_state_dict(D, NL).items()}
-    x = make_input(B, L, ci)
+    x = make_input(B, L, inp)
     with torch.no_grad():
         pred, aux = om.model_forward(sd, x.clone(), training=False)
     assert pred.shape == (B, (L + 7) // 8, 80) and aux.shape == (B, (L + 7) // 8, 48)
