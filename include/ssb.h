@@ -110,6 +110,7 @@ typedef struct {
   float* base;
   int64_t batch_stride;
   int32_t rows_per_batch, ld, d_t, d_off;
+  int64_t batch_stride_hi;  /* second batch level (tcgen05 batched GEMMs): batch = hi*div + lo */
 } ssb_scatter_t;
 
 typedef struct {
@@ -205,6 +206,9 @@ typedef struct {
   int64_t plane_stride;     /* elements between the hi and lo planes */
   int64_t batch_stride;     /* elements between batch items */
   int32_t batches, rows_out, L_src, C, ld, s_t, s_tap, off;
+  int32_t batch_div;        /* > 0: batch b = hi*batch_div + lo with strides (batch_stride, batch_stride_hi) */
+  int32_t reserved_;
+  int64_t batch_stride_hi;
 } ssb_tc_operand_t;
 
 SSB_API int ssb_split_bf16(const float* x, int64_t n, void* planes /* bf16 [2][n] */, void* stream);
@@ -217,6 +221,39 @@ SSB_API int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, i
 SSB_API int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_plane_stride,
                               int64_t N, int64_t K, float* dW, int64_t lddw, int accumulate,
                               void* stream);
+/* Batched forms (attention): one GEMM per batch item b, all in one launch.
+ *   C_b[t, n] = epi( sum_k A_b[t, k] * B_b'[n, k] ),   b' = b (b_mode 1), lo(b) (b_mode 2), 0 (b_mode 0)
+ *   B: rows = N (L_src), inner = K (C).  Output row (b, t) at
+ *   out.base + lo*batch_stride + hi*batch_stride_hi + (t*d_t + d_off)*ld,  (lo, hi) = (b % div, b / div),
+ *   div = A->batch_div. */
+SSB_API int ssb_gemm_tc_batched(const ssb_tc_operand_t* A, const ssb_tc_operand_t* B, int b_mode,
+                                int64_t N, int64_t K, const ssb_epilogue_t* epi, void* stream);
+/*   C_b[f, n] = sum_r X_b[r, f] * G_b[r, n]   (r < X->rows_out; f < K = X->C; n < N = G->C);
+ *   both operands are read transposed in place (UMMA MN-major).  Output row (b, f) as above. */
+SSB_API int ssb_gemm_tc_batched_tn(const ssb_tc_operand_t* X, const ssb_tc_operand_t* G, int64_t N,
+                                   int64_t K, const ssb_epilogue_t* epi, void* stream);
+
+/* ---- element-wise stages of the tensor-core attention path (csrc/attn_tc.cu) ------------
+ * Together with ssb_gemm_tc_batched{,_tn} they replace transformer.py:99-110 (+ :162-297)
+ * on the tensor cores: per (b, h) dense (T x T) logits, masked to the exact band here.
+ * Head dim is zero-padded to 128 in every bf16 plane tensor; Tp = T rounded up to 64. */
+SSB_API int ssb_pad_split_heads(const float* x, int64_t rows, int64_t ld_in, int64_t col_off,
+                                int64_t G, int64_t dh, void* planes /* (2, rows, G, 128) */,
+                                void* stream);
+SSB_API int ssb_transpose_split_heads(const float* x, int64_t ld_in, int64_t col_off, int64_t B,
+                                      int64_t T, int64_t H, int64_t dh, int64_t Tp,
+                                      void* planes /* (2, B*H, 128, Tp) */, void* stream);
+/* S (B*H, T, Tp): in raw q.k, out P = softmax(scale*S + R[k-q+W] inside the band); R (B*H, T, RW);
+ * Pd_planes (2, B*H, T, Tp) = split(dropout(P)). */
+SSB_API int ssb_attn_softmax_fwd(float* S, const float* R, int64_t B, int64_t H, int64_t T,
+                                 int64_t Tp, int64_t W, int64_t RW, int64_t dh, float drop_p,
+                                 uint64_t seed, uint32_t site, void* Pd_planes, void* stream);
+/* dS = P*(dPm - sum(P*dPm)), dPm = dropout-masked dP.  dS_planes (2, B*H, T, Tp) = split(scale*dS);
+ * dSband_planes (2, B*T, H, RWp) = split(dS) re-indexed by k-q+W (zero elsewhere). */
+SSB_API int ssb_attn_ds_bwd(const float* P, const float* dP, int64_t B, int64_t H, int64_t T,
+                            int64_t Tp, int64_t W, int64_t RWp, int64_t dh, float drop_p,
+                            uint64_t seed, uint32_t site, void* dS_planes, void* dSband_planes,
+                            void* stream);
 
 #ifdef __cplusplus
 }

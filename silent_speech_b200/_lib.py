@@ -30,7 +30,7 @@ class Gather(ctypes.Structure):
 class Scatter(ctypes.Structure):
     """ssb_scatter_t"""
     _fields_ = [("base", c_ptr), ("batch_stride", c_i64), ("rows_per_batch", c_i32), ("ld", c_i32),
-                ("d_t", c_i32), ("d_off", c_i32)]
+                ("d_t", c_i32), ("d_off", c_i32), ("batch_stride_hi", c_i64)]
 
 
 class Epilogue(ctypes.Structure):
@@ -44,7 +44,8 @@ class TcOperand(ctypes.Structure):
     """ssb_tc_operand_t"""
     _fields_ = [("planes", c_ptr), ("plane_stride", c_i64), ("batch_stride", c_i64),
                 ("batches", c_i32), ("rows_out", c_i32), ("L_src", c_i32), ("C", c_i32),
-                ("ld", c_i32), ("s_t", c_i32), ("s_tap", c_i32), ("off", c_i32)]
+                ("ld", c_i32), ("s_t", c_i32), ("s_tap", c_i32), ("off", c_i32),
+                ("batch_div", c_i32), ("reserved_", c_i32), ("batch_stride_hi", c_i64)]
 
 
 _PT = ctypes.POINTER(TcOperand)
@@ -72,6 +73,15 @@ _SIGNATURES = {
     "ssb_split_bf16": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "ssb_gemm_tc_kmajor": (c_int, [_PT, c_ptr, c_i64, c_i64, _PE, c_ptr]),
     "ssb_gemm_tc_wgrad": (c_int, [_PT, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_int, c_ptr]),
+    "ssb_gemm_tc_batched": (c_int, [_PT, _PT, c_int, c_i64, c_i64, _PE, c_ptr]),
+    "ssb_gemm_tc_batched_tn": (c_int, [_PT, _PT, c_i64, c_i64, _PE, c_ptr]),
+    "ssb_pad_split_heads": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    "ssb_transpose_split_heads": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                          c_ptr, c_ptr]),
+    "ssb_attn_softmax_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                     c_f32, c_u64, c_u32, c_ptr, c_ptr]),
+    "ssb_attn_ds_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
+                                c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
     "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,

@@ -55,9 +55,12 @@ struct TcParams {
   int M_valid_total;                             // rows of C (K-major: batches*rows_per_batch; MN: features)
   int N;
   int mn_major;
+  int mn_batched;                                // MN-major: one output per batch item (z = batch)
+  int batch_div;                                 // batch index -> (lo = b % div, hi = b / div)
+  int b_mode;                                    // B batch coords: 0 none, 1 (lo, hi), 2 (lo, 0)
   int tiles_x, tiles_y, splits;                   // persistent tile list
   // epilogue
-  float* out; int64_t out_batch_stride; int out_ld, out_dt, out_doff;
+  float* out; int64_t out_batch_stride, out_batch_stride_hi; int out_ld, out_dt, out_doff;
   const float* bias; const float* mask_src; float mask_scale;
   int relu, accumulate, atomic;
   float drop_p, drop_scale; uint32_t drop_thresh; uint64_t seed; uint32_t site;
@@ -83,12 +86,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3) {
+// 5-D tensor maps: (inner, row, batch_lo, batch_hi, plane)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
@@ -223,25 +227,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int kk = kb * BK;
             const int tap = kk / p.a_inner, c0 = kk - tap * p.a_inner;
             const int d1 = row0 * p.a_row_step + tap * p.a_tap_step + p.a_off;
-            tma_load_4d(st, &mapA, full_bar + 8 * s, c0, d1, batch, 0);
-            tma_load_4d(st + A_PLANE, &mapA, full_bar + 8 * s, c0, d1, batch, 1);
-            tma_load_4d(st + 2 * A_PLANE, &mapB, full_bar + 8 * s, kk, n0, 0, 0);
-            tma_load_4d(st + 2 * A_PLANE + B_PLANE, &mapB, full_bar + 8 * s, kk, n0, 0, 1);
+            const int lo = batch % p.batch_div, hi = batch / p.batch_div;
+            const int blo = p.b_mode ? lo : 0, bhi = p.b_mode == 1 ? hi : 0;
+            tma_load_5d(st, &mapA, full_bar + 8 * s, c0, d1, lo, hi, 0);
+            tma_load_5d(st + A_PLANE, &mapA, full_bar + 8 * s, c0, d1, lo, hi, 1);
+            tma_load_5d(st + 2 * A_PLANE, &mapB, full_bar + 8 * s, kk, n0, blo, bhi, 0);
+            tma_load_5d(st + 2 * A_PLANE + B_PLANE, &mapB, full_bar + 8 * s, kk, n0, blo, bhi, 1);
           } else {
             const int b = kb / p.chunks_per_batch;
             const int t0 = (kb - b * p.chunks_per_batch) * BK;
             const int tap = f0 / p.a_inner, c0 = f0 - tap * p.a_inner;
             const int d1 = t0 * p.a_row_step + tap * p.a_tap_step + p.a_off;
+            const int lo = b % p.batch_div, hi = b / p.batch_div;
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
               for (int h = 0; h < BM / 64; ++h)
-                tma_load_4d(st + pl * A_PLANE + h * 8192, &mapA, full_bar + 8 * s, c0 + 64 * h,
-                            d1, b, pl);
+                tma_load_5d(st + pl * A_PLANE + h * 8192, &mapA, full_bar + 8 * s, c0 + 64 * h,
+                            d1, lo, hi, pl);
 #pragma unroll
               for (int h = 0; h < BN / 64; ++h)
-                tma_load_4d(st + 2 * A_PLANE + pl * B_PLANE + h * 8192, &mapB, full_bar + 8 * s,
-                            n0 + 64 * h, t0, b, pl);
+                tma_load_5d(st + 2 * A_PLANE + pl * B_PLANE + h * 8192, &mapB, full_bar + 8 * s,
+                            n0 + 64 * h, t0, lo, hi, pl);
             }
           }
         }
@@ -314,13 +321,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int t = row0 + r;
         row_ok = t < p.rows_per_batch;
         grow = (int64_t)batch * p.rows_per_batch + t;
-        orow = p.out + (int64_t)batch * p.out_batch_stride +
+        orow = p.out + (int64_t)(batch % p.batch_div) * p.out_batch_stride +
+               (int64_t)(batch / p.batch_div) * p.out_batch_stride_hi +
                (int64_t)(t * p.out_dt + p.out_doff) * p.out_ld;
       } else {
         const int f = f0 + r;
         row_ok = f < p.M_valid_total;
         grow = f;
-        orow = p.out + (int64_t)f * p.out_ld;
+        orow = p.out + (int64_t)(f * p.out_dt + p.out_doff) * p.out_ld;
+        if (p.mn_batched) {   // z = batch item: every batch item has its own output block
+          const int bz = tile / tiles_xy;
+          grow += (int64_t)bz * p.M_valid_total;
+          orow += (int64_t)(bz % p.batch_div) * p.out_batch_stride +
+                  (int64_t)(bz / p.batch_div) * p.out_batch_stride_hi;
+        }
       }
       if (nkb == 0) row_ok = false;
       const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN + ((uint32_t)(lg * 32) << 16);
@@ -434,30 +448,47 @@ int get_encode(EncodeTiledFn* out) {
   return SSB_OK;
 }
 
-// 4-D bf16 map: dims (inner, rows, batch, plane); strides in ELEMENTS for dims 1..3
-int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t batch,
-             int64_t s_row, int64_t s_batch, int64_t s_plane, int box_inner, int box_rows,
-             int row_elem_stride) {
+// 5-D bf16 map: dims (inner, rows, batch_lo, batch_hi, plane); strides in ELEMENTS for dims 1..4
+int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t n_lo,
+             int64_t n_hi, int64_t s_row, int64_t s_lo, int64_t s_hi, int64_t s_plane,
+             int box_inner, int box_rows, int row_elem_stride) {
   EncodeTiledFn enc = nullptr;
   if (int rc = get_encode(&enc)) return rc;
   SSB_REQUIRE(((uintptr_t)base & 15) == 0, "gemm_tc: operand base must be 16 B aligned");
-  SSB_REQUIRE((s_row * 2) % 16 == 0 && (s_batch * 2) % 16 == 0 && (s_plane * 2) % 16 == 0,
-              "gemm_tc: operand strides must be multiples of 8 elements");
-  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batch, 2};
-  cuuint64_t strides[3] = {(cuuint64_t)s_row * 2, (cuuint64_t)s_batch * 2, (cuuint64_t)s_plane * 2};
-  cuuint32_t box[4] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1};
-  cuuint32_t estr[4] = {1, (cuuint32_t)row_elem_stride, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+  if (n_lo <= 1) s_lo = s_plane;   // unused dims still need a legal (16 B multiple) stride
+  if (n_hi <= 1) s_hi = s_plane;
+  SSB_REQUIRE(s_row % 8 == 0 && s_lo % 8 == 0 && s_hi % 8 == 0 && s_plane % 8 == 0,
+              "gemm_tc: operand strides must be multiples of 8 elements (%lld,%lld,%lld,%lld)",
+              (long long)s_row, (long long)s_lo, (long long)s_hi, (long long)s_plane);
+  cuuint64_t dims[5] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)(n_lo > 0 ? n_lo : 1),
+                        (cuuint64_t)(n_hi > 0 ? n_hi : 1), 2};
+  cuuint64_t strides[4] = {(cuuint64_t)s_row * 2, (cuuint64_t)s_lo * 2, (cuuint64_t)s_hi * 2,
+                           (cuuint64_t)s_plane * 2};
+  cuuint32_t box[5] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)row_elem_stride, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    ssb::set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld batch=%lld "
-                   "strides=(%lld,%lld,%lld) box=(%d,%d) estr=%d",
-                   (int)r, (long long)inner, (long long)rows, (long long)batch, (long long)s_row,
-                   (long long)s_batch, (long long)s_plane, box_inner, box_rows, row_elem_stride);
+    ssb::set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld lo=%lld hi=%lld "
+                   "strides=(%lld,%lld,%lld,%lld) box=(%d,%d) estr=%d",
+                   (int)r, (long long)inner, (long long)rows, (long long)n_lo, (long long)n_hi,
+                   (long long)s_row, (long long)s_lo, (long long)s_hi, (long long)s_plane,
+                   box_inner, box_rows, row_elem_stride);
     return SSB_ERR_ARG;
   }
   return SSB_OK;
+}
+
+// operand -> (n_lo, n_hi): batch_div <= 0 means a single batch level
+inline void batch_levels(const ssb_tc_operand_t* o, int64_t* n_lo, int64_t* n_hi) {
+  if (o->batch_div > 0 && o->batch_div < o->batches) {
+    *n_lo = o->batch_div;
+    *n_hi = (o->batches + o->batch_div - 1) / o->batch_div;
+  } else {
+    *n_lo = o->batches;
+    *n_hi = 1;
+  }
 }
 
 int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams p, dim3 tiles,
@@ -488,6 +519,7 @@ int fill_epi(const ssb_epilogue_t* e, int64_t N, TcParams* p) {
               "gemm_tc: bad output geometry / alignment");
   SSB_REQUIRE(e->drop_p >= 0.f && e->drop_p < 1.f, "gemm_tc: bad dropout p");
   p->out = e->out.base; p->out_batch_stride = e->out.batch_stride; p->out_ld = e->out.ld;
+  p->out_batch_stride_hi = e->out.batch_stride_hi;
   p->out_dt = e->out.d_t; p->out_doff = e->out.d_off;
   p->bias = e->bias; p->mask_src = e->mask_src; p->mask_scale = e->mask_scale;
   p->relu = e->relu; p->accumulate = e->accumulate; p->atomic = 0;
@@ -530,10 +562,14 @@ int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N
   SSB_REQUIRE(epi->out.rows_per_batch == A->rows_out, "gemm_tc: output rows_per_batch mismatch");
   CUtensorMap mapA, mapB;
   const int box_rows = BM * A->s_t;   // 128 rows at traversal stride s_t
-  if (int rc = make_map(&mapA, A->planes, A->C, A->L_src, A->batches, A->ld, A->batch_stride,
-                        A->plane_stride, BK, box_rows, A->s_t))
+  int64_t n_lo, n_hi;
+  batch_levels(A, &n_lo, &n_hi);
+  if (int rc = make_map(&mapA, A->planes, A->C, A->L_src, n_lo, n_hi, A->ld, A->batch_stride,
+                        A->batch_stride_hi, A->plane_stride, BK, box_rows, A->s_t))
     return rc;
-  if (int rc = make_map(&mapB, Bplanes, K, N, 1, K, N * K, N * K, BK, BN, 1)) return rc;
+  if (int rc = make_map(&mapB, Bplanes, K, N, 1, 1, K, N * K, N * K, N * K, BK, BN, 1)) return rc;
+  p.batch_div = (int)n_lo;
+  p.b_mode = 0;
   p.a_inner = A->C; p.a_row_step = A->s_t; p.a_tap_step = A->s_tap; p.a_off = A->off;
   p.rows_per_batch = A->rows_out;
   p.tiles_per_batch = (A->rows_out + BM - 1) / BM;
@@ -558,14 +594,16 @@ int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_
               "gemm_tc_wgrad: bad X geometry");
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap mapA, mapB;
-  if (int rc = make_map(&mapA, X->planes, X->C, X->L_src, X->batches, X->ld, X->batch_stride,
-                        X->plane_stride, 64, BK * X->s_t, X->s_t))
+  if (int rc = make_map(&mapA, X->planes, X->C, X->L_src, X->batches, 1, X->ld, X->batch_stride,
+                        X->plane_stride, X->plane_stride, 64, BK * X->s_t, X->s_t))
     return rc;
   // G: (batches, rows_out, N) row-major planes
-  if (int rc = make_map(&mapB, Gplanes, N, X->rows_out, X->batches, N, (int64_t)X->rows_out * N,
-                        g_plane_stride, 64, BK, 1))
+  if (int rc = make_map(&mapB, Gplanes, N, X->rows_out, X->batches, 1, N,
+                        (int64_t)X->rows_out * N, g_plane_stride, g_plane_stride, 64, BK, 1))
     return rc;
   TcParams p = {};
+  p.batch_div = X->batches;
+  p.b_mode = 1;
   p.out = dW; p.out_ld = (int)lddw; p.N = (int)N;
   p.a_inner = X->C; p.a_row_step = X->s_t; p.a_tap_step = X->s_tap; p.a_off = X->off;
   p.rows_per_batch = X->rows_out;
@@ -586,6 +624,75 @@ int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_
     SSB_CUDA(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)N * 4, (size_t)K, st));
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)(K / BM), (unsigned)splits);
   return launch(mapA, mapB, p, grid, st);
+}
+
+int ssb_gemm_tc_batched(const ssb_tc_operand_t* A, const ssb_tc_operand_t* B, int b_mode,
+                        int64_t N, int64_t K, const ssb_epilogue_t* epi, void* stream) {
+  SSB_REQUIRE(A && B && A->planes && B->planes, "gemm_tc_batched: null operand");
+  SSB_REQUIRE(K % BK == 0 && A->C == K && B->C == K, "gemm_tc_batched: K=%lld must be a multiple "
+              "of 64 and equal both inner extents (%d, %d)", (long long)K, A->C, B->C);
+  SSB_REQUIRE(A->batches >= 1 && A->rows_out >= 1 && A->s_t == 1 && b_mode >= 0 && b_mode <= 2,
+              "gemm_tc_batched: bad geometry");
+  TcParams p = {};
+  if (int rc = fill_epi(epi, N, &p)) return rc;
+  SSB_REQUIRE(epi->out.rows_per_batch == A->rows_out, "gemm_tc_batched: rows_per_batch mismatch");
+  int64_t a_lo, a_hi, b_lo, b_hi;
+  batch_levels(A, &a_lo, &a_hi);
+  batch_levels(B, &b_lo, &b_hi);
+  CUtensorMap mapA, mapB;
+  if (int rc = make_map(&mapA, A->planes, A->C, A->L_src, a_lo, a_hi, A->ld, A->batch_stride,
+                        A->batch_stride_hi, A->plane_stride, BK, BM, 1))
+    return rc;
+  if (int rc = make_map(&mapB, B->planes, B->C, B->L_src, b_lo, b_hi, B->ld, B->batch_stride,
+                        B->batch_stride_hi, B->plane_stride, BK, BN, 1))
+    return rc;
+  p.a_inner = A->C; p.a_row_step = 1; p.a_tap_step = 0; p.a_off = A->off;
+  p.rows_per_batch = A->rows_out;
+  p.tiles_per_batch = (A->rows_out + BM - 1) / BM;
+  p.chunks_per_batch = 1;
+  p.num_kb = (int)(K / BK);
+  p.kb_per_split = p.num_kb;
+  p.M_valid_total = A->batches * A->rows_out;
+  p.mn_major = 0;
+  p.batch_div = (int)a_lo;
+  p.b_mode = b_mode;
+  dim3 tiles((unsigned)((N + BN - 1) / BN), (unsigned)(A->batches * p.tiles_per_batch), 1);
+  return launch(mapA, mapB, p, tiles, (cudaStream_t)stream);
+}
+
+int ssb_gemm_tc_batched_tn(const ssb_tc_operand_t* X, const ssb_tc_operand_t* G, int64_t N,
+                           int64_t K, const ssb_epilogue_t* epi, void* stream) {
+  SSB_REQUIRE(X && G && X->planes && G->planes, "gemm_tc_batched_tn: null operand");
+  SSB_REQUIRE(X->C >= K && G->C >= N && X->batches == G->batches && X->rows_out == G->rows_out &&
+                  X->s_t == 1 && G->s_t == 1,
+              "gemm_tc_batched_tn: operand geometry mismatch");
+  TcParams p = {};
+  if (int rc = fill_epi(epi, N, &p)) return rc;
+  SSB_REQUIRE(epi->out.rows_per_batch == K, "gemm_tc_batched_tn: output rows_per_batch must be K");
+  int64_t x_lo, x_hi, g_lo, g_hi;
+  batch_levels(X, &x_lo, &x_hi);
+  batch_levels(G, &g_lo, &g_hi);
+  SSB_REQUIRE(x_lo == g_lo && x_hi == g_hi, "gemm_tc_batched_tn: batch levels differ");
+  CUtensorMap mapA, mapB;
+  if (int rc = make_map(&mapA, X->planes, X->C, X->L_src, x_lo, x_hi, X->ld, X->batch_stride,
+                        X->batch_stride_hi, X->plane_stride, 64, BK, 1))
+    return rc;
+  if (int rc = make_map(&mapB, G->planes, G->C, G->L_src, g_lo, g_hi, G->ld, G->batch_stride,
+                        G->batch_stride_hi, G->plane_stride, 64, BK, 1))
+    return rc;
+  p.a_inner = X->C; p.a_row_step = 1; p.a_tap_step = 0; p.a_off = X->off;
+  p.rows_per_batch = X->rows_out;
+  p.tiles_per_batch = 1;
+  p.chunks_per_batch = (X->rows_out + BK - 1) / BK;
+  p.num_kb = X->batches * p.chunks_per_batch;
+  p.kb_per_split = p.chunks_per_batch;
+  p.M_valid_total = (int)K;
+  p.mn_major = 1;
+  p.mn_batched = 1;
+  p.batch_div = (int)x_lo;
+  p.b_mode = 1;
+  dim3 tiles((unsigned)((N + BN - 1) / BN), (unsigned)((K + BM - 1) / BM), (unsigned)X->batches);
+  return launch(mapA, mapB, p, tiles, (cudaStream_t)stream);
 }
 
 }  // extern "C"

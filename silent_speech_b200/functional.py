@@ -554,7 +554,143 @@ class _BandAttnFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------
+# Tensor-core attention: the same banded relative-position attention, scheduled as batched
+# tcgen05 GEMMs (one batch item per (b, h)) around two fused element-wise kernels
+# (csrc/attn_tc.cu).  Per (b, h) the logits are a dense (T x T) tile masked to the exact band;
+# at T = 500 that is 2.5x the band's flops, on a pipe that is >20x faster than CUDA cores.
+# ------------------------------------------------------------------------------------------
+_HP = 128     # padded head dim of every plane tensor
+_RWP = 256    # padded band width (K of the positional dQ GEMM)
+
+
+def _op(planes, offset_elems, plane_stride, batches, rows, C, ld, s_lo, div=0, s_hi=0):
+    return TcOperand(planes.data_ptr() + 2 * offset_elems, plane_stride, s_lo, batches, rows, rows,
+                     C, ld, 1, 0, 0, div, 0, s_hi)
+
+
+def _bscatter(t, offset_elems, rows, ld, s_lo, s_hi):
+    return Scatter(t.data_ptr() + 4 * offset_elems, s_lo, rows, ld, 1, 0, s_hi)
+
+
+def _tc_batched(A, Bo, b_mode, N, K, epi):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_tc_batched(ctypes.byref(A), ctypes.byref(Bo), b_mode, N, K,
+                                       ctypes.byref(epi), _stream()))
+
+
+def _tc_batched_tn(X, G, N, K, epi):
+    lib = _lib.load()
+    _lib.check(lib.ssb_gemm_tc_batched_tn(ctypes.byref(X), ctypes.byref(G), N, K, ctypes.byref(epi),
+                                          _stream()))
+
+
+class _DenseTCAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, E, B, T, H, dh, W, p, seed, site):
+        lib = _lib.load()
+        _chk(qkv, "qkv")
+        M, D3 = qkv.shape
+        D = H * dh
+        BH = B * H
+        Tp = (T + 63) // 64 * 64
+        RW = (2 * W + 1 + 3) // 4 * 4
+        dev = qkv.device
+        bf = torch.bfloat16
+        st = _stream()
+        # split planes with heads zero-padded to 128: (2, B*T, 3H, 128) = [q heads | k heads | v heads]
+        qkvp = torch.empty((2, M, 3 * H, _HP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, D3, 0, 3 * H, dh, qkvp.data_ptr(), st))
+        vt = torch.empty((2, BH, _HP, Tp), dtype=bf, device=dev)
+        _lib.check(lib.ssb_transpose_split_heads(qkv.data_ptr(), D3, 2 * D, B, T, H, dh, Tp,
+                                                 vt.data_ptr(), st))
+        Ew = E[:, :2 * W + 1, :dh]
+        ep = split_planes(torch.nn.functional.pad(Ew, (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
+        ld_qkv = 3 * H * _HP
+        pq = M * ld_qkv
+        q_op = _op(qkvp, 0, pq, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
+        k_op = _op(qkvp, H * _HP, pq, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
+        # S = Q K^T (raw, unscaled)
+        S = torch.empty((BH, T, Tp), dtype=_f32, device=dev)
+        _tc_batched(q_op, k_op, 1, Tp, _HP, _epi(_bscatter(S, 0, T, Tp, T * Tp, H * T * Tp)))
+        # R = Q E^T  (positional logits, band layout)
+        R = torch.empty((BH, T, RW), dtype=_f32, device=dev)
+        e_op = _op(ep, 0, H * RW * _HP, H, RW, _HP, _HP, RW * _HP)
+        _tc_batched(q_op, e_op, 2, RW, _HP, _epi(_bscatter(R, 0, T, RW, T * RW, H * T * RW)))
+        # P = softmax(scale*S + R) inside the band (in place), dropout(P) as planes
+        pd = torch.empty((2, BH, T, Tp), dtype=bf, device=dev)
+        _lib.check(lib.ssb_attn_softmax_fwd(S.data_ptr(), R.data_ptr(), B, H, T, Tp, W, RW, dh, p,
+                                            seed & 0xFFFFFFFFFFFFFFFF, site, pd.data_ptr(), st))
+        # O = dropout(P) V
+        O = torch.empty((M, D), dtype=_f32, device=dev)
+        pd_op = _op(pd, 0, BH * T * Tp, BH, T, Tp, Tp, T * Tp, H, H * T * Tp)
+        vt_op = _op(vt, 0, BH * _HP * Tp, BH, _HP, Tp, Tp, _HP * Tp, H, H * _HP * Tp)
+        _tc_batched(pd_op, vt_op, 1, dh, Tp, _epi(_bscatter(O, 0, T, D, dh, T * D)))
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(qkv, qkvp, S, pd, E)
+        ctx.cfg = (B, T, H, dh, W, p, seed, site, Tp)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        lib = _lib.load()
+        qkv, qkvp, P, pd, E = ctx.saved_tensors
+        B, T, H, dh, W, p, seed, site, Tp = ctx.cfg
+        dO = dO.contiguous()
+        M, D3 = qkv.shape
+        D = H * dh
+        BH = B * H
+        dev = qkv.device
+        bf = torch.bfloat16
+        st = _stream()
+        ld_qkv = 3 * H * _HP
+        pq = M * ld_qkv
+        q_op = _op(qkvp, 0, pq, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
+        v_op = _op(qkvp, 2 * H * _HP, pq, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
+        dop = torch.empty((2, M, H, _HP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_pad_split_heads(dO.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), st))
+        do_op = _op(dop, 0, M * H * _HP, BH, T, _HP, H * _HP, _HP, H, T * H * _HP)
+        # dP = dO V^T
+        dP = torch.empty((BH, T, Tp), dtype=_f32, device=dev)
+        _tc_batched(do_op, v_op, 1, Tp, _HP, _epi(_bscatter(dP, 0, T, Tp, T * Tp, H * T * Tp)))
+        # dS (scaled planes for dQ / dK, band planes for the positional dQ)
+        dsp = torch.empty((2, BH, T, Tp), dtype=bf, device=dev)
+        dsb = torch.empty((2, M, H, _RWP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_attn_ds_bwd(P.data_ptr(), dP.data_ptr(), B, H, T, Tp, W, _RWP, dh, p,
+                                       seed & 0xFFFFFFFFFFFFFFFF, site, dsp.data_ptr(),
+                                       dsb.data_ptr(), st))
+        dqkv = torch.empty_like(qkv)
+        ds_op = _op(dsp, 0, BH * T * Tp, BH, T, Tp, Tp, T * Tp, H, H * T * Tp)
+        pd_op = _op(pd, 0, BH * T * Tp, BH, T, Tp, Tp, T * Tp, H, H * T * Tp)
+        # dQ = scale * dS K   (+ positional part dS_band E)
+        kt = torch.empty((2, BH, _HP, Tp), dtype=bf, device=dev)
+        _lib.check(lib.ssb_transpose_split_heads(qkv.data_ptr(), D3, D, B, T, H, dh, Tp,
+                                                 kt.data_ptr(), st))
+        kt_op = _op(kt, 0, BH * _HP * Tp, BH, _HP, Tp, Tp, _HP * Tp, H, H * _HP * Tp)
+        _tc_batched(ds_op, kt_op, 1, dh, Tp, _epi(_bscatter(dqkv, 0, T, D3, dh, T * D3)))
+        Ew = E[:, :2 * W + 1, :dh]
+        et = torch.nn.functional.pad(Ew, (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2)
+        etp = split_planes(et.contiguous())                       # (2, H, 128, RWP): [d][rel]
+        dsb_op = _op(dsb, 0, M * H * _RWP, BH, T, _RWP, H * _RWP, _RWP, H, T * H * _RWP)
+        et_op = _op(etp, 0, H * _HP * _RWP, H, _HP, _RWP, _RWP, _HP * _RWP)
+        _tc_batched(dsb_op, et_op, 2, dh, _RWP,
+                    _epi(_bscatter(dqkv, 0, T, D3, dh, T * D3), accumulate=1))
+        # dK = scale * dS^T Q ;  dV = dropout(P)^T dO     (reduction over queries: MN-major)
+        _tc_batched_tn(ds_op, q_op, dh, T, _epi(_bscatter(dqkv, D, T, D3, dh, T * D3)))
+        _tc_batched_tn(pd_op, do_op, dh, T, _epi(_bscatter(dqkv, 2 * D, T, D3, dh, T * D3)))
+        return dqkv, None, None, None, None, None, None, None, None, None
+
+
+def _tc_attn_ok(T, dh, W):
+    return _tc_enabled() and os.environ.get("SSB_ATTN", "tc") != "simt" and dh % 4 == 0 and \
+        dh <= _HP and 64 <= T <= 1024 and W <= 127
+
+
 def band_attention(qkv, E_pad, B, T, H, dh, W, p=0.0, seed=0, site=0):
+    """Banded relative-position attention.  Tensor-core schedule when the shape allows, else the
+    CUDA-core band kernels (csrc/attn.cu)."""
+    if _tc_attn_ok(T, dh, W):
+        return _DenseTCAttnFn.apply(qkv, E_pad, int(B), int(T), int(H), int(dh), int(W), float(p),
+                                    int(seed), int(site))
     return _BandAttnFn.apply(qkv, E_pad, int(B), int(T), int(H), int(dh), int(W), float(p),
                              int(seed), int(site))
-

@@ -253,9 +253,16 @@ def dense_attention_ref(qkv, E, B, T, H, dh, W):
     return o.permute(0, 2, 1, 3).reshape(B * T, D)
 
 
+@pytest.mark.parametrize("sched", ["simt", "tc"])
 @pytest.mark.parametrize("B,T,H,dh,W", [(2, 25, 8, 4, 99), (2, 125, 8, 4, 99), (1, 130, 2, 32, 99),
-                                        (2, 250, 8, 96, 99), (1, 33, 1, 8, 5), (1, 64, 2, 16, 31)])
-def test_band_attention_fwd_bwd(B, T, H, dh, W):
+                                        (2, 250, 8, 96, 99), (1, 33, 1, 8, 5), (1, 64, 2, 16, 31),
+                                        (3, 500, 8, 96, 99), (2, 126, 4, 16, 99)])
+def test_band_attention_fwd_bwd(B, T, H, dh, W, sched, monkeypatch):
+    """Both schedules of the same op: CUDA-core band kernels and the tensor-core (batched
+    tcgen05 GEMM) schedule, against a dense torch restatement."""
+    monkeypatch.setenv("SSB_ATTN", sched)
+    if sched == "tc" and not SF._tc_attn_ok(T, dh, W):
+        pytest.skip("shape not eligible for the tensor-core schedule")
     D = H * dh
     qkv = rnd(B * T, 3 * D, seed=1).requires_grad_(True)
     RW = (2 * W + 1 + 3) // 4 * 4
@@ -273,10 +280,12 @@ def test_band_attention_fwd_bwd(B, T, H, dh, W):
     close(qkv.grad[:, 2 * D:], qr.grad[:, 2 * D:], tol=5e-5, what="dv")
 
 
-def test_band_attention_dropout_is_consistent_between_fwd_and_bwd():
+@pytest.mark.parametrize("sched,T", [("simt", 40), ("tc", 96)])
+def test_band_attention_dropout_is_consistent_between_fwd_and_bwd(sched, T, monkeypatch):
     """With V = one-hot positions the forward output exposes the dropped probabilities; the
     backward must use the same mask: check d(sum O)/dV against the forward's P_drop."""
-    B, T, H, dh, W, p = 1, 40, 1, 40, 99, 0.3
+    monkeypatch.setenv("SSB_ATTN", sched)
+    B, H, dh, W, p = 1, 1, T, 99, 0.3
     D = H * dh
     qkv = torch.zeros(B * T, 3 * D, device=dev)
     qkv[:, :2 * D] = rnd(B * T, 2 * D, seed=1)
@@ -287,6 +296,8 @@ def test_band_attention_dropout_is_consistent_between_fwd_and_bwd():
     Pdrop = o.detach()                                    # (T, T)
     zero = (Pdrop == 0).float().mean().item()
     assert abs(zero - p) < 0.05, zero
+    if sched == "tc":
+        assert SF._tc_attn_ok(T, dh, W)
     g = rnd(T, D, seed=5)
     o.backward(g)
     dV_expected = Pdrop.t() @ g                           # dV = P_drop^T dO
