@@ -605,6 +605,7 @@ int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_
   p.batch_div = X->batches;
   p.b_mode = 1;
   p.out = dW; p.out_ld = (int)lddw; p.N = (int)N;
+  p.out_dt = 1; p.out_doff = 0;   // output row f of dW
   p.a_inner = X->C; p.a_row_step = X->s_t; p.a_tap_step = X->s_tap; p.a_off = X->off;
   p.rows_per_batch = X->rows_out;
   p.tiles_per_batch = 1;
