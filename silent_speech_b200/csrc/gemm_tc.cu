@@ -11,10 +11,10 @@
 //
 // Kernel shape (persistent: one CTA per SM walks 128 x 256 output tiles; 192 threads,
 // warp-specialised; two TMEM accumulators so the epilogue of a tile overlaps the next tile's MMAs):
-//   warp 0    TMA producer: per 64-deep k-block, the A_hi/A_lo (2 x 16 KB) and B_hi/B_lo
-//             (2 x 32 KB) tiles land in 128B-swizzled shared memory (2 stages x 96 KB),
+//   warp 0    TMA producer: per 32-deep k-block, the A_hi/A_lo (2 x 8 KB) and B_hi/B_lo
+//             (2 x 16 KB) tiles land in swizzled shared memory (4 stages x 48 KB),
 //             completion on an mbarrier (complete_tx).
-//   warp 1    TMEM allocator (2 x 256 fp32 columns) and single-thread MMA issuer: 4 x 3
+//   warp 1    TMEM allocator (2 x 256 fp32 columns) and single-thread MMA issuer: 2 x 3
 //             tcgen05.mma (M128 N256 K16) per k-block, tcgen05.commit releases the stage.
 //   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias / ReLU / dropout /
 //             mask / accumulate / split-K reduction, fp32 stores through the same
@@ -35,11 +35,15 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 2;
-constexpr int A_PLANE = BM * BK * 2;   // 16 KB
-constexpr int B_PLANE = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // 96 KB
+// 32-deep k-blocks in a 4-stage ring: a stage (48 KB) is consumed in ~0.4 us, so three stages of
+// prefetch cover ~1.2 us of DRAM latency (the first version, 2 x 96 KB with 64-deep blocks,
+// stalled on every HBM-cold operand: 340 us in-step vs 185 us L2-warm for the same GEMM).
+constexpr int BM = 128, BN = 256, BK = 32;
+constexpr int STAGES = 4;
+constexpr int A_PLANE = BM * BK * 2;   // 8 KB
+constexpr int B_PLANE = BN * BK * 2;   // 16 KB
+constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // 48 KB
+constexpr int MN_GROUP = BK * 128;     // bytes of one 64-element MN group of a stage (MN-major)
 constexpr int TMEM_COLS = 512;   // two 256-column fp32 accumulators
 constexpr int THREADS = 192;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -124,15 +128,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-// shared-memory matrix descriptor, 128B swizzle (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor);
+// layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                              uint32_t sbo_bytes) {
+                                              uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address   [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // leading offset  [16,30)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;       // stride offset   [32,46)
   d |= (uint64_t)1 << 46;                                 // version = 1 (Blackwell)
-  d |= (uint64_t)2 << 61;                                 // layout type = SWIZZLE_128B
+  d |= (uint64_t)layout << 61;                            // layout type
   return d;
 }
 
@@ -243,11 +248,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
               for (int h = 0; h < BM / 64; ++h)
-                tma_load_5d(st + pl * A_PLANE + h * 8192, &mapA, full_bar + 8 * s, c0 + 64 * h,
+                tma_load_5d(st + pl * A_PLANE + h * MN_GROUP, &mapA, full_bar + 8 * s, c0 + 64 * h,
                             d1, lo, hi, pl);
 #pragma unroll
               for (int h = 0; h < BN / 64; ++h)
-                tma_load_5d(st + 2 * A_PLANE + pl * B_PLANE + h * 8192, &mapB, full_bar + 8 * s,
+                tma_load_5d(st + 2 * A_PLANE + pl * B_PLANE + h * MN_GROUP, &mapB, full_bar + 8 * s,
                             n0 + 64 * h, t0, lo, hi, pl);
             }
           }
@@ -278,20 +283,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int k = 0; k < BK / 16; ++k) {
             uint64_t dah, dal, dbh, dbl;
             if (!p.mn_major) {
-              // K-major, SW128: rows of 128 B, 8-row groups 1024 B apart; +32 B per K=16 step
+              // K-major, SW64: rows of 64 B (32 bf16), 8-row groups 512 B apart; +32 B per K=16
               const uint32_t off = k * 32;
-              dah = make_desc(a_hi + off, 16, 1024);
-              dal = make_desc(a_lo + off, 16, 1024);
-              dbh = make_desc(b_hi + off, 16, 1024);
-              dbl = make_desc(b_lo + off, 16, 1024);
+              dah = make_desc(a_hi + off, 16, 512, 4);
+              dal = make_desc(a_lo + off, 16, 512, 4);
+              dbh = make_desc(b_hi + off, 16, 512, 4);
+              dbl = make_desc(b_lo + off, 16, 512, 4);
             } else {
-              // MN-major, SW128: 64-element MN groups 8 KB apart (LBO), 8-row K groups 1 KB
-              // apart (SBO); +2 KB per K=16 step
+              // MN-major, SW128: 64-element MN groups MN_GROUP (4 KB) apart (LBO), 8-row K groups
+              // 1 KB apart (SBO); +2 KB per K=16 step
               const uint32_t off = k * 2048;
-              dah = make_desc(a_hi + off, 8192, 1024);
-              dal = make_desc(a_lo + off, 8192, 1024);
-              dbh = make_desc(b_hi + off, 8192, 1024);
-              dbl = make_desc(b_lo + off, 8192, 1024);
+              dah = make_desc(a_hi + off, MN_GROUP, 1024, 2);
+              dal = make_desc(a_lo + off, MN_GROUP, 1024, 2);
+              dbh = make_desc(b_hi + off, MN_GROUP, 1024, 2);
+              dbl = make_desc(b_lo + off, MN_GROUP, 1024, 2);
             }
             const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
             umma_bf16(tmem_d, dah, dbh, idesc, acc0);
@@ -452,6 +457,9 @@ int get_encode(EncodeTiledFn* out) {
 int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t n_lo,
              int64_t n_hi, int64_t s_row, int64_t s_lo, int64_t s_hi, int64_t s_plane,
              int box_inner, int box_rows, int row_elem_stride) {
+  // K-major boxes are BK = 32 elements (64 B) wide -> SWIZZLE_64B; MN-major boxes are 64 wide
+  const CUtensorMapSwizzle swz =
+      box_inner * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   EncodeTiledFn enc = nullptr;
   if (int rc = get_encode(&enc)) return rc;
   SSB_REQUIRE(((uintptr_t)base & 15) == 0, "gemm_tc: operand base must be 16 B aligned");
@@ -467,7 +475,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, in
   cuuint32_t box[5] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1, 1, 1};
   cuuint32_t estr[5] = {1, (cuuint32_t)row_elem_stride, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     ssb::set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld lo=%lld hi=%lld "
