@@ -286,6 +286,32 @@ def run_ours(args):
         ms = timed(step_device, args.steps, args.warmup, world)
         launches = (_lib.launch_count - l0) // (args.steps + args.warmup)
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), world)
+    # host-side enqueue time per step (no synchronisation inside): shows whether the step is
+    # bounded by the GPU or by launching ~1000 kernels from Python
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_device()
+    host_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    torch.cuda.synchronize()
+
+    graph_ms = None
+    if args.graph_probe:
+        # EXPERIMENT (not a reported number): replay the step as one CUDA graph to see the
+        # GPU-only time.  Seeds / augmentation are frozen inside the graph, so this is not a
+        # valid training loop.
+        optim_c = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-7, fused=True,
+                                    capturable=True)
+        sidestream = torch.cuda.Stream()
+        sidestream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(sidestream):
+            for _ in range(3):
+                train_step(model, optim_c, dev_batch, "cuda", FRAMES, bucket, sync_loss=False)
+        torch.cuda.current_stream().wait_stream(sidestream)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            train_step(model, optim_c, dev_batch, "cuda", FRAMES, bucket, sync_loss=False)
+        graph_ms = timed(g.replay, args.steps, 2, world) / args.steps
 
     value = world * args.steps / (ms / 1e3)
     e2e = world * args.steps / (ms_e2e / 1e3)
@@ -300,7 +326,8 @@ def run_ours(args):
                        "l2": "per-step working set (~10 GB of activations) >> 126 MB L2"},
             "e2e": {"value": e2e, "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
+            "graph_probe_ms_per_step": graph_ms,
             "step_tflops": STEP_GFLOP * value / world / 1e3,
             "clocks": clk.summary()}
     if rank == 0:
@@ -331,6 +358,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-side", action="store_true", help="skip the DTW side metric")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--graph-probe", action="store_true",
+                    help="experiment: also time the step replayed as a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -108,6 +108,9 @@ _KERNELS_PER_CALL = {
     "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
+    "ssb_split_bf16": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,
+    "ssb_gemm_tc_batched_tn": 1, "ssb_pad_split_heads": 1, "ssb_transpose_split_heads": 1,
+    "ssb_attn_softmax_fwd": 1, "ssb_attn_ds_bwd": 1,
 }
 launch_count = 0   # running total of libssb kernel launches issued by this process
 
