@@ -193,7 +193,7 @@ def gemm_roofline(peaks):
             "ms_per_launch": ms}
 
 
-def dtw_side_metric(peaks, world, rank):
+def dtw_side_metric(peaks, world, rank, with_cpu):
     """cfg-2: DTW on 10k (500 x 600) cdist matrices; HBM roofline at 4 B/cell."""
     from silent_speech_b200 import align
     P, Tp, Tg = 10000, 500, 600
@@ -206,10 +206,47 @@ def dtw_side_metric(peaks, world, rank):
     ms = timed(lambda: align.align_batch(view), 5, 3, world) / 5
     cells = P * Tp * Tg * world
     gbs = 4.0 * P * Tp * Tg / ms / 1e6
-    return {"metric": "DTW Mcells/s (10k pairs 500x600 per GPU)", "value": cells / ms / 1e3,
-            "ms": ms, "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
-                                   "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                   "peak_source": peaks["_source"]}}
+    out = {"metric": "DTW Mcells/s (10k pairs 500x600 per GPU)", "value": cells / ms / 1e3,
+           "ms": ms, "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+                                  "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                  "peak_source": peaks["_source"],
+                                  "algorithmic_bytes_per_cell": 4}}
+    if with_cpu:   # CPU port of align.py (oracle C, OpenMP over pairs) on a bounded sample
+        from oracle import dtw as odtw
+        n = 512
+        host = cost[:n].cpu().numpy().transpose(0, 2, 1)
+        odtw.align_batch(host[:8])
+        t0 = time.perf_counter()
+        odtw.align_batch(host, threads=os.cpu_count())
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n * Tp * Tg / dt / 1e6, "unit": "Mcells/s",
+                               "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"{n} of the 10000 pairs"}
+    del cost
+    return out
+
+
+def mel_side_metric(peaks, with_cpu):
+    """log-mel of 32 x 10 s clips at 22.05 kHz; 1344 B/frame algorithmic."""
+    from silent_speech_b200 import data_utils as du
+    y = (torch.rand(32, 220500, device="cuda") * 2 - 1) * 0.5
+    f = lambda: du.mel_spectrogram(y, 1024, 80, 22050, 256, 1024, 0, 8000)
+    ms = timed(f, 10, 3, 1) / 10
+    frames = 32 * 861
+    gbs = 1344.0 * frames / ms / 1e6
+    out = {"metric": "mel kframes/s (32 clips x 10 s)", "value": frames / ms, "ms": ms,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_frame": 1344,
+                        "note": "fp32 radix-4 FFT in shared memory: compute-bound, not HBM-bound"}}
+    if with_cpu:
+        from oracle import mel as omel
+        yh = y[:4].cpu().numpy()
+        t0 = time.perf_counter()
+        omel.mel_spectrogram(yh)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 4 * 861 / dt / 1e3, "unit": "kframes/s", "cores": 1,
+                               "kind": "port", "sample": "4 of the 32 clips (numpy)"}
+    return out
 
 
 def cpu_port_step_time(n_utt, steps, warmup):
@@ -333,9 +370,11 @@ def run_ours(args):
     if rank == 0:
         line["roofline"] = gemm_roofline(peaks)
     if not args.no_side:
-        side = dtw_side_metric(peaks, world, rank)
+        side = dtw_side_metric(peaks, world, rank, rank == 0 and world == 1 and not args.no_cpu)
         if rank == 0:
             line["dtw"] = side
+        if rank == 0 and world == 1:
+            line["mel"] = mel_side_metric(peaks, not args.no_cpu)
     if rank == 0 and world == 1 and not args.no_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
         n_utt = 4

@@ -622,9 +622,22 @@ int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_
   p.M_valid_total = (int)K;
   p.mn_major = 1;
   const int tiles = (int)((K / BM) * ((N + BN - 1) / BN));
-  int splits = (ssb::num_sms() + tiles - 1) / tiles;
-  if (splits > p.num_kb / 4) splits = p.num_kb / 4;
-  if (splits < 1) splits = 1;
+  // split the token reduction so that tiles*splits fills whole waves of the persistent grid:
+  // maximise (tiles*s) / (ceil(tiles*s / SMs) * SMs); each split keeps >= 8 k-blocks
+  const int sms = ssb::num_sms() > 0 ? ssb::num_sms() : 148;
+  int max_s = p.num_kb / 8;
+  if (max_s > 32) max_s = 32;
+  if (max_s < 1) max_s = 1;
+  int splits = 1;
+  double best = 0.0;
+  for (int sp = 1; sp <= max_s; ++sp) {
+    const int tt = tiles * sp;
+    const double eff = (double)tt / (double)(((tt + sms - 1) / sms) * sms);
+    if (eff > best + 0.02) {
+      best = eff;
+      splits = sp;
+    }
+  }
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.atomic = splits > 1 ? 1 : 0;
