@@ -35,6 +35,13 @@ D_MODEL, N_LAYERS, BS, SEQ, FRAMES = 768, 6, 32, 4000, 500
 STEP_GFLOP = 6229.0       # algorithmic GFLOP per bs-32 step per GPU, SURVEY.md §8(d)
 
 
+def cpu_threads():
+    """Threads for the CPU arms: physical cores (logical / 2 with SMT; oversubscribing the 128
+    logical CPUs of this pool's hosts made the torch CPU step 20x slower)."""
+    n = int(os.environ.get("SSB_CPU_THREADS", "0"))
+    return n if n > 0 else max(1, (os.cpu_count() or 2) // 2)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -217,10 +224,10 @@ def dtw_side_metric(peaks, world, rank, with_cpu):
         host = cost[:n].cpu().numpy().transpose(0, 2, 1)
         odtw.align_batch(host[:8])
         t0 = time.perf_counter()
-        odtw.align_batch(host, threads=os.cpu_count())
+        odtw.align_batch(host, threads=cpu_threads())
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": n * Tp * Tg / dt / 1e6, "unit": "Mcells/s",
-                               "cores": os.cpu_count(), "kind": "port",
+                               "cores": cpu_threads(), "kind": "port",
                                "sample": f"{n} of the 10000 pairs"}
     del cost
     return out
@@ -274,8 +281,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun pins OMP_NUM_THREADS=1 per rank; the CPU arm uses every host core it can
-    torch.set_num_threads(os.cpu_count() or 1)
+    # torchrun pins OMP_NUM_THREADS=1 per rank; the CPU arm uses every physical host core
+    torch.set_num_threads(cpu_threads())
     n_utt = 4
     sec = cpu_port_step_time(n_utt, max(1, min(args.steps, 2)), 1 if args.warmup else 0)
     value = (n_utt / BS) / sec
@@ -376,7 +383,7 @@ def run_ours(args):
         if rank == 0 and world == 1:
             line["mel"] = mel_side_metric(peaks, not args.no_cpu)
     if rank == 0 and world == 1 and not args.no_cpu:
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(cpu_threads())
         n_utt = 4
         sec = cpu_port_step_time(n_utt, 1, 0)
         line["cpu_baseline"] = {"value": (n_utt / BS) / sec, "unit": "steps/s",

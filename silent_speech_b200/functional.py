@@ -217,6 +217,14 @@ class _LinearFn(torch.autograd.Function):
 
 
 def linear(x2d, Wg, bias=None):
+    """y = x @ Wg + bias.  Output widths that are not a multiple of 4 (the 38-way CTC head of
+    recognition_model.py:66) are zero-padded to the kernels' float4 granularity and sliced."""
+    N = Wg.shape[1]
+    if N % 4:
+        pad = 4 - N % 4
+        Wp = torch.nn.functional.pad(Wg, (0, pad)).contiguous()
+        bp = torch.nn.functional.pad(bias, (0, pad)) if bias is not None else None
+        return _LinearFn.apply(x2d, Wp, bp)[:, :N].contiguous()
     return _LinearFn.apply(x2d, Wg, bias)
 
 
