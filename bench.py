@@ -194,7 +194,10 @@ def gemm_roofline(peaks):
     tf = 2.0 * M * N * K / ms / 1e9
     peak = peaks.get("bf16_tflops", 1590.0)
     return {"bound": "tensor", "kernel": "gemm_tc_kernel bf16x3 (FFN1 16000x768x3072)",
-            "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak, "traffic": None,
+            "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture
+            # committed as profiles/r1_gemm_tc_persistent.txt (algorithmic: 58 MB in + 197 MB out)
+            "traffic": 201.5e6, "traffic_unit": "B/launch",
             "mma_per_logical_mma": 3, "tensor_pipe_frac": 3.0 * tf / peak,
             "peak_source": f"{peaks['_source']} cuBLAS bf16 burst (this kernel is timed alone)",
             "ms_per_launch": ms}
