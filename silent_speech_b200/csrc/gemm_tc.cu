@@ -9,13 +9,20 @@
 // cost of 3 bf16 MMAs = 1.5x a TF32 MMA.  Split planes take exactly the bytes of the fp32
 // tensor they replace (2 + 2 B per element).
 //
-// Kernel shape (persistent: one CTA per SM walks 128 x 256 output tiles; 192 threads,
-// warp-specialised; two TMEM accumulators so the epilogue of a tile overlaps the next tile's MMAs):
-//   warp 0    TMA producer: per 32-deep k-block, the A_hi/A_lo (2 x 8 KB) and B_hi/B_lo
-//             (2 x 16 KB) tiles land in swizzled shared memory (4 stages x 48 KB),
-//             completion on an mbarrier (complete_tx).
+// Kernel shape (persistent, 192 threads, warp-specialised; two TMEM accumulators so the epilogue
+// of a tile overlaps the next tile's MMAs).  Two instantiations:
+//   CTAS = 2  (default) a CTA PAIR per TPC walks 256 x 256 output tiles with
+//             tcgen05.mma.cta_group::2 (M256 N256 K16): each CTA stages its own 128 rows of A
+//             and HALF of B (128 rows), so the shared-memory traffic per MMA drops from
+//             12 KB read + 12 KB.. to 8 KB read per SM -- the 1-CTA form is shared-memory-
+//             bandwidth bound at ~61 % tensor-pipe activity (profiles/r1_gemm_tc_persistent.txt).
+//             6 stages x 32 KB per CTA; the leader CTA (rank 0) issues every MMA, its mbarriers
+//             collect the TMA bytes of both CTAs, commits are multicast to both.
+//   CTAS = 1  one CTA per SM, 128 x 256 tiles, 4 stages x 48 KB (small / odd-shaped problems).
+//   warp 0    TMA producer: per 32-deep k-block, the A_hi/A_lo and B_hi/B_lo tiles land in
+//             swizzled shared memory, completion on an mbarrier (complete_tx).
 //   warp 1    TMEM allocator (2 x 256 fp32 columns) and single-thread MMA issuer: 2 x 3
-//             tcgen05.mma (M128 N256 K16) per k-block, tcgen05.commit releases the stage.
+//             tcgen05.mma per k-block, tcgen05.commit releases the stage.
 //   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias / ReLU / dropout /
 //             mask / accumulate / split-K reduction, fp32 stores through the same
 //             (batch, row) -> address map as the CUDA-core engine (gemm_simt.cu).
@@ -39,14 +46,24 @@ namespace {
 // prefetch cover ~1.2 us of DRAM latency (the first version, 2 x 96 KB with 64-deep blocks,
 // stalled on every HBM-cold operand: 340 us in-step vs 185 us L2-warm for the same GEMM).
 constexpr int BM = 128, BN = 256, BK = 32;
-constexpr int STAGES = 4;
 constexpr int A_PLANE = BM * BK * 2;   // 8 KB
-constexpr int B_PLANE = BN * BK * 2;   // 16 KB
-constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // 48 KB
 constexpr int MN_GROUP = BK * 128;     // bytes of one 64-element MN group of a stage (MN-major)
 constexpr int TMEM_COLS = 512;   // two 256-column fp32 accumulators
 constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_ROW_BYTES = 36 * 4;                 // 32 fp32 + 4 pad: conflict-free both ways
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;    // one epilogue warp's transpose tile
+constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;         // 18 KB
+
+template <int CTAS>
+struct Cfg {
+  static constexpr int BMC = BM * CTAS;                    // output rows per tile (whole pair)
+  static constexpr int B_ROWS = BN / CTAS;                 // rows of B each CTA stages
+  static constexpr int B_PLANE = B_ROWS * BK * 2;          // 16 KB / 8 KB
+  static constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;   // 48 KB / 32 KB per CTA
+  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
+};
 
 struct TcParams {
   // operand addressing (see header comment)
@@ -90,29 +107,81 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "}" ::"r"(bar), "r"(parity)
       : "memory");
 }
-// 5-D tensor maps: (inner, row, batch_lo, batch_hi, plane)
+// 5-D tensor maps: (inner, row, batch_lo, batch_hi, plane).  CTAS == 2: the destination is this
+// CTA's shared memory, `bar` is the LEADER CTA's barrier as a shared::cluster address.
+template <int CTAS>
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
                                             int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
+  if constexpr (CTAS == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  }
 }
+template <int CTAS>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CTAS == 1) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
+// CTAS == 2: the arrival is multicast to the barrier at the same offset in BOTH CTAs
+template <int CTAS>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+  if constexpr (CTAS == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     bar)
+                 : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+        "[%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
                : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -141,61 +210,80 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
   return d;
 }
 
-// instruction descriptor (InstrDescriptor): D=f32, A=B=bf16, M=128, N=256
-__host__ __device__ constexpr uint32_t make_idesc(int mn_major) {
+// instruction descriptor (InstrDescriptor): D=f32, A=B=bf16, M=128 (256 for a CTA pair), N=256
+__host__ __device__ constexpr uint32_t make_idesc(int mn_major, int m) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mn_major & 1) << 15) |
-         ((uint32_t)(mn_major & 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(mn_major & 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Persistent: gridDim.x CTAs (one per SM) walk the tile list; the two 256-column TMEM
-// accumulators alternate so that the epilogue of tile i runs under the MMAs of tile i+1, and
-// the TMA ring keeps streaming across tile boundaries.
+// Persistent: gridDim.x / CTAS workers (a CTA, or a CTA pair on one TPC) walk the tile list; the
+// two 256-column TMEM accumulators alternate so that the epilogue of tile i runs under the MMAs
+// of tile i+1, and the TMA ring keeps streaming across tile boundaries.
+template <int CTAS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const TcParams p) {
+  using C = Cfg<CTAS>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_PLANE = C::B_PLANE;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ssb::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_ptr_smem = tempty_bar + 16;
+  const uint32_t epi_base = bars + 256;   // 4 x 4.5 KB transpose tiles of the epilogue warps
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - ssb::smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;   // 0 = leader (issues the MMAs)
+  const int worker = (int)blockIdx.x / CTAS, num_workers = (int)gridDim.x / CTAS;
   const int tiles_xy = p.tiles_x * p.tiles_y;
   const int total_tiles = tiles_xy * p.splits;
+  // barriers other CTAs signal are addressed in the leader's shared memory
+  const uint32_t full_bar_lead = CTAS == 2 ? map_to_cta(full_bar, 0) : full_bar;
+  const uint32_t tempty_bar_lead = CTAS == 2 ? map_to_cta(tempty_bar, 0) : tempty_bar;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(full_bar + 8 * s, 1);     // the leader's arrive.expect_tx (+ TMA bytes of all CTAS)
+      mbar_init(empty_bar + 8 * s, 1);    // one (multicast) tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, 4);   // one arrival per epilogue warp
+      mbar_init(tempty_bar + 8 * a, 4 * CTAS);   // one arrival per epilogue warp of every CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     tmem_ptr_smem),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTAS == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       tmem_ptr_smem),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {   // the same warp of both CTAs, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       tmem_ptr_smem),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers are initialised too
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  // tile -> coordinates (n fastest, so concurrently running CTAs share A rows and sweep B)
+  // tile -> coordinates (n fastest, so concurrently running workers share A rows and sweep B);
+  // row0 / f0 are THIS CTA's 128 rows of the (128 * CTAS)-row tile, nb0 its rows of B
   auto decode = [&](int tile, int& n0, int& batch, int& row0, int& f0, int& kb_begin, int& nkb) {
     const int z = tile / tiles_xy;
     const int rem = tile - z * tiles_xy;
@@ -204,40 +292,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     batch = 0; row0 = 0; f0 = 0;
     if (!p.mn_major) {
       batch = ty / p.tiles_per_batch;
-      row0 = (ty - batch * p.tiles_per_batch) * BM;
+      row0 = (ty - batch * p.tiles_per_batch) * C::BMC + rank * BM;
       kb_begin = 0;
       nkb = p.num_kb;
     } else {
-      f0 = ty * BM;
+      f0 = ty * C::BMC + rank * BM;
       kb_begin = z * p.kb_per_split;
       nkb = max(min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin, 0);
     }
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA stages its own operand rows) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers) {
         int n0, batch, row0, f0, kb_begin, nkb;
         decode(tile, n0, batch, row0, f0, kb_begin, nkb);
+        const int nb0 = n0 + rank * C::B_ROWS;
         for (int i = 0; i < nkb; ++i, ++it) {
           const int kb = kb_begin + i;
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar + 8 * s, ph ^ 1u);
           const uint32_t st = smem_base + s * STAGE_BYTES;
-          mbar_expect_tx(full_bar + 8 * s, STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(full_bar + 8 * s, CTAS * STAGE_BYTES);
+          const uint32_t fb = full_bar_lead + 8 * s;
           if (!p.mn_major) {
             const int kk = kb * BK;
             const int tap = kk / p.a_inner, c0 = kk - tap * p.a_inner;
             const int d1 = row0 * p.a_row_step + tap * p.a_tap_step + p.a_off;
             const int lo = batch % p.batch_div, hi = batch / p.batch_div;
             const int blo = p.b_mode ? lo : 0, bhi = p.b_mode == 1 ? hi : 0;
-            tma_load_5d(st, &mapA, full_bar + 8 * s, c0, d1, lo, hi, 0);
-            tma_load_5d(st + A_PLANE, &mapA, full_bar + 8 * s, c0, d1, lo, hi, 1);
-            tma_load_5d(st + 2 * A_PLANE, &mapB, full_bar + 8 * s, kk, n0, blo, bhi, 0);
-            tma_load_5d(st + 2 * A_PLANE + B_PLANE, &mapB, full_bar + 8 * s, kk, n0, blo, bhi, 1);
+            tma_load_5d<CTAS>(st, &mapA, fb, c0, d1, lo, hi, 0);
+            tma_load_5d<CTAS>(st + A_PLANE, &mapA, fb, c0, d1, lo, hi, 1);
+            tma_load_5d<CTAS>(st + 2 * A_PLANE, &mapB, fb, kk, nb0, blo, bhi, 0);
+            tma_load_5d<CTAS>(st + 2 * A_PLANE + B_PLANE, &mapB, fb, kk, nb0, blo, bhi, 1);
           } else {
             const int b = kb / p.chunks_per_batch;
             const int t0 = (kb - b * p.chunks_per_batch) * BK;
@@ -248,27 +338,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
               for (int h = 0; h < BM / 64; ++h)
-                tma_load_5d(st + pl * A_PLANE + h * MN_GROUP, &mapA, full_bar + 8 * s, c0 + 64 * h,
-                            d1, lo, hi, pl);
+                tma_load_5d<CTAS>(st + pl * A_PLANE + h * MN_GROUP, &mapA, fb, c0 + 64 * h, d1, lo,
+                                  hi, pl);
 #pragma unroll
-              for (int h = 0; h < BN / 64; ++h)
-                tma_load_5d(st + 2 * A_PLANE + pl * B_PLANE + h * MN_GROUP, &mapB, full_bar + 8 * s,
-                            n0 + 64 * h, t0, lo, hi, pl);
+              for (int h = 0; h < C::B_ROWS / 64; ++h)
+                tma_load_5d<CTAS>(st + 2 * A_PLANE + pl * B_PLANE + h * MN_GROUP, &mapB, fb,
+                                  nb0 + 64 * h, t0, lo, hi, pl);
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.mn_major);
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(p.mn_major, C::BMC);
       uint32_t it = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {
         int n0, batch, row0, f0, kb_begin, nkb;
         decode(tile, n0, batch, row0, f0, kb_begin, nkb);
         const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
-        mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);      // epilogue has drained this accumulator
+        mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);      // every epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN;
         for (int i = 0; i < nkb; ++i, ++it) {
@@ -299,49 +389,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               dbl = make_desc(b_lo + off, MN_GROUP, 1024, 2);
             }
             const uint32_t acc0 = (i > 0 || k > 0) ? 1u : 0u;
-            umma_bf16(tmem_d, dah, dbh, idesc, acc0);
-            umma_bf16(tmem_d, dah, dbl, idesc, 1u);
-            umma_bf16(tmem_d, dal, dbh, idesc, 1u);
+            umma_bf16<CTAS>(tmem_d, dah, dbh, idesc, acc0);
+            umma_bf16<CTAS>(tmem_d, dah, dbl, idesc, 1u);
+            umma_bf16<CTAS>(tmem_d, dal, dbh, idesc, 1u);
           }
-          umma_commit(empty_bar + 8 * s);   // frees this smem stage when the MMAs retire
+          umma_commit<CTAS>(empty_bar + 8 * s);   // frees this smem stage (in every CTA) when the MMAs retire
         }
-        umma_commit(tfull_bar + 8 * acc);   // accumulator complete
+        umma_commit<CTAS>(tfull_bar + 8 * acc);   // accumulator complete (in every CTA)
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..5 of every CTA: its own 128 rows) =====================
+    // tcgen05.ld hands every lane one ROW (32 consecutive columns).  Storing from that layout
+    // makes each warp store touch 32 rows x 16 B (32 half-used sectors: the 1-CTA profile showed
+    // l1tex at 75 %), so the 32 x 32 block is transposed through a padded shared-memory tile
+    // first: afterwards a warp instruction covers 4 rows x 128 contiguous bytes.
     const int lg = warp & 3;              // TMEM lane group this warp may read
-    const int r = lg * 32 + lane;         // row inside the tile == TMEM lane
+    const uint32_t stg = epi_base + (uint32_t)lg * EPI_WARP_BYTES;
+    const int rsub = lane >> 3;           // after the transpose: row (i*4 + rsub) of the 32-row group,
+    const int csub = (lane & 7) * 4;      // columns csub .. csub+3 of the 32-column block
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tcount) {
+    for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {
       int n0, batch, row0, f0, kb_begin, nkb;
       decode(tile, n0, batch, row0, f0, kb_begin, nkb);
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
       mbar_wait(tfull_bar + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      bool row_ok;
-      float* orow;
-      int64_t grow;   // global output row index (for mask / dropout addressing)
+      // first row this lane stores (rows advance by 4 per i), its address and global row index
+      int first, limit;
+      float* orow0;
+      int64_t grow0;   // global output row index (for mask / dropout addressing)
       if (!p.mn_major) {
-        const int t = row0 + r;
-        row_ok = t < p.rows_per_batch;
-        grow = (int64_t)batch * p.rows_per_batch + t;
-        orow = p.out + (int64_t)(batch % p.batch_div) * p.out_batch_stride +
-               (int64_t)(batch / p.batch_div) * p.out_batch_stride_hi +
-               (int64_t)(t * p.out_dt + p.out_doff) * p.out_ld;
+        first = row0 + lg * 32 + rsub;
+        limit = p.rows_per_batch;
+        grow0 = (int64_t)batch * p.rows_per_batch + first;
+        orow0 = p.out + (int64_t)(batch % p.batch_div) * p.out_batch_stride +
+                (int64_t)(batch / p.batch_div) * p.out_batch_stride_hi +
+                ((int64_t)first * p.out_dt + p.out_doff) * p.out_ld;
       } else {
-        const int f = f0 + r;
-        row_ok = f < p.M_valid_total;
-        grow = f;
-        orow = p.out + (int64_t)(f * p.out_dt + p.out_doff) * p.out_ld;
+        first = f0 + lg * 32 + rsub;
+        limit = p.M_valid_total;
+        grow0 = first;
+        orow0 = p.out + ((int64_t)first * p.out_dt + p.out_doff) * p.out_ld;
         if (p.mn_batched) {   // z = batch item: every batch item has its own output block
           const int bz = tile / tiles_xy;
-          grow += (int64_t)bz * p.M_valid_total;
-          orow += (int64_t)(bz % p.batch_div) * p.out_batch_stride +
-                  (int64_t)(bz / p.batch_div) * p.out_batch_stride_hi;
+          grow0 += (int64_t)bz * p.M_valid_total;
+          orow0 += (int64_t)(bz % p.batch_div) * p.out_batch_stride +
+                   (int64_t)(bz / p.batch_div) * p.out_batch_stride_hi;
         }
       }
-      if (nkb == 0) row_ok = false;
+      if (nkb == 0) limit = 0;
+      const int64_t row_step = (int64_t)4 * p.out_dt * p.out_ld;
       const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -349,28 +447,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint32_t v[32];
         tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!row_ok) continue;
-        const int nb = n0 + c * 32;
+        if (first - rsub >= limit) continue;   // warp-uniform: the whole 32-row group is padding
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = nb + j;
-          if (n >= p.N) break;
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                           stg + (uint32_t)lane * EPI_ROW_BYTES + (uint32_t)j * 4u),
+                       "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                       : "memory");
+        __syncwarp();
+        const int n = n0 + c * 32 + csub;
+        const bool n_ok = n < p.N;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && n_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 o;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "r"(stg + (uint32_t)(i * 4 + rsub) * EPI_ROW_BYTES + (uint32_t)csub * 4u)
+                       : "memory");
+          if (!n_ok || first + 4 * i >= limit) continue;
+          float* dst = orow0 + i * row_step + n;
           if (p.atomic) {
-            atomicAdd(orow + n + 0, o.x);
-            atomicAdd(orow + n + 1, o.y);
-            atomicAdd(orow + n + 2, o.z);
-            atomicAdd(orow + n + 3, o.w);
+            atomicAdd(reinterpret_cast<float4*>(dst), o);
             continue;
           }
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
+          o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
           if (p.relu) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
           }
+          const int64_t grow = grow0 + 4 * i;
           if (p.drop_p > 0.f) {
             const uint64_t e = (uint64_t)grow * (uint64_t)p.N + (uint64_t)n;
             const uint4 rnd = ssb::dropout_bits4(p.seed, p.site, e >> 2);
@@ -387,26 +493,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             o.w = mk.w > 0.f ? o.w * p.mask_scale : 0.f;
           }
           if (p.accumulate) {
-            const float4 old = *reinterpret_cast<const float4*>(orow + n);
+            const float4 old = *reinterpret_cast<const float4*>(dst);
             o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
           }
-          *reinterpret_cast<float4*>(orow + n) = o;
+          *reinterpret_cast<float4*>(dst) = o;
         }
+        __syncwarp();   // the staging tile is rewritten by the next column block
       }
-      // hand the accumulator back to the MMA warp
+      // hand the accumulator back to the (leader's) MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (lane == 0) {
+        if constexpr (CTAS == 1) mbar_arrive(tempty_bar + 8 * acc);
+        else mbar_arrive_cluster(tempty_bar_lead + 8 * acc);
+      }
     }
   }
 
+  // teardown: nobody may leave while the peer can still touch this CTA's shared memory / TMEM
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
+    if constexpr (CTAS == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"((uint32_t)TMEM_COLS)
+                   : "memory");
   }
 }
 
@@ -499,25 +616,55 @@ inline void batch_levels(const ssb_tc_operand_t* o, int64_t* n_lo, int64_t* n_hi
   }
 }
 
-int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams p, dim3 tiles,
-           cudaStream_t st) {
+// CTA pairs unless SSB_TC_CTAS=1 (read once); callers fall back to 1 per problem shape
+int default_ctas() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("SSB_TC_CTAS");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+
+template <int CTAS>
+int launch_impl(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, int64_t total,
+                cudaStream_t st) {
   static bool attr_set[64] = {false};
   int dev = 0;
   SSB_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    SSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  SMEM_BYTES));
+    SSB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  Cfg<CTAS>::SMEM_BYTES));
     attr_set[dev] = true;
   }
+  const int workers = ssb::num_sms() / CTAS;
+  const int grid = (int)(total < workers ? total : workers) * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CTAS > 1 ? 1 : 0;
+  SSB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTAS>, mapA, mapB, p));
+  SSB_LAUNCH_CHECK("gemm_tc_kernel");
+  return SSB_OK;
+}
+
+// tiles = (n tiles, row tiles of 128 * ctas, splits)
+int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams p, dim3 tiles, int ctas,
+           cudaStream_t st) {
   p.tiles_x = (int)tiles.x;
   p.tiles_y = (int)tiles.y;
   p.splits = (int)tiles.z;
   const int64_t total = (int64_t)tiles.x * tiles.y * tiles.z;
-  const int sms = ssb::num_sms();
-  const int grid = (int)(total < sms ? total : sms);
-  gemm_tc_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(mapA, mapB, p);
-  SSB_LAUNCH_CHECK("gemm_tc_kernel");
-  return SSB_OK;
+  return ctas == 2 ? launch_impl<2>(mapA, mapB, p, total, st)
+                   : launch_impl<1>(mapA, mapB, p, total, st);
 }
 
 int fill_epi(const ssb_epilogue_t* e, int64_t N, TcParams* p) {
@@ -575,19 +722,23 @@ int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N
   if (int rc = make_map(&mapA, A->planes, A->C, A->L_src, n_lo, n_hi, A->ld, A->batch_stride,
                         A->batch_stride_hi, A->plane_stride, BK, box_rows, A->s_t))
     return rc;
-  if (int rc = make_map(&mapB, Bplanes, K, N, 1, 1, K, N * K, N * K, N * K, BK, BN, 1)) return rc;
+  // a CTA pair covers 256 rows: not worth it when a batch item has no second half tile
+  const int ctas = A->rows_out > BM ? default_ctas() : 1;
+  const int bmc = BM * ctas;
+  if (int rc = make_map(&mapB, Bplanes, K, N, 1, 1, K, N * K, N * K, N * K, BK, BN / ctas, 1))
+    return rc;
   p.batch_div = (int)n_lo;
   p.b_mode = 0;
   p.a_inner = A->C; p.a_row_step = A->s_t; p.a_tap_step = A->s_tap; p.a_off = A->off;
   p.rows_per_batch = A->rows_out;
-  p.tiles_per_batch = (A->rows_out + BM - 1) / BM;
+  p.tiles_per_batch = (A->rows_out + bmc - 1) / bmc;
   p.chunks_per_batch = 1;
   p.num_kb = (int)(K / BK);
   p.kb_per_split = p.num_kb;
   p.M_valid_total = A->batches * A->rows_out;
   p.mn_major = 0;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)(A->batches * p.tiles_per_batch), 1);
-  return launch(mapA, mapB, p, grid, (cudaStream_t)stream);
+  return launch(mapA, mapB, p, grid, ctas, (cudaStream_t)stream);
 }
 
 int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_plane_stride,
@@ -621,10 +772,12 @@ int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_
   p.num_kb = X->batches * p.chunks_per_batch;
   p.M_valid_total = (int)K;
   p.mn_major = 1;
-  const int tiles = (int)((K / BM) * ((N + BN - 1) / BN));
+  const int ctas = K % (2 * BM) == 0 ? default_ctas() : 1;   // feature rows pair up
+  const int bmc = BM * ctas;
+  const int tiles = (int)((K / bmc) * ((N + BN - 1) / BN));
   // split the token reduction so that tiles*splits fills whole waves of the persistent grid:
-  // maximise (tiles*s) / (ceil(tiles*s / SMs) * SMs); each split keeps >= 8 k-blocks
-  const int sms = ssb::num_sms() > 0 ? ssb::num_sms() : 148;
+  // maximise (tiles*s) / (ceil(tiles*s / workers) * workers); each split keeps >= 8 k-blocks
+  const int sms = (ssb::num_sms() > 0 ? ssb::num_sms() : 148) / ctas;
   int max_s = p.num_kb / 8;
   if (max_s > 32) max_s = 32;
   if (max_s < 1) max_s = 1;
@@ -644,8 +797,8 @@ int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_
   p.accumulate = accumulate;
   if (splits > 1 && !accumulate)
     SSB_CUDA(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)N * 4, (size_t)K, st));
-  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)(K / BM), (unsigned)splits);
-  return launch(mapA, mapB, p, grid, st);
+  dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)(K / bmc), (unsigned)splits);
+  return launch(mapA, mapB, p, grid, ctas, st);
 }
 
 int ssb_gemm_tc_batched(const ssb_tc_operand_t* A, const ssb_tc_operand_t* B, int b_mode,
@@ -665,12 +818,14 @@ int ssb_gemm_tc_batched(const ssb_tc_operand_t* A, const ssb_tc_operand_t* B, in
   if (int rc = make_map(&mapA, A->planes, A->C, A->L_src, a_lo, a_hi, A->ld, A->batch_stride,
                         A->batch_stride_hi, A->plane_stride, BK, BM, 1))
     return rc;
+  const int ctas = A->rows_out > BM ? default_ctas() : 1;
+  const int bmc = BM * ctas;
   if (int rc = make_map(&mapB, B->planes, B->C, B->L_src, b_lo, b_hi, B->ld, B->batch_stride,
-                        B->batch_stride_hi, B->plane_stride, BK, BN, 1))
+                        B->batch_stride_hi, B->plane_stride, BK, BN / ctas, 1))
     return rc;
   p.a_inner = A->C; p.a_row_step = 1; p.a_tap_step = 0; p.a_off = A->off;
   p.rows_per_batch = A->rows_out;
-  p.tiles_per_batch = (A->rows_out + BM - 1) / BM;
+  p.tiles_per_batch = (A->rows_out + bmc - 1) / bmc;
   p.chunks_per_batch = 1;
   p.num_kb = (int)(K / BK);
   p.kb_per_split = p.num_kb;
@@ -679,7 +834,7 @@ int ssb_gemm_tc_batched(const ssb_tc_operand_t* A, const ssb_tc_operand_t* B, in
   p.batch_div = (int)a_lo;
   p.b_mode = b_mode;
   dim3 tiles((unsigned)((N + BN - 1) / BN), (unsigned)(A->batches * p.tiles_per_batch), 1);
-  return launch(mapA, mapB, p, tiles, (cudaStream_t)stream);
+  return launch(mapA, mapB, p, tiles, ctas, (cudaStream_t)stream);
 }
 
 int ssb_gemm_tc_batched_tn(const ssb_tc_operand_t* X, const ssb_tc_operand_t* G, int64_t N,
@@ -713,8 +868,10 @@ int ssb_gemm_tc_batched_tn(const ssb_tc_operand_t* X, const ssb_tc_operand_t* G,
   p.mn_batched = 1;
   p.batch_div = (int)x_lo;
   p.b_mode = 1;
-  dim3 tiles((unsigned)((N + BN - 1) / BN), (unsigned)((K + BM - 1) / BM), (unsigned)X->batches);
-  return launch(mapA, mapB, p, tiles, (cudaStream_t)stream);
+  const int ctas = K > BM ? default_ctas() : 1;
+  const int bmc = BM * ctas;
+  dim3 tiles((unsigned)((N + BN - 1) / BN), (unsigned)((K + bmc - 1) / bmc), (unsigned)X->batches);
+  return launch(mapA, mapB, p, tiles, ctas, (cudaStream_t)stream);
 }
 
 }  // extern "C"

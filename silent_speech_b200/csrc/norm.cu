@@ -78,23 +78,49 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
   }
 }
 
-// ---- finalize kernels (one thread per channel, fp64 accumulation over chunks) ---------
+// ---- finalize kernels: fp64 accumulation of the chunk partials, fixed order ----------------
+// block = (32 channels, 8 chunk-lanes); lane y adds chunks y, y+8, ...; lanes are combined in
+// shared memory in a fixed order (deterministic), thread y == 0 finishes the channel.
+constexpr int FIN_LANES = 8;
+#define FIN_GRID(C) dim3((unsigned)(((C) + 31) / 32)), dim3(32, FIN_LANES)
+
+__device__ __forceinline__ bool chunk_sums(const float* __restrict__ partials, int nchunks, int C,
+                                           int stride_slots, int c, double& s0, double& s1) {
+  __shared__ double sh[2][FIN_LANES][32];
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int k = threadIdx.y; k < nchunks; k += FIN_LANES) {
+      a += (double)partials[((int64_t)k * stride_slots) * C + c];
+      b += (double)partials[((int64_t)k * stride_slots + 1) * C + c];
+    }
+  }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return false;
+  s0 = 0.0; s1 = 0.0;
+#pragma unroll
+  for (int y = 0; y < FIN_LANES; ++y) {
+    s0 += sh[0][y][threadIdx.x];
+    s1 += sh[1][y][threadIdx.x];
+  }
+  return true;
+}
+
 __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
                                        float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int k = 0; k < nchunks; ++k) s += (double)partials[((int64_t)k * 2) * C + c];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, unused;
+  if (!chunk_sums(partials, nchunks, C, 2, c, s, unused)) return;
   out[c] = (accumulate ? out[c] : 0.f) + (float)s;
 }
 
 // training, pass 1: mean[c] = sum(x) / count
 __global__ void bn_mean_kernel(const float* __restrict__ partials, int nchunks, int C, double count,
                                float* __restrict__ mean) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int k = 0; k < nchunks; ++k) s += (double)partials[((int64_t)k * 2) * C + c];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, unused;
+  if (!chunk_sums(partials, nchunks, C, 2, c, s, unused)) return;
   mean[c] = (float)(s / count);
 }
 
@@ -106,10 +132,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchun
                                    float* running_var, float momentum, float eps,
                                    const float* __restrict__ mean, float* __restrict__ rstd,
                                    float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double m2 = 0.0;
-  for (int k = 0; k < nchunks; ++k) m2 += (double)partials[((int64_t)k * 2) * C + c];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double m2, unused;
+  if (!chunk_sums(partials, nchunks, C, 2, c, m2, unused)) return;
   const double mu = (double)mean[c];
   const double var = m2 / count;
   const float r = (float)(1.0 / sqrt(var + (double)eps));
@@ -178,13 +203,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int n
                                        double count, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ m_dz,
                                        float* __restrict__ m_dzx) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, sx = 0.0;
-  for (int k = 0; k < nchunks; ++k) {
-    s += (double)partials[((int64_t)k * 2) * C + c];
-    sx += (double)partials[((int64_t)k * 2 + 1) * C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double s, sx;
+  if (!chunk_sums(partials, nchunks, C, 2, c, s, sx)) return;
   dbeta[c] = (float)s;
   dgamma[c] = (float)sx;
   m_dz[c] = (float)(s / count);
@@ -383,13 +404,9 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
 __global__ void ln_param_grad_finalize_kernel(const float* __restrict__ partials, int nblk, int D,
                                               float* __restrict__ dgamma,
                                               float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= D) return;
-  double a = 0.0, b = 0.0;
-  for (int k = 0; k < nblk; ++k) {
-    a += (double)partials[((int64_t)k * 2) * D + c];
-    b += (double)partials[((int64_t)k * 2 + 1) * D + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a, b;
+  if (!chunk_sums(partials, nblk, D, 2, c, a, b)) return;
   dgamma[c] = (float)a;
   dbeta[c] = (float)b;
 }
@@ -429,8 +446,8 @@ int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumula
   col_partials_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
                                                (int)C, (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials<1>");
-  colsum_finalize_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>((const float*)workspace, nch,
-                                                                      (int)C, out, accumulate);
+  colsum_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, out,
+                                                 accumulate);
   SSB_LAUNCH_CHECK("colsum_finalize");
   return SSB_OK;
 }
@@ -457,12 +474,12 @@ int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* gamma, co
   col_partials_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
                                                (int)C, (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials<1>");
-  bn_mean_kernel<<<cb, 128, 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, mean);
+  bn_mean_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, mean);
   SSB_LAUNCH_CHECK("bn_mean");
   col_partials_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, mean, nullptr, rows, (int)C,
                                                (int)C, (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials<0>");
-  bn_finalize_kernel<<<cb, 128, 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, gamma,
+  bn_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, gamma,
                                          beta, running_mean, running_var, momentum, eps, mean,
                                          rstd, scale, shift);
   SSB_LAUNCH_CHECK("bn_finalize");
@@ -502,7 +519,7 @@ int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const flo
   col_partials_kernel<2><<<grid, 256, 0, st>>>(x, dy, mask_src, mean, rstd, rows, (int)C, (int)C,
                                                partials);
   SSB_LAUNCH_CHECK("col_partials<2>");
-  bn_bwd_finalize_kernel<<<cb, 128, 0, st>>>(partials, nch, (int)C, (double)rows, dgamma, dbeta,
+  bn_bwd_finalize_kernel<<<FIN_GRID(C), 0, st>>>(partials, nch, (int)C, (double)rows, dgamma, dbeta,
                                              m_dz, m_dzx);
   SSB_LAUNCH_CHECK("bn_bwd_finalize");
   const int64_t n4 = rows * C / 4;
@@ -555,8 +572,8 @@ int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, c
                                           thresh_of(drop_p), seed, site, d_res, d_branch,
                                           (float*)workspace);
   SSB_LAUNCH_CHECK("add_ln_bwd");
-  ln_param_grad_finalize_kernel<<<(unsigned)((D + 127) / 128), 128, 0, st>>>(
-      (const float*)workspace, nblk, (int)D, dgamma, dbeta);
+  ln_param_grad_finalize_kernel<<<FIN_GRID(D), 0, st>>>((const float*)workspace, nblk, (int)D,
+                                                        dgamma, dbeta);
   SSB_LAUNCH_CHECK("ln_param_grad_finalize");
   return SSB_OK;
 }

@@ -1,5 +1,5 @@
 """Bring-up checks of the tcgen05 GEMM (csrc/gemm_tc.cu) against fp64 torch references.
-usage: python tools/tc_gemm_check.py {split|kmajor|wgrad|conv1|conv2|perf}   (run each under `timeout`)"""
+usage: python tools/tc_gemm_check.py {split|kmajor|wgrad|conv1|conv2|perf|shapes|ffn|convgrad}   (run each under `timeout`)"""
 import os
 import sys
 import time
@@ -126,6 +126,49 @@ def t_perf():
 
 
 
+def t_shapes():
+    """in-step GEMM shapes of cfg-1 (16000 tokens), L2-warm and L2-flushed, epilogue variants"""
+    flush = torch.empty(64 * 1024 * 1024, device=dev)   # 256 MB > 126 MB L2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, cold):
+        for _ in range(2):
+            fn()
+        tot = 0.0
+        for _ in range(6):
+            if cold:
+                flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / 6
+
+    M = 16000
+    for (name, N, K, kw) in [("qkv", 2304, 768, {}), ("wo", 768, 768, {}),
+                             ("ffn1 relu", 3072, 768, dict(relu=1)),
+                             ("ffn1 relu+drop", 3072, 768, dict(relu=1, drop_p=0.2, seed=5, site=3)),
+                             ("ffn2", 768, 3072, {}), ("conv2-like", 768, 2304, {})]:
+        x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+        xp, wp = SF.split_planes(x), SF.split_planes(w)
+        y = torch.empty(M, N, device=dev)
+        op = SF.tc_operand_plain(xp, M, K)
+        ep = SF._epi(SF._scatter_plain(y.data_ptr(), M, N), bias=b, **kw)
+        fn = lambda: SF.gemm_tc_kmajor(op, wp, N, K, ep)
+        w_ms, c_ms = timeit(fn, False), timeit(fn, True)
+        fl = 2.0 * M * N * K / 1e9
+        print(f"shape {name:16s} {M}x{N}x{K}: warm {w_ms*1e3:6.1f} us {fl/w_ms:6.1f} TF/s | "
+              f"cold {c_ms*1e3:6.1f} us {fl/c_ms:6.1f} TF/s")
+        g = rnd(M, N, seed=4)
+        gp = SF.split_planes(g)
+        dW = torch.empty(K, N, device=dev)
+        fn = lambda: SF.gemm_tc_wgrad(op, gp, N, K, dW)
+        w_ms, c_ms = timeit(fn, False), timeit(fn, True)
+        print(f"      wgrad            K={K} N={N}: warm {w_ms*1e3:6.1f} us {fl/w_ms:6.1f} TF/s | "
+              f"cold {c_ms*1e3:6.1f} us {fl/c_ms:6.1f} TF/s")
+
+
 def t_ffn():
     """FFN-like chain pieces with every epilogue variant, odd sizes; each vs fp64."""
     import itertools
@@ -179,4 +222,4 @@ def t_convgrad():
 if __name__ == "__main__":
     what = sys.argv[1]
     {"split": t_split, "kmajor": t_kmajor, "wgrad": t_wgrad, "conv1": lambda: t_conv(1),
-     "conv2": lambda: t_conv(2), "perf": t_perf, "ffn": t_ffn, "convgrad": t_convgrad}[what]()
+     "conv2": lambda: t_conv(2), "perf": t_perf, "shapes": t_shapes, "ffn": t_ffn, "convgrad": t_convgrad}[what]()
