@@ -306,7 +306,7 @@ def run_reference(args):
 def run_ours(args):
     from silent_speech_b200 import _lib
     from silent_speech_b200.read_emg import synthetic_batch
-    from silent_speech_b200.training import GradientBucket, train_step
+    from silent_speech_b200.training import GradientBucket, GraphedTrainStep, train_step
     world, rank, local = dist_setup(args.gpus)
     peaks = load_peaks()
     _lib.load()   # fails loudly if the CUDA library is missing
@@ -321,17 +321,28 @@ def run_ours(args):
     random.seed(rank)
     torch.manual_seed(1000 + rank)
 
+    # the public training call: eager train_step, or (default) the same step with
+    # zero_grad + forward + dtw_loss + backward replayed as one CUDA graph per batch signature
+    graphed = None if args.eager else GraphedTrainStep(model, optim, "cuda", FRAMES, bucket)
+
     def step_device():
         # combine_fixed_length copies, so the in-place augmentation never touches dev_batch
-        train_step(model, optim, dev_batch, "cuda", FRAMES, bucket, sync_loss=False)
+        if graphed is not None:
+            graphed(dev_batch, sync_loss=False)
+        else:
+            train_step(model, optim, dev_batch, "cuda", FRAMES, bucket, sync_loss=False)
 
     def step_e2e():
-        train_step(model, optim, host_batch, "cuda", FRAMES, bucket, sync_loss=True)
+        if graphed is not None:
+            graphed(host_batch, sync_loss=True)
+        else:
+            train_step(model, optim, host_batch, "cuda", FRAMES, bucket, sync_loss=True)
 
     with ClockSampler(local) as clk:
-        l0 = _lib.launch_count
         ms = timed(step_device, args.steps, args.warmup, world)
-        launches = (_lib.launch_count - l0) // (args.steps + args.warmup)
+        l0 = _lib.launch_count          # libssb kernels of one steady-state step (graph replays
+        step_device()                   # count the kernels captured in the graph)
+        launches = _lib.launch_count - l0
     ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), world)
     # host-side enqueue time per step (no synchronisation inside): shows whether the step is
     # bounded by the GPU or by launching ~1000 kernels from Python
@@ -343,7 +354,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     graph_ms = None
-    if args.graph_probe:
+    if args.graph_probe and graphed is None:
         # EXPERIMENT (not a reported number): replay the step as one CUDA graph to see the
         # GPU-only time.  Seeds / augmentation are frozen inside the graph, so this is not a
         # valid training loop.
@@ -370,6 +381,8 @@ def run_ours(args):
                                    "16 silent (DTW, 600-frame targets) + 16 voiced synthetic "
                                    "utterances; fwd + dtw_loss + bwd + grad all-reduce + AdamW",
                        "dropout": 0.2, "parallelism": f"dp{world}",
+                       "launch": "eager" if graphed is None else
+                                 "CUDA graph (zero_grad+fwd+loss+bwd) + eager all-reduce + AdamW",
                        "l2": "per-step working set (~10 GB of activations) >> 126 MB L2"},
             "e2e": {"value": e2e, "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4},
@@ -407,8 +420,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-side", action="store_true", help="skip the DTW side metric")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--eager", action="store_true",
+                    help="launch every kernel from Python instead of replaying the CUDA graph")
     ap.add_argument("--graph-probe", action="store_true",
-                    help="experiment: also time the step replayed as a CUDA graph")
+                    help="experiment (with --eager): also time a whole-step CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -40,6 +40,13 @@ extern "C" {
 SSB_API int ssb_version(void);               /* 10000*major + 100*minor + patch */
 SSB_API const char* ssb_last_error(void);    /* thread-local, never NULL */
 SSB_API int ssb_device_sm_count(void);       /* SM count of the current device (148 on B200), <0 on error */
+/* Dropout keys for CUDA-graph replay.  Every dropout site keys Philox4x32-10 with the by-value
+ * `seed` argument of its entry point (one draw per forward pass: the reference's nn.Dropout,
+ * transformer.py:28-41, draws fresh masks per call).  A captured graph would freeze that value,
+ * so a process may register ONE device-resident 64-bit offset here: kernels launched afterwards
+ * use seed + *dev_seed_offset, read at execution time.  The caller owns the cell, bumps it
+ * between replays (a node of the same graph) and passes NULL to detach.  Process-global. */
+SSB_API int ssb_set_seed_source(const uint64_t* dev_seed_offset);
 
 /* ---- DTW alignment -------------------------------------------------------
  * Replaces align.py:5-14 (`time_warp`) and align.py:16-34 (`align_from_distances`),

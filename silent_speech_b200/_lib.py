@@ -57,6 +57,7 @@ _SIGNATURES = {
     "ssb_version": (ctypes.c_int, []),
     "ssb_last_error": (ctypes.c_char_p, []),
     "ssb_device_sm_count": (ctypes.c_int, []),
+    "ssb_set_seed_source": (ctypes.c_int, [c_ptr]),
     "ssb_dtw_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64, c_i64, c_i64]),
     "ssb_dtw_align_batch": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_ptr,
                                            c_ptr, c_i64, c_ptr]),

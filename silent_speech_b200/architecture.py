@@ -35,6 +35,15 @@ def _conv_weight(conv):
     return w.permute(2, 1, 0).reshape(w.shape[2] * w.shape[1], w.shape[0]).contiguous()
 
 
+def _shift_rows_device(x_raw, r_dev):
+    """architecture.py:64-68 with the shift r held in device memory (CUDA-graph friendly):
+    x_raw[:, :-r] = x_raw[:, r:]; x_raw[:, -r:] = 0, in place; r = 0 is the identity."""
+    L = x_raw.shape[1]
+    idx = torch.arange(L, device=x_raw.device) + r_dev
+    valid = (idx < L).to(x_raw.dtype).view(1, L, 1)
+    x_raw.copy_(x_raw.index_select(1, idx.clamp_(max=L - 1)) * valid)
+
+
 class ResBlock(nn.Module):
     """architecture.py:14-40.  Submodules exist for their parameters/buffers (checkpoint
     contract); forward runs the fused channels-last kernels."""
@@ -100,15 +109,22 @@ class Model(nn.Module):
         self.has_aux_out = num_aux_outs is not None
         if self.has_aux_out:
             self.w_aux = nn.Linear(model_size, num_aux_outs)
+        # None: the augmentation shift is drawn with Python's `random` per forward, as in the
+        # reference.  A 0-d int64 device tensor: the shift is read from it at execution time
+        # (training.GraphedTrainStep draws it on the host and fills the cell before each replay).
+        self.shift_source = None
 
     def forward(self, x_feat, x_raw, session_ids):
         # x_raw is (batch, time, electrode); x_feat and session_ids are ignored, as in the
         # reference (architecture.py:61)
         if self.training:
-            r = random.randrange(8)           # architecture.py:64-68, mutates the caller's tensor
-            if r > 0:
-                x_raw[:, :-r, :] = x_raw[:, r:, :].clone()
-                x_raw[:, -r:, :] = 0
+            if self.shift_source is not None:
+                _shift_rows_device(x_raw, self.shift_source)
+            else:
+                r = random.randrange(8)       # architecture.py:64-68, mutates the caller's tensor
+                if r > 0:
+                    x_raw[:, :-r, :] = x_raw[:, r:, :].clone()
+                    x_raw[:, -r:, :] = 0
         x = x_raw.to(torch.float32).contiguous()
         for blk in self.conv_blocks:
             x = blk.forward_cl(x)

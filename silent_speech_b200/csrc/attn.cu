@@ -41,6 +41,7 @@ struct AttnParams {
   float drop_p, drop_scale;
   uint32_t drop_thresh;
   uint64_t seed;
+  const uint64_t* seed_src;
   uint32_t site;
 };
 
@@ -50,7 +51,7 @@ __device__ __forceinline__ int smem_ld(int dh) { return dh + 4; }  // keeps LDS.
 // one Philox call per group (RW % 4 == 0 keeps groups aligned with the element index).
 __device__ __forceinline__ uint32_t keep_bits4(const AttnParams& p, int64_t token, int h, int g) {
   const uint64_t e4 = (((uint64_t)token * p.H + h) * p.RW >> 2) + g;
-  const uint4 r = ssb::dropout_bits4(p.seed, p.site, e4);
+  const uint4 r = ssb::dropout_bits4(ssb::eff_seed(p.seed, p.seed_src), p.site, e4);
   return (r.x >= p.drop_thresh ? 1u : 0u) | (r.y >= p.drop_thresh ? 2u : 0u) |
          (r.z >= p.drop_thresh ? 4u : 0u) | (r.w >= p.drop_thresh ? 8u : 0u);
 }
@@ -430,7 +431,7 @@ int make_params(const float* qkv, const float* R, float* P, float* O, const floa
   p->drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const double th = (double)drop_p * 4294967296.0;
   p->drop_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
-  p->seed = seed; p->site = site;
+  p->seed = seed; p->seed_src = ssb::seed_source(); p->site = site;
   return SSB_OK;
 }
 

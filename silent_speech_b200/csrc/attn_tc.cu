@@ -82,6 +82,7 @@ struct SmParams {
   float scale, drop_p, drop_scale;
   uint32_t drop_thresh;
   uint64_t seed;
+  const uint64_t* seed_src;
   uint32_t site;
 };
 
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const SmParams p)
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (int64_t)p.BH * p.T) return;
+  const uint64_t seed = ssb::eff_seed(p.seed, p.seed_src);
   const int q = (int)(row % p.T);
   float* Srow = p.S + row * p.Tp;
   const float* Rrow = p.R + row * p.RW;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) attn_softmax_fwd_kernel(const SmParams p)
       float4 pr = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
       *reinterpret_cast<float4*>(Srow + 4 * c4) = pr;
       if (p.drop_p > 0.f) {
-        const uint4 rnd = ssb::dropout_bits4(p.seed, p.site, (uint64_t)row * nv + c4);
+        const uint4 rnd = ssb::dropout_bits4(seed, p.site, (uint64_t)row * nv + c4);
         pr.x = rnd.x >= p.drop_thresh ? pr.x * p.drop_scale : 0.f;
         pr.y = rnd.y >= p.drop_thresh ? pr.y * p.drop_scale : 0.f;
         pr.z = rnd.z >= p.drop_thresh ? pr.z * p.drop_scale : 0.f;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(256) attn_ds_bwd_kernel(const SmParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (int64_t)p.BH * p.T) return;
+  const uint64_t seed = ssb::eff_seed(p.seed, p.seed_src);
   const int q = (int)(row % p.T);
   const int64_t bh = row / p.T;
   const int b = (int)(bh / p.H), h = (int)(bh % p.H);
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(256) attn_ds_bwd_kernel(const SmParams p) {
       pv[i] = *reinterpret_cast<const float4*>(Prow + 4 * c4);
       float4 d = *reinterpret_cast<const float4*>(dProw + 4 * c4);
       if (p.drop_p > 0.f) {
-        const uint4 rnd = ssb::dropout_bits4(p.seed, p.site, (uint64_t)row * nv + c4);
+        const uint4 rnd = ssb::dropout_bits4(seed, p.site, (uint64_t)row * nv + c4);
         d.x = rnd.x >= p.drop_thresh ? d.x * p.drop_scale : 0.f;
         d.y = rnd.y >= p.drop_thresh ? d.y * p.drop_scale : 0.f;
         d.z = rnd.z >= p.drop_thresh ? d.z * p.drop_scale : 0.f;
@@ -237,7 +240,7 @@ int fill(SmParams* p, int64_t B, int64_t H, int64_t T, int64_t Tp, int64_t W, in
   p->drop_p = drop_p; p->drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const double th = (double)drop_p * 4294967296.0;
   p->drop_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
-  p->seed = seed; p->site = site;
+  p->seed = seed; p->seed_src = ssb::seed_source(); p->site = site;
   return SSB_OK;
 }
 

@@ -53,6 +53,7 @@ struct Epilogue {
   float drop_scale;
   uint32_t drop_thresh;
   uint64_t seed;
+  const uint64_t* seed_src;
   uint32_t site;
 };
 
@@ -246,7 +247,7 @@ gemm_kernel(const Gather ga, const float* __restrict__ Bplain, int ldb, const We
       }
       if (ep.drop_p > 0.f) {
         const uint64_t e = (uint64_t)oa * (uint64_t)N + (uint64_t)n;  // n % 4 == 0
-        const uint4 rnd = ssb::dropout_bits4(ep.seed, ep.site, e >> 2);
+        const uint4 rnd = ssb::dropout_bits4(ssb::eff_seed(ep.seed, ep.seed_src), ep.site, e >> 2);
         v.x = rnd.x >= ep.drop_thresh ? v.x * ep.drop_scale : 0.f;
         v.y = rnd.y >= ep.drop_thresh ? v.y * ep.drop_scale : 0.f;
         v.z = rnd.z >= ep.drop_thresh ? v.z * ep.drop_scale : 0.f;
@@ -304,7 +305,7 @@ int fill_epilogue(const ssb_epilogue_t* e, int64_t M, int64_t N, Epilogue* out) 
   out->drop_scale = e->drop_p > 0.f ? 1.f / (1.f - e->drop_p) : 1.f;
   const double th = (double)e->drop_p * 4294967296.0;
   out->drop_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
-  out->seed = e->seed; out->site = e->site;
+  out->seed = e->seed; out->seed_src = ssb::seed_source(); out->site = e->site;
   return SSB_OK;
 }
 

@@ -16,16 +16,19 @@
 //             and HALF of B (128 rows), so the shared-memory traffic per MMA drops from
 //             12 KB read + 12 KB.. to 8 KB read per SM -- the 1-CTA form is shared-memory-
 //             bandwidth bound at ~61 % tensor-pipe activity (profiles/r1_gemm_tc_persistent.txt).
-//             6 stages x 32 KB per CTA; the leader CTA (rank 0) issues every MMA, its mbarriers
+//             5 stages x 32 KB per CTA; the leader CTA (rank 0) issues every MMA, its mbarriers
 //             collect the TMA bytes of both CTAs, commits are multicast to both.
-//   CTAS = 1  one CTA per SM, 128 x 256 tiles, 4 stages x 48 KB (small / odd-shaped problems).
+//   CTAS = 1  one CTA per SM, 128 x 256 tiles, 3 stages x 48 KB (small / odd-shaped problems).
 //   warp 0    TMA producer: per 32-deep k-block, the A_hi/A_lo and B_hi/B_lo tiles land in
 //             swizzled shared memory, completion on an mbarrier (complete_tx).
 //   warp 1    TMEM allocator (2 x 256 fp32 columns) and single-thread MMA issuer: 2 x 3
 //             tcgen05.mma per k-block, tcgen05.commit releases the stage.
-//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns at a time, bias / ReLU / dropout /
-//             mask / accumulate / split-K reduction, fp32 stores through the same
-//             (batch, row) -> address map as the CUDA-core engine (gemm_simt.cu).
+//   warps 2-9 epilogue (two per TMEM lane group, on even / odd 32-column blocks): tcgen05.ld
+//             32 lanes x 32 columns at a time, bias / ReLU / dropout / mask / accumulate /
+//             split-K reduction, fp32 stores through the same (batch, row) -> address map as
+//             the CUDA-core engine (gemm_simt.cu).  With K = 768 a 256 x 256 tile is only 9.4 us
+//             of MMAs: four warps could not drain 128 KB per CTA (Philox dropout, mask reads)
+//             in that time, so FFN1 / its data gradient were epilogue-bound.
 //
 // Operand forms (all expressed by the TMA tensor maps built on the host):
 //   K-major  C[m,n] = sum_k A[m,k] B[n,k]      forward and data gradients.  A may be an im2col
@@ -49,10 +52,11 @@ constexpr int BM = 128, BN = 256, BK = 32;
 constexpr int A_PLANE = BM * BK * 2;   // 8 KB
 constexpr int MN_GROUP = BK * 128;     // bytes of one 64-element MN group of a stage (MN-major)
 constexpr int TMEM_COLS = 512;   // two 256-column fp32 accumulators
-constexpr int THREADS = 192;
+constexpr int EPI_WARPS = 8;        // two per TMEM lane group: even / odd 32-column blocks
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_ROW_BYTES = 36 * 4;                 // 32 fp32 + 4 pad: conflict-free both ways
 constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;    // one epilogue warp's transpose tile
-constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;         // 18 KB
+constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;  // 36 KB
 
 template <int CTAS>
 struct Cfg {
@@ -60,7 +64,7 @@ struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;                 // rows of B each CTA stages
   static constexpr int B_PLANE = B_ROWS * BK * 2;          // 16 KB / 8 KB
   static constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;   // 48 KB / 32 KB per CTA
-  static constexpr int STAGES = CTAS == 2 ? 6 : 4;
+  static constexpr int STAGES = CTAS == 2 ? 5 : 3;
   static constexpr int SMEM_BYTES =
       STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 };
@@ -84,7 +88,7 @@ struct TcParams {
   float* out; int64_t out_batch_stride, out_batch_stride_hi; int out_ld, out_dt, out_doff;
   const float* bias; const float* mask_src; float mask_scale;
   int relu, accumulate, atomic;
-  float drop_p, drop_scale; uint32_t drop_thresh; uint64_t seed; uint32_t site;
+  float drop_p, drop_scale; uint32_t drop_thresh; uint64_t seed; const uint64_t* seed_src; uint32_t site;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -235,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_ptr_smem = tempty_bar + 16;
-  const uint32_t epi_base = bars + 256;   // 4 x 4.5 KB transpose tiles of the epilogue warps
+  const uint32_t epi_base = bars + 256;   // 4.5 KB transpose tile per epilogue warp
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_smem - ssb::smem_u32(smem_raw)));
 
@@ -257,7 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, 4 * CTAS);   // one arrival per epilogue warp of every CTA
+      mbar_init(tempty_bar + 8 * a, EPI_WARPS * CTAS);   // one arrival per epilogue warp of every CTA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -405,7 +409,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // l1tex at 75 %), so the 32 x 32 block is transposed through a padded shared-memory tile
     // first: afterwards a warp instruction covers 4 rows x 128 contiguous bytes.
     const int lg = warp & 3;              // TMEM lane group this warp may read
-    const uint32_t stg = epi_base + (uint32_t)lg * EPI_WARP_BYTES;
+    const int ew = warp - 2;              // 0..7: warps 2-5 take even column blocks, 6-9 odd ones
+    const int cpar = ew >> 2;
+    const uint64_t seed = ssb::eff_seed(p.seed, p.seed_src);
+    const uint32_t stg = epi_base + (uint32_t)ew * EPI_WARP_BYTES;
     const int rsub = lane >> 3;           // after the transpose: row (i*4 + rsub) of the 32-row group,
     const int csub = (lane & 7) * 4;      // columns csub .. csub+3 of the 32-column block
     uint32_t tcount = 0;
@@ -413,8 +420,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int n0, batch, row0, f0, kb_begin, nkb;
       decode(tile, n0, batch, row0, f0, kb_begin, nkb);
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
-      mbar_wait(tfull_bar + 8 * acc, aph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // first row this lane stores (rows advance by 4 per i), its address and global row index
       int first, limit;
       float* orow0;
@@ -441,13 +446,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (nkb == 0) limit = 0;
       const int64_t row_step = (int64_t)4 * p.out_dt * p.out_ld;
       const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN + ((uint32_t)(lg * 32) << 16);
+      const bool group_live = first - rsub < limit;   // warp-uniform: not a pure padding row group
+      // Operands the epilogue READS (ReLU/dropout mask source, accumulate target) are fetched for
+      // the whole 32 x 32 block before the accumulator is touched: eight independent 16 B loads
+      // per lane in flight instead of one dependent HBM round trip per output row (the masked
+      // FFN data gradient ran at 548 us vs 265 us for the same-shape forward GEMM).
+      float4 side[8];
+      auto prefetch = [&](int c) {
+        const int n = n0 + c * 32 + csub;
+        if (!(p.mask_src || p.accumulate) || !group_live || n >= p.N) return;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (first + 4 * i >= limit) continue;
+          if (p.mask_src)
+            side[i] = __ldg(reinterpret_cast<const float4*>(p.mask_src + (grow0 + 4 * i) * p.N + n));
+          else
+            side[i] = *reinterpret_cast<const float4*>(orow0 + i * row_step + n);
+        }
+      };
+      prefetch(cpar);
+      mbar_wait(tfull_bar + 8 * acc, aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = cpar; c < BN / 32; c += 2) {
         if (n0 + c * 32 >= p.N) break;    // warp-uniform: nothing to store in this column block
         uint32_t v[32];
         tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (first - rsub >= limit) continue;   // warp-uniform: the whole 32-row group is padding
+        if (!group_live) continue;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
@@ -459,46 +485,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool n_ok = n < p.N;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && n_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        float4 o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 o;
+        for (int i = 0; i < 8; ++i)
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                       : "=f"(o[i].x), "=f"(o[i].y), "=f"(o[i].z), "=f"(o[i].w)
                        : "r"(stg + (uint32_t)(i * 4 + rsub) * EPI_ROW_BYTES + (uint32_t)csub * 4u)
                        : "memory");
+        __syncwarp();   // the staging tile is rewritten by the next column block
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
           if (!n_ok || first + 4 * i >= limit) continue;
+          float4 r = o[i];
           float* dst = orow0 + i * row_step + n;
           if (p.atomic) {
-            atomicAdd(reinterpret_cast<float4*>(dst), o);
+            atomicAdd(reinterpret_cast<float4*>(dst), r);
             continue;
           }
-          o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+          r.x += bias4.x; r.y += bias4.y; r.z += bias4.z; r.w += bias4.w;
           if (p.relu) {
-            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
           }
-          const int64_t grow = grow0 + 4 * i;
           if (p.drop_p > 0.f) {
-            const uint64_t e = (uint64_t)grow * (uint64_t)p.N + (uint64_t)n;
-            const uint4 rnd = ssb::dropout_bits4(p.seed, p.site, e >> 2);
-            o.x = rnd.x >= p.drop_thresh ? o.x * p.drop_scale : 0.f;
-            o.y = rnd.y >= p.drop_thresh ? o.y * p.drop_scale : 0.f;
-            o.z = rnd.z >= p.drop_thresh ? o.z * p.drop_scale : 0.f;
-            o.w = rnd.w >= p.drop_thresh ? o.w * p.drop_scale : 0.f;
+            const uint64_t e = (uint64_t)(grow0 + 4 * i) * (uint64_t)p.N + (uint64_t)n;
+            const uint4 rnd = ssb::dropout_bits4(seed, p.site, e >> 2);
+            r.x = rnd.x >= p.drop_thresh ? r.x * p.drop_scale : 0.f;
+            r.y = rnd.y >= p.drop_thresh ? r.y * p.drop_scale : 0.f;
+            r.z = rnd.z >= p.drop_thresh ? r.z * p.drop_scale : 0.f;
+            r.w = rnd.w >= p.drop_thresh ? r.w * p.drop_scale : 0.f;
           }
           if (p.mask_src) {
-            const float4 mk = __ldg(reinterpret_cast<const float4*>(p.mask_src + grow * p.N + n));
-            o.x = mk.x > 0.f ? o.x * p.mask_scale : 0.f;
-            o.y = mk.y > 0.f ? o.y * p.mask_scale : 0.f;
-            o.z = mk.z > 0.f ? o.z * p.mask_scale : 0.f;
-            o.w = mk.w > 0.f ? o.w * p.mask_scale : 0.f;
+            const float4 mk = side[i];
+            r.x = mk.x > 0.f ? r.x * p.mask_scale : 0.f;
+            r.y = mk.y > 0.f ? r.y * p.mask_scale : 0.f;
+            r.z = mk.z > 0.f ? r.z * p.mask_scale : 0.f;
+            r.w = mk.w > 0.f ? r.w * p.mask_scale : 0.f;
+          } else if (p.accumulate) {
+            const float4 old = side[i];
+            r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
           }
-          if (p.accumulate) {
-            const float4 old = *reinterpret_cast<const float4*>(dst);
-            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-          }
-          *reinterpret_cast<float4*>(dst) = o;
+          o[i] = r;
         }
-        __syncwarp();   // the staging tile is rewritten by the next column block
+        // next block's side operands go out before this block's stores queue up behind them
+        if (c + 2 < BN / 32) prefetch(c + 2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!n_ok || first + 4 * i >= limit || p.atomic) continue;
+          *reinterpret_cast<float4*>(orow0 + i * row_step + n) = o[i];
+        }
       }
       // hand the accumulator back to the (leader's) MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -681,7 +715,7 @@ int fill_epi(const ssb_epilogue_t* e, int64_t N, TcParams* p) {
   p->drop_p = e->drop_p; p->drop_scale = e->drop_p > 0.f ? 1.f / (1.f - e->drop_p) : 1.f;
   const double th = (double)e->drop_p * 4294967296.0;
   p->drop_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
-  p->seed = e->seed; p->site = e->site;
+  p->seed = e->seed; p->seed_src = ssb::seed_source(); p->site = e->site;
   p->N = (int)N;
   return SSB_OK;
 }

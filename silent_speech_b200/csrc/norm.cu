@@ -254,12 +254,14 @@ __global__ void __launch_bounds__(256)
 add_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ branch,
                   const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows,
                   int D, float eps, float drop_p, float drop_scale, uint32_t drop_thresh,
-                  uint64_t seed, uint32_t site, float* __restrict__ z_out,
+                  uint64_t seed_base, const uint64_t* __restrict__ seed_src, uint32_t site,
+                  float* __restrict__ z_out,
                   float* __restrict__ y, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  const uint64_t seed = ssb::eff_seed(seed_base, seed_src);
   const int nv = D >> 2;
   float4 z[LN_MAXV];
   float s = 0.f;
@@ -322,11 +324,13 @@ __global__ void __launch_bounds__(256)
 add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                   const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ gamma, int64_t rows, int D, float drop_p,
-                  float drop_scale, uint32_t drop_thresh, uint64_t seed, uint32_t site,
+                  float drop_scale, uint32_t drop_thresh, uint64_t seed_base,
+                  const uint64_t* __restrict__ seed_src, uint32_t site,
                   float* __restrict__ d_res, float* __restrict__ d_branch,
                   float* __restrict__ partials /* [nblk][2][D] : dgamma, dbeta */) {
   __shared__ float sm[2][1024];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t seed = ssb::eff_seed(seed_base, seed_src);
   const int nv = D >> 2;
   for (int i = threadIdx.x; i < 2 * 1024; i += 256) (&sm[0][0])[i] = 0.f;
   __syncthreads();
@@ -543,7 +547,7 @@ int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const float* g
   const unsigned grid = (unsigned)((rows + 7) / 8);
   add_ln_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       res, branch, gamma, beta, rows, (int)D, eps, drop_p, drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,
-      thresh_of(drop_p), seed, site, z_out, y, mean, rstd);
+      thresh_of(drop_p), seed, ssb::seed_source(), site, z_out, y, mean, rstd);
   SSB_LAUNCH_CHECK("add_ln_fwd");
   return SSB_OK;
 }
@@ -569,7 +573,8 @@ int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, c
   const int nblk = (int)((rows + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA);
   add_ln_bwd_kernel<<<nblk, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, (int)D, drop_p,
                                           drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,
-                                          thresh_of(drop_p), seed, site, d_res, d_branch,
+                                          thresh_of(drop_p), seed, ssb::seed_source(), site, d_res,
+                                          d_branch,
                                           (float*)workspace);
   SSB_LAUNCH_CHECK("add_ln_bwd");
   ln_param_grad_finalize_kernel<<<FIN_GRID(D), 0, st>>>((const float*)workspace, nblk, (int)D,

@@ -1,6 +1,7 @@
 // Library-level entry points: version, error string, device query.
 #include "ssb_common.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace ssb {
 
@@ -19,6 +20,10 @@ int cuda_fail(cudaError_t e, const char* what) {
   (void)cudaGetLastError();
   return (int)e;
 }
+
+static std::atomic<const uint64_t*> g_seed_src{nullptr};
+const uint64_t* seed_source() { return g_seed_src.load(std::memory_order_relaxed); }
+void set_seed_source(const uint64_t* p) { g_seed_src.store(p, std::memory_order_relaxed); }
 
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -40,6 +45,11 @@ extern "C" {
 int ssb_version(void) { return 100; }  // 0.1.0
 
 const char* ssb_last_error(void) { return ssb::g_err; }
+
+int ssb_set_seed_source(const uint64_t* dev_seed_offset) {
+  ssb::set_seed_source(dev_seed_offset);
+  return SSB_OK;
+}
 
 int ssb_device_sm_count(void) {
   int n = ssb::num_sms();

@@ -35,6 +35,10 @@ int  cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
+// Device-resident dropout seed offset (ssb_set_seed_source): when set, every dropout site keys
+// Philox with seed + *src, so a captured CUDA graph draws fresh masks on every replay.
+const uint64_t* seed_source();
+
 // ---- small device helpers ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -81,6 +85,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     key.y += W1;
   }
   return ctr;
+}
+
+__device__ __forceinline__ uint64_t eff_seed(uint64_t seed, const uint64_t* src) {
+  return src ? seed + __ldg(src) : seed;
 }
 
 // keep-mask for 4 consecutive elements starting at element index 4*idx4 of dropout site `site`.

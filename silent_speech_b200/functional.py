@@ -33,6 +33,20 @@ def _stream():
     return _lib.current_stream()
 
 
+def set_seed_source(cell):
+    """Register (or detach with None) the device-resident dropout-seed offset: a 1-element int64
+    CUDA tensor the caller keeps alive and bumps between CUDA-graph replays (include/ssb.h,
+    ssb_set_seed_source)."""
+    lib = _lib.load()
+    if cell is None:
+        _lib.check(lib.ssb_set_seed_source(None))
+        return
+    _lib.require_cuda(cell, "seed cell")
+    if cell.dtype != torch.int64 or cell.numel() != 1:
+        raise TypeError("seed cell must be a 1-element int64 CUDA tensor")
+    _lib.check(lib.ssb_set_seed_source(cell.data_ptr()))
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
