@@ -262,6 +262,31 @@ SSB_API int ssb_attn_ds_bwd(const float* P, const float* dP, int64_t B, int64_t 
                             uint64_t seed, uint32_t site, void* dS_planes, void* dSband_planes,
                             void* stream);
 
+/* ---- fused banded relative-position attention (csrc/attn_fused.cu) ----------------------------
+ * Replaces the body of MultiHeadAttention.forward (transformer.py:99-110) and its autograd
+ * backward between the QKV projection and the output projection, with the relative-position
+ * logits of LearnedRelativePositionalEmbedding (transformer.py:162-297) in closed form.
+ *   qkv_planes : bf16 (2, B*T, 3H, 128) split planes of [q heads | k heads | v heads], zero
+ *                padded to 128 per head (ssb_pad_split_heads)
+ *   R          : fp32 (B*H, T, RW) positional logits q . E[rel], rel = k - q + W
+ *   O          : fp32 (B*T, H*dh);  stat_m / stat_linv : fp32 (B*H, T) row max and 1 / sum exp
+ * dh in {32, 64, 96}, W <= 99, RW <= 200 (RW % 4 == 0).  Dropout keys as everywhere else
+ * (seed, site, element), identical masks in forward and backward. */
+SSB_API int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_t T, int64_t H,
+                       int64_t dh, int64_t W, int64_t RW, float drop_p, uint64_t seed, uint32_t site,
+                       float* O, float* stat_m, float* stat_linv, void* stream);
+/* delta[b*H+h, q] = sum_d dO * O over the head's dh columns */
+SSB_API int ssb_attn_delta(const float* O, const float* dO, int64_t B, int64_t T, int64_t H, int64_t dh,
+                   float* delta, void* stream);
+/* dqkv (B*T, 3*H*dh): the dQ third must be zero on entry (content part is accumulated with
+ * red.global.add), dK / dV thirds are overwritten.  dSband_planes: bf16 (2, B*T, H, RWp), zero on
+ * entry; receives dS in band layout for the positional part of dQ (a tensor-core GEMM with E). */
+SSB_API int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const float* R,
+                       const float* stat_m, const float* stat_linv, const float* delta, int64_t B,
+                       int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW, float drop_p,
+                       uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,12 @@ _SIGNATURES = {
                                      c_f32, c_u64, c_u32, c_ptr, c_ptr]),
     "ssb_attn_ds_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
                                 c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
+    "ssb_attn_fused_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
+                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ssb_attn_delta": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+    "ssb_attn_fused_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64,
+                                   c_i64, c_i64, c_i64, c_f32, c_u64, c_u32, c_ptr, c_ptr, c_i64,
+                                   c_ptr]),
     "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,
@@ -112,6 +118,7 @@ _KERNELS_PER_CALL = {
     "ssb_split_bf16": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,
     "ssb_gemm_tc_batched_tn": 1, "ssb_pad_split_heads": 1, "ssb_transpose_split_heads": 1,
     "ssb_attn_softmax_fwd": 1, "ssb_attn_ds_bwd": 1,
+    "ssb_attn_fused_fwd": 1, "ssb_attn_delta": 1, "ssb_attn_fused_bwd": 1,
 }
 launch_count = 0   # running total of libssb kernel launches issued by this process
 

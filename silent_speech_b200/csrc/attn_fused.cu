@@ -1,0 +1,909 @@
+// Fused banded relative-position attention on tcgen05 (sm_100a): forward and backward.
+//
+// Same mathematics as attn.cu / attn_tc.cu (transformer.py:99-110 with the relative-position
+// logits of :162-297 in closed form):  logits[q,k] = q.k / sqrt(dh) + q.E[k-q+W]  inside the band
+// |k-q| <= W, softmax over k, dropout on the probabilities, O = P_drop V.  The multi-kernel
+// tensor-core schedule (attn_tc.cu) materialises dense (T x T) logits, probabilities and their
+// gradients in HBM: ~3.5 GB of traffic per layer for 13 GFLOP of band arithmetic, 29 % of the
+// cfg-1 training step.  Here nothing T x T leaves the SM:
+//
+//   forward   one CTA per (b, h, 128 queries); TMEM lane = query.  Q stays in shared memory,
+//             keys stream in 32-row chunks: S = Q K^T for the whole +-W window sits in TMEM
+//             (<= 352 fp32 columns); one thread per query row adds the positional logits from
+//             a 128 x RW shared-memory tile of R = Q E^T (skewed read, bank-conflict free),
+//             takes max / exp / sum, applies dropout and writes un-normalised P as bf16 hi/lo
+//             planes straight into the canonical SWIZZLE_64B K-major operand layout;
+//             O += P V_chunk accumulates in TMEM (V read MN-major from its natural [key][d]
+//             layout: no transposed copy), divided by the row sum at the end.  Saves (max, 1/sum).
+//   backward  one CTA per (b, h, 128 keys); TMEM lane = key, queries stream in 32-row chunks.
+//             S^T = K Q_c^T and dP^T = V dO_c^T are recomputed on the tensor cores, one thread
+//             per key forms P and dS = P (dP_drop - delta) from the saved row statistics, and the
+//             P_drop^T / dS^T tiles (software-written operand layout again) feed
+//             dV += P_drop^T dO_c, dK += dS^T Q_c (TMEM accumulators, stored once per tile) and
+//             dQ_c^T = K^T dS^T (lanes = head dim, red.global.add into dQ, coalesced).  dS is
+//             also written in band layout (bf16 planes) for the positional part of dQ, which
+//             stays a batched tensor-core GEMM with E (no gradient flows to E: SURVEY.md F3).
+//
+// Every product is bf16x3 (hi*hi + hi*lo + lo*hi, fp32 accumulation) like gemm_tc.cu.  The
+// operand formats used here (software-written SW64/SW128 K-major and MN-major tiles, one tile
+// under two roles) are pinned by tools/umma_probe.cu.
+#include "ssb_common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math_constants.h>
+#include <mutex>
+
+namespace {
+
+constexpr int QT = 128;          // TMEM lanes per tile (queries fwd, keys bwd)
+constexpr int CH = 32;           // streamed chunk rows (keys fwd, queries bwd)
+constexpr int DB = 32;           // head-dim block: one SWIZZLE_64B row (64 B of bf16)
+constexpr int BLK_BIG = QT * 64;   // bytes of a [128 rows][32 d] block  (8 KB)
+constexpr int BLK_SMALL = CH * 64; // bytes of a [32 rows][32 d] block   (2 KB)
+constexpr int MAX_NDB = 3;       // dh <= 96
+
+constexpr int KST = 3;           // forward: K / V ring depth
+constexpr int RBOX = 164;        // backward: width of a positional-logit box (159 needed, + <= 3 because
+                                 // the box must start on a 16 B boundary of the fp32 row)
+
+// ---- PTX wrappers (same forms as gemm_tc.cu) ---------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// wait for the n-th completion (n = 0, 1, ...) of a barrier that completes once per round
+__device__ __forceinline__ void mbar_wait_nth(uint32_t bar, int n) { mbar_wait(bar, (uint32_t)n & 1u); }
+
+__device__ __forceinline__ void tma_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                       int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                       int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// shared-memory matrix descriptor; layout 4 = SWIZZLE_64B (rows of 64 B, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t desc64(uint32_t addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// instruction descriptor: D = f32, A = B = bf16, M = 128
+__device__ __forceinline__ uint32_t idesc(int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+}
+// byte offset of 8 consecutive elements (16 B chunk `ch` = 0..3) of row `row` in a SW64 tile
+__device__ __forceinline__ uint32_t sw64_off(int row, int ch) {
+  return (uint32_t)(row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// (hi, lo) split of two values, packed pairwise
+__device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
+  lo = pack_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+}
+
+struct FusedParams {
+  int B, H, T, dh, ndb, W, RW, Tp4;       // Tp4 = round_up(T, 64) / 4: dropout counter pitch
+  float scale, drop_p, drop_scale;
+  uint32_t drop_thresh;
+  uint64_t seed;
+  const uint64_t* seed_src;
+  uint32_t site;
+  // forward
+  float* O;          // (B*T, H*dh)
+  float* stat_m;     // (B*H, T) row max of the logits
+  float* stat_linv;  // (B*H, T) 1 / sum exp
+  // backward
+  const float* delta;   // (B*H, T)  sum_d dO * O
+  float* dqkv;          // (B*T, 3*H*dh): dQ accumulated atomically (pre-zeroed), dK / dV stored
+  __nv_bfloat16* dsb;   // (2, B*T, H, RWp) band-layout dS planes (pre-zeroed)
+  int RWp;
+};
+
+// =================================================================================================
+// forward
+// =================================================================================================
+struct FwdSmem {   // byte offsets from the 1024-aligned base
+  static constexpr int Q = 0;                                         // 2 planes x ndb x 8 KB
+  static constexpr int KRING = Q + 2 * MAX_NDB * BLK_BIG;             // 48 KB
+  static constexpr int KSTAGE = 2 * MAX_NDB * BLK_SMALL;              // 12 KB
+  static constexpr int PHASE1_END = KRING + KST * KSTAGE;             // 84 KB
+  // phase 2 aliases the Q / K region once every S MMA has retired
+  static constexpr int VRING = 0;
+  static constexpr int PT = VRING + KST * KSTAGE;                     // 2 x (2 planes x 8 KB)
+  static constexpr int PHASE2_END = PT + 2 * 2 * BLK_BIG;             // 68 KB
+  static constexpr int R = PHASE1_END;                                // 128 x RW fp32 (<= 100 KB)
+  static constexpr int BARS = R + QT * 200 * 4;
+  static constexpr int TOTAL = BARS + 256;
+};
+static_assert(FwdSmem::PHASE2_END <= FwdSmem::PHASE1_END, "phase-2 buffers must fit the alias");
+
+__global__ void __launch_bounds__(160, 1)
+attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapR,
+                      const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ssb::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ssb::smem_u32(smem_raw));
+  const uint32_t bars = base + FwdSmem::BARS;
+  const uint32_t bar_q = bars, bar_r = bars + 8, bar_s = bars + 16, bar_o = bars + 24;
+  const uint32_t kfull = bars + 32, kempty = kfull + 8 * KST, vfull = kempty + 8 * KST,
+                 vempty = vfull + 8 * KST, pfull = vempty + 8 * KST, pempty = pfull + 16;
+  const uint32_t tmem_slot = pempty + 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
+  const int q0 = blockIdx.x * QT;
+  const int ndb = p.ndb;
+  // key window of this query tile (start rounded down to a dropout group of 4 keys)
+  const int kw0 = max(0, q0 - p.W) & ~7;
+  const int kw1 = min(p.T, q0 + QT + p.W);
+  const int nch = (kw1 - kw0 + CH - 1) / CH;
+  const int plane_q = ndb * BLK_BIG, plane_k = ndb * BLK_SMALL;
+
+  if (threadIdx.x == 128) {
+    for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);
+    for (int s = 0; s < KST; ++s) {
+      mbar_init(kfull + 8 * s, 1); mbar_init(kempty + 8 * s, 1);
+      mbar_init(vfull + 8 * s, 1); mbar_init(vempty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) { mbar_init(pfull + 8 * s, 4); mbar_init(pempty + 8 * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  const uint32_t tmem_o = tmem + 352;   // O accumulator columns [352, 352 + dh)
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- control thread: TMA + MMA issue ----------------
+      mbar_expect_tx(bar_q, 2 * ndb * BLK_BIG);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int blk = 0; blk < ndb; ++blk)
+          tma_5d(base + FwdSmem::Q + pl * plane_q + blk * BLK_BIG, &mapQ, bar_q, blk * DB, q0, h, b, pl);
+      mbar_expect_tx(bar_r, QT * p.RW * 4);
+      tma_3d(base + FwdSmem::R, &mapR, bar_r, 0, q0, bh);
+      auto load_kv = [&](const CUtensorMap* map, uint32_t ring, uint32_t full, int j) {
+        const int s = j % KST;
+        mbar_expect_tx(full + 8 * s, 2 * ndb * BLK_SMALL);
+        for (int pl = 0; pl < 2; ++pl)
+          for (int blk = 0; blk < ndb; ++blk)
+            tma_5d(ring + s * FwdSmem::KSTAGE + pl * plane_k + blk * BLK_SMALL, map, full + 8 * s,
+                   blk * DB, kw0 + j * CH, h, b, pl);
+      };
+      for (int j = 0; j < KST && j < nch; ++j) load_kv(&mapK, base + FwdSmem::KRING, kfull, j);
+      // phase 1: S[:, 32 j .. 32 j + 32) = Q K_j^T
+      const uint32_t id_s = idesc(CH, 0, 0);
+      mbar_wait(bar_q, 0);
+      for (int j = 0; j < nch; ++j) {
+        const int s = j % KST;
+        mbar_wait(kfull + 8 * s, (uint32_t)(j / KST) & 1u);
+        tc_fence_after();
+        const uint32_t qa = base + FwdSmem::Q, kb = base + FwdSmem::KRING + s * FwdSmem::KSTAGE;
+        const uint32_t d = tmem + (uint32_t)(j * CH);
+        uint32_t acc = 0;
+        for (int blk = 0; blk < ndb; ++blk)
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ah = desc64(qa + blk * BLK_BIG + ks * 32, 16);
+            const uint64_t al = desc64(qa + plane_q + blk * BLK_BIG + ks * 32, 16);
+            const uint64_t bhh = desc64(kb + blk * BLK_SMALL + ks * 32, 16);
+            const uint64_t bl = desc64(kb + plane_k + blk * BLK_SMALL + ks * 32, 16);
+            umma(d, ah, bhh, id_s, acc);
+            umma(d, ah, bl, id_s, 1u);
+            umma(d, al, bhh, id_s, 1u);
+            acc = 1u;
+          }
+        umma_commit(kempty + 8 * s);
+        if (j >= 1 && j - 1 + KST < nch) {   // refill the stage chunk j-1 used (its MMAs are older)
+          mbar_wait(kempty + 8 * ((j - 1) % KST), (uint32_t)((j - 1) / KST) & 1u);
+          load_kv(&mapK, base + FwdSmem::KRING, kfull, j - 1 + KST);
+        }
+      }
+      umma_commit(bar_s);
+      // phase 2: the Q / K region is dead once every S MMA retired
+      mbar_wait(bar_s, 0);
+      for (int j = 0; j < KST && j < nch; ++j) load_kv(&mapV, base + FwdSmem::VRING, vfull, j);
+      const uint32_t id_o = idesc(p.dh, 0, 1);
+      for (int j = 0; j < nch; ++j) {
+        const int s = j % KST, pb = j & 1;
+        mbar_wait(vfull + 8 * s, (uint32_t)(j / KST) & 1u);
+        mbar_wait(pfull + 8 * pb, (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t pa = base + FwdSmem::PT + pb * 2 * BLK_BIG;
+        const uint32_t vb = base + FwdSmem::VRING + s * FwdSmem::KSTAGE;
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t ah = desc64(pa + ks * 32, 16), al = desc64(pa + BLK_BIG + ks * 32, 16);
+          // V chunk [32 keys][dh] read MN-major: 16-key k-steps 1 KB apart, 32-wide d groups 2 KB apart
+          const uint64_t bhh = desc64(vb + ks * 1024, BLK_SMALL);
+          const uint64_t bl = desc64(vb + plane_k + ks * 1024, BLK_SMALL);
+          umma(tmem_o, ah, bhh, id_o, (j > 0 || ks > 0) ? 1u : 0u);
+          umma(tmem_o, ah, bl, id_o, 1u);
+          umma(tmem_o, al, bhh, id_o, 1u);
+        }
+        umma_commit(pempty + 8 * pb);
+        umma_commit(vempty + 8 * s);
+        if (j >= 1 && j - 1 + KST < nch) {
+          mbar_wait(vempty + 8 * ((j - 1) % KST), (uint32_t)((j - 1) / KST) & 1u);
+          load_kv(&mapV, base + FwdSmem::VRING, vfull, j - 1 + KST);
+        }
+      }
+      umma_commit(bar_o);
+    }
+  } else {
+    // ---------------- softmax threads: one query row each ----------------
+    const int i = threadIdx.x;            // row of the tile = TMEM lane
+    const int q = q0 + i;
+    const bool row_ok = q < p.T;
+    const uint64_t seed = ssb::eff_seed(p.seed, p.seed_src);
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t rrow = base + FwdSmem::R + (uint32_t)(i * p.RW) * 4u;
+    const int soff = kw0 - q + p.W;       // rel = column + soff
+    mbar_wait(bar_r, 0);
+    mbar_wait(bar_s, 0);
+    tc_fence_after();
+    float m = -CUDART_INF_F;
+    for (int j = 0; j < nch; ++j) {
+      uint32_t v[32];
+      tmem_ld32(tlane + (uint32_t)(j * CH), v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int col = j * CH + c, rel = col + soff;
+        if (row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W)
+          m = fmaxf(m, fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u)));
+      }
+    }
+    float sum = 0.f;
+    const int64_t drow = ((int64_t)bh * p.T + q) * p.Tp4;
+    for (int j = 0; j < nch; ++j) {
+      const int pb = j & 1;
+      uint32_t v[32];
+      tmem_ld32(tlane + (uint32_t)(j * CH), v);
+      tmem_wait_ld();
+      float e[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int col = j * CH + c, rel = col + soff;
+        const bool inb = row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W;
+        float x = 0.f;
+        if (inb)
+          x = expf(fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u)) - m);
+        e[c] = x;
+        sum += x;
+      }
+      if (p.drop_p > 0.f && row_ok) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const uint4 rnd = ssb::dropout_bits4(seed, p.site, (uint64_t)(drow + ((kw0 + j * CH) >> 2) + g));
+          e[4 * g + 0] = rnd.x >= p.drop_thresh ? e[4 * g + 0] * p.drop_scale : 0.f;
+          e[4 * g + 1] = rnd.y >= p.drop_thresh ? e[4 * g + 1] * p.drop_scale : 0.f;
+          e[4 * g + 2] = rnd.z >= p.drop_thresh ? e[4 * g + 2] * p.drop_scale : 0.f;
+          e[4 * g + 3] = rnd.w >= p.drop_thresh ? e[4 * g + 3] * p.drop_scale : 0.f;
+        }
+      }
+      // the P buffer is free once the MMAs of chunk j-2 have retired
+      if (j >= 2) mbar_wait(pempty + 8 * pb, (uint32_t)((j - 2) >> 1) & 1u);
+      const uint32_t pt = base + FwdSmem::PT + pb * 2 * BLK_BIG;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 hi, lo;
+        split_pack(e[8 * ch + 0], e[8 * ch + 1], hi.x, lo.x);
+        split_pack(e[8 * ch + 2], e[8 * ch + 3], hi.y, lo.y);
+        split_pack(e[8 * ch + 4], e[8 * ch + 5], hi.z, lo.z);
+        split_pack(e[8 * ch + 6], e[8 * ch + 7], hi.w, lo.w);
+        const uint32_t off = sw64_off(i, ch);
+        st_shared_v4(pt + off, hi);
+        st_shared_v4(pt + BLK_BIG + off, lo);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pfull + 8 * pb);
+    }
+    // epilogue: O = acc / sum
+    mbar_wait(bar_o, 0);
+    tc_fence_after();
+    const float linv = row_ok ? 1.f / sum : 0.f;
+    if (row_ok) {
+      p.stat_m[(int64_t)bh * p.T + q] = m;
+      p.stat_linv[(int64_t)bh * p.T + q] = linv;
+    }
+    float* orow = p.O + ((int64_t)b * p.T + q) * (p.H * p.dh) + h * p.dh;
+    for (int c0 = 0; c0 < p.dh; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tmem_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(orow + c0 + c) =
+              make_float4(__uint_as_float(v[c]) * linv, __uint_as_float(v[c + 1]) * linv,
+                          __uint_as_float(v[c + 2]) * linv, __uint_as_float(v[c + 3]) * linv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+struct BwdSmem {
+  static constexpr int K = 0;                                        // 2 planes x ndb x 8 KB
+  static constexpr int V = K + 2 * MAX_NDB * BLK_BIG;                // 48 KB
+  static constexpr int QD = V + 2 * MAX_NDB * BLK_BIG;               // 96 KB: 2 x {Q_c, dO_c}
+  static constexpr int QD_HALF = 2 * MAX_NDB * BLK_SMALL;            // 12 KB (Q_c or dO_c)
+  static constexpr int QD_STAGE = 2 * QD_HALF;                       // 24 KB
+  static constexpr int PD = QD + 2 * QD_STAGE;                       // 144 KB: P_drop^T planes
+  static constexpr int DS = PD + 2 * BLK_BIG;                        // 160 KB: dS^T planes
+  static constexpr int R = DS + 2 * BLK_BIG;                         // 176 KB: 2 x [32][164] fp32
+  static constexpr int R_STAGE = CH * RBOX * 4;                      // 20 KB
+  static constexpr int STATS = R + 2 * R_STAGE;                      // 216 KB: 2 x 3 x 32 fp32
+  static constexpr int BARS = STATS + 2 * 3 * CH * 4;
+  static constexpr int TOTAL = BARS + 256;
+};
+
+__global__ void __launch_bounds__(160, 1)
+attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
+                      const __grid_constant__ CUtensorMap mapR, const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ssb::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - ssb::smem_u32(smem_raw));
+  const uint32_t bars = base + BwdSmem::BARS;
+  const uint32_t kv_full = bars, qd_full = bars + 8 /*[2]*/, r_full = bars + 24 /*[2]*/,
+                 r_free = bars + 40 /*[2]*/, s_full = bars + 56 /*[2]*/, sp_free = bars + 72 /*[2]*/,
+                 tiles_full = bars + 88, mma2_done = bars + 96, ep_done = bars + 104 /*[2]*/;
+  const uint32_t tmem_slot = bars + 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
+  const int k0 = blockIdx.x * QT;
+  const int ndb = p.ndb;
+  const int qw0 = max(0, k0 - p.W);
+  const int qw1 = min(p.T, k0 + QT + p.W);
+  const int nch = (qw1 - qw0 + CH - 1) / CH;
+  const int plane_big = ndb * BLK_BIG, plane_small = ndb * BLK_SMALL;
+
+  if (threadIdx.x == 128) {
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(qd_full + 8 * s, 1); mbar_init(r_full + 8 * s, 1); mbar_init(r_free + 8 * s, 4);
+      mbar_init(s_full + 8 * s, 1); mbar_init(sp_free + 8 * s, 4); mbar_init(ep_done + 8 * s, 4);
+    }
+    mbar_init(tiles_full, 4);
+    mbar_init(mma2_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  // TMEM columns: [0,128) two {S^T, dP^T} pairs, [128,256) dV, [256,384) dK, [384,448) two dQ^T
+  const uint32_t t_dv = tmem + 128, t_dk = tmem + 256, t_dq = tmem + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- control thread ----------------
+      mbar_expect_tx(kv_full, 4 * ndb * BLK_BIG);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int blk = 0; blk < ndb; ++blk) {
+          tma_5d(base + BwdSmem::K + pl * plane_big + blk * BLK_BIG, &mapK, kv_full, blk * DB, k0, h, b, pl);
+          tma_5d(base + BwdSmem::V + pl * plane_big + blk * BLK_BIG, &mapV, kv_full, blk * DB, k0, h, b, pl);
+        }
+      auto load_qd = [&](int j) {
+        const int s = j & 1;
+        const uint32_t dst = base + BwdSmem::QD + s * BwdSmem::QD_STAGE;
+        mbar_expect_tx(qd_full + 8 * s, 4 * ndb * BLK_SMALL);
+        for (int pl = 0; pl < 2; ++pl)
+          for (int blk = 0; blk < ndb; ++blk) {
+            tma_5d(dst + pl * plane_small + blk * BLK_SMALL, &mapQ, qd_full + 8 * s, blk * DB,
+                   qw0 + j * CH, h, b, pl);
+            tma_5d(dst + BwdSmem::QD_HALF + pl * plane_small + blk * BLK_SMALL, &mapDO,
+                   qd_full + 8 * s, blk * DB, qw0 + j * CH, h, b, pl);
+          }
+      };
+      auto load_r = [&](int j) {
+        const int s = j & 1;
+        mbar_expect_tx(r_full + 8 * s, BwdSmem::R_STAGE);
+        // columns rel0 .. rel0 + 158 of rows q_c .. q_c + 31 (start rounded down to 4 floats: TMA
+        // faults on an inner coordinate that is not 16 B aligned); out-of-range parts are zero-filled
+        const int rel0 = k0 - (qw0 + j * CH) - (CH - 1) + p.W;
+        tma_3d(base + BwdSmem::R + s * BwdSmem::R_STAGE, &mapR, r_full + 8 * s, rel0 & ~3,
+               qw0 + j * CH, bh);
+      };
+      load_qd(0);
+      load_r(0);
+      if (nch > 1) { load_qd(1); load_r(1); }
+      const uint32_t id_s = idesc(CH, 0, 0), id_acc = idesc(p.dh, 0, 1), id_dq = idesc(CH, 1, 1);
+      auto mma1 = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(qd_full + 8 * s, (uint32_t)(j >> 1) & 1u);
+        if (j >= 2) mbar_wait(sp_free + 8 * s, (uint32_t)((j - 2) >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t qb = base + BwdSmem::QD + s * BwdSmem::QD_STAGE, dob = qb + BwdSmem::QD_HALF;
+        const uint32_t ka = base + BwdSmem::K, va = base + BwdSmem::V;
+        const uint32_t d_s = tmem + s * 64, d_p = d_s + 32;
+        uint32_t acc = 0;
+        for (int blk = 0; blk < ndb; ++blk)
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t oa = blk * BLK_BIG + ks * 32, ob = blk * BLK_SMALL + ks * 32;
+            umma(d_s, desc64(ka + oa, 16), desc64(qb + ob, 16), id_s, acc);
+            umma(d_s, desc64(ka + oa, 16), desc64(qb + plane_small + ob, 16), id_s, 1u);
+            umma(d_s, desc64(ka + plane_big + oa, 16), desc64(qb + ob, 16), id_s, 1u);
+            umma(d_p, desc64(va + oa, 16), desc64(dob + ob, 16), id_s, acc);
+            umma(d_p, desc64(va + oa, 16), desc64(dob + plane_small + ob, 16), id_s, 1u);
+            umma(d_p, desc64(va + plane_big + oa, 16), desc64(dob + ob, 16), id_s, 1u);
+            acc = 1u;
+          }
+        umma_commit(s_full + 8 * s);
+      };
+      mbar_wait(kv_full, 0);
+      mma1(0);
+      for (int j = 0; j < nch; ++j) {
+        if (j + 1 < nch) mma1(j + 1);
+        // second group of chunk j: needs its P_drop^T / dS^T tiles and a free dQ^T accumulator
+        const int s = j & 1;
+        mbar_wait_nth(tiles_full, j);
+        if (j >= 2) mbar_wait(ep_done + 8 * s, (uint32_t)((j - 2) >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t qb = base + BwdSmem::QD + s * BwdSmem::QD_STAGE, dob = qb + BwdSmem::QD_HALF;
+        const uint32_t pd = base + BwdSmem::PD, ds = base + BwdSmem::DS, ka = base + BwdSmem::K;
+        for (int ks = 0; ks < 2; ++ks) {   // K = 32 queries
+          const uint32_t oa = ks * 32, ob = ks * 1024;
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          umma(t_dv, desc64(pd + oa, 16), desc64(dob + ob, BLK_SMALL), id_acc, acc);
+          umma(t_dv, desc64(pd + oa, 16), desc64(dob + plane_small + ob, BLK_SMALL), id_acc, 1u);
+          umma(t_dv, desc64(pd + BLK_BIG + oa, 16), desc64(dob + ob, BLK_SMALL), id_acc, 1u);
+          umma(t_dk, desc64(ds + oa, 16), desc64(qb + ob, BLK_SMALL), id_acc, acc);
+          umma(t_dk, desc64(ds + oa, 16), desc64(qb + plane_small + ob, BLK_SMALL), id_acc, 1u);
+          umma(t_dk, desc64(ds + BLK_BIG + oa, 16), desc64(qb + ob, BLK_SMALL), id_acc, 1u);
+        }
+        // dQ_c^T [d][q] = K^T dS^T: both operands MN-major (rows = keys), K = 128 keys
+        const uint32_t d_q = t_dq + s * 32;
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t o = ks * 1024;
+          umma(d_q, desc64(ka + o, BLK_BIG), desc64(ds + o, BLK_BIG), id_dq, ks > 0 ? 1u : 0u);
+          umma(d_q, desc64(ka + o, BLK_BIG), desc64(ds + BLK_BIG + o, BLK_BIG), id_dq, 1u);
+          umma(d_q, desc64(ka + plane_big + o, BLK_BIG), desc64(ds + o, BLK_BIG), id_dq, 1u);
+        }
+        umma_commit(mma2_done);
+        // refill: {Q, dO} stage s is free when these MMAs retire; R stage s when the threads left it
+        if (j + 2 < nch) {
+          mbar_wait_nth(mma2_done, j);
+          load_qd(j + 2);
+          mbar_wait(r_free + 8 * s, (uint32_t)(j >> 1) & 1u);
+          load_r(j + 2);
+        }
+      }
+    }
+  } else {
+    // ---------------- one thread per key ----------------
+    const int i = threadIdx.x;
+    const int k = k0 + i;
+    const bool key_ok = k < p.T;
+    const int quad = lane & 3;
+    const uint64_t seed = ssb::eff_seed(p.seed, p.seed_src);
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int D = p.H * p.dh;
+    const int64_t band_plane = (int64_t)p.B * p.T * p.H * p.RWp;
+
+    // dQ_c^T: lane = head-dim index, column = query of chunk j.  `wait` only for the last chunk:
+    // earlier ones are called after this thread already observed completion j of mma2_done (a
+    // second wait on the same phase could miss it once the barrier has moved two phases on).
+    auto dq_epilogue = [&](int j, bool wait) {
+      const int s = j & 1;
+      if (wait) mbar_wait_nth(mma2_done, j);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tlane + 384 + (uint32_t)(s * 32), v);
+      tmem_wait_ld();
+      if (i < p.dh) {
+        float* dst = p.dqkv + ((int64_t)b * p.T + qw0 + j * CH) * (3 * D) + h * p.dh + i;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (qw0 + j * CH + c < p.T) atomicAdd(dst + (int64_t)c * (3 * D), __uint_as_float(v[c]) * p.scale);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ep_done + 8 * s);
+    };
+
+    for (int j = 0; j < nch; ++j) {
+      const int s = j & 1;
+      const int qc = qw0 + j * CH;
+      // row statistics of the chunk's queries -> shared memory (broadcast reads below)
+      float* st = reinterpret_cast<float*>(gen + BwdSmem::STATS) + s * 3 * CH;
+      if (i < 3 * CH) {
+        const int which = i / CH, c = i - which * CH, q = qc + c;
+        const float* src = which == 0 ? p.stat_m : which == 1 ? p.stat_linv : p.delta;
+        st[i] = q < p.T ? __ldg(src + (int64_t)bh * p.T + q) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(r_full + 8 * s, (uint32_t)(j >> 1) & 1u);
+      mbar_wait(s_full + 8 * s, (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tlane + (uint32_t)(s * 64), sv);
+      tmem_ld32(tlane + (uint32_t)(s * 64 + 32), dv);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sp_free + 8 * s);
+      // positional logits: box column = rel - (rel0 & ~3) = i - c + 31 + (rel0 & 3), row c
+      const int rsh = (k0 - qc - (CH - 1) + p.W) & 3;
+      const uint32_t rbase =
+          base + BwdSmem::R + s * BwdSmem::R_STAGE + (uint32_t)(i + CH - 1 + rsh) * 4u;
+      float pdv[32], dsv[32];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        // dropout words: one Philox call covers 4 consecutive keys (this quad) of one query;
+        // lane `quad` draws for column 4g + quad, then the 4 x 4 block is transposed in the quad
+        uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+        if (p.drop_p > 0.f) {
+          const int qd = qc + 4 * g + quad;
+          const uint4 rnd = ssb::dropout_bits4(
+              seed, p.site, (uint64_t)(((int64_t)bh * p.T + qd) * p.Tp4 + (k >> 2)));
+          w[0] = rnd.x; w[1] = rnd.y; w[2] = rnd.z; w[3] = rnd.w;
+          uint32_t x0 = (quad & 2) ? w[0] : w[2], x1 = (quad & 2) ? w[1] : w[3];
+          x0 = __shfl_xor_sync(0xffffffffu, x0, 2);
+          x1 = __shfl_xor_sync(0xffffffffu, x1, 2);
+          if (quad & 2) { w[0] = x0; w[1] = x1; } else { w[2] = x0; w[3] = x1; }
+          uint32_t y0 = (quad & 1) ? w[0] : w[1], y1 = (quad & 1) ? w[2] : w[3];
+          y0 = __shfl_xor_sync(0xffffffffu, y0, 1);
+          y1 = __shfl_xor_sync(0xffffffffu, y1, 1);
+          if (quad & 1) { w[0] = y0; w[2] = y1; } else { w[1] = y0; w[3] = y1; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = 4 * g + u, q = qc + c, rel = k - q + p.W;
+          const bool inb = key_ok && q < p.T && rel >= 0 && rel <= 2 * p.W;
+          float pr = 0.f;
+          if (inb) {
+            const float x = fmaf(__uint_as_float(sv[c]), p.scale,
+                                 ld_shared_f32(rbase + (uint32_t)(c * (RBOX - 1)) * 4u));
+            pr = expf(x - st[c]) * st[CH + c];
+          }
+          const bool keep = w[u] >= p.drop_thresh;
+          const float dpm = (keep && inb) ? __uint_as_float(dv[c]) * p.drop_scale : 0.f;
+          pdv[c] = keep ? pr * p.drop_scale : 0.f;
+          dsv[c] = pr * (dpm - st[2 * CH + c]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(r_free + 8 * s);
+      // band-layout dS (unscaled) for the positional part of dQ: consecutive lanes = consecutive rel
+      if (key_ok) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int q = qc + c, rel = k - q + p.W;
+          if (q < p.T && rel >= 0 && rel <= 2 * p.W) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(dsv[c]);
+            const int64_t o = (((int64_t)b * p.T + q) * p.H + h) * p.RWp + rel;
+            p.dsb[o] = hi;
+            p.dsb[band_plane + o] = __float2bfloat16_rn(dsv[c] - __bfloat162float(hi));
+          }
+        }
+      }
+      // the tiles are free once the second MMA group of chunk j-1 has retired
+      if (j >= 1) mbar_wait_nth(mma2_done, j - 1);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 hi, lo;
+        const uint32_t off = sw64_off(i, ch);
+        split_pack(pdv[8 * ch + 0], pdv[8 * ch + 1], hi.x, lo.x);
+        split_pack(pdv[8 * ch + 2], pdv[8 * ch + 3], hi.y, lo.y);
+        split_pack(pdv[8 * ch + 4], pdv[8 * ch + 5], hi.z, lo.z);
+        split_pack(pdv[8 * ch + 6], pdv[8 * ch + 7], hi.w, lo.w);
+        st_shared_v4(base + BwdSmem::PD + off, hi);
+        st_shared_v4(base + BwdSmem::PD + BLK_BIG + off, lo);
+        split_pack(dsv[8 * ch + 0], dsv[8 * ch + 1], hi.x, lo.x);
+        split_pack(dsv[8 * ch + 2], dsv[8 * ch + 3], hi.y, lo.y);
+        split_pack(dsv[8 * ch + 4], dsv[8 * ch + 5], hi.z, lo.z);
+        split_pack(dsv[8 * ch + 6], dsv[8 * ch + 7], hi.w, lo.w);
+        st_shared_v4(base + BwdSmem::DS + off, hi);
+        st_shared_v4(base + BwdSmem::DS + BLK_BIG + off, lo);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tiles_full);
+      if (j >= 1) dq_epilogue(j - 1, false);
+    }
+    dq_epilogue(nch - 1, true);   // also: every MMA of the tile has retired -> dV / dK are complete
+    float* krow = p.dqkv + ((int64_t)b * p.T + k) * (3 * D) + D + h * p.dh;
+    for (int c0 = 0; c0 < p.dh; c0 += 32) {
+      uint32_t a[32], g[32];
+      tmem_ld32(tlane + 256 + (uint32_t)c0, a);
+      tmem_ld32(tlane + 128 + (uint32_t)c0, g);
+      tmem_wait_ld();
+      if (key_ok) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          *reinterpret_cast<float4*>(krow + c0 + c) =
+              make_float4(__uint_as_float(a[c]) * p.scale, __uint_as_float(a[c + 1]) * p.scale,
+                          __uint_as_float(a[c + 2]) * p.scale, __uint_as_float(a[c + 3]) * p.scale);
+          *reinterpret_cast<float4*>(krow + D + c0 + c) =
+              make_float4(__uint_as_float(g[c]), __uint_as_float(g[c + 1]),
+                          __uint_as_float(g[c + 2]), __uint_as_float(g[c + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+  }
+}
+
+// delta[bh, q] = sum_d dO[b*T+q, h*dh+d] * O[...]: one warp per (row, head)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const float* __restrict__ O, const float* __restrict__ dO, int64_t rows, int T, int H,
+                  int dh, float* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (w >= rows * H) return;
+  const int64_t row = w / H;
+  const int h = (int)(w - row * H);
+  const float* a = O + row * (int64_t)(H * dh) + h * dh;
+  const float* g = dO + row * (int64_t)(H * dh) + h * dh;
+  float acc = 0.f;
+  for (int d = lane; d < dh; d += 32) acc += __ldg(a + d) * __ldg(g + d);
+  acc = ssb::warp_sum(acc);
+  if (lane == 0) {
+    const int64_t bb = row / T, q = row - bb * T;
+    delta[(bb * H + h) * T + q] = acc;
+  }
+}
+
+// ---- tensor maps ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_enc = nullptr;
+std::mutex g_enc_mutex;
+
+int get_enc(EncodeTiledFn* out) {
+  std::lock_guard<std::mutex> lk(g_enc_mutex);
+  if (!g_enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    SSB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+                "attn_fused: cuTensorMapEncodeTiled not available from the driver");
+    g_enc = (EncodeTiledFn)fn;
+  }
+  *out = g_enc;
+  return SSB_OK;
+}
+
+// head planes (2, B*T, G, 128) bf16: dims (d, t, head, batch, plane); box (32 d, box_rows t)
+int head_map(CUtensorMap* map, const void* planes, int64_t B, int64_t T, int64_t G, int64_t g0,
+             int64_t H, int box_rows) {
+  EncodeTiledFn enc = nullptr;
+  if (int rc = get_enc(&enc)) return rc;
+  const __nv_bfloat16* basep = (const __nv_bfloat16*)planes + g0 * 128;
+  SSB_REQUIRE(((uintptr_t)basep & 15) == 0, "attn_fused: planes must be 16 B aligned");
+  const int64_t ld = G * 128;
+  cuuint64_t dims[5] = {128, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)B, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, 256, (cuuint64_t)(T * ld) * 2,
+                           (cuuint64_t)(B * T * ld) * 2};
+  cuuint32_t box[5] = {DB, (cuuint32_t)box_rows, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)basep, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSB_REQUIRE(r == CUDA_SUCCESS, "attn_fused: cuTensorMapEncodeTiled (heads) failed (%d)", (int)r);
+  return SSB_OK;
+}
+
+// R (B*H, T, RW) fp32: dims (rel, t, bh); box (box_w, box_rows, 1), no swizzle
+int r_map(CUtensorMap* map, const float* R, int64_t BH, int64_t T, int64_t RW, int box_w, int box_rows) {
+  EncodeTiledFn enc = nullptr;
+  if (int rc = get_enc(&enc)) return rc;
+  SSB_REQUIRE(((uintptr_t)R & 15) == 0 && RW % 4 == 0, "attn_fused: R must be 16 B aligned, RW %% 4 == 0");
+  cuuint64_t dims[3] = {(cuuint64_t)RW, (cuuint64_t)T, (cuuint64_t)BH};
+  cuuint64_t strides[2] = {(cuuint64_t)RW * 4, (cuuint64_t)(T * RW) * 4};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)R, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSB_REQUIRE(r == CUDA_SUCCESS, "attn_fused: cuTensorMapEncodeTiled (R) failed (%d)", (int)r);
+  return SSB_OK;
+}
+
+int fill(FusedParams* p, int64_t B, int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW,
+         float drop_p, uint64_t seed, uint32_t site) {
+  SSB_REQUIRE(B >= 1 && H >= 1 && T >= 1 && B * H <= 65535, "attn_fused: bad B / H / T");
+  SSB_REQUIRE(dh % DB == 0 && dh >= DB && dh <= DB * MAX_NDB, "attn_fused: head dim %lld not in {32, 64, 96}",
+              (long long)dh);
+  SSB_REQUIRE(W >= 0 && W <= 99 && RW >= 2 * W + 1 && RW <= 200 && RW % 4 == 0,
+              "attn_fused: band W=%lld RW=%lld unsupported (W <= 99, RW <= 200)", (long long)W, (long long)RW);
+  SSB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attn_fused: bad dropout p");
+  p->B = (int)B; p->H = (int)H; p->T = (int)T; p->dh = (int)dh; p->ndb = (int)(dh / DB);
+  p->W = (int)W; p->RW = (int)RW;
+  p->Tp4 = (int)(((T + 63) / 64 * 64) / 4);
+  p->scale = 1.0f / sqrtf((float)dh);
+  p->drop_p = drop_p; p->drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const double th = (double)drop_p * 4294967296.0;
+  p->drop_thresh = th >= 4294967295.0 ? 0xffffffffu : (uint32_t)th;
+  p->seed = seed; p->seed_src = ssb::seed_source(); p->site = site;
+  return SSB_OK;
+}
+
+template <typename K>
+int set_smem(K kernel, int bytes) {
+  SSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return SSB_OK;
+}
+constexpr int FWD_SMEM_BYTES = FwdSmem::TOTAL + 1024;
+constexpr int BWD_SMEM_BYTES = BwdSmem::TOTAL + 1024;
+static_assert(FWD_SMEM_BYTES <= 232448 && BWD_SMEM_BYTES <= 232448, "shared memory budget");
+
+}  // namespace
+
+extern "C" {
+
+int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_t T, int64_t H,
+                       int64_t dh, int64_t W, int64_t RW, float drop_p, uint64_t seed, uint32_t site,
+                       float* O, float* stat_m, float* stat_linv, void* stream) {
+  FusedParams p = {};
+  if (int rc = fill(&p, B, T, H, dh, W, RW, drop_p, seed, site)) return rc;
+  SSB_REQUIRE(qkv_planes && R && O && stat_m && stat_linv, "attn_fused_fwd: null pointer");
+  SSB_REQUIRE(((uintptr_t)O & 15) == 0, "attn_fused_fwd: O must be 16 B aligned");
+  p.O = O; p.stat_m = stat_m; p.stat_linv = stat_linv;
+  CUtensorMap mq, mk, mv, mr;
+  if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, QT)) return rc;
+  if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, CH)) return rc;
+  if (int rc = head_map(&mv, qkv_planes, B, T, 3 * H, 2 * H, H, CH)) return rc;
+  if (int rc = r_map(&mr, R, B * H, T, RW, (int)RW, QT)) return rc;
+  const int smem = FWD_SMEM_BYTES;
+  if (int rc = set_smem(attn_fused_fwd_kernel, smem)) return rc;
+  dim3 grid((unsigned)((T + QT - 1) / QT), (unsigned)(B * H));
+  attn_fused_fwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(mq, mk, mv, mr, p);
+  SSB_LAUNCH_CHECK("attn_fused_fwd");
+  return SSB_OK;
+}
+
+int ssb_attn_delta(const float* O, const float* dO, int64_t B, int64_t T, int64_t H, int64_t dh,
+                   float* delta, void* stream) {
+  SSB_REQUIRE(O && dO && delta && B >= 1 && T >= 1 && H >= 1 && dh >= 1, "attn_delta: bad arguments");
+  const int64_t warps = B * T * H;
+  attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      O, dO, B * T, (int)T, (int)H, (int)dh, delta);
+  SSB_LAUNCH_CHECK("attn_delta");
+  return SSB_OK;
+}
+
+int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const float* R,
+                       const float* stat_m, const float* stat_linv, const float* delta, int64_t B,
+                       int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW, float drop_p,
+                       uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
+                       void* stream) {
+  FusedParams p = {};
+  if (int rc = fill(&p, B, T, H, dh, W, RW, drop_p, seed, site)) return rc;
+  SSB_REQUIRE(qkv_planes && dO_planes && R && stat_m && stat_linv && delta && dqkv && dSband_planes,
+              "attn_fused_bwd: null pointer");
+  SSB_REQUIRE(RWp >= 2 * W + 1 && ((uintptr_t)dqkv & 15) == 0, "attn_fused_bwd: bad RWp / alignment");
+  p.stat_m = const_cast<float*>(stat_m); p.stat_linv = const_cast<float*>(stat_linv);
+  p.delta = delta; p.dqkv = dqkv; p.dsb = (__nv_bfloat16*)dSband_planes; p.RWp = (int)RWp;
+  CUtensorMap mq, mk, mv, mdo, mr;
+  if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, CH)) return rc;
+  if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, QT)) return rc;
+  if (int rc = head_map(&mv, qkv_planes, B, T, 3 * H, 2 * H, H, QT)) return rc;
+  if (int rc = head_map(&mdo, dO_planes, B, T, H, 0, H, CH)) return rc;
+  if (int rc = r_map(&mr, R, B * H, T, RW, RBOX, CH)) return rc;
+  const int smem = BWD_SMEM_BYTES;
+  if (int rc = set_smem(attn_fused_bwd_kernel, smem)) return rc;
+  dim3 grid((unsigned)((T + QT - 1) / QT), (unsigned)(B * H));
+  attn_fused_bwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(mq, mk, mv, mdo, mr, p);
+  SSB_LAUNCH_CHECK("attn_fused_bwd");
+  return SSB_OK;
+}
+
+}  // extern "C"

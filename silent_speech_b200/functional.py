@@ -703,14 +703,93 @@ class _DenseTCAttnFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None, None, None, None
 
 
+class _FusedAttnFn(torch.autograd.Function):
+    """Fused band attention (csrc/attn_fused.cu): S, P, dP and dS never leave the SM.  Around the
+    two fused kernels only the positional GEMMs with E remain: R = Q E^T before the forward and
+    dQ += dS_band E after the backward (no gradient flows to E: SURVEY.md F3)."""
+
+    @staticmethod
+    def forward(ctx, qkv, E, B, T, H, dh, W, p, seed, site):
+        lib = _lib.load()
+        _chk(qkv, "qkv")
+        M, D3 = qkv.shape
+        D = H * dh
+        BH = B * H
+        RW = (2 * W + 1 + 3) // 4 * 4
+        dev = qkv.device
+        bf = torch.bfloat16
+        st = _stream()
+        qkvp = torch.empty((2, M, 3 * H, _HP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, D3, 0, 3 * H, dh, qkvp.data_ptr(), st))
+        Ew = E[:, :2 * W + 1, :dh]
+        ep = split_planes(torch.nn.functional.pad(Ew, (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
+        ld_qkv = 3 * H * _HP
+        q_op = _op(qkvp, 0, M * ld_qkv, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
+        R = torch.empty((BH, T, RW), dtype=_f32, device=dev)
+        e_op = _op(ep, 0, H * RW * _HP, H, RW, _HP, _HP, RW * _HP)
+        _tc_batched(q_op, e_op, 2, RW, _HP, _epi(_bscatter(R, 0, T, RW, T * RW, H * T * RW)))
+        O = torch.empty((M, D), dtype=_f32, device=dev)
+        stats = torch.empty((2, BH, T), dtype=_f32, device=dev)
+        _lib.check(lib.ssb_attn_fused_fwd(qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p,
+                                          seed & 0xFFFFFFFFFFFFFFFF, site, O.data_ptr(),
+                                          stats[0].data_ptr(), stats[1].data_ptr(), st))
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(qkvp, R, stats, O, E)
+        ctx.cfg = (B, T, H, dh, W, p, seed, site, RW)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        lib = _lib.load()
+        qkvp, R, stats, O, E = ctx.saved_tensors
+        B, T, H, dh, W, p, seed, site, RW = ctx.cfg
+        dO = dO.contiguous()
+        M, D = O.shape
+        D3 = 3 * D
+        BH = B * H
+        dev = O.device
+        bf = torch.bfloat16
+        st = _stream()
+        dop = torch.empty((2, M, H, _HP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_pad_split_heads(dO.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), st))
+        delta = torch.empty((BH, T), dtype=_f32, device=dev)
+        _lib.check(lib.ssb_attn_delta(O.data_ptr(), dO.data_ptr(), B, T, H, dh, delta.data_ptr(), st))
+        dqkv = torch.empty((M, D3), dtype=_f32, device=dev)
+        dqkv[:, :D].zero_()                                  # content dQ arrives by red.global.add
+        dsb = torch.zeros((2, M, H, _RWP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_attn_fused_bwd(qkvp.data_ptr(), dop.data_ptr(), R.data_ptr(),
+                                          stats[0].data_ptr(), stats[1].data_ptr(),
+                                          delta.data_ptr(), B, T, H, dh, W, RW, p,
+                                          seed & 0xFFFFFFFFFFFFFFFF, site, dqkv.data_ptr(),
+                                          dsb.data_ptr(), _RWP, st))
+        # positional part: dQ += dS_band E
+        Ew = E[:, :2 * W + 1, :dh]
+        et = torch.nn.functional.pad(Ew, (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2)
+        etp = split_planes(et.contiguous())                       # (2, H, 128, RWP): [d][rel]
+        dsb_op = _op(dsb, 0, M * H * _RWP, BH, T, _RWP, H * _RWP, _RWP, H, T * H * _RWP)
+        et_op = _op(etp, 0, H * _HP * _RWP, H, _HP, _RWP, _RWP, _HP * _RWP)
+        _tc_batched(dsb_op, et_op, 2, dh, _RWP,
+                    _epi(_bscatter(dqkv, 0, T, D3, dh, T * D3), accumulate=1))
+        return dqkv, None, None, None, None, None, None, None, None, None
+
+
+def _fused_attn_ok(B, T, H, dh, W):
+    return _tc_enabled() and os.environ.get("SSB_ATTN", "fused") == "fused" and \
+        dh in (32, 64, 96) and W <= 99 and 64 <= T <= 1024 and B * H <= 65535
+
+
 def _tc_attn_ok(T, dh, W):
-    return _tc_enabled() and os.environ.get("SSB_ATTN", "tc") != "simt" and dh % 4 == 0 and \
+    return _tc_enabled() and os.environ.get("SSB_ATTN", "fused") != "simt" and dh % 4 == 0 and \
         dh <= _HP and 64 <= T <= 1024 and W <= 127
 
 
 def band_attention(qkv, E_pad, B, T, H, dh, W, p=0.0, seed=0, site=0):
-    """Banded relative-position attention.  Tensor-core schedule when the shape allows, else the
-    CUDA-core band kernels (csrc/attn.cu)."""
+    """Banded relative-position attention: the fused tcgen05 kernels (csrc/attn_fused.cu) when the
+    shape allows, else the multi-kernel tensor-core schedule (csrc/attn_tc.cu), else the CUDA-core
+    band kernels (csrc/attn.cu).  SSB_ATTN=fused|tc|simt caps the choice (A/B testing)."""
+    if _fused_attn_ok(B, T, H, dh, W):
+        return _FusedAttnFn.apply(qkv, E_pad, int(B), int(T), int(H), int(dh), int(W), float(p),
+                                  int(seed), int(site))
     if _tc_attn_ok(T, dh, W):
         return _DenseTCAttnFn.apply(qkv, E_pad, int(B), int(T), int(H), int(dh), int(W), float(p),
                                     int(seed), int(site))

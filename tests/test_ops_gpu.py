@@ -253,16 +253,20 @@ def dense_attention_ref(qkv, E, B, T, H, dh, W):
     return o.permute(0, 2, 1, 3).reshape(B * T, D)
 
 
-@pytest.mark.parametrize("sched", ["simt", "tc"])
+@pytest.mark.parametrize("sched", ["simt", "tc", "fused"])
 @pytest.mark.parametrize("B,T,H,dh,W", [(2, 25, 8, 4, 99), (2, 125, 8, 4, 99), (1, 130, 2, 32, 99),
                                         (2, 250, 8, 96, 99), (1, 33, 1, 8, 5), (1, 64, 2, 16, 31),
-                                        (3, 500, 8, 96, 99), (2, 126, 4, 16, 99)])
+                                        (3, 500, 8, 96, 99), (2, 126, 4, 16, 99),
+                                        (1, 64, 2, 32, 31), (2, 300, 4, 64, 99), (1, 129, 1, 96, 5),
+                                        (1, 384, 2, 96, 99)])
 def test_band_attention_fwd_bwd(B, T, H, dh, W, sched, monkeypatch):
     """Both schedules of the same op: CUDA-core band kernels and the tensor-core (batched
     tcgen05 GEMM) schedule, against a dense torch restatement."""
     monkeypatch.setenv("SSB_ATTN", sched)
     if sched == "tc" and not SF._tc_attn_ok(T, dh, W):
         pytest.skip("shape not eligible for the tensor-core schedule")
+    if sched == "fused" and not SF._fused_attn_ok(B, T, H, dh, W):
+        pytest.skip("shape not eligible for the fused kernels")
     D = H * dh
     qkv = rnd(B * T, 3 * D, seed=1).requires_grad_(True)
     RW = (2 * W + 1 + 3) // 4 * 4
@@ -280,7 +284,7 @@ def test_band_attention_fwd_bwd(B, T, H, dh, W, sched, monkeypatch):
     close(qkv.grad[:, 2 * D:], qr.grad[:, 2 * D:], tol=5e-5, what="dv")
 
 
-@pytest.mark.parametrize("sched,T", [("simt", 40), ("tc", 96)])
+@pytest.mark.parametrize("sched,T", [("simt", 40), ("tc", 96), ("fused", 96)])
 def test_band_attention_dropout_is_consistent_between_fwd_and_bwd(sched, T, monkeypatch):
     """With V = one-hot positions the forward output exposes the dropped probabilities; the
     backward must use the same mask: check d(sum O)/dV against the forward's P_drop."""
@@ -298,9 +302,36 @@ def test_band_attention_dropout_is_consistent_between_fwd_and_bwd(sched, T, monk
     assert abs(zero - p) < 0.05, zero
     if sched == "tc":
         assert SF._tc_attn_ok(T, dh, W)
+    if sched == "fused":
+        assert SF._fused_attn_ok(B, T, H, dh, W)
     g = rnd(T, D, seed=5)
     o.backward(g)
     dV_expected = Pdrop.t() @ g                           # dV = P_drop^T dO
     close(qkv.grad[:, 2 * D:], dV_expected, tol=5e-5, what="dV with dropout")
     o2 = SF.band_attention(qkv.detach(), E, B, T, H, dh, W, p, 1234, 3)
     assert torch.equal(o2, Pdrop)
+
+
+@pytest.mark.parametrize("B,T,H,dh", [(2, 500, 8, 96), (1, 200, 2, 32)])
+def test_fused_attention_matches_tc_schedule_with_dropout(B, T, H, dh, monkeypatch):
+    """The fused kernels key dropout exactly like the multi-kernel tensor-core schedule (same
+    Philox counters per (row, 4 keys)), so with dropout ON both schedules must agree on the
+    output and on every gradient: pins the mask plumbing of the fused backward (lanes = keys,
+    4 x 4 cross-lane transpose of the Philox words)."""
+    W, p = 99, 0.2
+    D = H * dh
+    E = torch.zeros(H, 200, dh, device=dev)
+    E[:, :2 * W + 1] = rnd(H, 2 * W + 1, dh, seed=2, scale=dh ** -0.5)
+    g = rnd(B * T, D, seed=3)
+    out = {}
+    for sched in ("tc", "fused"):
+        monkeypatch.setenv("SSB_ATTN", sched)
+        qkv = rnd(B * T, 3 * D, seed=1).requires_grad_(True)
+        o = SF.band_attention(qkv, E, B, T, H, dh, W, p, 4321, 7)
+        o.backward(g)
+        out[sched] = (o.detach(), qkv.grad.detach())
+    assert SF._fused_attn_ok(B, T, H, dh, W)
+    close(out["fused"][0], out["tc"][0], tol=2e-5, what="O (dropout)")
+    close(out["fused"][1][:, :D], out["tc"][1][:, :D], tol=5e-5, what="dq (dropout)")
+    close(out["fused"][1][:, D:2 * D], out["tc"][1][:, D:2 * D], tol=5e-5, what="dk (dropout)")
+    close(out["fused"][1][:, 2 * D:], out["tc"][1][:, 2 * D:], tol=5e-5, what="dv (dropout)")
