@@ -43,6 +43,12 @@ constexpr int BLK_SMALL = CH * 64; // bytes of a [32 rows][32 d] block   (2 KB)
 constexpr int MAX_NDB = 3;       // dh <= 96
 
 constexpr int KST = 3;           // forward: K / V ring depth
+constexpr int NCW = 16;          // element-wise warps: 4 per TMEM lane group (a lone warp per
+                                 // scheduler cannot hide its own latencies: 341 / 708 us per layer
+                                 // with 4 warps)
+constexpr int NCT = NCW * 32;    // 512 element-wise threads
+constexpr int NTHREADS = NCT + 32;   // + the control warp (TMA + MMA issue)
+constexpr float LOG2E = 1.4426950408889634f;
 constexpr int RBOX = 164;        // backward: width of a positional-logit box (159 needed, + <= 3 because
                                  // the box must start on a 16 B boundary of the fp32 row)
 
@@ -116,6 +122,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -164,9 +194,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 }
 // (hi, lo) split of two values, packed pairwise
 __device__ __forceinline__ void split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
-  hi = (uint32_t)__bfloat16_as_ushort(ah) | ((uint32_t)__bfloat16_as_ushort(bh) << 16);
-  lo = pack_bf16(a - __bfloat162float(ah), b - __bfloat162float(bh));
+  hi = pack_bf16(a, b);                                   // one cvt.rn.bf16x2.f32 (a in the low half)
+  lo = pack_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
 struct FusedParams {
@@ -197,15 +226,18 @@ struct FwdSmem {   // byte offsets from the 1024-aligned base
   static constexpr int PHASE1_END = KRING + KST * KSTAGE;             // 84 KB
   // phase 2 aliases the Q / K region once every S MMA has retired
   static constexpr int VRING = 0;
-  static constexpr int PT = VRING + KST * KSTAGE;                     // 2 x (2 planes x 8 KB)
-  static constexpr int PHASE2_END = PT + 2 * 2 * BLK_BIG;             // 68 KB
+  static constexpr int PT = VRING + KST * KSTAGE;                     // P tiles 0..2 (2 planes x 8 KB each)
+  static constexpr int PHASE2_END = PT + 3 * 2 * BLK_BIG;             // 84 KB
   static constexpr int R = PHASE1_END;                                // 128 x RW fp32 (<= 100 KB)
-  static constexpr int BARS = R + QT * 200 * 4;
+  static constexpr int PT3 = R + QT * 200 * 4;                        // P tile 3
+  static constexpr int RED = PT3 + 2 * BLK_BIG;                       // [2][4][128] fp32 max / sum exchange
+  static constexpr int BARS = RED + 2 * 4 * QT * 4;
   static constexpr int TOTAL = BARS + 256;
+  static __device__ __forceinline__ int pt(int k) { return k < 3 ? PT + k * 2 * BLK_BIG : PT3; }
 };
 static_assert(FwdSmem::PHASE2_END <= FwdSmem::PHASE1_END, "phase-2 buffers must fit the alias");
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapR,
                       const FusedParams p) {
@@ -215,8 +247,8 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t bars = base + FwdSmem::BARS;
   const uint32_t bar_q = bars, bar_r = bars + 8, bar_s = bars + 16, bar_o = bars + 24;
   const uint32_t kfull = bars + 32, kempty = kfull + 8 * KST, vfull = kempty + 8 * KST,
-                 vempty = vfull + 8 * KST, pfull = vempty + 8 * KST, pempty = pfull + 16;
-  const uint32_t tmem_slot = pempty + 16;
+                 vempty = vfull + 8 * KST, pfull = vempty + 8 * KST, pempty = pfull + 32;
+  const uint32_t tmem_slot = pempty + 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
   const int q0 = blockIdx.x * QT;
@@ -227,16 +259,16 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const int nch = (kw1 - kw0 + CH - 1) / CH;
   const int plane_q = ndb * BLK_BIG, plane_k = ndb * BLK_SMALL;
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == NCT) {
     for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);
     for (int s = 0; s < KST; ++s) {
       mbar_init(kfull + 8 * s, 1); mbar_init(kempty + 8 * s, 1);
       mbar_init(vfull + 8 * s, 1); mbar_init(vempty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; ++s) { mbar_init(pfull + 8 * s, 4); mbar_init(pempty + 8 * s, 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(pfull + 8 * s, 4); mbar_init(pempty + 8 * s, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == NCW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -247,7 +279,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const uint32_t tmem_o = tmem + 352;   // O accumulator columns [352, 352 + dh)
 
-  if (warp == 4) {
+  if (warp == NCW) {
     if (lane == 0) {
       // ---------------- control thread: TMA + MMA issue ----------------
       mbar_expect_tx(bar_q, 2 * ndb * BLK_BIG);
@@ -298,11 +330,11 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       for (int j = 0; j < KST && j < nch; ++j) load_kv(&mapV, base + FwdSmem::VRING, vfull, j);
       const uint32_t id_o = idesc(p.dh, 0, 1);
       for (int j = 0; j < nch; ++j) {
-        const int s = j % KST, pb = j & 1;
+        const int s = j % KST, pb = j & 3;
         mbar_wait(vfull + 8 * s, (uint32_t)(j / KST) & 1u);
-        mbar_wait(pfull + 8 * pb, (uint32_t)(j >> 1) & 1u);
+        mbar_wait(pfull + 8 * pb, (uint32_t)(j >> 2) & 1u);
         tc_fence_after();
-        const uint32_t pa = base + FwdSmem::PT + pb * 2 * BLK_BIG;
+        const uint32_t pa = base + FwdSmem::pt(pb);
         const uint32_t vb = base + FwdSmem::VRING + s * FwdSmem::KSTAGE;
         for (int ks = 0; ks < 2; ++ks) {
           const uint64_t ah = desc64(pa + ks * 32, 16), al = desc64(pa + BLK_BIG + ks * 32, 16);
@@ -323,101 +355,139 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       umma_commit(bar_o);
     }
   } else {
-    // ---------------- softmax threads: one query row each ----------------
-    const int i = threadIdx.x;            // row of the tile = TMEM lane
+    // ---------------- softmax threads ----------------
+    // 4 warps per TMEM lane group: thread (lg, lane) owns query row i = 32 lg + lane, warp group
+    // cg = warp / 4 takes the key chunks j = cg (mod 4) of that row; row max and row sum are
+    // combined through shared memory.
+    const int lg = warp & 3, cg = warp >> 2;
+    const int i = lg * 32 + lane;         // row of the tile = TMEM lane
     const int q = q0 + i;
     const bool row_ok = q < p.T;
+    const int qa = q0 + lg * 32;          // first query row of this warp
     const uint64_t seed = ssb::eff_seed(p.seed, p.seed_src);
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)(lg * 32) << 16);
     const uint32_t rrow = base + FwdSmem::R + (uint32_t)(i * p.RW) * 4u;
     const int soff = kw0 - q + p.W;       // rel = column + soff
+    float* red = reinterpret_cast<float*>(gen + FwdSmem::RED);
+    // warp-uniform class of a key chunk: 0 = no (row, key) of this warp inside the band,
+    // 2 = every (row, key) inside the band and the sequence (no predicates needed), 1 = mixed
+    auto chunk_class = [&](int j) -> int {
+      const int kc = kw0 + j * CH;
+      if (qa >= p.T || kc >= p.T || kc > qa + 31 + p.W || kc + 31 < qa - p.W) return 0;
+      if (qa + 31 < p.T && kc + 31 < p.T && kc >= qa + 31 - p.W && kc + 31 <= qa + p.W) return 2;
+      return 1;
+    };
     mbar_wait(bar_r, 0);
     mbar_wait(bar_s, 0);
     tc_fence_after();
     float m = -CUDART_INF_F;
-    for (int j = 0; j < nch; ++j) {
-      uint32_t v[32];
-      tmem_ld32(tlane + (uint32_t)(j * CH), v);
-      tmem_wait_ld();
+    for (int j = cg; j < nch; j += 4) {
+      const int cls = chunk_class(j);
+      if (cls == 0) continue;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int col = j * CH + c, rel = col + soff;
-        if (row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W)
-          m = fmaxf(m, fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u)));
-      }
-    }
-    float sum = 0.f;
-    const int64_t drow = ((int64_t)bh * p.T + q) * p.Tp4;
-    for (int j = 0; j < nch; ++j) {
-      const int pb = j & 1;
-      uint32_t v[32];
-      tmem_ld32(tlane + (uint32_t)(j * CH), v);
-      tmem_wait_ld();
-      float e[32];
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[16];
+        tmem_ld16(tlane + (uint32_t)(j * CH + half * 16), v);
+        tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const int col = j * CH + c, rel = col + soff;
-        const bool inb = row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W;
-        float x = 0.f;
-        if (inb)
-          x = expf(fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u)) - m);
-        e[c] = x;
-        sum += x;
-      }
-      if (p.drop_p > 0.f && row_ok) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const uint4 rnd = ssb::dropout_bits4(seed, p.site, (uint64_t)(drow + ((kw0 + j * CH) >> 2) + g));
-          e[4 * g + 0] = rnd.x >= p.drop_thresh ? e[4 * g + 0] * p.drop_scale : 0.f;
-          e[4 * g + 1] = rnd.y >= p.drop_thresh ? e[4 * g + 1] * p.drop_scale : 0.f;
-          e[4 * g + 2] = rnd.z >= p.drop_thresh ? e[4 * g + 2] * p.drop_scale : 0.f;
-          e[4 * g + 3] = rnd.w >= p.drop_thresh ? e[4 * g + 3] * p.drop_scale : 0.f;
+        for (int c = 0; c < 16; ++c) {
+          const int col = j * CH + half * 16 + c, rel = col + soff;
+          const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u));
+          const bool ok = cls == 2 || (row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W);
+          m = fmaxf(m, ok ? y : -CUDART_INF_F);
         }
       }
-      // the P buffer is free once the MMAs of chunk j-2 have retired
-      if (j >= 2) mbar_wait(pempty + 8 * pb, (uint32_t)((j - 2) >> 1) & 1u);
-      const uint32_t pt = base + FwdSmem::PT + pb * 2 * BLK_BIG;
+    }
+    red[cg * QT + i] = m;
+    bar_compute();
+    m = fmaxf(fmaxf(red[i], red[QT + i]), fmaxf(red[2 * QT + i], red[3 * QT + i]));
+    if (!row_ok) m = 0.f;
+    const float mneg = -m * LOG2E;
+    float sum = 0.f;
+    const int64_t drow = ((int64_t)bh * p.T + q) * p.Tp4;
+    for (int j = cg; j < nch; j += 4) {
+      const int cls = chunk_class(j);
+      const int n = j >> 2;               // n-th use of P tile cg
+      const uint32_t pt = base + FwdSmem::pt(cg);
+      if (n >= 1) mbar_wait(pempty + 8 * cg, (uint32_t)(n - 1) & 1u);   // MMAs of chunk j-4 retired
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint4 hi, lo;
-        split_pack(e[8 * ch + 0], e[8 * ch + 1], hi.x, lo.x);
-        split_pack(e[8 * ch + 2], e[8 * ch + 3], hi.y, lo.y);
-        split_pack(e[8 * ch + 4], e[8 * ch + 5], hi.z, lo.z);
-        split_pack(e[8 * ch + 6], e[8 * ch + 7], hi.w, lo.w);
-        const uint32_t off = sw64_off(i, ch);
-        st_shared_v4(pt + off, hi);
-        st_shared_v4(pt + BLK_BIG + off, lo);
+      for (int half = 0; half < 2; ++half) {
+        float e[16];
+        if (cls == 0) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) e[c] = 0.f;
+        } else {
+          uint32_t v[16];
+          tmem_ld16(tlane + (uint32_t)(j * CH + half * 16), v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = j * CH + half * 16 + c, rel = col + soff;
+            const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u));
+            const bool ok = cls == 2 || (row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W);
+            const float x = ok ? ex2(fmaf(y, LOG2E, mneg)) : 0.f;
+            e[c] = x;
+            sum += x;
+          }
+          if (p.drop_p > 0.f) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 rnd = ssb::dropout_bits4(
+                  seed, p.site, (uint64_t)(drow + ((kw0 + j * CH + half * 16) >> 2) + g));
+              e[4 * g + 0] = rnd.x >= p.drop_thresh ? e[4 * g + 0] * p.drop_scale : 0.f;
+              e[4 * g + 1] = rnd.y >= p.drop_thresh ? e[4 * g + 1] * p.drop_scale : 0.f;
+              e[4 * g + 2] = rnd.z >= p.drop_thresh ? e[4 * g + 2] * p.drop_scale : 0.f;
+              e[4 * g + 3] = rnd.w >= p.drop_thresh ? e[4 * g + 3] * p.drop_scale : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint4 hi, lo;
+          split_pack(e[8 * c2 + 0], e[8 * c2 + 1], hi.x, lo.x);
+          split_pack(e[8 * c2 + 2], e[8 * c2 + 3], hi.y, lo.y);
+          split_pack(e[8 * c2 + 4], e[8 * c2 + 5], hi.z, lo.z);
+          split_pack(e[8 * c2 + 6], e[8 * c2 + 7], hi.w, lo.w);
+          const uint32_t off = sw64_off(i, half * 2 + c2);
+          st_shared_v4(pt + off, hi);
+          st_shared_v4(pt + BLK_BIG + off, lo);
+        }
       }
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pfull + 8 * pb);
+      if (lane == 0) mbar_arrive(pfull + 8 * cg);
     }
-    // epilogue: O = acc / sum
+    red[4 * QT + cg * QT + i] = sum;
+    bar_compute();
+    sum = (red[4 * QT + i] + red[5 * QT + i]) + (red[6 * QT + i] + red[7 * QT + i]);
+    // epilogue: O = acc / sum; warp group cg stores columns [cg dh/4, (cg+1) dh/4)
     mbar_wait(bar_o, 0);
     tc_fence_after();
     const float linv = row_ok ? 1.f / sum : 0.f;
-    if (row_ok) {
+    if (row_ok && cg == 0) {
       p.stat_m[(int64_t)bh * p.T + q] = m;
       p.stat_linv[(int64_t)bh * p.T + q] = linv;
     }
     float* orow = p.O + ((int64_t)b * p.T + q) * (p.H * p.dh) + h * p.dh;
-    for (int c0 = 0; c0 < p.dh; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_o + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    const int cw = p.dh >> 2;
+    for (int c0 = cg * cw; c0 < (cg + 1) * cw; c0 += 8) {
+      uint32_t v[8];
+      tmem_ld8(tlane + 352 + (uint32_t)c0, v);
       tmem_wait_ld();
       if (row_ok) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<float4*>(orow + c0 + c) =
-              make_float4(__uint_as_float(v[c]) * linv, __uint_as_float(v[c + 1]) * linv,
-                          __uint_as_float(v[c + 2]) * linv, __uint_as_float(v[c + 3]) * linv);
+        *reinterpret_cast<float4*>(orow + c0) =
+            make_float4(__uint_as_float(v[0]) * linv, __uint_as_float(v[1]) * linv,
+                        __uint_as_float(v[2]) * linv, __uint_as_float(v[3]) * linv);
+        *reinterpret_cast<float4*>(orow + c0 + 4) =
+            make_float4(__uint_as_float(v[4]) * linv, __uint_as_float(v[5]) * linv,
+                        __uint_as_float(v[6]) * linv, __uint_as_float(v[7]) * linv);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NCW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -441,7 +511,7 @@ struct BwdSmem {
   static constexpr int TOTAL = BARS + 256;
 };
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapDO,
                       const __grid_constant__ CUtensorMap mapR, const FusedParams p) {
@@ -462,17 +532,17 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const int nch = (qw1 - qw0 + CH - 1) / CH;
   const int plane_big = ndb * BLK_BIG, plane_small = ndb * BLK_SMALL;
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == NCT) {
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(qd_full + 8 * s, 1); mbar_init(r_full + 8 * s, 1); mbar_init(r_free + 8 * s, 4);
-      mbar_init(s_full + 8 * s, 1); mbar_init(sp_free + 8 * s, 4); mbar_init(ep_done + 8 * s, 4);
+      mbar_init(qd_full + 8 * s, 1); mbar_init(r_full + 8 * s, 1); mbar_init(r_free + 8 * s, NCW);
+      mbar_init(s_full + 8 * s, 1); mbar_init(sp_free + 8 * s, NCW); mbar_init(ep_done + 8 * s, NCW);
     }
-    mbar_init(tiles_full, 4);
+    mbar_init(tiles_full, NCW);
     mbar_init(mma2_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == NCW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -484,7 +554,7 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   // TMEM columns: [0,128) two {S^T, dP^T} pairs, [128,256) dV, [256,384) dK, [384,448) two dQ^T
   const uint32_t t_dv = tmem + 128, t_dk = tmem + 256, t_dq = tmem + 384;
 
-  if (warp == 4) {
+  if (warp == NCW) {
     if (lane == 0) {
       // ---------------- control thread ----------------
       mbar_expect_tx(kv_full, 4 * ndb * BLK_BIG);
@@ -580,13 +650,18 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       }
     }
   } else {
-    // ---------------- one thread per key ----------------
-    const int i = threadIdx.x;
+    // ---------------- element-wise threads ----------------
+    // 4 warps per TMEM lane group: thread (lg, lane) owns key row i = 32 lg + lane, warp group
+    // cg = warp / 4 owns query columns [8 cg, 8 cg + 8) of every 32-query chunk.
+    const int lg = warp & 3, cg = warp >> 2;
+    const int i = lg * 32 + lane;
     const int k = k0 + i;
     const bool key_ok = k < p.T;
+    const int ka = k0 + lg * 32;          // first key of this warp
+    const int c8 = cg * 8;
     const int quad = lane & 3;
     const uint64_t seed = ssb::eff_seed(p.seed, p.seed_src);
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tmem + ((uint32_t)(lg * 32) << 16);
     const int D = p.H * p.dh;
     const int64_t band_plane = (int64_t)p.B * p.T * p.H * p.RWp;
 
@@ -597,14 +672,15 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       const int s = j & 1;
       if (wait) mbar_wait_nth(mma2_done, j);
       tc_fence_after();
-      uint32_t v[32];
-      tmem_ld32(tlane + 384 + (uint32_t)(s * 32), v);
+      uint32_t v[8];
+      tmem_ld8(tlane + 384 + (uint32_t)(s * 32 + c8), v);
       tmem_wait_ld();
       if (i < p.dh) {
-        float* dst = p.dqkv + ((int64_t)b * p.T + qw0 + j * CH) * (3 * D) + h * p.dh + i;
+        const int qb = qw0 + j * CH + c8;
+        float* dst = p.dqkv + ((int64_t)b * p.T + qb) * (3 * D) + h * p.dh + i;
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (qw0 + j * CH + c < p.T) atomicAdd(dst + (int64_t)c * (3 * D), __uint_as_float(v[c]) * p.scale);
+        for (int c = 0; c < 8; ++c)
+          if (qb + c < p.T) atomicAdd(dst + (int64_t)c * (3 * D), __uint_as_float(v[c]) * p.scale);
       }
       tc_fence_before();
       __syncwarp();
@@ -616,93 +692,97 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       const int qc = qw0 + j * CH;
       // row statistics of the chunk's queries -> shared memory (broadcast reads below)
       float* st = reinterpret_cast<float*>(gen + BwdSmem::STATS) + s * 3 * CH;
-      if (i < 3 * CH) {
-        const int which = i / CH, c = i - which * CH, q = qc + c;
+      if (threadIdx.x < 3 * CH) {
+        const int which = threadIdx.x / CH, c = threadIdx.x - which * CH, q = qc + c;
         const float* src = which == 0 ? p.stat_m : which == 1 ? p.stat_linv : p.delta;
-        st[i] = q < p.T ? __ldg(src + (int64_t)bh * p.T + q) : 0.f;
+        st[threadIdx.x] = q < p.T ? __ldg(src + (int64_t)bh * p.T + q) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      bar_compute();
       mbar_wait(r_full + 8 * s, (uint32_t)(j >> 1) & 1u);
       mbar_wait(s_full + 8 * s, (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      uint32_t sv[32], dv[32];
-      tmem_ld32(tlane + (uint32_t)(s * 64), sv);
-      tmem_ld32(tlane + (uint32_t)(s * 64 + 32), dv);
+      uint32_t sv[8], dv[8];
+      tmem_ld8(tlane + (uint32_t)(s * 64 + c8), sv);
+      tmem_ld8(tlane + (uint32_t)(s * 64 + 32 + c8), dv);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sp_free + 8 * s);
+      // warp-uniform: does any (key of this warp, query of these 8 columns) fall inside the band?
+      const int qs = qc + c8;
+      const bool live = ka < p.T && qs < p.T && qs <= ka + 31 + p.W && qs + 7 >= ka - p.W;
       // positional logits: box column = rel - (rel0 & ~3) = i - c + 31 + (rel0 & 3), row c
       const int rsh = (k0 - qc - (CH - 1) + p.W) & 3;
       const uint32_t rbase =
           base + BwdSmem::R + s * BwdSmem::R_STAGE + (uint32_t)(i + CH - 1 + rsh) * 4u;
-      float pdv[32], dsv[32];
+      float pdv[8], dsv[8];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        // dropout words: one Philox call covers 4 consecutive keys (this quad) of one query;
-        // lane `quad` draws for column 4g + quad, then the 4 x 4 block is transposed in the quad
-        uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-        if (p.drop_p > 0.f) {
-          const int qd = qc + 4 * g + quad;
-          const uint4 rnd = ssb::dropout_bits4(
-              seed, p.site, (uint64_t)(((int64_t)bh * p.T + qd) * p.Tp4 + (k >> 2)));
-          w[0] = rnd.x; w[1] = rnd.y; w[2] = rnd.z; w[3] = rnd.w;
-          uint32_t x0 = (quad & 2) ? w[0] : w[2], x1 = (quad & 2) ? w[1] : w[3];
-          x0 = __shfl_xor_sync(0xffffffffu, x0, 2);
-          x1 = __shfl_xor_sync(0xffffffffu, x1, 2);
-          if (quad & 2) { w[0] = x0; w[1] = x1; } else { w[2] = x0; w[3] = x1; }
-          uint32_t y0 = (quad & 1) ? w[0] : w[1], y1 = (quad & 1) ? w[2] : w[3];
-          y0 = __shfl_xor_sync(0xffffffffu, y0, 1);
-          y1 = __shfl_xor_sync(0xffffffffu, y1, 1);
-          if (quad & 1) { w[0] = y0; w[2] = y1; } else { w[1] = y0; w[3] = y1; }
-        }
+      for (int c = 0; c < 8; ++c) { pdv[c] = 0.f; dsv[c] = 0.f; }
+      if (live) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int c = 4 * g + u, q = qc + c, rel = k - q + p.W;
-          const bool inb = key_ok && q < p.T && rel >= 0 && rel <= 2 * p.W;
-          float pr = 0.f;
-          if (inb) {
-            const float x = fmaf(__uint_as_float(sv[c]), p.scale,
-                                 ld_shared_f32(rbase + (uint32_t)(c * (RBOX - 1)) * 4u));
-            pr = expf(x - st[c]) * st[CH + c];
+        for (int g = 0; g < 2; ++g) {
+          // dropout words: one Philox call covers 4 consecutive keys (this quad) of one query;
+          // lane `quad` draws for column 4g + quad, then the 4 x 4 block is transposed in the quad
+          uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+          if (p.drop_p > 0.f) {
+            const int qd = qs + 4 * g + quad;
+            const uint4 rnd = ssb::dropout_bits4(
+                seed, p.site, (uint64_t)(((int64_t)bh * p.T + qd) * p.Tp4 + (k >> 2)));
+            w[0] = rnd.x; w[1] = rnd.y; w[2] = rnd.z; w[3] = rnd.w;
+            uint32_t x0 = (quad & 2) ? w[0] : w[2], x1 = (quad & 2) ? w[1] : w[3];
+            x0 = __shfl_xor_sync(0xffffffffu, x0, 2);
+            x1 = __shfl_xor_sync(0xffffffffu, x1, 2);
+            if (quad & 2) { w[0] = x0; w[1] = x1; } else { w[2] = x0; w[3] = x1; }
+            uint32_t y0 = (quad & 1) ? w[0] : w[1], y1 = (quad & 1) ? w[2] : w[3];
+            y0 = __shfl_xor_sync(0xffffffffu, y0, 1);
+            y1 = __shfl_xor_sync(0xffffffffu, y1, 1);
+            if (quad & 1) { w[0] = y0; w[2] = y1; } else { w[1] = y0; w[3] = y1; }
           }
-          const bool keep = w[u] >= p.drop_thresh;
-          const float dpm = (keep && inb) ? __uint_as_float(dv[c]) * p.drop_scale : 0.f;
-          pdv[c] = keep ? pr * p.drop_scale : 0.f;
-          dsv[c] = pr * (dpm - st[2 * CH + c]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cc = 4 * g + u, c = c8 + cc, q = qc + c, rel = k - q + p.W;
+            const bool inb = key_ok && q < p.T && rel >= 0 && rel <= 2 * p.W;
+            const float y = fmaf(__uint_as_float(sv[cc]), p.scale,
+                                 ld_shared_f32(rbase + (uint32_t)(c * (RBOX - 1)) * 4u));
+            const float pr = inb ? ex2((y - st[c]) * LOG2E) * st[CH + c] : 0.f;
+            const bool keep = w[u] >= p.drop_thresh;
+            const float dpm = (keep && inb) ? __uint_as_float(dv[cc]) * p.drop_scale : 0.f;
+            pdv[cc] = keep ? pr * p.drop_scale : 0.f;
+            dsv[cc] = pr * (dpm - st[2 * CH + c]);
+          }
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(r_free + 8 * s);
       // band-layout dS (unscaled) for the positional part of dQ: consecutive lanes = consecutive rel
-      if (key_ok) {
+      if (live && key_ok) {
+        __nv_bfloat16* brow = p.dsb + (((int64_t)b * p.T + qs) * p.H + h) * p.RWp + (k - qs + p.W);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int q = qc + c, rel = k - q + p.W;
+        for (int cc = 0; cc < 8; ++cc) {
+          const int q = qs + cc, rel = k - q + p.W;
           if (q < p.T && rel >= 0 && rel <= 2 * p.W) {
-            const __nv_bfloat16 hi = __float2bfloat16_rn(dsv[c]);
-            const int64_t o = (((int64_t)b * p.T + q) * p.H + h) * p.RWp + rel;
-            p.dsb[o] = hi;
-            p.dsb[band_plane + o] = __float2bfloat16_rn(dsv[c] - __bfloat162float(hi));
+            const __nv_bfloat16 hi = __float2bfloat16_rn(dsv[cc]);
+            __nv_bfloat16* o = brow + (int64_t)cc * (p.H * p.RWp - 1);
+            o[0] = hi;
+            o[band_plane] = __float2bfloat16_rn(dsv[cc] - __bfloat162float(hi));
           }
         }
       }
       // the tiles are free once the second MMA group of chunk j-1 has retired
       if (j >= 1) mbar_wait_nth(mma2_done, j - 1);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      {
         uint4 hi, lo;
-        const uint32_t off = sw64_off(i, ch);
-        split_pack(pdv[8 * ch + 0], pdv[8 * ch + 1], hi.x, lo.x);
-        split_pack(pdv[8 * ch + 2], pdv[8 * ch + 3], hi.y, lo.y);
-        split_pack(pdv[8 * ch + 4], pdv[8 * ch + 5], hi.z, lo.z);
-        split_pack(pdv[8 * ch + 6], pdv[8 * ch + 7], hi.w, lo.w);
+        const uint32_t off = sw64_off(i, cg);
+        split_pack(pdv[0], pdv[1], hi.x, lo.x);
+        split_pack(pdv[2], pdv[3], hi.y, lo.y);
+        split_pack(pdv[4], pdv[5], hi.z, lo.z);
+        split_pack(pdv[6], pdv[7], hi.w, lo.w);
         st_shared_v4(base + BwdSmem::PD + off, hi);
         st_shared_v4(base + BwdSmem::PD + BLK_BIG + off, lo);
-        split_pack(dsv[8 * ch + 0], dsv[8 * ch + 1], hi.x, lo.x);
-        split_pack(dsv[8 * ch + 2], dsv[8 * ch + 3], hi.y, lo.y);
-        split_pack(dsv[8 * ch + 4], dsv[8 * ch + 5], hi.z, lo.z);
-        split_pack(dsv[8 * ch + 6], dsv[8 * ch + 7], hi.w, lo.w);
+        split_pack(dsv[0], dsv[1], hi.x, lo.x);
+        split_pack(dsv[2], dsv[3], hi.y, lo.y);
+        split_pack(dsv[4], dsv[5], hi.z, lo.z);
+        split_pack(dsv[6], dsv[7], hi.w, lo.w);
         st_shared_v4(base + BwdSmem::DS + off, hi);
         st_shared_v4(base + BwdSmem::DS + BLK_BIG + off, lo);
       }
@@ -713,14 +793,15 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     }
     dq_epilogue(nch - 1, true);   // also: every MMA of the tile has retired -> dV / dK are complete
     float* krow = p.dqkv + ((int64_t)b * p.T + k) * (3 * D) + D + h * p.dh;
-    for (int c0 = 0; c0 < p.dh; c0 += 32) {
-      uint32_t a[32], g[32];
-      tmem_ld32(tlane + 256 + (uint32_t)c0, a);
-      tmem_ld32(tlane + 128 + (uint32_t)c0, g);
+    const int cw = p.dh >> 2;
+    for (int c0 = cg * cw; c0 < (cg + 1) * cw; c0 += 8) {
+      uint32_t a[8], g[8];
+      tmem_ld8(tlane + 256 + (uint32_t)c0, a);
+      tmem_ld8(tlane + 128 + (uint32_t)c0, g);
       tmem_wait_ld();
       if (key_ok) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
+        for (int c = 0; c < 8; c += 4) {
           *reinterpret_cast<float4*>(krow + c0 + c) =
               make_float4(__uint_as_float(a[c]) * p.scale, __uint_as_float(a[c + 1]) * p.scale,
                           __uint_as_float(a[c + 2]) * p.scale, __uint_as_float(a[c + 3]) * p.scale);
@@ -733,7 +814,7 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == NCW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
   }
@@ -865,7 +946,7 @@ int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_
   const int smem = FWD_SMEM_BYTES;
   if (int rc = set_smem(attn_fused_fwd_kernel, smem)) return rc;
   dim3 grid((unsigned)((T + QT - 1) / QT), (unsigned)(B * H));
-  attn_fused_fwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(mq, mk, mv, mr, p);
+  attn_fused_fwd_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(mq, mk, mv, mr, p);
   SSB_LAUNCH_CHECK("attn_fused_fwd");
   return SSB_OK;
 }
@@ -901,7 +982,7 @@ int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const floa
   const int smem = BWD_SMEM_BYTES;
   if (int rc = set_smem(attn_fused_bwd_kernel, smem)) return rc;
   dim3 grid((unsigned)((T + QT - 1) / QT), (unsigned)(B * H));
-  attn_fused_bwd_kernel<<<grid, 160, smem, (cudaStream_t)stream>>>(mq, mk, mv, mdo, mr, p);
+  attn_fused_bwd_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(mq, mk, mv, mdo, mr, p);
   SSB_LAUNCH_CHECK("attn_fused_bwd");
   return SSB_OK;
 }
