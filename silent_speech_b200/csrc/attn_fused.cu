@@ -47,7 +47,7 @@ constexpr int NCW = 16;          // element-wise warps: 4 per TMEM lane group (a
                                  // scheduler cannot hide its own latencies: 341 / 708 us per layer
                                  // with 4 warps)
 constexpr int NCT = NCW * 32;    // 512 element-wise threads
-constexpr int NTHREADS = NCT + 32;   // + the control warp (TMA + MMA issue)
+constexpr int NTHREADS = NCT + 64;   // + MMA-issue warp (NCW) and TMA-producer warp (NCW + 1)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr int RBOX = 164;        // backward: width of a positional-logit box (159 needed, + <= 3 because
                                  // the box must start on a 16 B boundary of the fp32 row)
@@ -109,7 +109,7 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+[[maybe_unused]] __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -179,6 +179,9 @@ __device__ __forceinline__ uint64_t desc64(uint32_t addr, uint32_t lbo_bytes) {
   d |= (uint64_t)4 << 61;
   return d;
 }
+// descriptor of the same tile `bytes` further on (16 B granular; no carry out of the 14-bit field
+// because shared-memory addresses stay below 256 KB)
+__device__ __forceinline__ uint64_t dadv(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
 // instruction descriptor: D = f32, A = B = bf16, M = 128
 __device__ __forceinline__ uint32_t idesc(int n, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
@@ -232,7 +235,7 @@ struct FwdSmem {   // byte offsets from the 1024-aligned base
   static constexpr int PT3 = R + QT * 200 * 4;                        // P tile 3
   static constexpr int RED = PT3 + 2 * BLK_BIG;                       // [2][4][128] fp32 max / sum exchange
   static constexpr int BARS = RED + 2 * 4 * QT * 4;
-  static constexpr int TOTAL = BARS + 256;
+  static constexpr int TOTAL = BARS + 512;
   static __device__ __forceinline__ int pt(int k) { return k < 3 ? PT + k * 2 * BLK_BIG : PT3; }
 };
 static_assert(FwdSmem::PHASE2_END <= FwdSmem::PHASE1_END, "phase-2 buffers must fit the alias");
@@ -249,6 +252,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t kfull = bars + 32, kempty = kfull + 8 * KST, vfull = kempty + 8 * KST,
                  vempty = vfull + 8 * KST, pfull = vempty + 8 * KST, pempty = pfull + 32;
   const uint32_t tmem_slot = pempty + 32;
+  const uint32_t sready = tmem_slot + 8;   // [11]: S columns of chunk j complete
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
   const int q0 = blockIdx.x * QT;
@@ -266,6 +270,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       mbar_init(vfull + 8 * s, 1); mbar_init(vempty + 8 * s, 1);
     }
     for (int s = 0; s < 4; ++s) { mbar_init(pfull + 8 * s, 4); mbar_init(pempty + 8 * s, 1); }
+    for (int s = 0; s < 11; ++s) mbar_init(sready + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NCW) {
@@ -279,15 +284,13 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const uint32_t tmem_o = tmem + 352;   // O accumulator columns [352, 352 + dh)
 
-  if (warp == NCW) {
+  if (warp == NCW + 1) {
     if (lane == 0) {
-      // ---------------- control thread: TMA + MMA issue ----------------
+      // ---------------- TMA producer ----------------
       mbar_expect_tx(bar_q, 2 * ndb * BLK_BIG);
       for (int pl = 0; pl < 2; ++pl)
         for (int blk = 0; blk < ndb; ++blk)
           tma_5d(base + FwdSmem::Q + pl * plane_q + blk * BLK_BIG, &mapQ, bar_q, blk * DB, q0, h, b, pl);
-      mbar_expect_tx(bar_r, QT * p.RW * 4);
-      tma_3d(base + FwdSmem::R, &mapR, bar_r, 0, q0, bh);
       auto load_kv = [&](const CUtensorMap* map, uint32_t ring, uint32_t full, int j) {
         const int s = j % KST;
         mbar_expect_tx(full + 8 * s, 2 * ndb * BLK_SMALL);
@@ -297,60 +300,64 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                    blk * DB, kw0 + j * CH, h, b, pl);
       };
       for (int j = 0; j < KST && j < nch; ++j) load_kv(&mapK, base + FwdSmem::KRING, kfull, j);
+      mbar_expect_tx(bar_r, QT * p.RW * 4);
+      tma_3d(base + FwdSmem::R, &mapR, bar_r, 0, q0, bh);
+      for (int j = KST; j < nch; ++j) {      // stage j % KST is free when chunk j - KST's MMAs retired
+        mbar_wait(kempty + 8 * (j % KST), (uint32_t)(j / KST - 1) & 1u);
+        load_kv(&mapK, base + FwdSmem::KRING, kfull, j);
+      }
+      // phase 2: the V ring aliases the Q / K region, dead once every S MMA has retired
+      mbar_wait(bar_s, 0);
+      for (int j = 0; j < nch; ++j) {
+        if (j >= KST) mbar_wait(vempty + 8 * (j % KST), (uint32_t)(j / KST - 1) & 1u);
+        load_kv(&mapV, base + FwdSmem::VRING, vfull, j);
+      }
+    }
+  } else if (warp == NCW) {
+    if (lane == 0) {
+      // ---------------- MMA issue ----------------
       // phase 1: S[:, 32 j .. 32 j + 32) = Q K_j^T
       const uint32_t id_s = idesc(CH, 0, 0);
+      const uint64_t dq_hi = desc64(base + FwdSmem::Q, 16), dq_lo = dadv(dq_hi, plane_q);
       mbar_wait(bar_q, 0);
       for (int j = 0; j < nch; ++j) {
         const int s = j % KST;
         mbar_wait(kfull + 8 * s, (uint32_t)(j / KST) & 1u);
         tc_fence_after();
-        const uint32_t qa = base + FwdSmem::Q, kb = base + FwdSmem::KRING + s * FwdSmem::KSTAGE;
+        const uint64_t dk_hi = desc64(base + FwdSmem::KRING + s * FwdSmem::KSTAGE, 16);
+        const uint64_t dk_lo = dadv(dk_hi, plane_k);
         const uint32_t d = tmem + (uint32_t)(j * CH);
         uint32_t acc = 0;
         for (int blk = 0; blk < ndb; ++blk)
           for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t ah = desc64(qa + blk * BLK_BIG + ks * 32, 16);
-            const uint64_t al = desc64(qa + plane_q + blk * BLK_BIG + ks * 32, 16);
-            const uint64_t bhh = desc64(kb + blk * BLK_SMALL + ks * 32, 16);
-            const uint64_t bl = desc64(kb + plane_k + blk * BLK_SMALL + ks * 32, 16);
-            umma(d, ah, bhh, id_s, acc);
-            umma(d, ah, bl, id_s, 1u);
-            umma(d, al, bhh, id_s, 1u);
+            const uint32_t oa = blk * BLK_BIG + ks * 32, ob = blk * BLK_SMALL + ks * 32;
+            umma(d, dadv(dq_hi, oa), dadv(dk_hi, ob), id_s, acc);
+            umma(d, dadv(dq_hi, oa), dadv(dk_lo, ob), id_s, 1u);
+            umma(d, dadv(dq_lo, oa), dadv(dk_hi, ob), id_s, 1u);
             acc = 1u;
           }
         umma_commit(kempty + 8 * s);
-        if (j >= 1 && j - 1 + KST < nch) {   // refill the stage chunk j-1 used (its MMAs are older)
-          mbar_wait(kempty + 8 * ((j - 1) % KST), (uint32_t)((j - 1) / KST) & 1u);
-          load_kv(&mapK, base + FwdSmem::KRING, kfull, j - 1 + KST);
-        }
+        umma_commit(sready + 8 * j);        // pass 1 of the softmax may read these 32 columns
       }
       umma_commit(bar_s);
-      // phase 2: the Q / K region is dead once every S MMA retired
-      mbar_wait(bar_s, 0);
-      for (int j = 0; j < KST && j < nch; ++j) load_kv(&mapV, base + FwdSmem::VRING, vfull, j);
+      // phase 2: O += P_j V_j
       const uint32_t id_o = idesc(p.dh, 0, 1);
       for (int j = 0; j < nch; ++j) {
         const int s = j % KST, pb = j & 3;
         mbar_wait(vfull + 8 * s, (uint32_t)(j / KST) & 1u);
         mbar_wait(pfull + 8 * pb, (uint32_t)(j >> 2) & 1u);
         tc_fence_after();
-        const uint32_t pa = base + FwdSmem::pt(pb);
-        const uint32_t vb = base + FwdSmem::VRING + s * FwdSmem::KSTAGE;
+        const uint64_t dp_hi = desc64(base + FwdSmem::pt(pb), 16), dp_lo = dadv(dp_hi, BLK_BIG);
+        // V chunk [32 keys][dh] read MN-major: 16-key k-steps 1 KB apart, 32-wide d groups 2 KB apart
+        const uint64_t dv_hi = desc64(base + FwdSmem::VRING + s * FwdSmem::KSTAGE, BLK_SMALL);
+        const uint64_t dv_lo = dadv(dv_hi, plane_k);
         for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t ah = desc64(pa + ks * 32, 16), al = desc64(pa + BLK_BIG + ks * 32, 16);
-          // V chunk [32 keys][dh] read MN-major: 16-key k-steps 1 KB apart, 32-wide d groups 2 KB apart
-          const uint64_t bhh = desc64(vb + ks * 1024, BLK_SMALL);
-          const uint64_t bl = desc64(vb + plane_k + ks * 1024, BLK_SMALL);
-          umma(tmem_o, ah, bhh, id_o, (j > 0 || ks > 0) ? 1u : 0u);
-          umma(tmem_o, ah, bl, id_o, 1u);
-          umma(tmem_o, al, bhh, id_o, 1u);
+          umma(tmem_o, dadv(dp_hi, ks * 32), dadv(dv_hi, ks * 1024), id_o, (j > 0 || ks > 0) ? 1u : 0u);
+          umma(tmem_o, dadv(dp_hi, ks * 32), dadv(dv_lo, ks * 1024), id_o, 1u);
+          umma(tmem_o, dadv(dp_lo, ks * 32), dadv(dv_hi, ks * 1024), id_o, 1u);
         }
         umma_commit(pempty + 8 * pb);
         umma_commit(vempty + 8 * s);
-        if (j >= 1 && j - 1 + KST < nch) {
-          mbar_wait(vempty + 8 * ((j - 1) % KST), (uint32_t)((j - 1) / KST) & 1u);
-          load_kv(&mapV, base + FwdSmem::VRING, vfull, j - 1 + KST);
-        }
       }
       umma_commit(bar_o);
     }
@@ -378,28 +385,37 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       return 1;
     };
     mbar_wait(bar_r, 0);
-    mbar_wait(bar_s, 0);
-    tc_fence_after();
     float m = -CUDART_INF_F;
     for (int j = cg; j < nch; j += 4) {
       const int cls = chunk_class(j);
       if (cls == 0) continue;
+      mbar_wait(sready + 8 * j, 0);
+      tc_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[16];
         tmem_ld16(tlane + (uint32_t)(j * CH + half * 16), v);
         tmem_wait_ld();
+        const uint32_t ra = rrow + (uint32_t)(j * CH + half * 16 + soff) * 4u;
+        if (cls == 2) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int col = j * CH + half * 16 + c, rel = col + soff;
-          const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u));
-          const bool ok = cls == 2 || (row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W);
-          m = fmaxf(m, ok ? y : -CUDART_INF_F);
+          for (int c = 0; c < 16; ++c)
+            m = fmaxf(m, fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4)));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const int col = j * CH + half * 16 + c, rel = col + soff;
+            const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4));
+            const bool ok = row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W;
+            m = fmaxf(m, ok ? y : -CUDART_INF_F);
+          }
         }
       }
     }
     red[cg * QT + i] = m;
     bar_compute();
+    // the P tiles alias the Q / K buffers: every S MMA must have retired before the first write
+    mbar_wait(bar_s, 0);
     m = fmaxf(fmaxf(red[i], red[QT + i]), fmaxf(red[2 * QT + i], red[3 * QT + i]));
     if (!row_ok) m = 0.f;
     const float mneg = -m * LOG2E;
@@ -409,7 +425,6 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       const int cls = chunk_class(j);
       const int n = j >> 2;               // n-th use of P tile cg
       const uint32_t pt = base + FwdSmem::pt(cg);
-      if (n >= 1) mbar_wait(pempty + 8 * cg, (uint32_t)(n - 1) & 1u);   // MMAs of chunk j-4 retired
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float e[16];
@@ -420,14 +435,23 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           uint32_t v[16];
           tmem_ld16(tlane + (uint32_t)(j * CH + half * 16), v);
           tmem_wait_ld();
+          const uint32_t ra = rrow + (uint32_t)(j * CH + half * 16 + soff) * 4u;
+          if (cls == 2) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int col = j * CH + half * 16 + c, rel = col + soff;
-            const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(rrow + (uint32_t)rel * 4u));
-            const bool ok = cls == 2 || (row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W);
-            const float x = ok ? ex2(fmaf(y, LOG2E, mneg)) : 0.f;
-            e[c] = x;
-            sum += x;
+            for (int c = 0; c < 16; ++c) {
+              const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4));
+              e[c] = ex2(fmaf(y, LOG2E, mneg));
+              sum += e[c];
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const int col = j * CH + half * 16 + c, rel = col + soff;
+              const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4));
+              const bool ok = row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W;
+              e[c] = ok ? ex2(fmaf(y, LOG2E, mneg)) : 0.f;
+              sum += e[c];
+            }
           }
           if (p.drop_p > 0.f) {
 #pragma unroll
@@ -441,16 +465,21 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
             }
           }
         }
+        uint4 hi[2], lo[2];
 #pragma unroll
         for (int c2 = 0; c2 < 2; ++c2) {
-          uint4 hi, lo;
-          split_pack(e[8 * c2 + 0], e[8 * c2 + 1], hi.x, lo.x);
-          split_pack(e[8 * c2 + 2], e[8 * c2 + 3], hi.y, lo.y);
-          split_pack(e[8 * c2 + 4], e[8 * c2 + 5], hi.z, lo.z);
-          split_pack(e[8 * c2 + 6], e[8 * c2 + 7], hi.w, lo.w);
+          split_pack(e[8 * c2 + 0], e[8 * c2 + 1], hi[c2].x, lo[c2].x);
+          split_pack(e[8 * c2 + 2], e[8 * c2 + 3], hi[c2].y, lo[c2].y);
+          split_pack(e[8 * c2 + 4], e[8 * c2 + 5], hi[c2].z, lo[c2].z);
+          split_pack(e[8 * c2 + 6], e[8 * c2 + 7], hi[c2].w, lo[c2].w);
+        }
+        // only now is the tile needed: the MMAs of chunk j-4 (its previous user) must have retired
+        if (half == 0 && n >= 1) mbar_wait(pempty + 8 * cg, (uint32_t)(n - 1) & 1u);
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
           const uint32_t off = sw64_off(i, half * 2 + c2);
-          st_shared_v4(pt + off, hi);
-          st_shared_v4(pt + BLK_BIG + off, lo);
+          st_shared_v4(pt + off, hi[c2]);
+          st_shared_v4(pt + BLK_BIG + off, lo[c2]);
         }
       }
       fence_async_smem();
@@ -521,8 +550,9 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t bars = base + BwdSmem::BARS;
   const uint32_t kv_full = bars, qd_full = bars + 8 /*[2]*/, r_full = bars + 24 /*[2]*/,
                  r_free = bars + 40 /*[2]*/, s_full = bars + 56 /*[2]*/, sp_free = bars + 72 /*[2]*/,
-                 tiles_full = bars + 88, mma2_done = bars + 96, ep_done = bars + 104 /*[2]*/;
-  const uint32_t tmem_slot = bars + 128;
+                 tiles_full = bars + 88, mma2_done = bars + 96, ep_done = bars + 104 /*[2]*/,
+                 qd_free = bars + 120 /*[2]*/;
+  const uint32_t tmem_slot = bars + 136;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.y, b = bh / p.H, h = bh - b * p.H;
   const int k0 = blockIdx.x * QT;
@@ -537,6 +567,7 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     for (int s = 0; s < 2; ++s) {
       mbar_init(qd_full + 8 * s, 1); mbar_init(r_full + 8 * s, 1); mbar_init(r_free + 8 * s, NCW);
       mbar_init(s_full + 8 * s, 1); mbar_init(sp_free + 8 * s, NCW); mbar_init(ep_done + 8 * s, NCW);
+      mbar_init(qd_free + 8 * s, 1);
     }
     mbar_init(tiles_full, NCW);
     mbar_init(mma2_done, 1);
@@ -554,9 +585,9 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   // TMEM columns: [0,128) two {S^T, dP^T} pairs, [128,256) dV, [256,384) dK, [384,448) two dQ^T
   const uint32_t t_dv = tmem + 128, t_dk = tmem + 256, t_dq = tmem + 384;
 
-  if (warp == NCW) {
+  if (warp == NCW + 1) {
     if (lane == 0) {
-      // ---------------- control thread ----------------
+      // ---------------- TMA producer ----------------
       mbar_expect_tx(kv_full, 4 * ndb * BLK_BIG);
       for (int pl = 0; pl < 2; ++pl)
         for (int blk = 0; blk < ndb; ++blk) {
@@ -587,25 +618,44 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       load_qd(0);
       load_r(0);
       if (nch > 1) { load_qd(1); load_r(1); }
+      for (int j = 0; j + 2 < nch; ++j) {
+        const int s = j & 1;
+        mbar_wait(r_free + 8 * s, (uint32_t)(j >> 1) & 1u);     // threads are done with R stage s
+        load_r(j + 2);
+        mbar_wait(qd_free + 8 * s, (uint32_t)(j >> 1) & 1u);    // dV / dK MMAs of chunk j retired
+        load_qd(j + 2);
+      }
+    }
+  } else if (warp == NCW) {
+    if (lane == 0) {
+      // ---------------- MMA issue ----------------
       const uint32_t id_s = idesc(CH, 0, 0), id_acc = idesc(p.dh, 0, 1), id_dq = idesc(CH, 1, 1);
+      // K / V tiles as K-major A operands (S^T, dP^T) and K as the MN-major A operand of dQ^T
+      const uint64_t k_hi = desc64(base + BwdSmem::K, 16), k_lo = dadv(k_hi, plane_big);
+      const uint64_t v_hi = desc64(base + BwdSmem::V, 16), v_lo = dadv(v_hi, plane_big);
+      const uint64_t kt_hi = desc64(base + BwdSmem::K, BLK_BIG), kt_lo = dadv(kt_hi, plane_big);
+      const uint64_t pd_hi = desc64(base + BwdSmem::PD, 16), pd_lo = dadv(pd_hi, BLK_BIG);
+      const uint64_t ds_hi = desc64(base + BwdSmem::DS, 16), ds_lo = dadv(ds_hi, BLK_BIG);
+      const uint64_t dst_hi = desc64(base + BwdSmem::DS, BLK_BIG), dst_lo = dadv(dst_hi, BLK_BIG);
       auto mma1 = [&](int j) {
         const int s = j & 1;
         mbar_wait(qd_full + 8 * s, (uint32_t)(j >> 1) & 1u);
         if (j >= 2) mbar_wait(sp_free + 8 * s, (uint32_t)((j - 2) >> 1) & 1u);
         tc_fence_after();
-        const uint32_t qb = base + BwdSmem::QD + s * BwdSmem::QD_STAGE, dob = qb + BwdSmem::QD_HALF;
-        const uint32_t ka = base + BwdSmem::K, va = base + BwdSmem::V;
+        const uint64_t q_hi = desc64(base + BwdSmem::QD + s * BwdSmem::QD_STAGE, 16);
+        const uint64_t q_lo = dadv(q_hi, plane_small);
+        const uint64_t o_hi = dadv(q_hi, BwdSmem::QD_HALF), o_lo = dadv(o_hi, plane_small);
         const uint32_t d_s = tmem + s * 64, d_p = d_s + 32;
         uint32_t acc = 0;
         for (int blk = 0; blk < ndb; ++blk)
           for (int ks = 0; ks < 2; ++ks) {
             const uint32_t oa = blk * BLK_BIG + ks * 32, ob = blk * BLK_SMALL + ks * 32;
-            umma(d_s, desc64(ka + oa, 16), desc64(qb + ob, 16), id_s, acc);
-            umma(d_s, desc64(ka + oa, 16), desc64(qb + plane_small + ob, 16), id_s, 1u);
-            umma(d_s, desc64(ka + plane_big + oa, 16), desc64(qb + ob, 16), id_s, 1u);
-            umma(d_p, desc64(va + oa, 16), desc64(dob + ob, 16), id_s, acc);
-            umma(d_p, desc64(va + oa, 16), desc64(dob + plane_small + ob, 16), id_s, 1u);
-            umma(d_p, desc64(va + plane_big + oa, 16), desc64(dob + ob, 16), id_s, 1u);
+            umma(d_s, dadv(k_hi, oa), dadv(q_hi, ob), id_s, acc);
+            umma(d_s, dadv(k_hi, oa), dadv(q_lo, ob), id_s, 1u);
+            umma(d_s, dadv(k_lo, oa), dadv(q_hi, ob), id_s, 1u);
+            umma(d_p, dadv(v_hi, oa), dadv(o_hi, ob), id_s, acc);
+            umma(d_p, dadv(v_hi, oa), dadv(o_lo, ob), id_s, 1u);
+            umma(d_p, dadv(v_lo, oa), dadv(o_hi, ob), id_s, 1u);
             acc = 1u;
           }
         umma_commit(s_full + 8 * s);
@@ -617,36 +667,35 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         // second group of chunk j: needs its P_drop^T / dS^T tiles and a free dQ^T accumulator
         const int s = j & 1;
         mbar_wait_nth(tiles_full, j);
-        if (j >= 2) mbar_wait(ep_done + 8 * s, (uint32_t)((j - 2) >> 1) & 1u);
         tc_fence_after();
-        const uint32_t qb = base + BwdSmem::QD + s * BwdSmem::QD_STAGE, dob = qb + BwdSmem::QD_HALF;
-        const uint32_t pd = base + BwdSmem::PD, ds = base + BwdSmem::DS, ka = base + BwdSmem::K;
+        // Q_c / dO_c read MN-major (rows = queries): 16-row k-steps 1 KB apart, d groups 2 KB apart
+        const uint64_t qm_hi = desc64(base + BwdSmem::QD + s * BwdSmem::QD_STAGE, BLK_SMALL);
+        const uint64_t qm_lo = dadv(qm_hi, plane_small);
+        const uint64_t om_hi = dadv(qm_hi, BwdSmem::QD_HALF), om_lo = dadv(om_hi, plane_small);
         for (int ks = 0; ks < 2; ++ks) {   // K = 32 queries
           const uint32_t oa = ks * 32, ob = ks * 1024;
           const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-          umma(t_dv, desc64(pd + oa, 16), desc64(dob + ob, BLK_SMALL), id_acc, acc);
-          umma(t_dv, desc64(pd + oa, 16), desc64(dob + plane_small + ob, BLK_SMALL), id_acc, 1u);
-          umma(t_dv, desc64(pd + BLK_BIG + oa, 16), desc64(dob + ob, BLK_SMALL), id_acc, 1u);
-          umma(t_dk, desc64(ds + oa, 16), desc64(qb + ob, BLK_SMALL), id_acc, acc);
-          umma(t_dk, desc64(ds + oa, 16), desc64(qb + plane_small + ob, BLK_SMALL), id_acc, 1u);
-          umma(t_dk, desc64(ds + BLK_BIG + oa, 16), desc64(qb + ob, BLK_SMALL), id_acc, 1u);
+          umma(t_dv, dadv(pd_hi, oa), dadv(om_hi, ob), id_acc, acc);
+          umma(t_dv, dadv(pd_hi, oa), dadv(om_lo, ob), id_acc, 1u);
+          umma(t_dv, dadv(pd_lo, oa), dadv(om_hi, ob), id_acc, 1u);
+          umma(t_dk, dadv(ds_hi, oa), dadv(qm_hi, ob), id_acc, acc);
+          umma(t_dk, dadv(ds_hi, oa), dadv(qm_lo, ob), id_acc, 1u);
+          umma(t_dk, dadv(ds_lo, oa), dadv(qm_hi, ob), id_acc, 1u);
         }
+        umma_commit(qd_free + 8 * s);       // the {Q_c, dO_c} stage may be refilled
         // dQ_c^T [d][q] = K^T dS^T: both operands MN-major (rows = keys), K = 128 keys
+        if (j >= 2) {
+          mbar_wait(ep_done + 8 * s, (uint32_t)((j - 2) >> 1) & 1u);
+          tc_fence_after();
+        }
         const uint32_t d_q = t_dq + s * 32;
         for (int ks = 0; ks < 8; ++ks) {
           const uint32_t o = ks * 1024;
-          umma(d_q, desc64(ka + o, BLK_BIG), desc64(ds + o, BLK_BIG), id_dq, ks > 0 ? 1u : 0u);
-          umma(d_q, desc64(ka + o, BLK_BIG), desc64(ds + BLK_BIG + o, BLK_BIG), id_dq, 1u);
-          umma(d_q, desc64(ka + plane_big + o, BLK_BIG), desc64(ds + o, BLK_BIG), id_dq, 1u);
+          umma(d_q, dadv(kt_hi, o), dadv(dst_hi, o), id_dq, ks > 0 ? 1u : 0u);
+          umma(d_q, dadv(kt_hi, o), dadv(dst_lo, o), id_dq, 1u);
+          umma(d_q, dadv(kt_lo, o), dadv(dst_hi, o), id_dq, 1u);
         }
         umma_commit(mma2_done);
-        // refill: {Q, dO} stage s is free when these MMAs retire; R stage s when the threads left it
-        if (j + 2 < nch) {
-          mbar_wait_nth(mma2_done, j);
-          load_qd(j + 2);
-          mbar_wait(r_free + 8 * s, (uint32_t)(j >> 1) & 1u);
-          load_r(j + 2);
-        }
       }
     }
   } else {
