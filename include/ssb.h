@@ -130,6 +130,12 @@ typedef struct {
   float drop_p;           /* inverted dropout after relu; 0 disables */
   uint64_t seed;          /* Philox key */
   uint32_t site;          /* Philox stream id of this dropout site */
+  /* tcgen05 engine only (ssb_gemm_tc_kmajor; the CUDA-core engine rejects them): */
+  void* planes_out;       /* also write the result as bf16 split planes, plain (M, N) per plane;
+                             with out.base == NULL the fp32 result is not written at all */
+  int64_t planes_stride;  /* elements between the hi and lo output planes */
+  const void* mask_planes; /* instead of mask_src: bf16 hi plane (M, N) of the mask source
+                              (hi = bf16(x) keeps the sign and zero-ness of x) */
 } ssb_epilogue_t;
 
 /* C[m,n] = epi( sum_k A(m,k) * W[k*ldw + n] ) */
@@ -152,6 +158,10 @@ SSB_API int64_t ssb_col_partials_bytes(int64_t rows, int64_t C);
 /* out[c] (+)= sum_r x[r,c]   (bias gradients) */
 SSB_API int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumulate,
                        void* workspace, int64_t workspace_bytes, void* stream);
+/* same, x given as bf16 split planes [2][rows][C] (x = hi + lo); C a multiple of 8 */
+SSB_API int ssb_colsum_planes(const void* planes, int64_t plane_stride, int64_t rows, int64_t C,
+                              float* out, int accumulate, void* workspace,
+                              int64_t workspace_bytes, void* stream);
 /* nn.BatchNorm1d statistics (architecture.py:19,21,25).  training != 0: batch mean / biased var
  * over rows, running stats updated in place (momentum, unbiased var); else running stats.
  * Produces mean, rstd and the fused affine  scale = gamma*rstd, shift = beta - mean*scale. */

@@ -37,7 +37,8 @@ class Epilogue(ctypes.Structure):
     """ssb_epilogue_t"""
     _fields_ = [("out", Scatter), ("bias", c_ptr), ("mask_src", c_ptr), ("mask_scale", c_f32),
                 ("relu", c_i32), ("accumulate", c_i32), ("drop_p", c_f32), ("seed", c_u64),
-                ("site", c_u32)]
+                ("site", c_u32), ("planes_out", c_ptr), ("planes_stride", c_i64),
+                ("mask_planes", c_ptr)]
 
 
 class TcOperand(ctypes.Structure):
@@ -91,6 +92,7 @@ _SIGNATURES = {
                                    c_ptr]),
     "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
+    "ssb_colsum_planes": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_bn_apply": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64,
@@ -112,7 +114,7 @@ _SIGNATURES = {
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
 _KERNELS_PER_CALL = {
     "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
-    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
+    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
     "ssb_split_bf16": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,

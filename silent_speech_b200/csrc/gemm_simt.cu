@@ -269,6 +269,123 @@ gemm_kernel(const Gather ga, const float* __restrict__ Bplain, int ldb, const We
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Thin reductions (K <= 32): the first ResBlock reads the 8-channel EMG (architecture.py:18,24:
+// K = 3*8 and K = 8).  The 128x128 tile engine above wastes 80-95 % of its A tile there and the
+// weight gradient (a 24 x 768 result reduced over 64 000 rows) ran at 5 TF/s.  Here a thread owns
+// 4 output columns x ALL K: the K x 4 weight block (NN) or accumulator block (TN) lives in
+// registers, A rows are warp-broadcast loads, and the wide operand streams through once.
+// block = 64 column lanes (float4 -> 256 columns) x 4 row lanes.
+// ---------------------------------------------------------------------------------------
+template <int K4>   // K padded to 4*K4
+__device__ __forceinline__ void thin_load_a(const Gather& ga, int m, int K, float4 (&a)[K4]) {
+#pragma unroll
+  for (int q = 0; q < K4; ++q) {
+    a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (4 * q < K) {
+      bool valid;
+      const float* src = gather_ptr(ga, m, 4 * q, valid);
+      if (valid) a[q] = ldg4(src);
+    }
+  }
+}
+
+template <int K4>
+__global__ void __launch_bounds__(256)
+thin_nn_kernel(const Gather ga, const float* __restrict__ W, int ldw, const Epilogue ep, int M,
+               int N, int K, int rows_per_cta) {
+  const int nl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int n = (blockIdx.x * 64 + nl) * 4;
+  if (n >= N) return;
+  float4 w[4 * K4];
+#pragma unroll
+  for (int k = 0; k < 4 * K4; ++k)
+    w[k] = k < K ? ldg4(W + (int64_t)k * ldw + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ep.bias) bias = ldg4(ep.bias + n);
+  const int m0 = blockIdx.y * rows_per_cta;
+  const int m1 = min(M, m0 + rows_per_cta);
+  for (int m = m0 + rl; m < m1; m += 4) {
+    float4 a[K4];
+    thin_load_a<K4>(ga, m, K, a);
+    float4 v = bias;
+#pragma unroll
+    for (int q = 0; q < K4; ++q) {
+      const float av[4] = {a[q].x, a[q].y, a[q].z, a[q].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 ww = w[4 * q + j];
+        v.x = fmaf(av[j], ww.x, v.x); v.y = fmaf(av[j], ww.y, v.y);
+        v.z = fmaf(av[j], ww.z, v.z); v.w = fmaf(av[j], ww.w, v.w);
+      }
+    }
+    if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    const int b = m / ep.out.rows_per_batch, t = m - b * ep.out.rows_per_batch;
+    float* row = ep.out.base + (int64_t)b * ep.out.batch_stride +
+                 (int64_t)(t * ep.out.d_t + ep.out.d_off) * ep.out.ld;
+    *reinterpret_cast<float4*>(row + n) = v;
+  }
+}
+
+template <int K4>
+__global__ void __launch_bounds__(256)
+thin_tn_kernel(const Gather ga, const float* __restrict__ G, int ldg, float* __restrict__ dW,
+               int lddw, int M, int N, int K, int rows_per_cta) {
+  __shared__ float4 red[3][64];
+  const int nl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int n = (blockIdx.x * 64 + nl) * 4;
+  const bool n_ok = n < N;
+  float4 acc[4 * K4];
+#pragma unroll
+  for (int k = 0; k < 4 * K4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int m0 = blockIdx.y * rows_per_cta;
+  const int m1 = min(M, m0 + rows_per_cta);
+  if (n_ok) {
+    for (int m = m0 + rl; m < m1; m += 4) {
+      float4 a[K4];
+      thin_load_a<K4>(ga, m, K, a);
+      const float4 g = ldg4(G + (int64_t)m * ldg + n);
+#pragma unroll
+      for (int q = 0; q < K4; ++q) {
+        const float av[4] = {a[q].x, a[q].y, a[q].z, a[q].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4& c = acc[4 * q + j];
+          c.x = fmaf(av[j], g.x, c.x); c.y = fmaf(av[j], g.y, c.y);
+          c.z = fmaf(av[j], g.z, c.z); c.w = fmaf(av[j], g.w, c.w);
+        }
+      }
+    }
+  }
+  // combine the 4 row lanes (fixed order), then one vector atomic per (k, 4 columns) and CTA
+#pragma unroll
+  for (int k = 0; k < 4 * K4; ++k) {
+    if (k < K) {   // uniform
+      if (rl > 0) red[rl - 1][nl] = acc[k];
+      __syncthreads();
+      if (rl == 0 && n_ok) {
+        float4 c = acc[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float4 o = red[i][nl];
+          c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
+        }
+        atomicAdd(reinterpret_cast<float4*>(dW + (int64_t)k * lddw + n), c);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int thin_rows_per_cta(int64_t M, int64_t N) {
+  const int col_blocks = (int)((N + 255) / 256);
+  int row_blocks = (4 * ssb::num_sms() + col_blocks - 1) / col_blocks;
+  int64_t per = (M + row_blocks - 1) / row_blocks;
+  per = (per + 3) / 4 * 4;
+  return (int)(per < 4 ? 4 : per);
+}
+
 int check_gather(const ssb_gather_t* g, int64_t M, int64_t K) {
   SSB_REQUIRE(g && g->base, "gemm: null A");
   SSB_REQUIRE(g->rows_per_batch > 0 && g->C > 0 && g->L_src > 0 && g->ld >= g->C,
@@ -291,6 +408,8 @@ Gather to_gather(const ssb_gather_t* g) {
 
 int fill_epilogue(const ssb_epilogue_t* e, int64_t M, int64_t N, Epilogue* out) {
   SSB_REQUIRE(e && e->out.base, "gemm: null output");
+  SSB_REQUIRE(!e->planes_out && !e->mask_planes,
+              "gemm: split-plane epilogue operands exist on the tcgen05 engine only");
   SSB_REQUIRE(e->out.rows_per_batch > 0 && e->out.ld >= N && e->out.ld % 4 == 0 &&
                   e->out.batch_stride % 4 == 0 && ((uintptr_t)e->out.base & 15) == 0,
               "gemm: bad output geometry / alignment");
@@ -320,6 +439,20 @@ int ssb_gemm_nn(const ssb_gather_t* A, const float* W, int64_t ldw, const ssb_ep
   SSB_REQUIRE(W && ldw >= N && ldw % 4 == 0 && ((uintptr_t)W & 15) == 0, "gemm_nn: bad W");
   Epilogue ep;
   if (int rc = fill_epilogue(epi, M, N, &ep)) return rc;
+  if (K <= 32 && M >= 4096 && ep.drop_p == 0.f && !ep.mask_src && !ep.accumulate) {
+    const int per = thin_rows_per_cta(M, N);
+    dim3 tg((unsigned)((N + 255) / 256), (unsigned)((M + per - 1) / per));
+    cudaStream_t st = (cudaStream_t)stream;
+    const Gather ga = to_gather(A);
+    switch ((K + 3) / 4 > 4 ? ((K + 7) / 8) * 2 : (int)((K + 3) / 4)) {
+      case 1: case 2: thin_nn_kernel<2><<<tg, 256, 0, st>>>(ga, W, (int)ldw, ep, (int)M, (int)N, (int)K, per); break;
+      case 3: case 4: thin_nn_kernel<4><<<tg, 256, 0, st>>>(ga, W, (int)ldw, ep, (int)M, (int)N, (int)K, per); break;
+      case 6: thin_nn_kernel<6><<<tg, 256, 0, st>>>(ga, W, (int)ldw, ep, (int)M, (int)N, (int)K, per); break;
+      default: thin_nn_kernel<8><<<tg, 256, 0, st>>>(ga, W, (int)ldw, ep, (int)M, (int)N, (int)K, per); break;
+    }
+    SSB_LAUNCH_CHECK("thin_nn");
+    return SSB_OK;
+  }
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
   SSB_REQUIRE(grid.y <= 65535, "gemm_nn: M too large for grid.y");
   WeightNT dummy = {};
@@ -358,6 +491,21 @@ int ssb_gemm_tn(const ssb_gather_t* A, const float* G, int64_t ldg, float* dW, i
                   ((uintptr_t)G & 15) == 0 && ((uintptr_t)dW & 15) == 0,
               "gemm_tn: bad G / dW geometry");
   cudaStream_t st = (cudaStream_t)stream;
+  if (K <= 32 && M >= 4096) {
+    if (!accumulate)
+      SSB_CUDA(cudaMemset2DAsync(dW, (size_t)lddw * 4, 0, (size_t)N * 4, (size_t)K, st));
+    const int per = thin_rows_per_cta(M, N);
+    dim3 tg((unsigned)((N + 255) / 256), (unsigned)((M + per - 1) / per));
+    const Gather ga = to_gather(A);
+    switch ((K + 3) / 4 > 4 ? ((K + 7) / 8) * 2 : (int)((K + 3) / 4)) {
+      case 1: case 2: thin_tn_kernel<2><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
+      case 3: case 4: thin_tn_kernel<4><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
+      case 6: thin_tn_kernel<6><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
+      default: thin_tn_kernel<8><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
+    }
+    SSB_LAUNCH_CHECK("thin_tn");
+    return SSB_OK;
+  }
   const int tiles = (int)(((N + BN - 1) / BN) * ((K + BM - 1) / BM));
   int splits = 1;
   const int sms = ssb::num_sms();

@@ -87,6 +87,8 @@ struct TcParams {
   // epilogue
   float* out; int64_t out_batch_stride, out_batch_stride_hi; int out_ld, out_dt, out_doff;
   const float* bias; const float* mask_src; float mask_scale;
+  __nv_bfloat16* planes; int64_t planes_stride;   // optional split-plane copy of the result, plain (M, N)
+  const __nv_bfloat16* mask_planes;               // mask source given as its bf16 hi plane
   int relu, accumulate, atomic;
   float drop_p, drop_scale; uint32_t drop_thresh; uint64_t seed; const uint64_t* seed_src; uint32_t site;
 };
@@ -454,11 +456,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float4 side[8];
       auto prefetch = [&](int c) {
         const int n = n0 + c * 32 + csub;
-        if (!(p.mask_src || p.accumulate) || !group_live || n >= p.N) return;
+        if (!(p.mask_src || p.mask_planes || p.accumulate) || !group_live || n >= p.N) return;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (first + 4 * i >= limit) continue;
-          if (p.mask_src)
+          if (p.mask_planes) {   // 4 bf16: only sign / zero-ness matter
+            const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.mask_planes + (grow0 + 4 * i) * p.N + n));
+            side[i] = make_float4(__uint_as_float(m.x << 16), __uint_as_float(m.x & 0xffff0000u),
+                                  __uint_as_float(m.y << 16), __uint_as_float(m.y & 0xffff0000u));
+          } else if (p.mask_src)
             side[i] = __ldg(reinterpret_cast<const float4*>(p.mask_src + (grow0 + 4 * i) * p.N + n));
           else
             side[i] = *reinterpret_cast<const float4*>(orow0 + i * row_step + n);
@@ -514,7 +520,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             r.z = rnd.z >= p.drop_thresh ? r.z * p.drop_scale : 0.f;
             r.w = rnd.w >= p.drop_thresh ? r.w * p.drop_scale : 0.f;
           }
-          if (p.mask_src) {
+          if (p.mask_src || p.mask_planes) {
             const float4 mk = side[i];
             r.x = mk.x > 0.f ? r.x * p.mask_scale : 0.f;
             r.y = mk.y > 0.f ? r.y * p.mask_scale : 0.f;
@@ -528,10 +534,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         // next block's side operands go out before this block's stores queue up behind them
         if (c + 2 < BN / 32) prefetch(c + 2);
+        if (p.out) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (!n_ok || first + 4 * i >= limit || p.atomic) continue;
-          *reinterpret_cast<float4*>(orow0 + i * row_step + n) = o[i];
+          for (int i = 0; i < 8; ++i) {
+            if (!n_ok || first + 4 * i >= limit || p.atomic) continue;
+            *reinterpret_cast<float4*>(orow0 + i * row_step + n) = o[i];
+          }
+        }
+        if (p.planes) {   // x = hi + lo, the operand format of the next GEMM (no split pass)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!n_ok || first + 4 * i >= limit) continue;
+            const float4 r = o[i];
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(r.x, r.y), h23 = __floats2bfloat162_rn(r.z, r.w);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(r.x - __low2float(h01), r.y - __high2float(h01));
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(r.z - __low2float(h23), r.w - __high2float(h23));
+            __nv_bfloat16* dst = p.planes + (grow0 + 4 * i) * p.N + n;
+            *reinterpret_cast<uint2*>(dst) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(dst + p.planes_stride) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+          }
         }
       }
       // hand the accumulator back to the (leader's) MMA warp
@@ -702,10 +725,17 @@ int launch(const CUtensorMap& mapA, const CUtensorMap& mapB, TcParams p, dim3 ti
 }
 
 int fill_epi(const ssb_epilogue_t* e, int64_t N, TcParams* p) {
-  SSB_REQUIRE(e && e->out.base, "gemm_tc: null output");
+  SSB_REQUIRE(e && (e->out.base || e->planes_out), "gemm_tc: null output");
   SSB_REQUIRE(N % 4 == 0 && e->out.ld >= N && e->out.ld % 4 == 0 && e->out.batch_stride % 4 == 0 &&
                   ((uintptr_t)e->out.base & 15) == 0,
               "gemm_tc: bad output geometry / alignment");
+  SSB_REQUIRE(!(e->mask_src && e->mask_planes), "gemm_tc: mask_src and mask_planes are exclusive");
+  SSB_REQUIRE(((uintptr_t)e->planes_out & 7) == 0 && ((uintptr_t)e->mask_planes & 7) == 0 &&
+                  e->planes_stride % 4 == 0,
+              "gemm_tc: split-plane epilogue operands must be 8 B aligned");
+  SSB_REQUIRE(e->out.base || !e->accumulate, "gemm_tc: accumulate needs an fp32 output");
+  p->planes = (__nv_bfloat16*)e->planes_out; p->planes_stride = e->planes_stride;
+  p->mask_planes = (const __nv_bfloat16*)e->mask_planes;
   SSB_REQUIRE(e->drop_p >= 0.f && e->drop_p < 1.f, "gemm_tc: bad dropout p");
   p->out = e->out.base; p->out_batch_stride = e->out.batch_stride; p->out_ld = e->out.ld;
   p->out_batch_stride_hi = e->out.batch_stride_hi;
@@ -844,6 +874,7 @@ int ssb_gemm_tc_batched(const ssb_tc_operand_t* A, const ssb_tc_operand_t* B, in
               "gemm_tc_batched: bad geometry");
   TcParams p = {};
   if (int rc = fill_epi(epi, N, &p)) return rc;
+  SSB_REQUIRE(!p.planes && !p.mask_planes, "gemm_tc batched: split-plane epilogue operands unsupported");
   SSB_REQUIRE(epi->out.rows_per_batch == A->rows_out, "gemm_tc_batched: rows_per_batch mismatch");
   int64_t a_lo, a_hi, b_lo, b_hi;
   batch_levels(A, &a_lo, &a_hi);
@@ -879,6 +910,7 @@ int ssb_gemm_tc_batched_tn(const ssb_tc_operand_t* X, const ssb_tc_operand_t* G,
               "gemm_tc_batched_tn: operand geometry mismatch");
   TcParams p = {};
   if (int rc = fill_epi(epi, N, &p)) return rc;
+  SSB_REQUIRE(!p.planes && !p.mask_planes, "gemm_tc batched: split-plane epilogue operands unsupported");
   SSB_REQUIRE(epi->out.rows_per_batch == K, "gemm_tc_batched_tn: output rows_per_batch must be K");
   int64_t x_lo, x_hi, g_lo, g_hi;
   batch_levels(X, &x_lo, &x_hi);

@@ -7,6 +7,8 @@
 // All tensors are (rows, C) fp32 with C contiguous; per-channel quantities are column
 // reductions.  Reductions are two-stage and deterministic: a grid of CTAs writes fp32
 // partials per row chunk, a finalize kernel adds them in fp64 in a fixed order.
+#include <cuda_bf16.h>
+
 #include "ssb_common.cuh"
 
 namespace {
@@ -75,6 +77,42 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
     }
     if (rl == 0 || MODE == 2)
       *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 2 + rl) * C + c) = a;
+  }
+}
+
+// column sums of a tensor held as bf16 split planes (x = hi + lo): 32 column-lanes x 8 columns
+__global__ void __launch_bounds__(256)
+col_partials_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
+                           int64_t rows, int C, float* __restrict__ partials /* [nchunks][2][C] */) {
+  __shared__ float red[8][32][9];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cl) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * RCH;
+  const int64_t r1 = min(rows, r0 + RCH);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi + r * C + c));
+      const uint4 l = __ldg(reinterpret_cast<const uint4*>(lo + r * C + c));
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[2 * j] += __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+        s[2 * j + 1] += __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[rl][cl][j] = s[j];
+  __syncthreads();
+  if (rl == 0 && c < C) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = red[0][cl][j];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) a += red[i][cl][j];
+      partials[((int64_t)blockIdx.y * 2) * C + c + j] = a;
+    }
   }
 }
 
@@ -450,6 +488,28 @@ int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumula
   col_partials_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
                                                (int)C, (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials<1>");
+  colsum_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, out,
+                                                 accumulate);
+  SSB_LAUNCH_CHECK("colsum_finalize");
+  return SSB_OK;
+}
+
+int ssb_colsum_planes(const void* planes, int64_t plane_stride, int64_t rows, int64_t C,
+                      float* out, int accumulate, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
+  SSB_REQUIRE(planes && rows > 0 && C > 0 && C % 8 == 0 && ((uintptr_t)planes & 15) == 0 &&
+                  plane_stride % 8 == 0,
+              "colsum_planes: rows=%lld C=%lld (C %% 8 == 0, 16 B aligned planes)", (long long)rows,
+              (long long)C);
+  SSB_REQUIRE(out && workspace && workspace_bytes >= ssb_col_partials_bytes(rows, C),
+              "colsum_planes: bad out/workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nch = nchunks_for(rows);
+  dim3 grid((unsigned)((C + 255) / 256), (unsigned)nch);
+  const __nv_bfloat16* hi = (const __nv_bfloat16*)planes;
+  col_partials_planes_kernel<<<grid, 256, 0, st>>>(hi, hi + plane_stride, rows, (int)C,
+                                                   (float*)workspace);
+  SSB_LAUNCH_CHECK("col_partials_planes");
   colsum_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, out,
                                                  accumulate);
   SSB_LAUNCH_CHECK("colsum_finalize");

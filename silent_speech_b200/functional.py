@@ -60,10 +60,15 @@ def _scatter_plain(ptr, M, ld):
 
 
 def _epi(out, bias=None, relu=0, accumulate=0, mask_src=None, mask_scale=1.0, drop_p=0.0, seed=0,
-         site=0):
+         site=0, planes_out=None, mask_planes=None):
+    """ssb_epilogue_t.  planes_out: (2, M, N) bf16 tensor receiving the result as split planes
+    (tcgen05 engine); mask_planes: bf16 hi plane (M, N) standing in for mask_src."""
     return Epilogue(out, bias.data_ptr() if bias is not None else None,
                     mask_src.data_ptr() if mask_src is not None else None, mask_scale, int(relu),
-                    int(accumulate), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site))
+                    int(accumulate), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site),
+                    planes_out.data_ptr() if planes_out is not None else None,
+                    planes_out[0].numel() if planes_out is not None else 0,
+                    mask_planes.data_ptr() if mask_planes is not None else None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -103,6 +108,17 @@ def colsum(x2d, out=None, accumulate=False):
 # ------------------------------------------------------------------------------------------
 # tcgen05 path: bf16 hi/lo split planes + tensor-core GEMMs (csrc/gemm_tc.cu)
 # ------------------------------------------------------------------------------------------
+
+
+def colsum_planes(planes):
+    """Column sums of a (2, rows, C) split-plane tensor (x = hi + lo)."""
+    lib = _lib.load()
+    _, rows, C = planes.shape
+    out = torch.empty(C, dtype=_f32, device=planes.device)
+    ws = _ws(lib.ssb_col_partials_bytes(rows, C), planes.device)
+    _lib.check(lib.ssb_colsum_planes(planes.data_ptr(), rows * C, rows, C, out.data_ptr(), 0,
+                                     ws.data_ptr(), ws.numel(), _stream()))
+    return out
 
 
 def split_planes(x):
@@ -246,33 +262,72 @@ def linear(x2d, Wg, bias=None):
 # FFN:  y = dropout(relu(x @ W1 + b1)) @ W2 + b2          transformer.py:57
 # ------------------------------------------------------------------------------------------
 class _FFNFn(torch.autograd.Function):
+    """On the tcgen05 engine the hidden activation h and its gradient dh exist only as bf16
+    split planes: the producing GEMM's epilogue writes the operand format of the consuming
+    GEMMs directly (no fp32 copy, no split pass), the ReLU/dropout mask of the backward is read
+    off h's hi plane, and the bias gradient sums the planes."""
+
     @staticmethod
     def forward(ctx, x, W1, b1, W2, b2, p, seed, site):
         _chk(x, "x"), _chk(W1, "W1"), _chk(W2, "W2")
         M, K = x.shape
         F_ = W1.shape[1]
         N = W2.shape[1]
-        h = torch.empty((M, F_), dtype=_f32, device=x.device)
+        dev = x.device
+        y = torch.empty((M, N), dtype=_f32, device=dev)
+        ctx.p = p
+        ctx.planes = (_tc_fwd_ok(M, F_, K) and _tc_fwd_ok(M, N, F_) and _tc_wgrad_ok(M, F_, K)
+                      and _tc_wgrad_ok(M, N, F_) and _tc_fwd_ok(M, K, F_) and _tc_fwd_ok(M, F_, N))
+        if ctx.planes:
+            xp = split_planes(x)
+            hp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
+            gemm_tc_kmajor(tc_operand_plain(xp, M, K), split_planes(W1.t().contiguous()), F_, K,
+                           _epi(_scatter_plain(None, M, F_), bias=b1, relu=1, drop_p=p, seed=seed,
+                                site=site, planes_out=hp))
+            gemm_tc_kmajor(tc_operand_plain(hp, M, F_), split_planes(W2.t().contiguous()), N, F_,
+                           _epi(_scatter_plain(y.data_ptr(), M, N), bias=b2))
+            ctx.save_for_backward(W1, W2, xp, hp)
+            return y
+        h = torch.empty((M, F_), dtype=_f32, device=dev)
         xp = mm_fwd(x, W1, dict(bias=b1, relu=1, drop_p=p, seed=seed, site=site), h, M, F_, K)
-        y = torch.empty((M, N), dtype=_f32, device=x.device)
         hp = mm_fwd(h, W2, dict(bias=b2), y, M, N, F_)
         ctx.save_for_backward(x, W1, W2, h, xp if _tc_wgrad_ok(M, F_, K) else None,
                               hp if _tc_wgrad_ok(M, N, F_) else None)
-        ctx.p = p
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, W1, W2, h, xp, hp = ctx.saved_tensors
         dy = dy.contiguous()
+        scale = 1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0
+        if ctx.planes:
+            W1, W2, xp, hp = ctx.saved_tensors
+            M, K = xp.shape[1:]
+            F_ = W1.shape[1]
+            N = W2.shape[1]
+            dev = dy.device
+            dyp = split_planes(dy)
+            dW2 = torch.empty_like(W2)
+            gemm_tc_wgrad(tc_operand_plain(hp, M, F_), dyp, N, F_, dW2)
+            db2 = colsum(dy)
+            # dh = (dy @ W2^T) * (h > 0) / (1 - p): relu and dropout masks both read off h
+            dhp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
+            gemm_tc_kmajor(tc_operand_plain(dyp, M, N), split_planes(W2), F_, N,
+                           _epi(_scatter_plain(None, M, F_), mask_planes=hp[0], mask_scale=scale,
+                                planes_out=dhp))
+            dW1 = torch.empty_like(W1)
+            gemm_tc_wgrad(tc_operand_plain(xp, M, K), dhp, F_, K, dW1)
+            db1 = colsum_planes(dhp)
+            dx = torch.empty((M, K), dtype=_f32, device=dev)
+            gemm_tc_kmajor(tc_operand_plain(dhp, M, F_), split_planes(W1), K, F_,
+                           _epi(_scatter_plain(dx.data_ptr(), M, K)))
+            return dx, dW1, db1, dW2, db2, None, None, None
+        x, W1, W2, h, xp, hp = ctx.saved_tensors
         M, K = x.shape
         F_ = W1.shape[1]
         N = W2.shape[1]
-        scale = 1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0
         dW2 = torch.empty_like(W2)
         dyp = mm_wgrad(h, dy, dW2, M, N, F_, xp=hp)
         db2 = colsum(dy)
-        # dh = (dy @ W2^T) * (h > 0) / (1 - p): relu and dropout masks both read off h
         dh = torch.empty_like(h)
         mm_dgrad(dy, W2, dict(mask_src=h, mask_scale=scale), dh, M, N, F_, dyp=dyp)
         dW1 = torch.empty_like(W1)

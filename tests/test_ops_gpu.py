@@ -27,7 +27,8 @@ def rnd(*shape, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("M,K,N", [(64, 32, 48), (300, 768, 80), (1000, 24, 768), (257, 100, 132),
-                                   (4096, 768, 768)])
+                                   (4096, 768, 768), (5000, 24, 768), (4097, 32, 260),
+                                   (6000, 20, 64)])
 def test_linear_fwd_bwd(M, K, N):
     x = rnd(M, K, seed=1).requires_grad_(True)
     W = rnd(K, N, seed=2, scale=K ** -0.5).requires_grad_(True)
@@ -109,6 +110,41 @@ def test_ffn_tensor_core_engine_vs_fp64(M, D, Fh):
     close(x.grad, dh @ W1d.t(), tol=5e-5, what="dx")
 
 
+def test_gemm_epilogue_split_plane_operands():
+    """tcgen05 epilogue: planes_out (with and without the fp32 copy) equals split_planes of the
+    fp32 result bit for bit; mask_planes (hi plane) equals mask_src; colsum_planes = colsum."""
+    from silent_speech_b200.functional import (_epi, _scatter_plain, colsum, colsum_planes,
+                                               gemm_tc_kmajor, split_planes, tc_operand_plain)
+    M, K, N = 1000, 128, 520
+    x, W, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+    xp, wp = split_planes(x), split_planes(W)
+    y = torch.empty(M, N, device=dev)
+    gemm_tc_kmajor(tc_operand_plain(xp, M, K), wp, N, K,
+                   _epi(_scatter_plain(y.data_ptr(), M, N), bias=b, relu=1))
+    want = split_planes(y)
+    for with_fp32 in (True, False):
+        y2 = torch.full((M, N), float("nan"), device=dev)
+        pl = torch.zeros(2, M, N, dtype=torch.bfloat16, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(xp, M, K), wp, N, K,
+                       _epi(_scatter_plain(y2.data_ptr() if with_fp32 else None, M, N), bias=b,
+                            relu=1, planes_out=pl))
+        assert torch.equal(pl, want)
+        assert torch.equal(y2, y) if with_fp32 else torch.isnan(y2).all()
+    g = rnd(M, K, seed=4)
+    outs = []
+    for kw in (dict(mask_src=y), dict(mask_planes=want[0])):
+        o = torch.empty(M, N, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(split_planes(g), M, K), wp, N, K,
+                       _epi(_scatter_plain(o.data_ptr(), M, N), mask_scale=1.25, **kw))
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1]) and (outs[0] == 0).float().mean() > 0.3
+    close(colsum_planes(want), colsum(y), tol=1e-5, what="colsum_planes")
+    with pytest.raises(RuntimeError):      # CUDA-core engine rejects split-plane epilogue operands
+        from silent_speech_b200.functional import _gather_plain, gemm_nn
+        gemm_nn(_gather_plain(x.data_ptr(), M, K, K), W.t().contiguous(),
+                _epi(_scatter_plain(y.data_ptr(), M, N), planes_out=pl), M, N, K)
+
+
 def test_ffn_dropout_statistics_and_consistency():
     M, D, Fh, p = 512, 32, 3072, 0.2
     x = rnd(M, D, seed=1).requires_grad_(True)
@@ -143,7 +179,10 @@ def test_ffn_dropout_statistics_and_consistency():
                                               (2, 40, 32, 32, 3, 1), (2, 41, 32, 48, 3, 2),
                                               (2, 41, 32, 48, 1, 2), (2, 40, 32, 48, 1, 2),
                                               (4, 500, 64, 64, 3, 1), (1, 1, 8, 16, 3, 2),
-                                              (2, 2, 16, 16, 3, 2), (2, 250, 768, 768, 3, 2)])
+                                              (2, 2, 16, 16, 3, 2), (2, 250, 768, 768, 3, 2),
+                                              # thin-K kernels (K <= 32, >= 4096 output rows):
+                                              (5, 2001, 8, 768, 3, 2), (3, 4000, 8, 132, 1, 2),
+                                              (2, 4100, 4, 64, 3, 1)])
 def test_conv_fwd_bwd(B, L, Cin, Cout, k, s):
     x = rnd(B, L, Cin, seed=1).requires_grad_(True)
     w = rnd(Cout, Cin, k, seed=2, scale=(Cin * k) ** -0.5).requires_grad_(True)
