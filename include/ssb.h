@@ -297,6 +297,36 @@ SSB_API int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, co
                        uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
                        void* stream);
 
+/* ---- fused log_softmax + CTC loss (csrc/ctc.cu) ------------------------------------------------
+ * Replaces recognition_model.py:96-101: F.log_softmax(pred, 2) -> pad_sequence ->
+ * F.ctc_loss(pred, y, lengths, text_int_lengths, blank) and its backward.
+ *   logits (N, T, C) fp32, batch-first, frames >= input_lengths[n] are padding;
+ *   targets (N, Lmax) int64 (device), entries >= target_lengths[n] ignored; lengths int64 (device);
+ *   nll (N): negative log-likelihood per utterance (+inf when no alignment exists);
+ *   grad_logits (N, T, C) or NULL: d nll[n] / d logits (softmax - occupancy; 0 on padding frames
+ *   and for infeasible utterances), scaled by 1 / (N * max(L_n, 1)) when mean_reduction != 0
+ *   (= the gradient of torch's default reduction='mean').
+ * 2*Lmax + 1 <= 1024.  workspace: ssb_ctc_workspace_bytes (the alpha table). */
+SSB_API int64_t ssb_ctc_workspace_bytes(int64_t N, int64_t T, int64_t Lmax);
+SSB_API int ssb_ctc_loss_fused(const float* logits, int64_t N, int64_t T, int64_t C,
+                               const int64_t* targets, int64_t Lmax, const int64_t* input_lengths,
+                               const int64_t* target_lengths, int64_t blank, int mean_reduction,
+                               float* nll, float* grad_logits, void* workspace,
+                               int64_t workspace_bytes, void* stream);
+
+/* ---- fused AdamW on flat buffers (csrc/optim.cu) ------------------------------------------------
+ * Replaces optim.step() of torch.optim.AdamW(model.parameters(), weight_decay=l2) with the
+ * per-iteration learning rate of transduction_model.py:178-189,210.
+ * p, g, m, v: flat fp32 buffers of n elements (parameters, gradients = the data-parallel bucket,
+ * exp_avg, exp_avg_sq), 16 B aligned.  torch.optim.AdamW arithmetic (decoupled weight decay,
+ * bias-corrected moments); g is multiplied by grad_scale first (1 / world_size of the mean).
+ * lr_cell (float) and step_cell (int64) are DEVICE cells owned by the caller: the call first
+ * increments *step_cell, then updates with *lr_cell, both read at execution time, so a captured
+ * CUDA graph replays a valid optimiser step. */
+SSB_API int ssb_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n,
+                           const float* lr_cell, int64_t* step_cell, float beta1, float beta2,
+                           float eps, float weight_decay, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

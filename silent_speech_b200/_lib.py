@@ -92,6 +92,11 @@ _SIGNATURES = {
                                    c_ptr]),
     "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
+    "ssb_ctc_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
+    "ssb_ctc_loss_fused": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
+                                   c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ssb_adamw_flat": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_f32, c_f32, c_f32,
+                               c_f32, c_f32, c_ptr]),
     "ssb_colsum_planes": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
@@ -114,7 +119,7 @@ _SIGNATURES = {
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
 _KERNELS_PER_CALL = {
     "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
-    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
+    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 1, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
     "ssb_split_bf16": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,

@@ -75,3 +75,71 @@ def dtw_loss(predictions, phoneme_predictions, example, phoneme_eval=False,
                     for a, b in zip(pp.flatten().tolist(), YP.flatten().tolist()):
                         phoneme_confusion[a, b] += 1
     return total / total_length, correct_phones / total_length
+
+
+# ------------------------------------------------------------------------------------------
+# fused log_softmax + CTC (csrc/ctc.cu)                      recognition_model.py:96-101
+# ------------------------------------------------------------------------------------------
+class _CtcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, input_lengths, target_lengths, blank, mean):
+        from . import _lib
+        lib = _lib.load()
+        _lib.require_cuda(logits, "logits")
+        if logits.dtype != torch.float32 or logits.dim() != 3:
+            raise TypeError("ctc_loss: logits must be float32 (N, T, C)")
+        logits = logits.contiguous()
+        N, T, C = logits.shape
+        dev = logits.device
+        targets = targets.to(device=dev, dtype=torch.int64).contiguous().view(N, -1)
+        il = torch.as_tensor(input_lengths, dtype=torch.int64).to(dev).contiguous()
+        tl = torch.as_tensor(target_lengths, dtype=torch.int64).to(dev).contiguous()
+        Lmax = targets.shape[1]
+        nll = torch.empty(N, dtype=torch.float32, device=dev)
+        need_grad = ctx.needs_input_grad[0]
+        grad = torch.empty_like(logits) if need_grad else None
+        ws = torch.empty(max(16, lib.ssb_ctc_workspace_bytes(N, T, Lmax)), dtype=torch.uint8,
+                         device=dev)
+        _lib.check(lib.ssb_ctc_loss_fused(
+            logits.data_ptr(), N, T, C, targets.data_ptr() if Lmax else None, Lmax, il.data_ptr(),
+            tl.data_ptr(), int(blank), int(mean), nll.data_ptr(),
+            grad.data_ptr() if need_grad else None, ws.data_ptr(), ws.numel(),
+            _lib.current_stream()))
+        ctx.save_for_backward(grad)
+        ctx.mean = mean
+        if mean:     # torch reduction='mean': per-utterance loss / target length, then batch mean
+            return (nll / tl.clamp(min=1).to(nll.dtype)).mean()
+        return nll
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        if ctx.mean:
+            return grad * g, None, None, None, None, None
+        return grad * g.view(-1, 1, 1), None, None, None, None, None
+
+
+def ctc_loss(logits, targets, input_lengths, target_lengths, blank=0, reduction='mean'):
+    """Fused replacement for recognition_model.py:96-101:
+
+        pred = F.log_softmax(pred, 2); pred = pad_sequence(decollate_tensor(pred, lengths))
+        loss = F.ctc_loss(pred, y, lengths, text_int_lengths, blank=n_chars)
+
+    logits: (N, T, C) batch-first, UN-normalised model outputs padded in time; targets (N, Lmax)
+    padded int64; lengths as lists or tensors.  reduction: 'mean' (torch default: per-utterance
+    loss / target length, batch mean), 'sum', or 'none'.  One kernel computes the row
+    log-softmax, alpha/beta recursions, the loss and d loss / d logits."""
+    if reduction not in ('mean', 'sum', 'none'):
+        raise ValueError(reduction)
+    out = _CtcFn.apply(logits, targets, input_lengths, target_lengths, int(blank), reduction == 'mean')
+    return out.sum() if reduction == 'sum' else out
+
+
+def ctc_loss_from_chunks(pred, example, blank):
+    """recognition_model.py:94-101 on the model's chunked output: `pred` (n_chunks, 200, C) as
+    returned by Model on combine_fixed_length batches, `example` a collate_raw dict with
+    'lengths', 'text_int', 'text_int_lengths'."""
+    seqs = decollate_tensor(pred, example['lengths'])
+    logits = torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True)
+    y = torch.nn.utils.rnn.pad_sequence(example['text_int'], batch_first=True)
+    return ctc_loss(logits, y, example['lengths'], example['text_int_lengths'], blank)

@@ -36,10 +36,15 @@ class GradientBucket:
     def zero(self):
         self.flat.zero_()
 
-    def allreduce_mean(self):
+    def allreduce_mean(self, optim=None):
+        """Sum over ranks, then the mean: as a pass over the bucket, or (optim = FlatAdamW)
+        folded into the fused optimiser kernel as its grad_scale."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.mul_(1.0 / dist.get_world_size())
+            if hasattr(optim, "grad_scale"):
+                optim.grad_scale = 1.0 / dist.get_world_size()
+            else:
+                self.flat.mul_(1.0 / dist.get_world_size())
 
 
 def to_device(batch, device):
@@ -64,7 +69,7 @@ def train_step(model, optim, batch, device, seq_len_frames=200, bucket=None, syn
     loss, _ = dtw_loss(pred, phoneme_pred, b)
     loss.backward()
     if bucket is not None:
-        bucket.allreduce_mean()
+        bucket.allreduce_mean(optim)
     optim.step()
     return loss.item() if sync_loss else loss.detach()
 
@@ -153,6 +158,6 @@ class GraphedTrainStep:
         graph.replay()
         _lib.launch_count += nk
         self.kernels_per_replay = nk
-        self.bucket.allreduce_mean()
+        self.bucket.allreduce_mean(self.optim)
         self.optim.step()
         return loss.item() if sync_loss else loss
