@@ -229,6 +229,10 @@ typedef struct {
 } ssb_tc_operand_t;
 
 SSB_API int ssb_split_bf16(const float* x, int64_t n, void* planes /* bf16 [2][n] */, void* stream);
+/* transposed: planes[p][c][r] = split(x[r][c]) of a row-major (rows, cols) fp32 matrix (both
+ * multiples of 8): the W^T operand of an nn.Linear data gradient without an fp32 transpose. */
+SSB_API int ssb_split_bf16_t(const float* x, int64_t rows, int64_t cols,
+                             void* planes /* bf16 [2][cols][rows] */, void* stream);
 /* C[(b,t), n] = epi( sum_k A((b,t), k) * B[n, k] );  B planes: [2][N][K] bf16 (K contiguous).
  * K % 64 == 0, C % 64 == 0.  epi->out.rows_per_batch must equal A->rows_out. */
 SSB_API int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N, int64_t K,

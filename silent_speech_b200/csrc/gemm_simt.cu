@@ -278,16 +278,23 @@ gemm_kernel(const Gather ga, const float* __restrict__ Bplain, int ldb, const We
 // registers, A rows are warp-broadcast loads, and the wide operand streams through once.
 // block = 64 column lanes (float4 -> 256 columns) x 4 row lanes.
 // ---------------------------------------------------------------------------------------
+constexpr int THIN_ROWS = 64;   // A rows staged per shared-memory chunk
+
+// cooperative gather of rows [mc, mc + THIN_ROWS) of A into shared memory (zero beyond m1 / K):
+// the index arithmetic of the gather and the global-load latency are paid once per chunk by the
+// whole CTA instead of per row by every warp (148-register kernels run 8 warps per SM).
 template <int K4>   // K padded to 4*K4
-__device__ __forceinline__ void thin_load_a(const Gather& ga, int m, int K, float4 (&a)[K4]) {
-#pragma unroll
-  for (int q = 0; q < K4; ++q) {
-    a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (4 * q < K) {
+__device__ __forceinline__ void thin_stage_a(const Gather& ga, int mc, int m1, int K,
+                                             float4 (*As)[K4]) {
+  for (int i = threadIdx.x; i < THIN_ROWS * K4; i += blockDim.x) {
+    const int r = i / K4, q = i - r * K4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mc + r < m1 && 4 * q < K) {
       bool valid;
-      const float* src = gather_ptr(ga, m, 4 * q, valid);
-      if (valid) a[q] = ldg4(src);
+      const float* src = gather_ptr(ga, mc + r, 4 * q, valid);
+      if (valid) v = ldg4(src);
     }
+    As[r][q] = v;
   }
 }
 
@@ -295,36 +302,44 @@ template <int K4>
 __global__ void __launch_bounds__(256)
 thin_nn_kernel(const Gather ga, const float* __restrict__ W, int ldw, const Epilogue ep, int M,
                int N, int K, int rows_per_cta) {
+  __shared__ float4 As[THIN_ROWS][K4];
   const int nl = threadIdx.x & 63, rl = threadIdx.x >> 6;
   const int n = (blockIdx.x * 64 + nl) * 4;
-  if (n >= N) return;
+  const bool n_ok = n < N;
   float4 w[4 * K4];
 #pragma unroll
   for (int k = 0; k < 4 * K4; ++k)
-    w[k] = k < K ? ldg4(W + (int64_t)k * ldw + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    w[k] = (n_ok && k < K) ? ldg4(W + (int64_t)k * ldw + n) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (ep.bias) bias = ldg4(ep.bias + n);
+  if (ep.bias && n_ok) bias = ldg4(ep.bias + n);
   const int m0 = blockIdx.y * rows_per_cta;
   const int m1 = min(M, m0 + rows_per_cta);
-  for (int m = m0 + rl; m < m1; m += 4) {
-    float4 a[K4];
-    thin_load_a<K4>(ga, m, K, a);
-    float4 v = bias;
+  for (int mc = m0; mc < m1; mc += THIN_ROWS) {
+    __syncthreads();
+    thin_stage_a<K4>(ga, mc, m1, K, As);
+    __syncthreads();
+    if (!n_ok) continue;
+    const int rend = min(THIN_ROWS, m1 - mc);
+    for (int r = rl; r < rend; r += 4) {
+      float4 v = bias;
 #pragma unroll
-    for (int q = 0; q < K4; ++q) {
-      const float av[4] = {a[q].x, a[q].y, a[q].z, a[q].w};
+      for (int q = 0; q < K4; ++q) {
+        const float4 a = As[r][q];
+        const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 ww = w[4 * q + j];
-        v.x = fmaf(av[j], ww.x, v.x); v.y = fmaf(av[j], ww.y, v.y);
-        v.z = fmaf(av[j], ww.z, v.z); v.w = fmaf(av[j], ww.w, v.w);
+        for (int j = 0; j < 4; ++j) {
+          const float4 ww = w[4 * q + j];
+          v.x = fmaf(av[j], ww.x, v.x); v.y = fmaf(av[j], ww.y, v.y);
+          v.z = fmaf(av[j], ww.z, v.z); v.w = fmaf(av[j], ww.w, v.w);
+        }
       }
+      if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      const int m = mc + r;
+      const int b = m / ep.out.rows_per_batch, t = m - b * ep.out.rows_per_batch;
+      float* row = ep.out.base + (int64_t)b * ep.out.batch_stride +
+                   (int64_t)(t * ep.out.d_t + ep.out.d_off) * ep.out.ld;
+      *reinterpret_cast<float4*>(row + n) = v;
     }
-    if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    const int b = m / ep.out.rows_per_batch, t = m - b * ep.out.rows_per_batch;
-    float* row = ep.out.base + (int64_t)b * ep.out.batch_stride +
-                 (int64_t)(t * ep.out.d_t + ep.out.d_off) * ep.out.ld;
-    *reinterpret_cast<float4*>(row + n) = v;
   }
 }
 
@@ -332,6 +347,7 @@ template <int K4>
 __global__ void __launch_bounds__(256)
 thin_tn_kernel(const Gather ga, const float* __restrict__ G, int ldg, float* __restrict__ dW,
                int lddw, int M, int N, int K, int rows_per_cta) {
+  __shared__ float4 As[THIN_ROWS][K4];
   __shared__ float4 red[3][64];
   const int nl = threadIdx.x & 63, rl = threadIdx.x >> 6;
   const int n = (blockIdx.x * 64 + nl) * 4;
@@ -341,19 +357,31 @@ thin_tn_kernel(const Gather ga, const float* __restrict__ G, int ldg, float* __r
   for (int k = 0; k < 4 * K4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   const int m0 = blockIdx.y * rows_per_cta;
   const int m1 = min(M, m0 + rows_per_cta);
-  if (n_ok) {
-    for (int m = m0 + rl; m < m1; m += 4) {
-      float4 a[K4];
-      thin_load_a<K4>(ga, m, K, a);
-      const float4 g = ldg4(G + (int64_t)m * ldg + n);
+  for (int mc = m0; mc < m1; mc += THIN_ROWS) {
+    __syncthreads();
+    thin_stage_a<K4>(ga, mc, m1, K, As);
+    __syncthreads();
+    if (!n_ok) continue;
+    const int rend = min(THIN_ROWS, m1 - mc);
+    // the wide operand: up to 16 independent 16 B loads per thread in flight
+    float4 g[THIN_ROWS / 4];
+#pragma unroll
+    for (int i = 0; i < THIN_ROWS / 4; ++i) {
+      const int r = rl + 4 * i;
+      g[i] = r < rend ? ldg4(G + (int64_t)(mc + r) * ldg + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < THIN_ROWS / 4; ++i) {
+      const int r = rl + 4 * i;      // rows >= rend were staged as zeros
 #pragma unroll
       for (int q = 0; q < K4; ++q) {
-        const float av[4] = {a[q].x, a[q].y, a[q].z, a[q].w};
+        const float4 a = As[r][q];
+        const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float4& c = acc[4 * q + j];
-          c.x = fmaf(av[j], g.x, c.x); c.y = fmaf(av[j], g.y, c.y);
-          c.z = fmaf(av[j], g.z, c.z); c.w = fmaf(av[j], g.w, c.w);
+          c.x = fmaf(av[j], g[i].x, c.x); c.y = fmaf(av[j], g[i].y, c.y);
+          c.z = fmaf(av[j], g[i].z, c.z); c.w = fmaf(av[j], g[i].w, c.w);
         }
       }
     }

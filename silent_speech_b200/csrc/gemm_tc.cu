@@ -605,6 +605,34 @@ split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64
   }
 }
 
+// transposed variant: planes[p][c][r] = split(x[r][c]) for a row-major (rows, cols) matrix: the
+// data-gradient operand W^T of an nn.Linear weight without a transposed fp32 copy.
+// block (32, 8) handles a 64-row x 32-column tile through shared memory; stores are bf16x2.
+__global__ void __launch_bounds__(256)
+split_t_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int rows, int cols,
+               int64_t plane_stride) {
+  __shared__ float tile[64][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    tile[ty + 8 * i][tx] = (r < rows && c < cols) ? __ldg(x + (int64_t)r * cols + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + 2 * tx;
+    if (c >= cols || r >= rows) continue;      // rows is even: r + 1 < rows too
+    const float a = tile[2 * tx][ty + 8 * i], b = tile[2 * tx + 1][ty + 8 * i];
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a - __low2float(hi), b - __high2float(hi));
+    __nv_bfloat16* dst = out + (int64_t)c * rows + r;
+    *reinterpret_cast<__nv_bfloat162*>(dst) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(dst + plane_stride) = lo;
+  }
+}
+
 // ---- tensor-map construction (driver entry point fetched at run time; no libcuda link) --------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -765,6 +793,21 @@ int ssb_split_bf16(const float* x, int64_t n, void* planes, void* stream) {
   const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
   split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)planes, n8, n);
   SSB_LAUNCH_CHECK("split_kernel");
+  return SSB_OK;
+}
+
+int ssb_split_bf16_t(const float* x, int64_t rows, int64_t cols, void* planes, void* stream) {
+  if (rows == 0 || cols == 0) return SSB_OK;
+  SSB_REQUIRE(x && planes && rows > 0 && cols > 0 && rows % 8 == 0 && cols % 8 == 0 &&
+                  rows < (1 << 30) && cols < (1 << 30),
+              "split_bf16_t: rows=%lld cols=%lld must be multiples of 8", (long long)rows,
+              (long long)cols);
+  SSB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 15) == 0,
+              "split_bf16_t: pointers must be 16 B aligned");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 63) / 64));
+  split_t_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)planes, (int)rows,
+                                                                (int)cols, rows * cols);
+  SSB_LAUNCH_CHECK("split_t_kernel");
   return SSB_OK;
 }
 

@@ -358,6 +358,10 @@ add_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ branc
 // backward: d_res = dz, d_branch = dz * dropmask * scale; per-CTA partial dgamma/dbeta
 constexpr int LN_ROWS_PER_CTA = 64;
 
+// NV = float4 per lane actually needed (D <= 128 * NV): the register arrays are sized by it, so
+// D = 768 runs with 6-wide state instead of the 8-wide maximum (208 -> ~128 registers, two CTAs
+// per SM).  gamma is re-read per row (L1-resident) instead of living in registers.
+template <int NV>
 __global__ void __launch_bounds__(256)
 add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                   const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -372,29 +376,28 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
   const int nv = D >> 2;
   for (int i = threadIdx.x; i < 2 * 1024; i += 256) (&sm[0][0])[i] = 0.f;
   __syncthreads();
-  float4 dg[LN_MAXV], db[LN_MAXV], g4[LN_MAXV];
+  float4 dg[NV], db[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[i] = dg[i];
-    const int v = lane + i * 32;
-    g4[i] = v < nv ? *reinterpret_cast<const float4*>(gamma + v * 4) : dg[i];
   }
   const int64_t r0 = (int64_t)blockIdx.x * LN_ROWS_PER_CTA;
   const int64_t r1 = min(rows, r0 + LN_ROWS_PER_CTA);
   for (int64_t row = r0 + warp; row < r1; row += 8) {
     const float mu = mean[row], rs = rstd[row];
-    float4 gy[LN_MAXV], xh[LN_MAXV];
+    float4 gy[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nv) {
         const float4 d = __ldg(reinterpret_cast<const float4*>(dy + row * D) + v);
         const float4 zz = __ldg(reinterpret_cast<const float4*>(z + row * D) + v);
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + v);
         xh[i] = make_float4((zz.x - mu) * rs, (zz.y - mu) * rs, (zz.z - mu) * rs,
                             (zz.w - mu) * rs);
-        gy[i] = make_float4(d.x * g4[i].x, d.y * g4[i].y, d.z * g4[i].z, d.w * g4[i].w);
+        gy[i] = make_float4(d.x * g4.x, d.y * g4.y, d.z * g4.z, d.w * g4.w);
         s1 += gy[i].x + gy[i].y + gy[i].z + gy[i].w;
         s2 += gy[i].x * xh[i].x + gy[i].y * xh[i].y + gy[i].z * xh[i].z + gy[i].w * xh[i].w;
         dg[i].x = fmaf(d.x, xh[i].x, dg[i].x); dg[i].y = fmaf(d.y, xh[i].y, dg[i].y);
@@ -405,7 +408,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
     s1 = ssb::warp_sum(s1) / (float)D;
     s2 = ssb::warp_sum(s2) / (float)D;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int v = lane + i * 32;
       if (v < nv) {
         float4 o;
@@ -427,7 +430,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
   }
   // cross-warp reduction of the per-lane column partials
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < nv) {
       atomicAdd(&sm[0][v * 4 + 0], dg[i].x); atomicAdd(&sm[0][v * 4 + 1], dg[i].y);
@@ -631,11 +634,17 @@ int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, c
               "add_dropout_ln_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int nblk = (int)((rows + LN_ROWS_PER_CTA - 1) / LN_ROWS_PER_CTA);
-  add_ln_bwd_kernel<<<nblk, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, (int)D, drop_p,
-                                          drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,
-                                          thresh_of(drop_p), seed, ssb::seed_source(), site, d_res,
-                                          d_branch,
-                                          (float*)workspace);
+#define SSB_LN_BWD(NV)                                                                        \
+  add_ln_bwd_kernel<NV><<<nblk, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, (int)D, drop_p,       \
+                                              drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,           \
+                                              thresh_of(drop_p), seed, ssb::seed_source(), site,   \
+                                              d_res, d_branch, (float*)workspace)
+  const int nvl = (int)((D / 4 + 31) / 32);
+  if (nvl <= 2) SSB_LN_BWD(2);
+  else if (nvl <= 4) SSB_LN_BWD(4);
+  else if (nvl <= 6) SSB_LN_BWD(6);
+  else SSB_LN_BWD(8);
+#undef SSB_LN_BWD
   SSB_LAUNCH_CHECK("add_ln_bwd");
   ln_param_grad_finalize_kernel<<<FIN_GRID(D), 0, st>>>((const float*)workspace, nblk, (int)D,
                                                         dgamma, dbeta);

@@ -110,14 +110,53 @@ def colsum(x2d, out=None, accumulate=False):
 # ------------------------------------------------------------------------------------------
 
 
-def colsum_planes(planes):
+def colsum_planes(planes, out=None, accumulate=False):
     """Column sums of a (2, rows, C) split-plane tensor (x = hi + lo)."""
     lib = _lib.load()
     _, rows, C = planes.shape
-    out = torch.empty(C, dtype=_f32, device=planes.device)
+    if out is None:
+        out = torch.empty(C, dtype=_f32, device=planes.device)
     ws = _ws(lib.ssb_col_partials_bytes(rows, C), planes.device)
-    _lib.check(lib.ssb_colsum_planes(planes.data_ptr(), rows * C, rows, C, out.data_ptr(), 0,
-                                     ws.data_ptr(), ws.numel(), _stream()))
+    _lib.check(lib.ssb_colsum_planes(planes.data_ptr(), rows * C, rows, C, out.data_ptr(),
+                                     int(accumulate), ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# gradient sinks: with a training.GradientBucket the .grad of every parameter is a fixed view of
+# one flat buffer.  Backward bodies that own a parameter gradient may then ACCUMULATE it straight
+# into that view (the weight-gradient GEMM's epilogue / split-K atomics, the column-sum finalize)
+# and return None to autograd, instead of materialising a temporary that AccumulateGrad adds with
+# one more launch and pass per parameter.
+# ------------------------------------------------------------------------------------------
+_sinks = {}
+
+
+def register_grad_sinks(params):
+    """params: iterable of nn.Parameter whose .grad are persistent views (GradientBucket)."""
+    import weakref
+    for p in params:
+        _sinks[id(p)] = (weakref.ref(p), p.grad)
+
+
+def _sink(t):
+    """The registered gradient view of parameter object `t`, if it is still t.grad."""
+    ent = _sinks.get(id(t))
+    if ent is None or ent[0]() is not t or not t.requires_grad:
+        return None
+    g = t.grad
+    if g is None or g.data_ptr() != ent[1].data_ptr():
+        return None
+    return ent[1]
+
+
+def split_planes_t(x2d):
+    """fp32 (rows, cols) -> bf16 planes (2, cols, rows) of the TRANSPOSE (one fused pass)."""
+    lib = _lib.load()
+    _chk(x2d, "x")
+    rows, cols = x2d.shape
+    out = torch.empty((2, cols, rows), dtype=torch.bfloat16, device=x2d.device)
+    _lib.check(lib.ssb_split_bf16_t(x2d.data_ptr(), rows, cols, out.data_ptr(), _stream()))
     return out
 
 
@@ -225,6 +264,7 @@ class _LinearFn(torch.autograd.Function):
         keep_planes = xp is not None and ctx.needs_input_grad[1] and _tc_wgrad_ok(M, N, K)
         ctx.save_for_backward(x, Wg, xp if keep_planes else None)
         ctx.has_bias = bias is not None
+        ctx.sink_b = _sink(bias) if bias is not None else None
         return y
 
     @staticmethod
@@ -242,7 +282,10 @@ class _LinearFn(torch.autograd.Function):
             dW = torch.empty_like(Wg)
             mm_wgrad(x, dy, dW, M, N, K, xp=xp, dyp=dyp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy)
+            if ctx.sink_b is not None:
+                colsum(dy, out=ctx.sink_b, accumulate=True)
+            else:
+                db = colsum(dy)
         return dx, dW, db
 
 
@@ -336,6 +379,71 @@ class _FFNFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         mm_dgrad(dh, W1, {}, dx, M, F_, K, dyp=dhp)
         return dx, dW1, db1, dW2, db2, None, None, None
+
+
+class _FFNNativeFn(torch.autograd.Function):
+    """_FFNFn's split-plane path on nn.Linear-layout weights (w1: (F, K), w2: (N, F)), i.e. on the
+    parameters themselves: forward splits them as they lie, the data gradients split their
+    transpose in one fused pass, and the weight gradients come out of the tensor-core GEMM in
+    parameter layout (dW^T = dy^T x) - straight into the gradient bucket when one is registered."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, p, seed, site):
+        _chk(x, "x"), _chk(w1, "w1"), _chk(w2, "w2")
+        M, K = x.shape
+        F_, N = w1.shape[0], w2.shape[0]
+        dev = x.device
+        xp = split_planes(x)
+        hp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(xp, M, K), split_planes(w1), F_, K,
+                       _epi(_scatter_plain(None, M, F_), bias=b1, relu=1, drop_p=p, seed=seed,
+                            site=site, planes_out=hp))
+        y = torch.empty((M, N), dtype=_f32, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(hp, M, F_), split_planes(w2), N, F_,
+                       _epi(_scatter_plain(y.data_ptr(), M, N), bias=b2))
+        ctx.save_for_backward(w1, w2, xp, hp)
+        ctx.p = p
+        ctx.sinks = tuple(_sink(t) for t in (w1, b1, w2, b2))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        w1, w2, xp, hp = ctx.saved_tensors
+        s_w1, s_b1, s_w2, s_b2 = ctx.sinks
+        dy = dy.contiguous()
+        M, K = xp.shape[1:]
+        F_, N = w1.shape[0], w2.shape[0]
+        dev = dy.device
+        scale = 1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0
+        dyp = split_planes(dy)
+        dW2 = s_w2 if s_w2 is not None else torch.empty_like(w2)          # (N, F) = dy^T h
+        gemm_tc_wgrad(tc_operand_plain(dyp, M, N), hp, F_, N, dW2, accumulate=s_w2 is not None)
+        db2 = colsum(dy, out=s_b2, accumulate=s_b2 is not None)
+        dhp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(dyp, M, N), split_planes_t(w2), F_, N,
+                       _epi(_scatter_plain(None, M, F_), mask_planes=hp[0], mask_scale=scale,
+                            planes_out=dhp))
+        dW1 = s_w1 if s_w1 is not None else torch.empty_like(w1)          # (F, K) = dh^T x
+        gemm_tc_wgrad(tc_operand_plain(dhp, M, F_), xp, K, F_, dW1, accumulate=s_w1 is not None)
+        db1 = colsum_planes(dhp, out=s_b1, accumulate=s_b1 is not None)
+        dx = torch.empty((M, K), dtype=_f32, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(dhp, M, F_), split_planes_t(w1), K, F_,
+                       _epi(_scatter_plain(dx.data_ptr(), M, K)))
+        return (dx, None if s_w1 is not None else dW1, None if s_b1 is not None else db1,
+                None if s_w2 is not None else dW2, None if s_b2 is not None else db2,
+                None, None, None)
+
+
+def ffn_native(x2d, w1, b1, w2, b2, p=0.0, seed=0, site=0):
+    """FFN on nn.Linear-layout weights (linear1.weight (F, K), linear2.weight (N, F))."""
+    M, K = x2d.shape
+    F_, N = w1.shape[0], w2.shape[0]
+    ok = (_tc_fwd_ok(M, F_, K) and _tc_fwd_ok(M, N, F_) and _tc_fwd_ok(M, K, F_)
+          and _tc_fwd_ok(M, F_, N) and _tc_wgrad_ok(M, F_, N) and _tc_wgrad_ok(M, K, F_)
+          and K % 8 == 0 and b1 is not None and b2 is not None)
+    if ok:
+        return _FFNNativeFn.apply(x2d, w1, b1, w2, b2, float(p), int(seed), int(site))
+    return ffn(x2d, w1.t().contiguous(), b1, w2.t().contiguous(), b2, p, seed, site)
 
 
 def ffn(x2d, W1g, b1, W2g, b2, p=0.0, seed=0, site=0):
@@ -681,8 +789,8 @@ class _DenseTCAttnFn(torch.autograd.Function):
         vt = torch.empty((2, BH, _HP, Tp), dtype=bf, device=dev)
         _lib.check(lib.ssb_transpose_split_heads(qkv.data_ptr(), D3, 2 * D, B, T, H, dh, Tp,
                                                  vt.data_ptr(), st))
-        Ew = E[:, :2 * W + 1, :dh]
-        ep = split_planes(torch.nn.functional.pad(Ew, (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
+        ep = _const_planes(E, ("fwd", W, dh, RW), lambda: torch.nn.functional.pad(
+            E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
         ld_qkv = 3 * H * _HP
         pq = M * ld_qkv
         q_op = _op(qkvp, 0, pq, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
@@ -745,9 +853,8 @@ class _DenseTCAttnFn(torch.autograd.Function):
                                                  kt.data_ptr(), st))
         kt_op = _op(kt, 0, BH * _HP * Tp, BH, _HP, Tp, Tp, _HP * Tp, H, H * _HP * Tp)
         _tc_batched(ds_op, kt_op, 1, dh, Tp, _epi(_bscatter(dqkv, 0, T, D3, dh, T * D3)))
-        Ew = E[:, :2 * W + 1, :dh]
-        et = torch.nn.functional.pad(Ew, (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2)
-        etp = split_planes(et.contiguous())                       # (2, H, 128, RWP): [d][rel]
+        etp = _const_planes(E, ("bwd", W, dh), lambda: torch.nn.functional.pad(    # (2, H, 128, RWP)
+            E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2).contiguous())
         dsb_op = _op(dsb, 0, M * H * _RWP, BH, T, _RWP, H * _RWP, _RWP, H, T * H * _RWP)
         et_op = _op(etp, 0, H * _HP * _RWP, H, _HP, _RWP, _RWP, _HP * _RWP)
         _tc_batched(dsb_op, et_op, 2, dh, _RWP,
@@ -756,6 +863,38 @@ class _DenseTCAttnFn(torch.autograd.Function):
         _tc_batched_tn(ds_op, q_op, dh, T, _epi(_bscatter(dqkv, D, T, D3, dh, T * D3)))
         _tc_batched_tn(pd_op, do_op, dh, T, _epi(_bscatter(dqkv, 2 * D, T, D3, dh, T * D3)))
         return dqkv, None, None, None, None, None, None, None, None, None
+
+
+_band_bufs = {}
+
+
+def _band_scratch(key):
+    buf = _band_bufs.get(key)
+    if buf is None:
+        B, T, H, W, rwp, dev = key
+        buf = torch.zeros((2, B * T, H, rwp), dtype=torch.bfloat16, device=dev)
+        if torch.cuda.is_current_stream_capturing():
+            return buf                  # graph-pool memory must not outlive the capture
+        if len(_band_bufs) >= 4:        # bounded: drop the oldest geometry
+            _band_bufs.pop(next(iter(_band_bufs)))
+        _band_bufs[key] = buf
+    return buf
+
+
+def _const_planes(E, key, make):
+    """Split planes derived from the constant positional table E, cached on the tensor object
+    (transformer.LearnedRelativePositionalEmbedding.padded_table keeps E alive while valid)."""
+    cache = getattr(E, "_ssb_planes", None)
+    if cache is not None and cache[0] == E._version and key in cache[1]:
+        return cache[1][key]
+    planes = split_planes(make())
+    if torch.cuda.is_current_stream_capturing():
+        return planes                   # graph-pool memory must not outlive the capture
+    if cache is None or cache[0] != E._version:
+        cache = (E._version, {})
+        E._ssb_planes = cache
+    cache[1][key] = planes
+    return planes
 
 
 class _FusedAttnFn(torch.autograd.Function):
@@ -776,8 +915,8 @@ class _FusedAttnFn(torch.autograd.Function):
         st = _stream()
         qkvp = torch.empty((2, M, 3 * H, _HP), dtype=bf, device=dev)
         _lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, D3, 0, 3 * H, dh, qkvp.data_ptr(), st))
-        Ew = E[:, :2 * W + 1, :dh]
-        ep = split_planes(torch.nn.functional.pad(Ew, (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
+        ep = _const_planes(E, ("fwd", W, dh, RW), lambda: torch.nn.functional.pad(
+            E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
         ld_qkv = 3 * H * _HP
         q_op = _op(qkvp, 0, M * ld_qkv, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
         R = torch.empty((BH, T, RW), dtype=_f32, device=dev)
@@ -811,16 +950,19 @@ class _FusedAttnFn(torch.autograd.Function):
         _lib.check(lib.ssb_attn_delta(O.data_ptr(), dO.data_ptr(), B, T, H, dh, delta.data_ptr(), st))
         dqkv = torch.empty((M, D3), dtype=_f32, device=dev)
         dqkv[:, :D].zero_()                                  # content dQ arrives by red.global.add
-        dsb = torch.zeros((2, M, H, _RWP), dtype=bf, device=dev)
+        # band-layout dS: the kernel overwrites exactly the in-band, in-sequence entries - the same
+        # set every call for a given geometry - and everything else must read 0.  One persistent
+        # buffer per geometry, zeroed once, replaces a 131 MB fill per layer and step (backward
+        # passes of successive layers are stream-ordered, so they can share it).
+        dsb = _band_scratch((B, T, H, W, _RWP, dev))
         _lib.check(lib.ssb_attn_fused_bwd(qkvp.data_ptr(), dop.data_ptr(), R.data_ptr(),
                                           stats[0].data_ptr(), stats[1].data_ptr(),
                                           delta.data_ptr(), B, T, H, dh, W, RW, p,
                                           seed & 0xFFFFFFFFFFFFFFFF, site, dqkv.data_ptr(),
                                           dsb.data_ptr(), _RWP, st))
         # positional part: dQ += dS_band E
-        Ew = E[:, :2 * W + 1, :dh]
-        et = torch.nn.functional.pad(Ew, (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2)
-        etp = split_planes(et.contiguous())                       # (2, H, 128, RWP): [d][rel]
+        etp = _const_planes(E, ("bwd", W, dh), lambda: torch.nn.functional.pad(    # (2, H, 128, RWP)
+            E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2).contiguous())
         dsb_op = _op(dsb, 0, M * H * _RWP, BH, T, _RWP, H * _RWP, _RWP, H, T * H * _RWP)
         et_op = _op(etp, 0, H * _HP * _RWP, H, _HP, _RWP, _RWP, _HP * _RWP)
         _tc_batched(dsb_op, et_op, 2, dh, _RWP,

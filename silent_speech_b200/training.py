@@ -32,6 +32,7 @@ class GradientBucket:
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        F_.register_grad_sinks(self.params)      # backward bodies may accumulate in place
 
     def zero(self):
         self.flat.zero_()

@@ -47,11 +47,21 @@ class LearnedRelativePositionalEmbedding(nn.Module):
         nn.init.normal_(self.embeddings, mean=0.0, std=embedding_dim ** (-0.5))
 
     def padded_table(self):
-        """(H, RW, dh) constant with RW = 2*max_relative_pos rounded up to a multiple of 4."""
-        with torch.no_grad():
-            e = self.embeddings[..., 0]
-            rw = (e.shape[1] + 1 + 3) // 4 * 4
-            return torch.nn.functional.pad(e, (0, 0, 0, rw - e.shape[1])).contiguous()
+        """(H, RW, dh) constant with RW = 2*max_relative_pos rounded up to a multiple of 4.
+        The table never trains (F3), so the padded copy - and the operand planes the attention
+        kernels derive from it, which functional caches ON this tensor - are rebuilt only when
+        the parameter is written (load_state_dict, .to())."""
+        emb = self.embeddings
+        key = (emb._version, emb.data_ptr(), emb.device)
+        if getattr(self, "_table_key", None) != key:
+            with torch.no_grad():
+                e = emb[..., 0]
+                rw = (e.shape[1] + 1 + 3) // 4 * 4
+                table = torch.nn.functional.pad(e, (0, 0, 0, rw - e.shape[1])).contiguous()
+            if torch.cuda.is_current_stream_capturing():
+                return table            # graph-pool memory must not outlive the capture
+            self._table, self._table_key = table, key
+        return self._table
 
 
 class MultiHeadAttention(nn.Module):
@@ -125,9 +135,8 @@ class TransformerEncoderLayer(nn.Module):
         x1 = F_.add_dropout_layernorm(x2d, a, self.norm1.weight, self.norm1.bias,
                                       self.dropout1.p if tr else 0.0, seed, site0 + 1,
                                       self.norm1.eps)
-        f = F_.ffn(x1, self.linear1.weight.t().contiguous(), self.linear1.bias,
-                   self.linear2.weight.t().contiguous(), self.linear2.bias,
-                   self.dropout.p if tr else 0.0, seed, site0 + 2)
+        f = F_.ffn_native(x1, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                          self.linear2.bias, self.dropout.p if tr else 0.0, seed, site0 + 2)
         return F_.add_dropout_layernorm(x1, f, self.norm2.weight, self.norm2.bias,
                                         self.dropout2.p if tr else 0.0, seed, site0 + 3,
                                         self.norm2.eps)

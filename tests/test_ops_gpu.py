@@ -145,6 +145,52 @@ def test_gemm_epilogue_split_plane_operands():
                 _epi(_scatter_plain(y.data_ptr(), M, N), planes_out=pl), M, N, K)
 
 
+def test_ffn_native_layout_and_gradient_sinks():
+    """ffn_native (nn.Linear-layout weights, transposed split, parameter-layout weight gradients)
+    equals ffn on the transposed copies; with registered gradient sinks the gradients are
+    accumulated into the persistent .grad views and autograd receives None."""
+    M, D, Fh, p = 1000, 768, 3072, 0.2
+    x = rnd(M, D, seed=1)
+    w1 = rnd(Fh, D, seed=2, scale=D ** -0.5)
+    b1 = rnd(Fh, seed=3, scale=0.1)
+    w2 = rnd(D, Fh, seed=4, scale=Fh ** -0.5)
+    b2 = rnd(D, seed=5, scale=0.1)
+    g = rnd(M, D, seed=6)
+
+    def run(native, sinks):
+        ps = [torch.nn.Parameter(t.clone()) for t in (w1, b1, w2, b2)]
+        xx = x.clone().requires_grad_(True)
+        if sinks:
+            for q in ps:
+                q.grad = torch.full_like(q, 0.5)          # pre-existing content must be kept
+            SF.register_grad_sinks(ps)
+        if native:
+            y = SF.ffn_native(xx, ps[0], ps[1], ps[2], ps[3], p, 11, 3)
+        else:
+            y = SF.ffn(xx, ps[0].t().contiguous(), ps[1], ps[2].t().contiguous(), ps[3], p, 11, 3)
+        y.backward(g)
+        return [y.detach(), xx.grad] + [q.grad - (0.5 if sinks else 0.0) for q in ps]
+
+    base = run(False, False)
+    for native, sinks in ((True, False), (True, True)):
+        got = run(native, sinks)
+        assert torch.equal(got[0], base[0])                                  # same forward GEMMs
+        for a, b, n in zip(got[1:], base[1:], "dx dw1 db1 dw2 db2".split()):
+            close(a, b, tol=2e-5, what=f"{n} native={native} sinks={sinks}")
+    # a parameter whose .grad was replaced no longer has a sink
+    q = torch.nn.Parameter(w1.clone())
+    q.grad = torch.zeros_like(q)
+    SF.register_grad_sinks([q])
+    assert SF._sink(q) is q.grad
+    q.grad = torch.zeros_like(q)
+    assert SF._sink(q) is None
+
+
+def test_split_planes_transposed():
+    x = rnd(200, 136, seed=9)
+    assert torch.equal(SF.split_planes_t(x), SF.split_planes(x.t().contiguous()))
+
+
 def test_ffn_dropout_statistics_and_consistency():
     M, D, Fh, p = 512, 32, 3072, 0.2
     x = rnd(M, D, seed=1).requires_grad_(True)
