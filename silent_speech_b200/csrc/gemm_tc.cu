@@ -417,6 +417,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t stg = epi_base + (uint32_t)ew * EPI_WARP_BYTES;
     const int rsub = lane >> 3;           // after the transpose: row (i*4 + rsub) of the 32-row group,
     const int csub = (lane & 7) * 4;      // columns csub .. csub+3 of the 32-column block
+    // "wide" lane map for split-plane epilogue operands: row (i*8 + rsubw), 8 columns per lane, so
+    // a lane's share of a bf16 plane row is one 16 B store (the 4-column map made 8 B stores and
+    // the plane-emitting FFN GEMMs ran 25 % slower than their fp32-output twins)
+    const bool wide = p.planes != nullptr || p.mask_planes != nullptr;
+    const int rsubw = lane >> 2, csubw = (lane & 3) * 8;
     uint32_t tcount = 0;
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {
       int n0, batch, row0, f0, kb_begin, nkb;
@@ -454,21 +459,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       // per lane in flight instead of one dependent HBM round trip per output row (the masked
       // FFN data gradient ran at 548 us vs 265 us for the same-shape forward GEMM).
       float4 side[8];
+      // wide map (K-major plain output only): first row, global row index and fp32 row pointer
+      const int firstw = row0 + lg * 32 + rsubw;
+      const int64_t groww0 = (int64_t)batch * p.rows_per_batch + firstw;
+      float* const oroww0 = p.out + (int64_t)(batch % p.batch_div) * p.out_batch_stride +
+                            (int64_t)(batch / p.batch_div) * p.out_batch_stride_hi +
+                            ((int64_t)firstw * p.out_dt + p.out_doff) * p.out_ld;
+      const int64_t row_stepw = (int64_t)8 * p.out_dt * p.out_ld;
       auto prefetch = [&](int c) {
+        if (!(p.mask_src || p.mask_planes || p.accumulate) || !group_live) return;
+        if (wide) {
+          const int n = n0 + c * 32 + csubw;
+          if (n >= p.N) return;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (firstw + 8 * i >= limit) continue;
+            const int64_t e = (groww0 + 8 * i) * p.N + n;
+            if (p.mask_planes) {   // 8 bf16: only sign / zero-ness matter
+              const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask_planes + e));
+              side[2 * i] = make_float4(__uint_as_float(m.x << 16), __uint_as_float(m.x & 0xffff0000u),
+                                        __uint_as_float(m.y << 16), __uint_as_float(m.y & 0xffff0000u));
+              side[2 * i + 1] = make_float4(__uint_as_float(m.z << 16), __uint_as_float(m.z & 0xffff0000u),
+                                            __uint_as_float(m.w << 16), __uint_as_float(m.w & 0xffff0000u));
+            } else if (p.mask_src) {
+              side[2 * i] = __ldg(reinterpret_cast<const float4*>(p.mask_src + e));
+              side[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(p.mask_src + e + 4));
+            } else {
+              side[2 * i] = *reinterpret_cast<const float4*>(oroww0 + i * row_stepw + n);
+              side[2 * i + 1] = *reinterpret_cast<const float4*>(oroww0 + i * row_stepw + n + 4);
+            }
+          }
+          return;
+        }
         const int n = n0 + c * 32 + csub;
-        if (!(p.mask_src || p.mask_planes || p.accumulate) || !group_live || n >= p.N) return;
+        if (n >= p.N) return;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (first + 4 * i >= limit) continue;
-          if (p.mask_planes) {   // 4 bf16: only sign / zero-ness matter
-            const uint2 m = __ldg(reinterpret_cast<const uint2*>(p.mask_planes + (grow0 + 4 * i) * p.N + n));
-            side[i] = make_float4(__uint_as_float(m.x << 16), __uint_as_float(m.x & 0xffff0000u),
-                                  __uint_as_float(m.y << 16), __uint_as_float(m.y & 0xffff0000u));
-          } else if (p.mask_src)
+          if (p.mask_src)
             side[i] = __ldg(reinterpret_cast<const float4*>(p.mask_src + (grow0 + 4 * i) * p.N + n));
           else
             side[i] = *reinterpret_cast<const float4*>(orow0 + i * row_step + n);
         }
+      };
+      // bias / ReLU / dropout / mask / accumulate on 4 consecutive outputs starting at element e
+      auto epi_math = [&](float4 r, const float4 bias4, const float4 sd, const uint64_t e) {
+        r.x += bias4.x; r.y += bias4.y; r.z += bias4.z; r.w += bias4.w;
+        if (p.relu) {
+          r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+        }
+        if (p.drop_p > 0.f) {
+          const uint4 rnd = ssb::dropout_bits4(seed, p.site, e >> 2);
+          r.x = rnd.x >= p.drop_thresh ? r.x * p.drop_scale : 0.f;
+          r.y = rnd.y >= p.drop_thresh ? r.y * p.drop_scale : 0.f;
+          r.z = rnd.z >= p.drop_thresh ? r.z * p.drop_scale : 0.f;
+          r.w = rnd.w >= p.drop_thresh ? r.w * p.drop_scale : 0.f;
+        }
+        if (p.mask_src || p.mask_planes) {
+          r.x = sd.x > 0.f ? r.x * p.mask_scale : 0.f;
+          r.y = sd.y > 0.f ? r.y * p.mask_scale : 0.f;
+          r.z = sd.z > 0.f ? r.z * p.mask_scale : 0.f;
+          r.w = sd.w > 0.f ? r.w * p.mask_scale : 0.f;
+        } else if (p.accumulate) {
+          r.x += sd.x; r.y += sd.y; r.z += sd.z; r.w += sd.w;
+        }
+        return r;
       };
       prefetch(cpar);
       mbar_wait(tfull_bar + 8 * acc, aph);
@@ -487,6 +542,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                        "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
                        : "memory");
         __syncwarp();
+        if (wide) {
+          const int n = n0 + c * 32 + csubw;
+          const bool n_ok = n < p.N;
+          float4 biasA = make_float4(0.f, 0.f, 0.f, 0.f), biasB = biasA;
+          if (p.bias && n_ok) {
+            biasA = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            biasB = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+          }
+          float4 oA[4], oB[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t a = stg + (uint32_t)(i * 8 + rsubw) * EPI_ROW_BYTES + (uint32_t)csubw * 4u;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(oA[i].x), "=f"(oA[i].y), "=f"(oA[i].z), "=f"(oA[i].w) : "r"(a) : "memory");
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(oB[i].x), "=f"(oB[i].y), "=f"(oB[i].z), "=f"(oB[i].w) : "r"(a + 16u) : "memory");
+          }
+          __syncwarp();   // the staging tile is rewritten by the next column block
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (!n_ok || firstw + 8 * i >= limit) continue;
+            const uint64_t e = (uint64_t)(groww0 + 8 * i) * (uint64_t)p.N + (uint64_t)n;
+            oA[i] = epi_math(oA[i], biasA, side[2 * i], e);
+            oB[i] = epi_math(oB[i], biasB, side[2 * i + 1], e + 4);
+          }
+          if (c + 2 < BN / 32) prefetch(c + 2);
+          if (p.out) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (!n_ok || firstw + 8 * i >= limit) continue;
+              *reinterpret_cast<float4*>(oroww0 + i * row_stepw + n) = oA[i];
+              *reinterpret_cast<float4*>(oroww0 + i * row_stepw + n + 4) = oB[i];
+            }
+          }
+          if (p.planes) {   // x = hi + lo, the operand format of the next GEMM (no split pass)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (!n_ok || firstw + 8 * i >= limit) continue;
+              const float f[8] = {oA[i].x, oA[i].y, oA[i].z, oA[i].w, oB[i].x, oB[i].y, oB[i].z, oB[i].w};
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(f[2 * j] - __low2float(h),
+                                                               f[2 * j + 1] - __high2float(h));
+                hw[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lw[j] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+              __nv_bfloat16* dst = p.planes + (groww0 + 8 * i) * p.N + n;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(dst + p.planes_stride) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            }
+          }
+          continue;
+        }
         const int n = n0 + c * 32 + csub;
         const bool n_ok = n < p.N;
         float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -520,7 +630,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             r.z = rnd.z >= p.drop_thresh ? r.z * p.drop_scale : 0.f;
             r.w = rnd.w >= p.drop_thresh ? r.w * p.drop_scale : 0.f;
           }
-          if (p.mask_src || p.mask_planes) {
+          if (p.mask_src) {
             const float4 mk = side[i];
             r.x = mk.x > 0.f ? r.x * p.mask_scale : 0.f;
             r.y = mk.y > 0.f ? r.y * p.mask_scale : 0.f;
@@ -539,21 +649,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int i = 0; i < 8; ++i) {
             if (!n_ok || first + 4 * i >= limit || p.atomic) continue;
             *reinterpret_cast<float4*>(orow0 + i * row_step + n) = o[i];
-          }
-        }
-        if (p.planes) {   // x = hi + lo, the operand format of the next GEMM (no split pass)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (!n_ok || first + 4 * i >= limit) continue;
-            const float4 r = o[i];
-            const __nv_bfloat162 h01 = __floats2bfloat162_rn(r.x, r.y), h23 = __floats2bfloat162_rn(r.z, r.w);
-            const __nv_bfloat162 l01 = __floats2bfloat162_rn(r.x - __low2float(h01), r.y - __high2float(h01));
-            const __nv_bfloat162 l23 = __floats2bfloat162_rn(r.z - __low2float(h23), r.w - __high2float(h23));
-            __nv_bfloat16* dst = p.planes + (grow0 + 4 * i) * p.N + n;
-            *reinterpret_cast<uint2*>(dst) =
-                make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-            *reinterpret_cast<uint2*>(dst + p.planes_stride) =
-                make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
           }
         }
       }
@@ -758,9 +853,9 @@ int fill_epi(const ssb_epilogue_t* e, int64_t N, TcParams* p) {
                   ((uintptr_t)e->out.base & 15) == 0,
               "gemm_tc: bad output geometry / alignment");
   SSB_REQUIRE(!(e->mask_src && e->mask_planes), "gemm_tc: mask_src and mask_planes are exclusive");
-  SSB_REQUIRE(((uintptr_t)e->planes_out & 7) == 0 && ((uintptr_t)e->mask_planes & 7) == 0 &&
-                  e->planes_stride % 4 == 0,
-              "gemm_tc: split-plane epilogue operands must be 8 B aligned");
+  SSB_REQUIRE(((uintptr_t)e->planes_out & 15) == 0 && ((uintptr_t)e->mask_planes & 15) == 0 &&
+                  e->planes_stride % 8 == 0 && ((!e->planes_out && !e->mask_planes) || N % 8 == 0),
+              "gemm_tc: split-plane epilogue operands need 16 B alignment and N %% 8 == 0");
   SSB_REQUIRE(e->out.base || !e->accumulate, "gemm_tc: accumulate needs an fp32 output");
   p->planes = (__nv_bfloat16*)e->planes_out; p->planes_stride = e->planes_stride;
   p->mask_planes = (const __nv_bfloat16*)e->mask_planes;
