@@ -170,28 +170,32 @@ SSB_API int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* g
                          float momentum, float eps, int training, float* mean, float* rstd,
                          float* scale, float* shift, void* workspace, int64_t workspace_bytes,
                          void* stream);
-/* y = [relu]( (x-mean)*scale + beta [+ (x2-mean2)*scale2 + beta2] )   (architecture.py:32-40) */
+/* y = [relu]( (x-mean)*scale + beta [+ (x2-mean2)*scale2 + beta2] )   (architecture.py:32-40)
+ * The *_planes arguments of this family are optional (NULL) second outputs: the same result as
+ * bf16 split planes [2][rows][C] (ssb_split_bf16 format) for the tcgen05 GEMM that consumes it. */
 SSB_API int ssb_bn_apply(const float* x, const float* mean, const float* scale, const float* beta,
                          const float* x2, const float* mean2, const float* scale2,
                          const float* beta2, int relu, int64_t rows, int64_t C, float* y,
-                         void* stream);
+                         void* y_planes, void* stream);
 /* BatchNorm backward through an optional ReLU mask (dz = dy * (mask_src > 0)).
  * workspace >= ssb_col_partials_bytes(rows, C) + 8*C bytes. */
 SSB_API int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const float* mean,
                        const float* rstd, const float* gamma, int training, int64_t rows,
-                       int64_t C, float* dx, float* dgamma, float* dbeta, void* workspace,
-                       int64_t workspace_bytes, void* stream);
+                       int64_t C, float* dx, void* dx_planes, float* dgamma, float* dbeta,
+                       void* workspace, int64_t workspace_bytes, void* stream);
 /* z = res + dropout(branch); y = LayerNorm(z)*gamma + beta   (transformer.py:55-56,58-59) */
 SSB_API int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const float* gamma,
                                    const float* beta, int64_t rows, int64_t D, float eps,
                                    float drop_p, uint64_t seed, uint32_t site, float* z_out,
-                                   float* y, float* mean, float* rstd, void* stream);
+                                   float* y, float* mean, float* rstd, void* y_planes,
+                                   void* stream);
 SSB_API int64_t ssb_add_dropout_ln_bwd_workspace_bytes(int64_t rows, int64_t D);
 SSB_API int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean,
                                    const float* rstd, const float* gamma, int64_t rows, int64_t D,
                                    float drop_p, uint64_t seed, uint32_t site, float* d_res,
-                                   float* d_branch, float* dgamma, float* dbeta, void* workspace,
-                                   int64_t workspace_bytes, void* stream);
+                                   float* d_branch, void* d_branch_planes, float* dgamma,
+                                   float* dbeta, void* workspace, int64_t workspace_bytes,
+                                   void* stream);
 
 /* ---- banded relative-position attention ------------------------------------------
  * Replaces transformer.py:99-110 (logits, softmax, dropout, PV) with the relative-position

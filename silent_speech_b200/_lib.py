@@ -102,15 +102,15 @@ _SIGNATURES = {
     "ssb_bn_stats": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_f32, c_int,
                              c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_bn_apply": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64,
-                             c_i64, c_ptr, c_ptr]),
+                             c_i64, c_ptr, c_ptr, c_ptr]),
     "ssb_bn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr,
-                           c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+                           c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_add_dropout_ln_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_f32,
-                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ssb_add_dropout_ln_bwd_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_add_dropout_ln_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32,
-                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
-                                       c_ptr]),
+                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                       c_i64, c_ptr]),
     "ssb_band_attn_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
     "ssb_band_attn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,

@@ -15,6 +15,21 @@ namespace {
 
 constexpr int RCH = 256;  // rows per partial chunk
 
+// optional second output of the element-wise kernels: the same 4 values as bf16 split planes
+// (x = hi + lo), i.e. already in the operand format of the tcgen05 GEMM that consumes them, so no
+// separate fp32 -> planes pass runs.  idx4 = float4 index into the plain tensor.
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* planes, int64_t plane_stride,
+                                              int64_t idx4, const float4 v) {
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+  const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+  const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+  __nv_bfloat16* dst = planes + 4 * idx4;
+  *reinterpret_cast<uint2*>(dst) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+  *reinterpret_cast<uint2*>(dst + plane_stride) =
+      make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+}
+
 // ---- column partial sums -------------------------------------------------------------
 // MODE 0: sum((x-mean)^2)                         (BatchNorm variance, second pass: the two-pass
 //         form is immune to the cancellation of E[x^2]-mean^2 on near-constant channels, where
@@ -211,7 +226,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                 const float* __restrict__ scale, const float* __restrict__ beta,
                 const float* __restrict__ x2, const float* __restrict__ mean2,
                 const float* __restrict__ scale2, const float* __restrict__ beta2, int relu,
-                int64_t n4, int C4, float* __restrict__ y) {
+                int64_t n4, int C4, float* __restrict__ y, __nv_bfloat16* __restrict__ y_planes) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
@@ -233,6 +248,7 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
     reinterpret_cast<float4*>(y)[i] = o;
+    if (y_planes) store_planes4(y_planes, 4 * n4, i, o);
   }
 }
 
@@ -256,7 +272,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask
                     const float* __restrict__ x, const float* __restrict__ mean,
                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                     const float* __restrict__ m_dz, const float* __restrict__ m_dzx, int64_t n4,
-                    int C4, float* __restrict__ dx) {
+                    int C4, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_planes) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
@@ -281,6 +297,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask
     o.z = ga.z * rs.z * (g.z - a.z - (v.z - mu.z) * rs.z * bq.z);
     o.w = ga.w * rs.w * (g.w - a.w - (v.w - mu.w) * rs.w * bq.w);
     reinterpret_cast<float4*>(dx)[i] = o;
+    if (dx_planes) store_planes4(dx_planes, 4 * n4, i, o);
   }
 }
 
@@ -295,7 +312,7 @@ add_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ branc
                   uint64_t seed_base, const uint64_t* __restrict__ seed_src, uint32_t site,
                   float* __restrict__ z_out,
                   float* __restrict__ y, float* __restrict__ mean_out,
-                  float* __restrict__ rstd_out) {
+                  float* __restrict__ rstd_out, __nv_bfloat16* __restrict__ y_planes) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -346,6 +363,7 @@ add_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ branc
       o.z = (z[i].z - mu) * rs * g.z + b.z;
       o.w = (z[i].w - mu) * rs * g.w + b.w;
       reinterpret_cast<float4*>(y + row * D)[v] = o;
+      if (y_planes) store_planes4(y_planes, rows * D, row * nv + v, o);
       if (z_out) reinterpret_cast<float4*>(z_out + row * D)[v] = z[i];
     }
   }
@@ -369,6 +387,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
                   float drop_scale, uint32_t drop_thresh, uint64_t seed_base,
                   const uint64_t* __restrict__ seed_src, uint32_t site,
                   float* __restrict__ d_res, float* __restrict__ d_branch,
+                  __nv_bfloat16* __restrict__ d_branch_planes,
                   float* __restrict__ partials /* [nblk][2][D] : dgamma, dbeta */) {
   __shared__ float sm[2][1024];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -425,6 +444,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
           o.w = rnd.w >= drop_thresh ? o.w * drop_scale : 0.f;
         }
         reinterpret_cast<float4*>(d_branch + row * D)[v] = o;
+        if (d_branch_planes) store_planes4(d_branch_planes, rows * D, row * nv + v, o);
       }
     }
   }
@@ -555,7 +575,7 @@ int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* gamma, co
 
 int ssb_bn_apply(const float* x, const float* mean, const float* scale, const float* beta,
                  const float* x2, const float* mean2, const float* scale2, const float* beta2,
-                 int relu, int64_t rows, int64_t C, float* y, void* stream) {
+                 int relu, int64_t rows, int64_t C, float* y, void* y_planes, void* stream) {
   if (int rc = check_rows_c(x, rows, C, "bn_apply")) return rc;
   SSB_REQUIRE(mean && scale && beta && y && (!x2 || (mean2 && scale2 && beta2)),
               "bn_apply: null pointer");
@@ -563,15 +583,16 @@ int ssb_bn_apply(const float* x, const float* mean, const float* scale, const fl
   const int64_t blocks = (n4 + 255) / 256;
   const int grid = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
   bn_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mean, scale, beta, x2, mean2, scale2,
-                                                          beta2, relu, n4, (int)(C / 4), y);
+                                                          beta2, relu, n4, (int)(C / 4), y,
+                                                          (__nv_bfloat16*)y_planes);
   SSB_LAUNCH_CHECK("bn_apply");
   return SSB_OK;
 }
 
 int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const float* mean,
                const float* rstd, const float* gamma, int training, int64_t rows, int64_t C,
-               float* dx, float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
-               void* stream) {
+               float* dx, void* dx_planes, float* dgamma, float* dbeta, void* workspace,
+               int64_t workspace_bytes, void* stream) {
   if (int rc = check_rows_c(x, rows, C, "bn_bwd")) return rc;
   SSB_REQUIRE(dy && mean && rstd && gamma && dx && dgamma && dbeta, "bn_bwd: null pointer");
   const int64_t need = ssb_col_partials_bytes(rows, C) + 2 * C * 4;
@@ -594,7 +615,7 @@ int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const flo
   const int g2 = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
   bn_bwd_apply_kernel<<<g2, 256, 0, st>>>(dy, mask_src, x, mean, rstd, gamma,
                                           training ? m_dz : nullptr, training ? m_dzx : nullptr,
-                                          n4, (int)(C / 4), dx);
+                                          n4, (int)(C / 4), dx, (__nv_bfloat16*)dx_planes);
   SSB_LAUNCH_CHECK("bn_bwd_apply");
   return SSB_OK;
 }
@@ -602,7 +623,7 @@ int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const flo
 int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const float* gamma,
                            const float* beta, int64_t rows, int64_t D, float eps, float drop_p,
                            uint64_t seed, uint32_t site, float* z_out, float* y, float* mean,
-                           float* rstd, void* stream) {
+                           float* rstd, void* y_planes, void* stream) {
   if (int rc = check_rows_c(res, rows, D, "add_dropout_ln_fwd")) return rc;
   SSB_REQUIRE(D <= 1024, "add_dropout_ln_fwd: D=%lld > 1024 not built", (long long)D);
   SSB_REQUIRE(branch && gamma && beta && y, "add_dropout_ln_fwd: null pointer");
@@ -610,7 +631,8 @@ int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const float* g
   const unsigned grid = (unsigned)((rows + 7) / 8);
   add_ln_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       res, branch, gamma, beta, rows, (int)D, eps, drop_p, drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,
-      thresh_of(drop_p), seed, ssb::seed_source(), site, z_out, y, mean, rstd);
+      thresh_of(drop_p), seed, ssb::seed_source(), site, z_out, y, mean, rstd,
+      (__nv_bfloat16*)y_planes);
   SSB_LAUNCH_CHECK("add_ln_fwd");
   return SSB_OK;
 }
@@ -624,8 +646,8 @@ int64_t ssb_add_dropout_ln_bwd_workspace_bytes(int64_t rows, int64_t D) {
 int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
                            const float* gamma, int64_t rows, int64_t D, float drop_p,
                            uint64_t seed, uint32_t site, float* d_res, float* d_branch,
-                           float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
-                           void* stream) {
+                           void* d_branch_planes, float* dgamma, float* dbeta, void* workspace,
+                           int64_t workspace_bytes, void* stream) {
   if (int rc = check_rows_c(dy, rows, D, "add_dropout_ln_bwd")) return rc;
   SSB_REQUIRE(D <= 1024, "add_dropout_ln_bwd: D=%lld > 1024 not built", (long long)D);
   SSB_REQUIRE(z && mean && rstd && gamma && d_res && d_branch && dgamma && dbeta,
@@ -638,7 +660,8 @@ int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, c
   add_ln_bwd_kernel<NV><<<nblk, 256, 0, st>>>(dy, z, mean, rstd, gamma, rows, (int)D, drop_p,       \
                                               drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f,           \
                                               thresh_of(drop_p), seed, ssb::seed_source(), site,   \
-                                              d_res, d_branch, (float*)workspace)
+                                              d_res, d_branch, (__nv_bfloat16*)d_branch_planes,   \
+                                              (float*)workspace)
   const int nvl = (int)((D / 4 + 31) / 32);
   if (nvl <= 2) SSB_LN_BWD(2);
   else if (nvl <= 4) SSB_LN_BWD(4);

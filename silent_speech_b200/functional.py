@@ -150,6 +150,27 @@ def _sink(t):
     return ent[1]
 
 
+def attach_planes(t, planes):
+    """Remember that `planes` (2, *t.shape) are the split planes of t's CURRENT contents (a
+    producer kernel wrote both).  Consumers pick them up through planes_of()."""
+    t._ssb_planes = (t._version, planes)
+    return t
+
+
+def planes_of(t):
+    """Split planes of t: the ones its producer already wrote, if t was not modified since
+    (in-place autograd accumulation bumps _version), else a split pass."""
+    ent = getattr(t, "_ssb_planes", None)
+    if ent is not None and ent[0] == t._version and tuple(ent[1].shape[1:]) == tuple(t.shape):
+        return ent[1]
+    return split_planes(t)
+
+
+def _want_planes(rows, C):
+    """Would a tcgen05 GEMM consume a (rows, C) activation?  (else planes would be wasted writes)"""
+    return _tc_enabled() and rows >= 64 and C % 64 == 0
+
+
 def split_planes_t(x2d):
     """fp32 (rows, cols) -> bf16 planes (2, cols, rows) of the TRANSPOSE (one fused pass)."""
     lib = _lib.load()
@@ -216,7 +237,7 @@ def mm_fwd(x, Wg, epi_kwargs, out, M, N, K, xp=None):
     scat = _scatter_plain(out.data_ptr(), M, N)
     if _tc_fwd_ok(M, N, K):
         if xp is None:
-            xp = split_planes(x)
+            xp = planes_of(x)
         wp = split_planes(Wg.t().contiguous())                    # [N][K], K contiguous
         gemm_tc_kmajor(tc_operand_plain(xp, M, K), wp, N, K, _epi(scat, **epi_kwargs))
         return xp
@@ -229,7 +250,7 @@ def mm_dgrad(dy, Wg, epi_kwargs, out, M, N, K, dyp=None):
     scat = _scatter_plain(out.data_ptr(), M, K)
     if _tc_fwd_ok(M, K, N):
         if dyp is None:
-            dyp = split_planes(dy)
+            dyp = planes_of(dy)
         gemm_tc_kmajor(tc_operand_plain(dyp, M, N), split_planes(Wg), K, N, _epi(scat, **epi_kwargs))
         return dyp
     gemm_nt(_gather_plain(dy.data_ptr(), M, N, N), Wg, N, (0,), _epi(scat, **epi_kwargs), M, K, N)
@@ -240,9 +261,9 @@ def mm_wgrad(x, dy, dW, M, N, K, xp=None, dyp=None):
     """dW[K,N] = x[M,K]^T @ dy[M,N]."""
     if _tc_wgrad_ok(M, N, K):
         if xp is None:
-            xp = split_planes(x)
+            xp = planes_of(x)
         if dyp is None:
-            dyp = split_planes(dy)
+            dyp = planes_of(dy)
         gemm_tc_wgrad(tc_operand_plain(xp, M, K), dyp, N, K, dW)
         return dyp
     gemm_tn(_gather_plain(x.data_ptr(), M, K, K), dy, dW, M, N, K)
@@ -322,7 +343,7 @@ class _FFNFn(torch.autograd.Function):
         ctx.planes = (_tc_fwd_ok(M, F_, K) and _tc_fwd_ok(M, N, F_) and _tc_wgrad_ok(M, F_, K)
                       and _tc_wgrad_ok(M, N, F_) and _tc_fwd_ok(M, K, F_) and _tc_fwd_ok(M, F_, N))
         if ctx.planes:
-            xp = split_planes(x)
+            xp = planes_of(x)
             hp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
             gemm_tc_kmajor(tc_operand_plain(xp, M, K), split_planes(W1.t().contiguous()), F_, K,
                            _epi(_scatter_plain(None, M, F_), bias=b1, relu=1, drop_p=p, seed=seed,
@@ -348,7 +369,7 @@ class _FFNFn(torch.autograd.Function):
             F_ = W1.shape[1]
             N = W2.shape[1]
             dev = dy.device
-            dyp = split_planes(dy)
+            dyp = planes_of(dy)
             dW2 = torch.empty_like(W2)
             gemm_tc_wgrad(tc_operand_plain(hp, M, F_), dyp, N, F_, dW2)
             db2 = colsum(dy)
@@ -393,7 +414,7 @@ class _FFNNativeFn(torch.autograd.Function):
         M, K = x.shape
         F_, N = w1.shape[0], w2.shape[0]
         dev = x.device
-        xp = split_planes(x)
+        xp = planes_of(x)
         hp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
         gemm_tc_kmajor(tc_operand_plain(xp, M, K), split_planes(w1), F_, K,
                        _epi(_scatter_plain(None, M, F_), bias=b1, relu=1, drop_p=p, seed=seed,
@@ -415,7 +436,7 @@ class _FFNNativeFn(torch.autograd.Function):
         F_, N = w1.shape[0], w2.shape[0]
         dev = dy.device
         scale = 1.0 / (1.0 - ctx.p) if ctx.p > 0 else 1.0
-        dyp = split_planes(dy)
+        dyp = planes_of(dy)
         dW2 = s_w2 if s_w2 is not None else torch.empty_like(w2)          # (N, F) = dy^T h
         gemm_tc_wgrad(tc_operand_plain(dyp, M, N), hp, F_, N, dW2, accumulate=s_w2 is not None)
         db2 = colsum(dy, out=s_b2, accumulate=s_b2 is not None)
@@ -472,7 +493,7 @@ class _ConvFn(torch.autograd.Function):
         off = -1 if ksize == 3 else 0
         xp = None
         if _tc_fwd_ok(M, Cout, ksize * Cin, Cin):
-            xp = split_planes(x)
+            xp = planes_of(x)
             wp = split_planes(Wg.t().contiguous())               # [Cout][(tap, ci)]
             gemm_tc_kmajor(tc_operand_conv(xp, B, L, Cin, Lout, stride, 1, off), wp, Cout,
                            ksize * Cin, _epi(Scatter(y.data_ptr(), Lout * Cout, Lout, Cout, 1, 0),
@@ -501,8 +522,8 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dW = torch.empty_like(Wg)
             if _tc_wgrad_ok(M, Cout, K, Cin):
-                dyp = split_planes(dy)
-                xpl = xp_saved if xp_saved is not None else split_planes(x)
+                dyp = planes_of(dy)
+                xpl = xp_saved if xp_saved is not None else planes_of(x)
                 gemm_tc_wgrad(tc_operand_conv(xpl, B, L, Cin, Lout, stride, 1, off), dyp, Cout, K, dW)
             else:
                 gemm_tn(_conv_gather(x, L, Cin, Lout, ksize, stride), dy2, dW, M, Cout, K)
@@ -513,7 +534,7 @@ class _ConvFn(torch.autograd.Function):
             W3 = Wg.view(ksize, Cin, Cout)
             use_tc = _tc_fwd_ok(B * L // max(stride, 1), Cin, Cout, Cout)
             if use_tc and dyp is None:
-                dyp = split_planes(dy)
+                dyp = planes_of(dy)
 
             def run(rows, taps, tap_off, tapmap, d_t, d_off, dst, accumulate=0):
                 """dst rows (b, t*d_t + d_off) = sum_j dy[b, t + j + tap_off] . W_tapmap[j]^T"""
@@ -572,14 +593,17 @@ def _bn_bwd(dy2, mask_src, x2, stats, gamma, training):
     rows, C = x2.shape
     dev = x2.device
     dx = torch.empty_like(x2)
+    dxp = (torch.empty((2, rows, C), dtype=torch.bfloat16, device=dev)
+           if _want_planes(rows, C) else None)
     dg = torch.empty(C, dtype=_f32, device=dev)
     db = torch.empty(C, dtype=_f32, device=dev)
     ws = _ws(lib.ssb_col_partials_bytes(rows, C) + 8 * C, dev)
     _lib.check(lib.ssb_bn_bwd(dy2.data_ptr(), mask_src.data_ptr() if mask_src is not None else None,
                               x2.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
                               gamma.data_ptr(), int(training), rows, C, dx.data_ptr(),
+                              dxp.data_ptr() if dxp is not None else None,
                               dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-    return dx, dg, db
+    return dx, dg, db, dxp
 
 
 class _BNActFn(torch.autograd.Function):
@@ -601,12 +625,17 @@ class _BNActFn(torch.autograd.Function):
             xb2 = xb.view(-1, C)
             sb = _bn_stats(xb2, gb, bb, rmb, rvb, training, momentum, eps)
         y = torch.empty_like(xa)
+        yp = (torch.empty((2,) + tuple(shape), dtype=torch.bfloat16, device=xa.device)
+              if _want_planes(rows, C) else None)
         _lib.check(lib.ssb_bn_apply(xa2.data_ptr(), sa[0].data_ptr(), sa[2].data_ptr(), ba.data_ptr(),
                                     xb2.data_ptr() if xb2 is not None else None,
                                     sb[0].data_ptr() if sb is not None else None,
                                     sb[2].data_ptr() if sb is not None else None,
                                     bb.data_ptr() if sb is not None else None, int(relu), rows,
-                                    C, y.data_ptr(), _stream()))
+                                    C, y.data_ptr(), yp.data_ptr() if yp is not None else None,
+                                    _stream()))
+        if yp is not None:
+            attach_planes(y, yp)     # the next convolution's operand, written by this kernel
         ctx.training, ctx.relu, ctx.two = training, relu, xb is not None
         if ctx.two:
             ctx.save_for_backward(xa, ga, sa, y, xb, gb, sb)
@@ -624,13 +653,16 @@ class _BNActFn(torch.autograd.Function):
         C = xa.shape[-1]
         dy2 = dy.view(-1, C)
         mask = y.view(-1, C) if ctx.relu else None
-        dxa, dga, dba = _bn_bwd(dy2, mask, xa.view(-1, C), sa, ga, ctx.training)
+        def shaped(d, dp, like):     # gradient of a convolution output + its operand planes
+            d = d.view_as(like)
+            return attach_planes(d, dp.view((2,) + tuple(like.shape))) if dp is not None else d
+        dxa, dga, dba, dxap = _bn_bwd(dy2, mask, xa.view(-1, C), sa, ga, ctx.training)
         dxb = dgb = dbb = None
         if ctx.two:
-            dxb, dgb, dbb = _bn_bwd(dy2, mask, xb.view(-1, C), sb, gb, ctx.training)
-            dxb = dxb.view_as(xb)
-        return (dxa.view_as(xa), dga, dba, None, None, dxb, dgb, dbb, None, None, None, None, None,
-                None)
+            dxb, dgb, dbb, dxbp = _bn_bwd(dy2, mask, xb.view(-1, C), sb, gb, ctx.training)
+            dxb = shaped(dxb, dxbp, xb)
+        return (shaped(dxa, dxap, xa), dga, dba, None, None, dxb, dgb, dbb, None, None, None, None,
+                None, None)
 
 
 def bn_act(xa, ga, ba, rma, rva, training, relu, xb=None, gb=None, bb=None, rmb=None, rvb=None,
@@ -651,13 +683,17 @@ class _AddDropLNFn(torch.autograd.Function):
         dev = res.device
         need_bwd = any(ctx.needs_input_grad[:4])
         y = torch.empty_like(res)
+        yp = (torch.empty((2, rows, D), dtype=torch.bfloat16, device=dev)
+              if _want_planes(rows, D) else None)
         z = torch.empty_like(res) if need_bwd else None
         stat = torch.empty((2, rows), dtype=_f32, device=dev) if need_bwd else None
         _lib.check(lib.ssb_add_dropout_ln_fwd(
             res.data_ptr(), branch.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, D, eps, p,
             seed & 0xFFFFFFFFFFFFFFFF, site, z.data_ptr() if need_bwd else None, y.data_ptr(),
             stat[0].data_ptr() if need_bwd else None, stat[1].data_ptr() if need_bwd else None,
-            _stream()))
+            yp.data_ptr() if yp is not None else None, _stream()))
+        if yp is not None:
+            attach_planes(y, yp)     # operand of the next QKV / FFN GEMM
         if need_bwd:
             ctx.save_for_backward(z, stat, gamma)
         ctx.cfg = (p, seed, site)
@@ -673,13 +709,18 @@ class _AddDropLNFn(torch.autograd.Function):
         dev = z.device
         d_res = torch.empty_like(z)
         d_branch = torch.empty_like(z)
+        dbp = (torch.empty((2, rows, D), dtype=torch.bfloat16, device=dev)
+               if _want_planes(rows, D) else None)
         dg = torch.empty(D, dtype=_f32, device=dev)
         db = torch.empty(D, dtype=_f32, device=dev)
         ws = _ws(lib.ssb_add_dropout_ln_bwd_workspace_bytes(rows, D), dev)
         _lib.check(lib.ssb_add_dropout_ln_bwd(
             dy.data_ptr(), z.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(), gamma.data_ptr(),
             rows, D, p, seed & 0xFFFFFFFFFFFFFFFF, site, d_res.data_ptr(), d_branch.data_ptr(),
+            dbp.data_ptr() if dbp is not None else None,
             dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+        if dbp is not None:
+            attach_planes(d_branch, dbp)   # dy operand of the branch's backward GEMMs
         return d_res, d_branch, dg, db, None, None, None, None
 
 

@@ -186,6 +186,44 @@ def test_ffn_native_layout_and_gradient_sinks():
     assert SF._sink(q) is None
 
 
+def test_producer_kernels_emit_exact_operand_planes():
+    """BatchNorm apply / backward and add+dropout+LayerNorm forward / backward attach the bf16
+    split planes of their result (written by the same kernel): bit-identical to a split pass over
+    the fp32 result, picked up by planes_of(), dropped after an in-place modification."""
+    rows, C = 520, 128
+    xa = rnd(1, rows, C, seed=1).requires_grad_(True)
+    xb = rnd(1, rows, C, seed=2).requires_grad_(True)
+    ps = [(rnd(C, seed=10 + i, scale=0.3) + (1.0 if i % 2 == 0 else 0.0)).requires_grad_(True)
+          for i in range(4)]
+    rm = [torch.zeros(C, device=dev) for _ in range(2)]
+    rv = [torch.ones(C, device=dev) for _ in range(2)]
+    y = SF.bn_act(xa, ps[0], ps[1], rm[0], rv[0], True, True, xb, ps[2], ps[3], rm[1], rv[1])
+    assert torch.equal(SF.planes_of(y), SF.split_planes(y.detach())) and hasattr(y, "_ssb_planes")
+    got = {}
+
+    def grab(key):
+        def hook(g):
+            got[key] = (g, getattr(g, "_ssb_planes", None))
+        return hook
+    xa.register_hook(grab("a"))
+    y.backward(rnd(1, rows, C, seed=3))
+    g, ent = got["a"]
+    assert ent is not None and torch.equal(ent[1], SF.split_planes(g.contiguous()))
+
+    res, br = rnd(rows, C, seed=4).requires_grad_(True), rnd(rows, C, seed=5).requires_grad_(True)
+    gam, bet = (rnd(C, seed=6) + 1).requires_grad_(True), rnd(C, seed=7).requires_grad_(True)
+    o = SF.add_dropout_layernorm(res, br, gam, bet, 0.2, 99, 5)
+    assert torch.equal(SF.planes_of(o), SF.split_planes(o.detach())) and hasattr(o, "_ssb_planes")
+    br.register_hook(grab("b"))
+    o.backward(rnd(rows, C, seed=8))
+    g, ent = got["b"]
+    assert ent is not None and torch.equal(ent[1], SF.split_planes(g.contiguous()))
+    # stale planes are never used
+    with torch.no_grad():
+        o.add_(1.0)
+    assert torch.equal(SF.planes_of(o), SF.split_planes(o.detach()))
+
+
 def test_split_planes_transposed():
     x = rnd(200, 136, seed=9)
     assert torch.equal(SF.split_planes_t(x), SF.split_planes(x.t().contiguous()))
