@@ -16,6 +16,8 @@ travel to the GPU box, so this arm times its CPU port (oracle/, torch fp32 on al
 on a bounded sample of the same workload.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import random
@@ -428,10 +430,27 @@ def main():
     ap.add_argument("--graph-probe", action="store_true",
                     help="experiment (with --eager): also time a whole-step CUDA graph")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line, the JSON result: libraries that write to fd 1 on their own
+    # (NCCL prints its version banner there) go to stderr while the run is in progress
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    lines = [l for l in buf.getvalue().splitlines() if l.strip()]
+    for l in lines[:-1]:
+        print(l, file=sys.stderr)
+    if lines:
+        print(lines[-1], flush=True)
 
 
 if __name__ == "__main__":
