@@ -134,7 +134,9 @@ col_partials_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bflo
 // ---- finalize kernels: fp64 accumulation of the chunk partials, fixed order ----------------
 // block = (32 channels, 8 chunk-lanes); lane y adds chunks y, y+8, ...; lanes are combined in
 // shared memory in a fixed order (deterministic), thread y == 0 finishes the channel.
-constexpr int FIN_LANES = 8;
+constexpr int FIN_LANES = 32;   // 8 lanes left 31 dependent fp64 adds per thread on 24 CTAs: 10-20 us
+                                // per finalize, 63 of them per step; 32 lanes: 8 adds, then a fixed-order
+                                // shared-memory combine
 #define FIN_GRID(C) dim3((unsigned)(((C) + 31) / 32)), dim3(32, FIN_LANES)
 
 __device__ __forceinline__ bool chunk_sums(const float* __restrict__ partials, int nchunks, int C,
