@@ -112,10 +112,13 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     _lib.require_cuda(y, "y")
     if y.dim() != 2:
         raise ValueError("y must be (batch, samples)")
-    if torch.min(y) < -1.:
-        print('min value is ', torch.min(y))
-    if torch.max(y) > 1.:
-        print('max value is ', torch.max(y))
+    # data_utils.py:40-43 warns about samples outside [-1, 1]; one fused reduction and one
+    # host read instead of up to four reductions with a sync each
+    lo, hi = torch.stack(torch.aminmax(y)).tolist()
+    if lo < -1.:
+        print('min value is ', lo)
+    if hi > 1.:
+        print('max value is ', hi)
     lib = _lib.load()
     y = y.to(torch.float32)
     if y.stride(1) != 1:

@@ -1,6 +1,7 @@
 """GPU: the recognition configuration (recognition_model.py:66,96-101): the same Model with a
 single 38-way head (no aux output) under stock CTC loss, forward + backward; and eval-mode
 un-chunked inference of a whole utterance (transduction_model.py:60-64)."""
+import math
 import random
 
 import pytest
@@ -57,3 +58,41 @@ def test_eval_whole_utterance_inference():
         a2, _ = m(None, x, None)
     assert a.shape == (1, 348, 80) and b.shape == (1, 348, 48)
     assert torch.equal(a, a2)                           # eval: no dropout, deterministic
+
+
+def test_cfg5_shape_ctc_step_engines_agree(monkeypatch):
+    """BASELINE cfg-5 geometry (768-dim model, L = 6000 -> T = 750, 38-way head, CTC) at reduced
+    batch / depth: one forward + fused CTC + backward on the tensor-core path (fused attention with
+    a ragged last key tile: 750 = 5 * 128 + 110) against the CUDA-core attention engine on the same
+    weights, and against stock F.ctc_loss on the same logits."""
+    from silent_speech_b200 import architecture as A
+    from silent_speech_b200.losses import ctc_loss
+    FL = flags.FLAGS
+    if not FL.is_parsed():
+        FL(["t"])
+    FL.model_size, FL.num_layers, FL.dropout = 768, 2, 0.0
+    torch.manual_seed(0)
+    m = A.Model(112, 38).cuda().train()
+    x = torch.randn(2, 6000, 8, generator=torch.Generator().manual_seed(1)).cuda()
+    tgt = torch.randint(0, 37, (2, 120), generator=torch.Generator().manual_seed(2)).cuda()
+    il, tl = torch.tensor([750, 700]), torch.tensor([120, 95])
+    res = {}
+    for eng in ("fused", "simt"):
+        monkeypatch.setenv("SSB_ATTN", eng)
+        m.zero_grad()
+        random.seed(4)
+        out = m(None, x.clone(), None)
+        assert out.shape == (2, 750, 38)
+        loss = ctc_loss(out, tgt, il, tl, blank=37)
+        loss.backward()
+        res[eng] = (out.detach(), loss.item(), m.w_out.weight.grad.clone(),
+                    m.transformer.layers[0].self_attn.w_q.grad.clone())
+    stock = F.ctc_loss(F.log_softmax(res["fused"][0].double(), 2).transpose(0, 1), tgt, il, tl,
+                       blank=37).item()
+    assert abs(res["fused"][1] - stock) < 1e-4 * abs(stock)
+    assert math.isfinite(res["fused"][1])
+    a, b = res["fused"], res["simt"]
+    assert ((a[0] - b[0]).norm() / b[0].norm()).item() < 2e-4
+    assert abs(a[1] - b[1]) < 1e-4 * abs(b[1])
+    for i in (2, 3):
+        assert ((a[i] - b[i]).norm() / b[i].norm()).item() < 2e-2
