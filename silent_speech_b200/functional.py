@@ -910,14 +910,15 @@ _band_bufs = {}
 
 
 def _band_scratch(key):
+    """Persistent zero-initialised (2, B*T, H, RWp) bf16 buffer for one attention geometry.
+    Never evicted: a captured CUDA graph may hold its address for as long as the process lives
+    (one buffer per distinct (B, T) a training run sees; 131 MB at cfg-1)."""
     buf = _band_bufs.get(key)
     if buf is None:
         B, T, H, W, rwp, dev = key
         buf = torch.zeros((2, B * T, H, rwp), dtype=torch.bfloat16, device=dev)
         if torch.cuda.is_current_stream_capturing():
-            return buf                  # graph-pool memory must not outlive the capture
-        if len(_band_bufs) >= 4:        # bounded: drop the oldest geometry
-            _band_bufs.pop(next(iter(_band_bufs)))
+            return buf                  # graph-pool memory: owned by that graph, not cached
         _band_bufs[key] = buf
     return buf
 

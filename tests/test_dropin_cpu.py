@@ -80,3 +80,20 @@ print("OK")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_opt_in_pieces_have_no_cpu_path():
+    """§8 f2 / f3 entry points follow the same rule as the rest of the package: CPU tensors raise,
+    nothing falls back to torch."""
+    import pytest
+    import torch
+    from silent_speech_b200 import _lib
+    from silent_speech_b200.losses import ctc_loss
+    from silent_speech_b200.optim import FlatAdamW
+    from silent_speech_b200.training import GradientBucket
+    with pytest.raises(_lib.SSBError):
+        ctc_loss(torch.randn(2, 10, 5, requires_grad=True), torch.zeros(2, 3, dtype=torch.int64),
+                 [10, 10], [3, 2], blank=4)
+    m = torch.nn.Linear(4, 4)
+    with pytest.raises(TypeError):
+        FlatAdamW(GradientBucket(m))
