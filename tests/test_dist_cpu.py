@@ -43,7 +43,18 @@ def _worker(rank, world, port, q):
     local = bucket.flat.clone()
     assert torch.equal(m.a.weight.grad.flatten(), bucket.flat[:12])     # grads alias the bucket
     bucket.allreduce_mean()
-    q.put((rank, local, bucket.flat.clone()))
+    mean = bucket.flat.clone()
+    # with a fused optimiser (FlatAdamW exposes grad_scale) the bucket keeps the SUM and the
+    # 1/world of the mean is handed to the optimiser kernel instead of a pass over the bucket
+    bucket.flat.copy_(local)
+
+    class Opt:
+        grad_scale = 1.0
+    opt = Opt()
+    bucket.allreduce_mean(opt)
+    assert opt.grad_scale == 0.5
+    assert torch.allclose(bucket.flat * opt.grad_scale, mean)
+    q.put((rank, local, mean))
     dist.destroy_process_group()
 
 
