@@ -6,6 +6,7 @@ reference file:line it follows:
   oracle/mel.py         data_utils.py:29-62      (numpy)
   oracle/model.py       architecture.py, transformer.py  (torch fp32, CPU)
   oracle/step.py        transduction_model.py:98-157,196-212 (loss + train step, CPU)
+  oracle/ctc.py         recognition_model.py:96-101      (numpy fp64 log-softmax + CTC)
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference`
 legs may import this package.  silent_speech_b200/ never does.

@@ -96,3 +96,29 @@ def test_ctc_through_the_model_head():
         grads.append((loss.item(), m.w_out.weight.grad.clone()))
     assert abs(grads[0][0] - grads[1][0]) < 1e-4 * abs(grads[1][0])
     assert ((grads[0][1] - grads[1][1]).norm() / grads[1][1].norm()).item() < 1e-3
+
+
+def test_ctc_kernel_matches_golden_fixture_and_oracle():
+    """The committed fixture (tests/golden/ctc_golden.npz: the reference's formulation executed in
+    fp64 by make_golden_ctc.py) and the numpy oracle on the same inputs."""
+    import os
+
+    import numpy as np
+    from oracle import ctc as octc
+    from silent_speech_b200.losses import ctc_loss
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ctc_golden.npz"))
+    for i in range(int(G["n_cases"])):
+        logits = torch.from_numpy(G[f"c{i}_logits"]).cuda().requires_grad_(True)
+        targets = torch.from_numpy(G[f"c{i}_targets"]).cuda()
+        il, tl = torch.from_numpy(G[f"c{i}_il"]), torch.from_numpy(G[f"c{i}_tl"])
+        blank = logits.shape[2] - 1
+        loss = ctc_loss(logits, targets, il, tl, blank=blank)
+        loss.backward()
+        want, gwant = float(G[f"c{i}_loss"]), G[f"c{i}_grad_mean"]
+        assert abs(loss.item() - want) < 2e-5 * abs(want), (i, loss.item(), want)
+        got = logits.grad.double().cpu().numpy()
+        assert np.linalg.norm(got - gwant) / np.linalg.norm(gwant) < 3e-4, i
+        oloss, ograd = octc.ctc_loss_mean(G[f"c{i}_logits"], G[f"c{i}_targets"], G[f"c{i}_il"],
+                                          G[f"c{i}_tl"], blank)
+        assert abs(loss.item() - oloss) < 2e-5 * abs(oloss)
+        assert np.linalg.norm(got - ograd) / np.linalg.norm(ograd) < 3e-4
