@@ -11,9 +11,17 @@ channels per GPU (T = 500 frames; 16 silent utterances with 600-frame targets al
 through silent_speech_b200.training.train_step with HOST (pinned) batches, H2D copies and the
 loss read-back inside the timed region.  Rank 0 prints ONE JSON line.
 
-`--impl reference`: the reference's own CPU implementation of the step is Python and cannot
-travel to the GPU box, so this arm times its CPU port (oracle/, torch fp32 on all host cores)
-on a bounded sample of the same workload.
+`--workload cfg5` switches to BASELINE.json's configs[4] per GPU: the recognition model
+(recognition_model.py:89-109: same Model, one 38-way head, log-softmax + CTC, optimiser every
+second batch) on 32 utterances x 6000 samples (T = 750).  cfg-1 stays the default headline.
+
+`--impl reference`: the UNMODIFIED reference (baseline/_ref, a verbatim copy of its Python made
+by baseline/install_ref.py; /root/reference in the build container) executing the same step
+through its own Model / dtw_loss / numba align.py / torch AdamW on the host cores
+(`cpu_baseline.kind = "reference"`), full batch; the line reports the steps it actually ran.
+`--ref-device cuda` runs that same stock-PyTorch reference on the B200 (informational leg,
+embedded by the default arm as `reference_on_b200`).  Only if the copy is missing does the arm
+fall back to the CPU port in oracle/ (`kind = "port"`).
 """
 import argparse
 import contextlib
@@ -144,7 +152,9 @@ def timed(fn, steps, warmup, world):
     return t.item()
 
 
-def build_model():
+def build_model(ctc_outs=None):
+    """cfg-1: Model(112, 80, 48) (transduction_model.py:169); cfg-5: Model(112, 38)
+    (recognition_model.py:66)."""
     from absl import flags
     from silent_speech_b200 import architecture
     F = flags.FLAGS
@@ -152,6 +162,8 @@ def build_model():
         F([sys.argv[0]])
     F.model_size, F.num_layers, F.dropout = D_MODEL, N_LAYERS, 0.2
     torch.manual_seed(0)
+    if ctc_outs is not None:
+        return architecture.Model(112, ctc_outs).cuda().train()
     return architecture.Model(112, 80, 48).cuda().train()
 
 
@@ -162,47 +174,110 @@ def batch_bytes(batch):
     return n
 
 
-def gemm_roofline(peaks):
-    """Dominant kernel = the tcgen05 GEMM (gemm_tc_kernel).  Time the largest forward GEMM of
-    the step alone (FFN1: 16000 x 768 -> 3072, bias + ReLU epilogue) with CUDA events on the
-    launching stream, L2 flushed between launches.  `achieved` counts ALGORITHMIC flops
-    (2*M*N*K); the kernel issues 3 bf16 MMAs per logical MMA (hi/lo split for fp32-class
-    accuracy), so the tensor pipe itself runs at 3x that rate (`tensor_pipe_frac`)."""
-    from silent_speech_b200 import functional as SF
-    M, K, N = BS * FRAMES, D_MODEL, 3072
-    x = torch.randn(M, K, device="cuda")
-    W = torch.randn(N, K, device="cuda") * K ** -0.5
-    b = torch.zeros(N, device="cuda")
-    y = torch.empty(M, N, device="cuda")
-    xp, wp = SF.split_planes(x), SF.split_planes(W)
-    op = SF.tc_operand_plain(xp, M, K)
-    ep = SF._epi(SF._scatter_plain(y.data_ptr(), M, N), bias=b, relu=1)
-    scratch = torch.empty(64 * 1024 * 1024, device="cuda")   # 256 MB > L2: flushed between launches
-
-    def launch():
-        SF.gemm_tc_kmajor(op, wp, N, K, ep)
+def _time_launch(launch, scratch, reps=5):
+    """CUDA-event time of one launch on the launching (current) stream, L2 flushed before each."""
     for _ in range(3):
         launch()
-    times = []
-    for _ in range(5):
+    ts = []
+    for _ in range(reps):
         scratch.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         launch()
         e1.record()
         torch.cuda.synchronize()
-        times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
-    tf = 2.0 * M * N * K / ms / 1e9
+        ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts)
+
+
+def ffn_instep_launches():
+    """The three dominant gemm_tc_kernel launches of a cfg-1 step, built exactly as
+    functional._FFNNativeFn issues them (operands as split planes, same epilogues):
+      ffn1_fwd   h  = dropout(relu(x W1^T + b1))   16000 x 768 -> 3072, Philox dropout, planes out
+      ffn2_fwd   y  = h W2^T + b2                  16000 x 3072 -> 768, fp32 out
+      ffn_dgrad  dh = (dy W2) * mask(h) / (1-p)    16000 x 768 -> 3072, mask off h's hi plane,
+                                                   planes out
+    Returns [(name, launch_fn, flops)] plus the tensors that must stay alive."""
+    from silent_speech_b200 import functional as SF
+    M, K, Fh = BS * FRAMES, D_MODEL, 3072
+    dev = "cuda"
+    x = torch.randn(M, K, device=dev)
+    w1 = torch.randn(Fh, K, device=dev) * K ** -0.5
+    w2 = torch.randn(K, Fh, device=dev) * Fh ** -0.5
+    b1, b2 = torch.zeros(Fh, device=dev), torch.zeros(K, device=dev)
+    dy = torch.randn(M, K, device=dev)
+    xp, w1p, w2p, w2tp, dyp = (SF.split_planes(x), SF.split_planes(w1), SF.split_planes(w2),
+                               SF.split_planes_t(w2), SF.split_planes(dy))
+    hp = torch.empty((2, M, Fh), dtype=torch.bfloat16, device=dev)
+    dhp = torch.empty((2, M, Fh), dtype=torch.bfloat16, device=dev)
+    y = torch.empty(M, K, device=dev)
+    e1 = SF._epi(SF._scatter_plain(None, M, Fh), bias=b1, relu=1, drop_p=0.2, seed=1234, site=2,
+                 planes_out=hp)
+    e2 = SF._epi(SF._scatter_plain(y.data_ptr(), M, K), bias=b2)
+    e3 = SF._epi(SF._scatter_plain(None, M, Fh), mask_planes=hp[0], mask_scale=1.25, planes_out=dhp)
+    opx, oph, opdy = (SF.tc_operand_plain(xp, M, K), SF.tc_operand_plain(hp, M, Fh),
+                      SF.tc_operand_plain(dyp, M, K))
+    fl = 2.0 * M * K * Fh
+    launches = [("ffn1_fwd(bias+relu+dropout, planes out)", lambda: SF.gemm_tc_kmajor(opx, w1p, Fh, K, e1), fl),
+                ("ffn2_fwd(bias, fp32 out)", lambda: SF.gemm_tc_kmajor(oph, w2p, K, Fh, e2), fl),
+                ("ffn_dgrad(mask planes in, planes out)", lambda: SF.gemm_tc_kmajor(opdy, w2tp, Fh, K, e3), fl)]
+    keep = (x, w1, w2, b1, b2, dy, xp, w1p, w2p, w2tp, dyp, hp, dhp, y, e1, e2, e3, opx, oph, opdy)
+    return launches, keep
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, parsed from the committed ncu
+    capture of `python bench.py --roofline-only` (profiles/r2_roofline_traffic.json, written by
+    tools/ncu_traffic.py from the .ncu-rep of exactly these launches).  None if not captured."""
+    path = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
+    try:
+        return json.load(open(path)).get(key)
+    except Exception:
+        return None
+
+
+def gemm_roofline(peaks, ms_per_step=None, gflop_step=STEP_GFLOP):
+    """Dominant kernel = gemm_tc_kernel (53 % of the step).  Its three largest IN-STEP launches
+    (the FFN GEMMs with the epilogues the step really uses) are timed alone with CUDA events on
+    the launching stream, L2 flushed between launches; `achieved` is the flop-weighted rate over
+    the three, counting ALGORITHMIC flops (2*M*N*K) — the kernel issues 3 bf16 MMAs per logical
+    MMA (hi/lo split for fp32-class accuracy), so the tensor pipe itself runs at 3x that rate
+    (`tensor_pipe_frac`).  `step_frac` is the whole training step against the SUSTAINED peak."""
+    launches, keep = ffn_instep_launches()
+    _M, _K, _F = BS * FRAMES, D_MODEL, 3072
+    scratch = torch.empty(64 * 1024 * 1024, device="cuda")   # 256 MB > L2: flushed between launches
+    rows, tot_ms, tot_fl = [], 0.0, 0.0
+    tr = ncu_traffic("gemm_tc") or {}
+    for name, fn, fl in launches:
+        ms = _time_launch(fn, scratch)
+        rows.append({"launch": name, "ms": ms, "tflops": fl / ms / 1e9,
+                     "traffic": tr.get(name.split("(")[0])})
+        tot_ms += ms
+        tot_fl += fl
+    tf = tot_fl / tot_ms / 1e9
     peak = peaks.get("bf16_tflops", 1590.0)
-    return {"bound": "tensor", "kernel": "gemm_tc_kernel bf16x3 (FFN1 16000x768x3072)",
-            "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full capture
-            # committed as profiles/r1_gemm_tc_persistent.txt (algorithmic: 58 MB in + 197 MB out)
-            "traffic": 201.5e6, "traffic_unit": "B/launch",
-            "mma_per_logical_mma": 3, "tensor_pipe_frac": 3.0 * tf / peak,
-            "peak_source": f"{peaks['_source']} cuBLAS bf16 burst (this kernel is timed alone)",
-            "ms_per_launch": ms}
+    traffic = (sum(r["traffic"] for r in rows) / len(rows)
+               if all(r["traffic"] is not None for r in rows) else None)
+    out = {"bound": "tensor", "kernel": "gemm_tc_kernel bf16x3, mean over the 3 in-step FFN launches "
+                                        "(16000 x 768 x 3072 each)",
+           "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+           "traffic": traffic, "traffic_unit": "B/launch (mean of the 3; ncu capture of these launches: "
+                                               "profiles/r2_gemm_tc_instep.txt)",
+           # operands are bf16 hi/lo planes (4 B/element, like fp32); the mask is one bf16 plane
+           "algorithmic_bytes_per_launch": {"ffn1_fwd": 4 * (_M * _K + _F * _K + _M * _F),
+                                            "ffn2_fwd": 4 * (_M * _F + _F * _K + _M * _K),
+                                            "ffn_dgrad": 4 * (_M * _K + _F * _K + _M * _F) + 2 * _M * _F},
+           "mma_per_logical_mma": 3, "tensor_pipe_frac": 3.0 * tf / peak,
+           "peak_source": f"{peaks['_source']} cuBLAS bf16 burst (launches timed alone)",
+           "launches": rows, "ms_per_launch": tot_ms / len(rows)}
+    if ms_per_step:
+        sus = peaks.get("bf16_tflops_sustained", 1400.0)
+        st = gflop_step / ms_per_step
+        out["step"] = {"algorithmic_tflops": st, "peak_sustained": sus, "frac": st / sus,
+                       "tensor_pipe_frac_if_all_gemm": 3.0 * st / sus,
+                       "note": "whole step (GEMMs + attention + normalisation + loss + optimiser) "
+                               "against the sustained cuBLAS bf16 rate"}
+    return out
 
 
 def dtw_side_metric(peaks, world, rank, with_cpu):
@@ -275,18 +350,38 @@ def mel_side_metric(peaks, with_cpu):
     return out
 
 
+WORKLOADS = {
+    # name: metric, frames/utterance, algorithmic GFLOP per bs-32 step per GPU
+    "cfg1": {"metric": METRIC, "frames": 500, "gflop": 6229.0},
+    "cfg5": {"metric": "recognition (CTC) steps/sec (seq_len=6000, bs=32)", "frames": 750,
+             "gflop": 9346.0},
+}
+N_CHARS = 37            # recognition_model.py:65: len(text_transform.chars); blank = 37, 38 outputs
+CTC_TARGET_LEN = 100    # synthetic transcript length per utterance (real ones are <= ~150 chars)
+
+
+def make_batch(workload, n_utt, seed, pin=True):
+    """collate_raw-shaped synthetic batch for a workload."""
+    from silent_speech_b200.read_emg import synthetic_batch
+    batch = synthetic_batch(n_utt, WORKLOADS[workload]["frames"], seed=seed)
+    if workload == "cfg5":
+        g = torch.Generator().manual_seed(seed + 77)
+        batch["text_int"] = [torch.randint(0, N_CHARS, (CTC_TARGET_LEN,), generator=g)
+                             for _ in range(n_utt)]
+        batch["text_int_lengths"] = [CTC_TARGET_LEN] * n_utt
+    return batch
+
+
 def cpu_port_step_time(n_utt, steps, warmup):
-    """The reference step's CPU port (oracle/) on `n_utt` of the 32 utterances, all host cores."""
+    """FALLBACK when baseline/_ref is missing: the reference step's CPU port (oracle/) on `n_utt`
+    of the 32 utterances, all host cores."""
     from oracle import model as om
     from oracle import step as ostep
-    from silent_speech_b200.read_emg import synthetic_batch
     torch.manual_seed(0)
     sd = om.formula_state_dict(D_MODEL, N_LAYERS)
     params = ostep.make_params(sd)
     optim = ostep.make_optimizer(params)
-    batch = synthetic_batch(n_utt, FRAMES, seed=1234)
-    batch = {k: ([t.clone() if torch.is_tensor(t) else t for t in v] if isinstance(v, list) else v)
-             for k, v in batch.items()}
+    batch = make_batch("cfg1", n_utt, 1234)
     random.seed(0)
     for _ in range(warmup):
         ostep.train_step(params, optim, batch, FRAMES, dropout_p=0.2)
@@ -296,139 +391,351 @@ def cpu_port_step_time(n_utt, steps, warmup):
     return (time.perf_counter() - t0) / steps
 
 
+def reference_step_fn(workload, n_utt, device, d_model=D_MODEL, n_layers=N_LAYERS, seq_frames=None,
+                      batch=None):
+    """One training step of the UNMODIFIED reference, through its own public code path:
+    cfg1 — transduction_model.py:197-210 (combine_fixed_length, Model, transduction_model.dtw_loss
+           with the numba align.py, loss.item(), backward, torch.optim.AdamW(weight_decay=l2));
+    cfg5 — recognition_model.py:89-107 (Model with one 38-way head, F.log_softmax, pad_sequence,
+           F.ctc_loss(blank=n_chars), backward, optimiser every second batch).
+    Returns a zero-argument callable, or None when the reference copy is absent."""
+    from baseline import refenv
+    if refenv.reference_dir() is None:
+        return None
+    import torch.nn.functional as F
+    from absl import flags
+    if workload == "cfg1":
+        (tm,) = refenv.import_reference("transduction_model")
+    ra, rdu = refenv.import_reference("architecture", "data_utils")
+    FL = flags.FLAGS
+    if not FL.is_parsed():
+        FL([sys.argv[0]])
+    FL.model_size, FL.num_layers, FL.dropout = d_model, n_layers, 0.2
+    frames = seq_frames or WORKLOADS[workload]["frames"]
+    torch.manual_seed(0)
+    random.seed(0)
+    if batch is None:
+        batch = make_batch(workload, n_utt, 1234)
+    if workload == "cfg1":
+        model = refenv.fix_transformer_shim(ra.Model(112, 80, 48)).to(device).train()
+        optim = torch.optim.AdamW(model.parameters(), weight_decay=1e-7)    # FLAGS.l2 default
+
+        def step():
+            optim.zero_grad()
+            X_raw = rdu.combine_fixed_length([t.to(device, non_blocking=True)
+                                              for t in batch['raw_emg']], frames * 8)
+            pred, phoneme_pred = model(None, X_raw, None)
+            loss, _ = tm.dtw_loss(pred, phoneme_pred, batch)
+            lv = loss.item()
+            loss.backward()
+            optim.step()
+            return lv
+        return step
+    model = refenv.fix_transformer_shim(ra.Model(112, N_CHARS + 1)).to(device).train()
+    optim = torch.optim.AdamW(model.parameters(), lr=3e-4, weight_decay=0)
+    optim.zero_grad()
+    state = {"batch_idx": 0}
+
+    def step():
+        X_raw = rdu.combine_fixed_length(batch['raw_emg'], frames * 8).to(device)
+        pred = model(None, X_raw, None)
+        pred = F.log_softmax(pred, 2)
+        pred = torch.nn.utils.rnn.pad_sequence(rdu.decollate_tensor(pred, batch['lengths']),
+                                               batch_first=False)
+        y = torch.nn.utils.rnn.pad_sequence(batch['text_int'], batch_first=True).to(device)
+        loss = F.ctc_loss(pred, y, batch['lengths'], batch['text_int_lengths'], blank=N_CHARS)
+        lv = loss.item()
+        loss.backward()
+        if (state["batch_idx"] + 1) % 2 == 0:
+            optim.step()
+            optim.zero_grad()
+        state["batch_idx"] += 1
+        return lv
+    return step
+
+
+def time_host(fn, steps, warmup, cuda=False):
+    for _ in range(warmup):
+        fn()
+    if cuda:
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    if cuda:
+        torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun pins OMP_NUM_THREADS=1 per rank; the CPU arm uses every physical host core
-    torch.set_num_threads(cpu_threads())
-    n_utt = 4
-    sec = cpu_port_step_time(n_utt, max(1, min(args.steps, 2)), 1 if args.warmup else 0)
-    value = (n_utt / BS) / sec
+    wl = WORKLOADS[args.workload]
+    on_cuda = args.ref_device == "cuda"
+    if on_cuda:
+        torch.backends.cuda.matmul.allow_tf32 = bool(args.tf32)
+        torch.backends.cudnn.allow_tf32 = bool(args.tf32)
+        steps, warmup = max(1, args.steps), max(1, args.warmup)
+    else:
+        # torchrun pins OMP_NUM_THREADS=1 per rank; the CPU arm uses every physical host core
+        torch.set_num_threads(cpu_threads())
+        # bounded: a full bs-32 reference step is ~10-40 s of host time
+        steps, warmup = max(1, min(args.steps, 3)), (1 if args.warmup else 0)
+    step = reference_step_fn(args.workload, BS, "cuda" if on_cuda else "cpu")
+    cfg0 = None
+    if step is not None:
+        kind, n_utt, scale = "reference", BS, 1.0
+        sec = time_host(step, steps, warmup, cuda=on_cuda)
+        sample = (f"full batch: {BS} utterances x {steps} timed step(s) after {warmup} warm-up, the "
+                  f"unmodified reference (baseline/_ref) on {'cuda:0' if on_cuda else 'host cores'}")
+        if not on_cuda and args.workload == "cfg1":
+            # BASELINE.md B0 / BASELINE.json configs[0]: the reference's own CPU-runnable case
+            from silent_speech_b200.read_emg import EMGDataset      # 2 x 1000 samples: T = 125
+            ds = EMGDataset(num_examples=2, frames=125, seed=99)
+            ds._items[0]['silent'], ds._items[1]['silent'] = True, False
+            b0 = EMGDataset.collate_raw([ds[0], ds[1]])
+            s0 = reference_step_fn("cfg1", 2, "cpu", 256, 2, seq_frames=125, batch=b0)
+            t = sorted(time_host(s0, 1, 0) for _ in range(13))[3:]       # 3 warm-ups dropped
+            cfg0 = {"workload": "cfg-0: 2 utterances x 1000 samples, d_model 256, 2 layers, "
+                                "fwd + dtw_loss + bwd + AdamW", "median_s_per_step": t[len(t) // 2],
+                    "steps_per_s": 1.0 / t[len(t) // 2], "timed_steps": len(t)}
+    else:
+        if args.workload != "cfg1":
+            print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing and the "
+                              "CPU port covers cfg1 only"}))
+            return
+        kind, n_utt = "port", 4
+        steps, warmup = max(1, min(args.steps, 2)), (1 if args.warmup else 0)
+        sec = cpu_port_step_time(n_utt, steps, warmup) * BS / n_utt
+        sample = (f"EXTRAPOLATED: CPU port (oracle/) on {n_utt} of {BS} utterances x {steps} step(s), "
+                  f"time scaled by {BS // n_utt}")
+    value = 1.0 / sec
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sec * 1e3 * BS / n_utt, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg-1 step (768/6, seq_len 4000) on the CPU port, sample = "
-                                   f"{n_utt} of {BS} utterances per step, scaled to bs-32 steps/s"},
-            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_utt}/{BS} utterances x {max(1, min(args.steps, 2))} step(s)"},
+    line = {"impl": "reference", "metric": wl["metric"], "value": value, "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "requested": {"steps": args.steps, "warmup": args.warmup},
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if not (on_cuda and args.tf32) else "tf32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload} step (768/6, bs 32, seq_len "
+                                   f"{wl['frames'] * 8}) executed by the reference itself",
+                       "device": "cuda:0 (stock PyTorch eager)" if on_cuda else "host CPU",
+                       "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind,
+                             "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
+    if cfg0 is not None:
+        line["cfg0_reference_step"] = cfg0
     print(json.dumps(line))
+
+
+def dp_check(model, bucket, batch, frames, task, world, rank):
+    """On-hardware correctness of the data-parallel exchange (N > 1).  One extra (untimed)
+    forward + backward per arm on each rank's own utterances, same dropout seed and shift:
+      * plain: per-rank checksums of the LOCAL gradients, then one all-reduce of the whole bucket;
+      * overlapped: the segmented all-reduce issued from backward hooks (what the timed step runs).
+    Checks: the reduced bucket is bit-identical on every rank; its sum equals the sum over ranks
+    of the local sums (to fp32 summation noise); the overlapped exchange reproduces the plain
+    one; parameters are still bit-identical across ranks after the timed optimiser steps."""
+    import torch.distributed as dist
+    from silent_speech_b200.training import OverlappedAllReduce, _forward_backward, to_device
+    b = to_device(batch, "cuda")
+
+    def fwd_bwd(overlap):
+        bucket.zero()
+        torch.manual_seed(4242 + rank)
+        random.seed(77)
+        _forward_backward(model, b, frames, task, N_CHARS, overlap)
+
+    def bits(t):
+        return int(t.view(torch.int32).to(torch.int64).sum().item())
+
+    def gather(v):
+        out = [None] * world
+        dist.all_gather_object(out, v)
+        return out
+
+    fwd_bwd(None)
+    local_sum, local_abs = bucket.flat.double().sum().item(), bucket.flat.double().abs().sum().item()
+    dist.all_reduce(bucket.flat, op=dist.ReduceOp.SUM)
+    plain = bucket.flat.clone()
+    sums, abss = gather(local_sum), gather(local_abs)
+    red_bits = gather(bits(plain))
+    red_sum = plain.double().sum().item()
+    fwd_bwd(OverlappedAllReduce(bucket))
+    ov_diff = ((bucket.flat - plain).double().norm() / (plain.double().norm() + 1e-30)).item()
+    ov_bits = gather(bits(bucket.flat))
+    pbits = gather(sum(bits(p.data.view(-1)) for p in model.parameters()))
+    ov_diffs = gather(ov_diff)
+    return {"ranks": world,
+            "reduced_bucket_identical_on_all_ranks": len(set(red_bits)) == 1 and len(set(ov_bits)) == 1,
+            "sum_of_reduced_vs_sum_of_local": abs(red_sum - sum(sums)) / (sum(abss) + 1e-30),
+            "overlapped_vs_plain_rel_l2": max(ov_diffs),
+            "params_identical_on_all_ranks_after_timed_steps": len(set(pbits)) == 1,
+            "ok": bool(len(set(red_bits)) == 1 and len(set(ov_bits)) == 1 and len(set(pbits)) == 1
+                       and abs(red_sum - sum(sums)) <= 1e-5 * sum(abss) and max(ov_diffs) < 1e-5)}
+
+
+def reference_on_b200(workload):
+    """Informational: the UNMODIFIED reference as it would run on this box (it selects 'cuda' when
+    present, transduction_model.py:246) — stock PyTorch eager kernels, fp32 and TF32 — in a
+    subprocess after our own timing, same batch and step."""
+    out = {}
+    for name, extra in (("fp32", []), ("tf32", ["--tf32"])):
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--ref-device",
+               "cuda", "--workload", workload, "--steps", "4", "--warmup", "2"] + extra
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600,
+                               env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
+            line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            out[name] = ({"steps_per_s": line["value"], "ms_per_step": line["ms_per_step"]}
+                         if "value" in line else line)
+        except Exception as e:      # informational leg: never fails the bench
+            out[name] = {"error": repr(e)[:300]}
+    out["what"] = ("unmodified reference step (baseline/_ref: Model + dtw_loss with numba align on "
+                   "the host / F.ctc_loss + AdamW) on cuda:0 with stock PyTorch kernels")
+    return out
 
 
 def run_ours(args):
     from silent_speech_b200 import _lib
-    from silent_speech_b200.read_emg import synthetic_batch
-    from silent_speech_b200.training import GradientBucket, GraphedTrainStep, train_step
+    from silent_speech_b200.training import (GradientBucket, GraphedTrainStep, broadcast_model,
+                                             ctc_train_step, train_step, CtcAccumulator)
     world, rank, local = dist_setup(args.gpus)
     peaks = load_peaks()
     _lib.load()   # fails loudly if the CUDA library is missing
+    wl = WORKLOADS[args.workload]
+    frames = wl["frames"]
+    task = "transduction" if args.workload == "cfg1" else "recognition"
 
     from silent_speech_b200.optim import FlatAdamW
-    model = build_model()
+    model = build_model(None if task == "transduction" else N_CHARS + 1)
+    broadcast_model(model)
     bucket = GradientBucket(model)
-    # transduction_model.py:178: AdamW(weight_decay=1e-7), here as one fused pass over the flat
-    # parameter / gradient buckets (csrc/optim.cu)
-    optim = FlatAdamW(bucket, lr=1e-3, weight_decay=1e-7)
-    host_batch = synthetic_batch(BS, FRAMES, seed=1234 + rank)      # pinned host tensors
+    # transduction_model.py:178 AdamW(weight_decay=1e-7) / recognition_model.py:71 AdamW(lr=3e-4,
+    # weight_decay=0), here as one fused pass over the flat parameter / gradient buckets
+    optim = (FlatAdamW(bucket, lr=1e-3, weight_decay=1e-7) if task == "transduction"
+             else FlatAdamW(bucket, lr=3e-4, weight_decay=0.0))
+    host_batch = make_batch(args.workload, BS, 1234 + rank)      # pinned host tensors
     dev_batch = dict(host_batch)
-    for k in ('raw_emg', 'audio_features', 'phonemes'):
+    keys = ('raw_emg', 'audio_features', 'phonemes') if task == "transduction" else ('raw_emg', 'text_int')
+    for k in keys:
         dev_batch[k] = [t.cuda() for t in host_batch[k]]
     random.seed(rank)
     torch.manual_seed(1000 + rank)
+    accumulate = 1 if task == "transduction" else 2          # recognition_model.py:104-107
 
-    # the public training call: eager train_step, or (default) the same step with
-    # zero_grad + forward + dtw_loss + backward replayed as one CUDA graph per batch signature
-    graphed = None if args.eager else GraphedTrainStep(model, optim, "cuda", FRAMES, bucket)
+    # the public training call: eager step, or (default) the same step with forward + loss +
+    # backward (+ the overlapped gradient all-reduce at N > 1) replayed as one CUDA graph
+    overlap = world > 1 and not args.no_overlap and accumulate == 1
+    graphed = None if args.eager else GraphedTrainStep(model, optim, "cuda", frames, bucket, task=task,
+                                                       accumulate=accumulate, blank=N_CHARS,
+                                                       overlap=overlap)
+    acc = CtcAccumulator(accumulate)
 
-    def step_device():
-        # combine_fixed_length copies, so the in-place augmentation never touches dev_batch
+    def run(batch, sync):
         if graphed is not None:
-            graphed(dev_batch, sync_loss=False)
-        else:
-            train_step(model, optim, dev_batch, "cuda", FRAMES, bucket, sync_loss=False)
+            return graphed(batch, sync_loss=sync)
+        if task == "transduction":
+            return train_step(model, optim, batch, "cuda", frames, bucket, sync_loss=sync)
+        return ctc_train_step(model, optim, batch, "cuda", frames, bucket, N_CHARS, acc, sync)
 
-    def step_e2e():
-        if graphed is not None:
-            graphed(host_batch, sync_loss=True)
-        else:
-            train_step(model, optim, host_batch, "cuda", FRAMES, bucket, sync_loss=True)
-
+    # combine_fixed_length copies, so the in-place augmentation never touches the batches
     with ClockSampler(local) as clk:
-        ms = timed(step_device, args.steps, args.warmup, world)
+        ms = timed(lambda: run(dev_batch, False), args.steps, args.warmup, world)
         l0 = _lib.launch_count          # libssb kernels of one steady-state step (graph replays
-        step_device()                   # count the kernels captured in the graph)
+        run(dev_batch, False)           # count the kernels captured in the graph)
         launches = _lib.launch_count - l0
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2), world)
-    # host-side enqueue time per step (no synchronisation inside): shows whether the step is
-    # bounded by the GPU or by launching ~1000 kernels from Python
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_device()
-    host_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    torch.cuda.synchronize()
-
-    graph_ms = None
-    if args.graph_probe and graphed is None:
-        # EXPERIMENT (not a reported number): replay the step as one CUDA graph to see the
-        # GPU-only time.  Seeds / augmentation are frozen inside the graph, so this is not a
-        # valid training loop.
-        optim_c = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-7, fused=True,
-                                    capturable=True)
-        sidestream = torch.cuda.Stream()
-        sidestream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(sidestream):
-            for _ in range(3):
-                train_step(model, optim_c, dev_batch, "cuda", FRAMES, bucket, sync_loss=False)
-        torch.cuda.current_stream().wait_stream(sidestream)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            train_step(model, optim_c, dev_batch, "cuda", FRAMES, bucket, sync_loss=False)
-        graph_ms = timed(g.replay, args.steps, 2, world) / args.steps
+    cur_acc = graphed.acc if graphed is not None else acc
+    while cur_acc.micro % accumulate:
+        run(dev_batch, False)           # finish the accumulation window
+    ms_e2e = timed(lambda: run(host_batch, True), args.steps, max(1, args.warmup // 2), world)
 
     value = world * args.steps / (ms / 1e3)
     e2e = world * args.steps / (ms_e2e / 1e3)
-    line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world,
+    h2d = sum(t.numel() * t.element_size() for k in keys for t in host_batch[k])
+    if task == "transduction":
+        what = ("cfg-1: d_model 768, 6 layers, bs 32/GPU, seq_len 4000 (T=500), 16 silent (DTW, "
+                "600-frame targets) + 16 voiced synthetic utterances; fwd + dtw_loss + bwd + grad "
+                "all-reduce + AdamW")
+    else:
+        what = ("cfg-5 per GPU: recognition model d_model 768, 6 layers, 38-way CTC head, bs 32/GPU, "
+                f"seq_len 6000 (T=750), {CTC_TARGET_LEN}-char synthetic transcripts; fwd + fused "
+                "log-softmax/CTC + bwd every batch, grad all-reduce + AdamW every 2nd batch "
+                "(recognition_model.py:104-107)")
+    line = {"metric": wl["metric"], "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "cfg-1: d_model 768, 6 layers, bs 32/GPU, seq_len 4000 (T=500), "
-                                   "16 silent (DTW, 600-frame targets) + 16 voiced synthetic "
-                                   "utterances; fwd + dtw_loss + bwd + grad all-reduce + AdamW",
-                       "dropout": 0.2, "parallelism": f"dp{world}",
+            "config": {"workload": what, "dropout": 0.2, "parallelism": f"dp{world}",
                        "launch": "eager" if graphed is None else
-                                 "CUDA graph (zero_grad+fwd+loss+bwd) + eager all-reduce + fused flat AdamW",
+                                 "CUDA graph (fwd+loss+bwd" + ("+segmented NCCL all-reduce on a side "
+                                 "stream" if overlap else "") + ") + fused flat AdamW",
+                       "arithmetic": "fp32-class: bf16 hi/lo split operands, 3 tcgen05 MMAs per "
+                                     "logical MMA, fp32 accumulate",
                        "l2": "per-step working set (~10 GB of activations) >> 126 MB L2"},
             "e2e": {"value": e2e, "unit": "steps/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": batch_bytes(host_batch), "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "host_enqueue_ms_per_step": host_ms,
-            "graph_probe_ms_per_step": graph_ms,
-            "step_tflops": STEP_GFLOP * value / world / 1e3,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "step_tflops": wl["gflop"] * value / world / 1e3,
             "clocks": clk.summary()}
+    if world > 1:
+        chk = dp_check(model, bucket, host_batch, frames, task, world, rank)
+        if rank == 0:
+            line["dp_check"] = chk
     if rank == 0:
-        line["roofline"] = gemm_roofline(peaks)
-    if not args.no_side:
+        line["roofline"] = gemm_roofline(peaks, ms / args.steps, wl["gflop"])
+    if task == "recognition" and rank == 0:
+        line["ctc"] = ctc_side_metric(frames)
+    if not args.no_side and task == "transduction":
         side = dtw_side_metric(peaks, world, rank, rank == 0 and world == 1 and not args.no_cpu)
         if rank == 0:
             line["dtw"] = side
         if rank == 0 and world == 1:
             line["mel"] = mel_side_metric(peaks, not args.no_cpu)
     if rank == 0 and world == 1 and not args.no_cpu:
+        # bounded sample of the same workload on the host cores: the unmodified reference on 4 of
+        # the 32 utterances, 1 timed step after 1 warm-up (the full-batch run is --impl reference)
         torch.set_num_threads(cpu_threads())
         n_utt = 4
-        sec = cpu_port_step_time(n_utt, 1, 0)
+        step = reference_step_fn(args.workload, n_utt, "cpu")
+        if step is not None:
+            sec, kind = time_host(step, 1, 1), "reference"
+        else:
+            sec, kind = cpu_port_step_time(n_utt, 1, 0), "port"
         line["cpu_baseline"] = {"value": (n_utt / BS) / sec, "unit": "steps/s",
-                                "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"{n_utt}/{BS} utterances x 1 step, scaled to bs-32 steps/s"}
+                                "cores": torch.get_num_threads(), "kind": kind,
+                                "sample": f"{n_utt}/{BS} utterances x 1 step (after 1 warm-up), "
+                                          f"rate scaled to bs-32 steps/s"}
+        if not args.no_torch_leg:
+            line["reference_on_b200"] = reference_on_b200(args.workload)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def ctc_side_metric(frames):
+    """ctc_fused_kernel alone at cfg-5 size (32 utterances x 750 frames x 38 classes)."""
+    from silent_speech_b200.losses import ctc_loss
+    g = torch.Generator(device="cuda").manual_seed(3)
+    logits = torch.randn(BS, frames, N_CHARS + 1, device="cuda", generator=g).requires_grad_(True)
+    y = torch.randint(0, N_CHARS, (BS, CTC_TARGET_LEN), device="cuda", generator=g)
+    il = torch.full((BS,), frames, dtype=torch.int64, device="cuda")
+    tl = torch.full((BS,), CTC_TARGET_LEN, dtype=torch.int64, device="cuda")
+    f = lambda: ctc_loss(logits, y, il, tl, blank=N_CHARS, reduction='sum')
+    ms = timed(f, 20, 3, 1) / 20
+    import torch.nn.functional as F
+    g2 = lambda: F.ctc_loss(F.log_softmax(logits, 2).transpose(0, 1), y, il, tl, blank=N_CHARS,
+                            reduction='sum')
+    ms_t = timed(g2, 20, 3, 1) / 20
+    return {"kernel": "ctc_fused_kernel (log-softmax + alpha/beta + d/dlogits), forward call",
+            "ms": ms, "torch_log_softmax_ctc_forward_ms": ms_t,
+            "bound": "latency: 750 sequential frames x 201 states per utterance",
+            "state_updates_per_s": 2.0 * BS * frames * (2 * CTC_TARGET_LEN + 1) / ms * 1e3}
 
 
 def main():
@@ -437,13 +744,27 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg1", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference: run the unmodified reference on the host or on cuda:0")
+    ap.add_argument("--tf32", action="store_true", help="--ref-device cuda: allow TF32")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: one all-reduce after backward instead of the overlapped segments")
+    ap.add_argument("--no-torch-leg", action="store_true",
+                    help="skip the informational reference-on-B200 (stock PyTorch) leg")
+    ap.add_argument("--roofline-only", action="store_true",
+                    help="launch only the roofline kernels (the command profiled by ncu)")
     ap.add_argument("--no-side", action="store_true", help="skip the DTW side metric")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--eager", action="store_true",
                     help="launch every kernel from Python instead of replaying the CUDA graph")
-    ap.add_argument("--graph-probe", action="store_true",
-                    help="experiment (with --eager): also time a whole-step CUDA graph")
     args = ap.parse_args()
+    if args.roofline_only:
+        torch.cuda.set_device(0)
+        from silent_speech_b200 import _lib
+        _lib.load()
+        print(json.dumps(gemm_roofline(load_peaks())), file=sys.stderr)
+        return
     # stdout carries exactly ONE line, the JSON result: libraries that write to fd 1 on their own
     # (NCCL prints its version banner there) go to stderr while the run is in progress
     sys.stdout.flush()

@@ -1,6 +1,15 @@
-"""Drop-in module `read_emg`: put this directory ahead of the reference checkout on sys.path and the
-reference's unmodified transduction_model.py / recognition_model.py import the B200 hot path
-(`from read_emg import ...`) instead of their own read_emg.py.  See INTEGRATION.md."""
+"""Drop-in module `read_emg`.
+
+The dataset (EMGDataset, SizeAwareSampler, the signal filtering of read_emg.py:27-100) is NOT
+part of the accelerated hot path: with dropin/ ahead of the reference checkout on sys.path this
+shim hands the reference's OWN read_emg.py back unchanged, so `python transduction_model.py`
+trains on the real corpus (its `from data_utils import load_audio, ...` then picks up the GPU
+mel-spectrogram through dropin/data_utils.py).
+
+Only when SSB_SYNTHETIC_CORPUS=1 is set — tests and benchmarks on a box without the Zenodo
+corpus — does it export the synthetic-utterance mirror `silent_speech_b200.read_emg`, which
+honours the same item / collate_raw / sampler contract with seeded random tensors and ignores
+the data-directory flags.  It says so on stderr.  See INTEGRATION.md."""
 import os as _os
 import sys as _sys
 
@@ -8,7 +17,18 @@ _root = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 if _root not in _sys.path:
     _sys.path.insert(1, _root)
 
-from silent_speech_b200.read_emg import *  # noqa: F401,F403,E402
-from silent_speech_b200 import read_emg as _impl  # noqa: E402
+if _os.environ.get("SSB_SYNTHETIC_CORPUS") == "1":
+    print("dropin/read_emg: SSB_SYNTHETIC_CORPUS=1 -> SYNTHETIC utterances (random tensors), the "
+          "data-directory flags are ignored", file=_sys.stderr)
+    from silent_speech_b200 import read_emg as _impl  # noqa: E402
+else:
+    from _defer import load_shadowed as _load_shadowed  # noqa: E402
+    _impl = _load_shadowed("read_emg")
+    if _impl is None:
+        raise ImportError(
+            "dropin/read_emg: the dataset loader is not part of the B200 hot path and no reference "
+            "read_emg.py was found further down sys.path.  Run from the reference checkout (or put "
+            "it on PYTHONPATH after dropin/), or set SSB_SYNTHETIC_CORPUS=1 to use the synthetic "
+            "corpus mirror for tests and benchmarks.")
 
 globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

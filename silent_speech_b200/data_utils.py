@@ -215,18 +215,51 @@ class TextTransform(object):
         return ''.join(self.chars[i] for i in ints)
 
 
+def _frame_rms_max(audio, frame_length=2048, hop_length=512):
+    """max over frames of librosa.feature.rms(y=audio) (its defaults: centred frames of 2048,
+    hop 512, zero padding), used by data_utils.py:19-27.  Host-side dataset preparation."""
+    a = np.pad(np.asarray(audio, dtype=np.float64), frame_length // 2)
+    n = 1 + (len(a) - frame_length) // hop_length
+    if n <= 0:
+        return float(np.sqrt(np.mean(a * a))) if len(a) else 0.0
+    c = np.concatenate([[0.0], np.cumsum(a * a)])
+    starts = np.arange(n) * hop_length
+    power = (c[starts + frame_length] - c[starts]) / frame_length
+    return float(np.sqrt(np.maximum(power, 0.0)).max())
+
+
+def normalize_volume(audio):
+    """data_utils.py:19-27."""
+    max_rms = _frame_rms_max(audio) + 0.01
+    audio = audio * (0.2 / max_rms)
+    max_val = np.abs(audio).max()
+    if max_val > 1.0:
+        audio = audio / max_val
+    return audio
+
+
 def load_audio(filename, start=None, end=None, max_frames=None, renormalize_volume=False):
-    """data_utils.py:64-83: read a clip (soundfile), clip to [-1, 1], log-mel on the GPU.
-    Returns (frames, 80) numpy like the reference.  Needs `soundfile`; 16 kHz resampling and
-    volume renormalisation (librosa) are dataset preparation outside the hot path."""
+    """data_utils.py:64-83: read a clip (soundfile), optional volume normalisation and
+    16 kHz -> 22.05 kHz resampling (host-side dataset preparation; resampling needs librosa like
+    the reference), clip to [-1, 1], log-mel ON THE GPU (csrc/mel.cu).  Returns (frames, 80)
+    numpy like the reference."""
     import soundfile as sf
     audio, r = sf.read(filename)
     if len(audio.shape) > 1:
         audio = audio[:, 0]
     if start is not None or end is not None:
         audio = audio[start:end]
-    if renormalize_volume or r != 22050:
-        raise _lib.SSBError(-3, "load_audio: resampling / volume renormalisation are not built")
+    if renormalize_volume:
+        audio = normalize_volume(audio)
+    if r == 16000:
+        try:
+            import librosa
+        except ImportError as e:
+            raise _lib.SSBError(-3, "load_audio: 16 kHz input needs librosa.resample (host-side "
+                                    "dataset preparation, not part of the GPU path)") from e
+        audio = librosa.resample(audio, orig_sr=16000, target_sr=22050)
+    else:
+        assert r == 22050
     audio = np.clip(audio, -1, 1)
     y = torch.tensor(audio, dtype=torch.float32).unsqueeze(0).cuda()
     mspec = mel_spectrogram(y, 1024, 80, 22050, 256, 1024, 0, 8000, center=False)

@@ -906,20 +906,53 @@ class _DenseTCAttnFn(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None, None, None, None
 
 
-_band_bufs = {}
+_band_bufs = {}            # LRU: (B, T, H, W, rwp, dev, stream) -> zero-initialised buffer
+_BAND_LRU = 3
+_capture_keepalive = []    # buffers whose addresses were baked into the graph being captured
+_exec_stream = None        # while capturing: the stream the graph will be REPLAYED on
+
+
+def set_capture_execution_stream(stream_handle):
+    """A CUDA graph is captured on torch's private capture stream but executes on the stream that
+    replays it.  Per-stream scratch (below) must be keyed by the latter: the capturer passes the
+    handle of its replay stream before capture and None afterwards."""
+    global _exec_stream
+    _exec_stream = stream_handle
+
+
+
+def take_capture_keepalive():
+    """Buffers from this module's caches that the CUDA graph captured since the last call holds by
+    ADDRESS.  The capturer (training.GraphedTrainStep) stores the list next to the graph, so the
+    caches below may evict freely without ever freeing memory a graph still replays into."""
+    global _capture_keepalive
+    out, _capture_keepalive = _capture_keepalive, []
+    return out
 
 
 def _band_scratch(key):
-    """Persistent zero-initialised (2, B*T, H, RWp) bf16 buffer for one attention geometry.
-    Never evicted: a captured CUDA graph may hold its address for as long as the process lives
-    (one buffer per distinct (B, T) a training run sees; 131 MB at cfg-1)."""
-    buf = _band_bufs.get(key)
+    """Zero-initialised (2, B*T, H, RWp) bf16 buffer for one attention geometry ON ONE STREAM.
+    The fused backward overwrites exactly the in-band, in-sequence entries - the same set every
+    call for a given geometry - and everything else must read 0, so the buffer is zeroed once and
+    reused by every layer (their backward passes are ordered on the stream the key names; another
+    stream gets its own buffer).  Bounded: real SizeAwareSampler batches change B almost every
+    step, so only the _BAND_LRU most recent geometries are kept (131 MB each at cfg-1); a buffer
+    captured into a CUDA graph is additionally kept alive by that graph's owner."""
+    key = key + (_exec_stream if _exec_stream is not None
+                 else torch.cuda.current_stream().cuda_stream,)
+    buf = _band_bufs.pop(key, None)
     if buf is None:
-        B, T, H, W, rwp, dev = key
-        buf = torch.zeros((2, B * T, H, rwp), dtype=torch.bfloat16, device=dev)
+        B, T, H, W, rwp, dev, _ = key
         if torch.cuda.is_current_stream_capturing():
-            return buf                  # graph-pool memory: owned by that graph, not cached
-        _band_bufs[key] = buf
+            # first sight of this geometry under capture (GraphedTrainStep runs one eager step
+            # first, so this is rare): graph-pool memory, zeroed by a captured memset per replay
+            return torch.zeros((2, B * T, H, rwp), dtype=torch.bfloat16, device=dev)
+        buf = torch.zeros((2, B * T, H, rwp), dtype=torch.bfloat16, device=dev)
+    _band_bufs[key] = buf                      # most recently used last
+    while len(_band_bufs) > _BAND_LRU:
+        _band_bufs.pop(next(iter(_band_bufs)))
+    if torch.cuda.is_current_stream_capturing():
+        _capture_keepalive.append(buf)
     return buf
 
 

@@ -80,6 +80,14 @@ def dtw_loss(predictions, phoneme_predictions, example, phoneme_eval=False,
 # ------------------------------------------------------------------------------------------
 # fused log_softmax + CTC (csrc/ctc.cu)                      recognition_model.py:96-101
 # ------------------------------------------------------------------------------------------
+def _lengths_on(x, dev):
+    """int64 length vector on `dev`; a tensor already there is used as is (no copy: the caller
+    may be under CUDA-graph capture, where a pageable H2D copy is illegal)."""
+    if torch.is_tensor(x) and x.device == dev and x.dtype == torch.int64:
+        return x.contiguous()
+    return torch.as_tensor(x, dtype=torch.int64).to(dev).contiguous()
+
+
 class _CtcFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, targets, input_lengths, target_lengths, blank, mean):
@@ -92,8 +100,8 @@ class _CtcFn(torch.autograd.Function):
         N, T, C = logits.shape
         dev = logits.device
         targets = targets.to(device=dev, dtype=torch.int64).contiguous().view(N, -1)
-        il = torch.as_tensor(input_lengths, dtype=torch.int64).to(dev).contiguous()
-        tl = torch.as_tensor(target_lengths, dtype=torch.int64).to(dev).contiguous()
+        il = _lengths_on(input_lengths, dev)
+        tl = _lengths_on(target_lengths, dev)
         Lmax = targets.shape[1]
         nll = torch.empty(N, dtype=torch.float32, device=dev)
         need_grad = ctx.needs_input_grad[0]
@@ -142,4 +150,6 @@ def ctc_loss_from_chunks(pred, example, blank):
     seqs = decollate_tensor(pred, example['lengths'])
     logits = torch.nn.utils.rnn.pad_sequence(seqs, batch_first=True)
     y = torch.nn.utils.rnn.pad_sequence(example['text_int'], batch_first=True)
-    return ctc_loss(logits, y, example['lengths'], example['text_int_lengths'], blank)
+    # device-resident length vectors when the caller prepared them (training.GraphedTrainStep)
+    return ctc_loss(logits, y, example.get('lengths_dev', example['lengths']),
+                    example.get('text_int_lengths_dev', example['text_int_lengths']), blank)

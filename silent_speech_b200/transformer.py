@@ -157,10 +157,15 @@ class TransformerEncoder(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList([copy.deepcopy(encoder_layer) for _ in range(num_layers)])
         self.num_layers = num_layers
+        # optional callable (layer_index, layer_input): training.OverlappedAllReduce hangs its
+        # "gradients of layers >= i are complete" hooks on the layer inputs through it
+        self.layer_input_hook = None
 
     def forward_tokens(self, x2d, B, T):
         seed = _fresh_seed() if self.training else 0
         for i, layer in enumerate(self.layers):
+            if self.layer_input_hook is not None:
+                self.layer_input_hook(i, x2d)
             x2d = layer.forward_tokens(x2d, B, T, seed, 4 * i)
         return x2d
 
