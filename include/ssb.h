@@ -37,7 +37,14 @@ extern "C" {
 #define SSB_ERR_WORKSPACE (-4) /* workspace too small */
 
 /* ---- library ------------------------------------------------------------ */
-SSB_API int ssb_version(void);               /* 10000*major + 100*minor + patch */
+/* Bumped whenever a struct layout or a signature in this header changes; the Python binding
+ * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
+#define SSB_ABI_VERSION 200
+SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
+/* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
+ * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t; -1 otherwise), so a foreign-language
+ * binding can verify its mirror of the layouts at load time. */
+SSB_API int64_t ssb_sizeof(int which);
 SSB_API const char* ssb_last_error(void);    /* thread-local, never NULL */
 SSB_API int ssb_device_sm_count(void);       /* SM count of the current device (148 on B200), <0 on error */
 /* Dropout keys for CUDA-graph replay.  Every dropout site keys Philox4x32-10 with the by-value
@@ -74,6 +81,12 @@ SSB_API int ssb_dtw_time_warp_batch(const float* cost, int64_t npairs, int64_t p
                             int64_t M, int64_t stride_i, int64_t stride_j, float* dtw,
                             int32_t* path, void* workspace, int64_t workspace_bytes,
                             void* stream);
+/* float64 variant (align.py:6 follows the caller's dtype: a float64 matrix is accumulated and
+ * compared in float64).  `dtw` (same strides as `cost`) is required: it is output and workspace.
+ * Any positive strides.  Interface parity only - the training path passes fp32. */
+SSB_API int ssb_dtw_time_warp_batch_f64(const double* cost, int64_t npairs, int64_t pair_stride,
+                                int64_t N, int64_t M, int64_t stride_i, int64_t stride_j,
+                                double* dtw, int32_t* path, void* stream);
 
 /* ---- log-mel spectrogram ---------------------------------------------------
  * Replaces data_utils.py:39-62 (`mel_spectrogram`, center=False) together with

@@ -56,6 +56,7 @@ _PE = ctypes.POINTER(Epilogue)
 # name -> (restype, argtypes); mirrors include/ssb.h one to one (tests check the symbol list)
 _SIGNATURES = {
     "ssb_version": (ctypes.c_int, []),
+    "ssb_sizeof": (c_i64, [ctypes.c_int]),
     "ssb_last_error": (ctypes.c_char_p, []),
     "ssb_device_sm_count": (ctypes.c_int, []),
     "ssb_set_seed_source": (ctypes.c_int, [c_ptr]),
@@ -64,6 +65,8 @@ _SIGNATURES = {
                                            c_ptr, c_i64, c_ptr]),
     "ssb_dtw_time_warp_batch": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                                c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ssb_dtw_time_warp_batch_f64": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
+                                                   c_ptr, c_ptr, c_ptr]),
     "ssb_mel_num_frames": (c_i64, [c_i64, ctypes.c_int, ctypes.c_int]),
     "ssb_mel_fwd": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_f32, c_ptr,
@@ -119,7 +122,7 @@ _SIGNATURES = {
 
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
 _KERNELS_PER_CALL = {
-    "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
+    "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_dtw_time_warp_batch_f64": 1, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
     "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 1, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
@@ -163,10 +166,11 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH) or os.environ.get("SSB_REBUILD") == "1":
-            from . import build as _build  # needs nvcc; raises loudly when impossible
-            _build.build()
+        from . import build as _build
+        if os.environ.get("SSB_REBUILD") == "1" or _build.is_stale():
+            _build.build(force=os.environ.get("SSB_REBUILD") == "1")  # needs nvcc; raises loudly
         lib = ctypes.CDLL(LIB_PATH)
+        _check_abi(lib)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError => header/library mismatch, fail loudly
             fn.restype = res
@@ -175,6 +179,25 @@ def load():
                 setattr(lib, name, _counted(fn, _KERNELS_PER_CALL[name]))
         _lib = lib
     return _lib
+
+
+ABI_VERSION = 200      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+
+
+def _check_abi(lib):
+    """A stale or foreign libssb.so must not load: same ABI version, and the ctypes mirrors of the
+    descriptor structs have the size the C compiler gave them."""
+    lib.ssb_version.restype = ctypes.c_int
+    got = lib.ssb_version()
+    if got != ABI_VERSION:
+        raise SSBError(-4, f"libssb.so reports ABI {got}, this package binds ABI {ABI_VERSION}: "
+                           f"rebuild (python -m silent_speech_b200.build --force)")
+    lib.ssb_sizeof.restype = c_i64
+    lib.ssb_sizeof.argtypes = [ctypes.c_int]
+    for which, cls in enumerate((Gather, Scatter, Epilogue, TcOperand)):
+        if lib.ssb_sizeof(which) != ctypes.sizeof(cls):
+            raise SSBError(-4, f"struct layout mismatch for {cls.__name__}: library "
+                               f"{lib.ssb_sizeof(which)} B, ctypes {ctypes.sizeof(cls)} B")
 
 
 def last_error():

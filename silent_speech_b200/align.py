@@ -23,9 +23,9 @@ def _device():
 def _prepare(cost):
     """-> (tensor, npairs, pair_stride, N, M, stride_i, stride_j) for the C ABI."""
     _lib.require_cuda(cost, "cost")
-    if cost.dtype != torch.float32:
-        raise TypeError("DTW kernels compute in fp32 (the dtype the reference feeds them, "
-                        "transduction_model.py:126); got %s" % cost.dtype)
+    if cost.dtype not in (torch.float32, torch.float64):
+        raise TypeError("DTW accumulates in the caller's floating dtype like align.py:6 "
+                        "(float32 or float64); got %s" % cost.dtype)
     t = cost.unsqueeze(0) if cost.dim() == 2 else cost
     if t.dim() != 3:
         raise ValueError("cost must be (N, M) or (P, N, M)")
@@ -51,6 +51,13 @@ def align_batch(cost, return_dtw=False):
     path = torch.empty((P, N), dtype=torch.int32, device=t.device)
     if P == 0:
         return (path, torch.empty_like(t)) if return_dtw else path
+    if t.dtype == torch.float64:     # interface parity (align.py:6 follows the input dtype)
+        dtw = torch.empty_strided(t.shape, t.stride(), dtype=torch.float64, device=t.device)
+        with torch.cuda.device(t.device):
+            _lib.check(lib.ssb_dtw_time_warp_batch_f64(t.data_ptr(), P, sp, N, M, si, sj,
+                                                       dtw.data_ptr(), path.data_ptr(),
+                                                       _lib.current_stream()))
+        return (path, dtw) if return_dtw else path
     ws_bytes = lib.ssb_dtw_workspace_bytes(P, N, M, si, sj)
     if ws_bytes < 0:
         raise _lib.SSBError(ws_bytes, _lib.last_error())
@@ -71,8 +78,10 @@ def _to_device(a):
     a = np.asarray(a)
     if a.ndim != 2:
         raise ValueError("expected a 2-D cost matrix")
-    if a.dtype != np.float32:
-        raise TypeError("DTW kernels compute in fp32; got %s" % a.dtype)
+    if a.dtype not in (np.float32, np.float64):
+        if a.dtype.kind not in "fiu":
+            raise TypeError("expected a real-valued cost matrix; got %s" % a.dtype)
+        a = a.astype(np.float64)      # numba's zeros_like would keep an integer dtype: not supported
     dev = _device()
     if a.flags.c_contiguous or a.size == 0:
         return torch.from_numpy(a).to(dev, non_blocking=False)

@@ -384,9 +384,82 @@ int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64
   return SSB_OK;
 }
 
+// ---- fp64 path (interface parity) ------------------------------------------------------------
+// align.py:6 allocates the accumulated-cost table with zeros_like(costs): the reference follows
+// the caller's dtype, so a float64 matrix is accumulated and compared in float64.  Nothing on
+// the training path does that (transduction_model.py:126 passes fp32), so this is a plain
+// anti-diagonal wavefront, one CTA per pair, that writes the fp64 table (the caller's `dtw`
+// buffer doubles as the workspace) and backtraces it with the reference's first-wins order.
+__global__ void __launch_bounds__(256) dtw_f64_kernel(const double* __restrict__ cost_all,
+                                                     double* __restrict__ dtw_all, int npairs,
+                                                     int64_t pair_stride, int N, int M, int64_t si,
+                                                     int64_t sj, int32_t* __restrict__ path_all) {
+  const double INF = CUDART_INF;
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const double* cost = cost_all + (int64_t)pair * pair_stride;
+    double* dtw = dtw_all + (int64_t)pair * pair_stride;
+    for (int d = 0; d <= N + M - 2; ++d) {
+      const int lo = max(0, d - (M - 1)), hi = min(N - 1, d);
+      for (int i = lo + (int)threadIdx.x; i <= hi; i += blockDim.x) {
+        const int j = d - i;
+        double v;
+        if (i == 0 && j == 0) {
+          v = 0.0;
+        } else if (i == 0 || j == 0) {
+          v = INF;
+        } else {
+          const double up = dtw[(i - 1) * si + j * sj], left = dtw[i * si + (j - 1) * sj],
+                       diag = dtw[(i - 1) * si + (j - 1) * sj];
+          double m = up;
+          if (left < m) m = left;
+          if (diag < m) m = diag;
+          v = cost[i * si + j * sj] + m;
+        }
+        dtw[i * si + j * sj] = v;
+      }
+      __syncthreads();   // block-wide visibility of this anti-diagonal's global stores
+    }
+    int32_t* path = path_all + (int64_t)pair * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) path[i] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int i = N - 1, j = M - 1;
+      while (i > 0 && j > 0) {    // align.py:24-26: min over [(i-1,j), (i,j-1), (i-1,j-1)], first wins
+        path[i] = j;
+        const double up = dtw[(i - 1) * si + j * sj], left = dtw[i * si + (j - 1) * sj],
+                     diag = dtw[(i - 1) * si + (j - 1) * sj];
+        int ni = i - 1, nj = j;
+        double m = up;
+        if (left < m) { m = left; ni = i; nj = j - 1; }
+        if (diag < m) { ni = i - 1; nj = j - 1; }
+        i = ni;
+        j = nj;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int ssb_dtw_time_warp_batch_f64(const double* cost, int64_t npairs, int64_t pair_stride, int64_t N,
+                                int64_t M, int64_t stride_i, int64_t stride_j, double* dtw,
+                                int32_t* path, void* stream) {
+  SSB_REQUIRE(N >= 1 && M >= 1 && N < (1 << 30) && M < (1 << 30), "dtw: bad shape %lld x %lld",
+              (long long)N, (long long)M);
+  SSB_REQUIRE(stride_i >= 1 && stride_j >= 1, "dtw: strides must be positive");
+  SSB_REQUIRE(npairs >= 0 && npairs < (1LL << 31), "dtw: bad npairs %lld", (long long)npairs);
+  if (npairs == 0) return SSB_OK;
+  SSB_REQUIRE(cost && dtw && path, "dtw: null pointer");
+  const int grid = (int)(npairs < 8LL * ssb::num_sms() ? npairs : 8LL * ssb::num_sms());
+  dtw_f64_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cost, dtw, (int)npairs, pair_stride, (int)N,
+                                                        (int)M, stride_i, stride_j, path);
+  SSB_LAUNCH_CHECK("dtw_f64_kernel");
+  return SSB_OK;
+}
+
 
 int64_t ssb_dtw_workspace_bytes(int64_t npairs, int64_t N, int64_t M, int64_t stride_i,
                                 int64_t stride_j) {

@@ -42,7 +42,17 @@ int num_sms() {
 
 extern "C" {
 
-int ssb_version(void) { return 100; }  // 0.1.0
+int ssb_version(void) { return SSB_ABI_VERSION; }
+
+int64_t ssb_sizeof(int which) {
+  switch (which) {
+    case 0: return (int64_t)sizeof(ssb_gather_t);
+    case 1: return (int64_t)sizeof(ssb_scatter_t);
+    case 2: return (int64_t)sizeof(ssb_epilogue_t);
+    case 3: return (int64_t)sizeof(ssb_tc_operand_t);
+    default: return -1;
+  }
+}
 
 const char* ssb_last_error(void) { return ssb::g_err; }
 

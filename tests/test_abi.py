@@ -25,8 +25,27 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.ssb_version() >= 100
+    hdr = open(os.path.join(ROOT, "include", "ssb.h")).read()
+    abi = int(re.search(r"#define\s+SSB_ABI_VERSION\s+(\d+)", hdr).group(1))
+    assert lib.ssb_version() == abi == _lib.ABI_VERSION       # header, library, binding agree
     assert isinstance(_lib.last_error(), str)
+
+
+def test_struct_mirrors_match_the_compiled_layouts():
+    """a .so built from an older ssb.h must not load silently; the ctypes mirrors of
+    the descriptor structs are checked against sizeof() as compiled (also at every load())."""
+    import ctypes
+    lib = _lib.load()
+    for which, cls in enumerate((_lib.Gather, _lib.Scatter, _lib.Epilogue, _lib.TcOperand)):
+        assert lib.ssb_sizeof(which) == ctypes.sizeof(cls), cls.__name__
+    assert lib.ssb_sizeof(99) == -1
+
+
+def test_staleness_is_decided_by_source_content():
+    from silent_speech_b200 import build
+    assert not build.is_stale()
+    h = build.source_hash()
+    assert open(build.HASH_PATH).read().strip() == h and len(h) == 64
 
 
 def test_dtw_workspace_query_and_validation():

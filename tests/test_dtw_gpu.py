@@ -97,6 +97,32 @@ def test_inf_costs_and_errors():
     assert align.align_from_distances(a) == odtw.align_from_distances(a)
     assert align.align_from_distances(a.T) == odtw.align_from_distances(a.T)
     with pytest.raises(TypeError):
-        align.align_from_distances(a.astype(np.float64))
+        align.align_from_distances(a.astype(np.complex64))
     with pytest.raises(Exception):
         align.align_batch(torch.zeros(3, 4))  # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("name", ["rand_C", "rand_T", "ties_T", "sub_fp32_eps", "row", "col", "inf"])
+def test_fp64_inputs_follow_the_reference_dtype(golden_dir, name):
+    """align.py:6: float64 costs are accumulated and compared in float64.  Paths and tables
+    bit-exact with the reference's own float64 run (dtw_golden_f64.npz) through the drop-in API."""
+    import os
+    g = np.load(os.path.join(golden_dir, "dtw_golden_f64.npz"))
+    a = g[f"{name}_input"]
+    if int(g[f"{name}_fortran"]):
+        a = a.T.copy().T
+    assert align.align_from_distances(a) == g[f"{name}_path"].tolist()
+    d = align.time_warp(a)
+    assert d.dtype == np.float64
+    np.testing.assert_array_equal(d, g[f"{name}_dtw"])
+    if name == "sub_fp32_eps":      # the float32 kernel on the rounded costs ties differently
+        assert align.align_from_distances(a.astype(np.float32)) == odtw.align_from_distances(
+            a.astype(np.float32))
+
+
+def test_fp64_batch_on_device():
+    rs = np.random.RandomState(12)
+    c = torch.from_numpy(np.abs(rs.randn(5, 44, 38))).cuda()         # (P, M, N) float64 blocks
+    p = align.align_batch(c.transpose(1, 2)).cpu().numpy()           # F-ordered pairs (38 x 44)
+    for i in range(5):
+        assert p[i].tolist() == odtw.align_from_distances(c[i].cpu().numpy().T)

@@ -55,3 +55,23 @@ def test_batch_matches_single():
     got = odtw.align_batch(view, threads=2)
     for p in range(7):
         assert got[p].tolist() == odtw.align_from_distances(view[p])
+
+
+F64_CASES = ["rand_C", "rand_T", "ties_T", "sub_fp32_eps", "row", "col", "inf"]
+
+
+def f64_case(g, name):
+    a = g[f"{name}_input"]
+    return a.T.copy().T if int(g[f"{name}_fortran"]) else a     # restore the F-ordered view
+
+
+@pytest.mark.parametrize("name", F64_CASES)
+def test_fp64_oracle_matches_reference_golden(golden_dir, name):
+    """float64 in -> float64 accumulation (align.py:6): table and path bit-exact with the
+    reference's numba run (tests/golden/make_golden_dtw_f64.py)."""
+    g = np.load(os.path.join(golden_dir, "dtw_golden_f64.npz"))
+    a = f64_case(g, name)
+    assert a.dtype == np.float64
+    d = odtw.time_warp(a)
+    np.testing.assert_array_equal(d, g[f"{name}_dtw"])
+    assert odtw.align_from_distances(a) == g[f"{name}_path"].tolist()
