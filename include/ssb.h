@@ -39,10 +39,11 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 200
+#define SSB_ABI_VERSION 201
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
- * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t; -1 otherwise), so a foreign-language
+ * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t;
+ * -1 otherwise), so a foreign-language
  * binding can verify its mirror of the layouts at load time. */
 SSB_API int64_t ssb_sizeof(int which);
 SSB_API const char* ssb_last_error(void);    /* thread-local, never NULL */
@@ -81,6 +82,62 @@ SSB_API int ssb_dtw_time_warp_batch(const float* cost, int64_t npairs, int64_t p
                             int64_t M, int64_t stride_i, int64_t stride_j, float* dtw,
                             int32_t* path, void* workspace, int64_t workspace_bytes,
                             void* stream);
+/* Ragged batches: ONE launch aligns pairs of different shapes (every silent utterance of a real
+ * SizeAwareSampler batch has its own (T_target, T_pred): transduction_model.py:111-128 loops over
+ * them with one host round trip each).  Matrix p is stored like the reference's `costs` tensor,
+ * (M_p = T_pred rows) x (N_p = T_target columns) row-major with row pitch pitch_p >= N_p, starting
+ * at cost_base + cost_off_p, and is aligned as its `.T` view exactly as transduction_model.py:126
+ * passes it: DTW rows i = target frames.  ssb_dtw_ragged_plan is a pure HOST function: it fills
+ * the host table (which the caller uploads; device copy = table_dev), returns the workspace size
+ * in bytes (negative on error) and the batch maxima {max N, max M}.  path is (npairs, max_N) int32,
+ * rows >= N_p are set to 0.  vectorized != 0 promises that cost_base is 16 B aligned and every
+ * cost_off_p and pitch_p is a multiple of 4 floats (16 B loads). */
+typedef struct ssb_dtw_pair {
+  int64_t cost_off;   /* float offset of the matrix from cost_base */
+  int64_t dirs_off;   /* filled by the plan: word offset into the workspace */
+  int64_t pitch;      /* floats between consecutive T_pred rows */
+  int32_t N, M;       /* DTW rows (target frames), DTW columns (predicted frames) */
+  int32_t nbands, nch;/* filled by the plan */
+} ssb_dtw_pair_t;
+SSB_API int64_t ssb_dtw_ragged_plan(int64_t npairs, const int64_t* N, const int64_t* M,
+                                    const int64_t* cost_off, const int64_t* pitch,
+                                    ssb_dtw_pair_t* table_out, int64_t* max_dims_out);
+SSB_API int ssb_dtw_align_ragged(const float* cost_base, int64_t npairs,
+                                 const ssb_dtw_pair_t* table_dev, int64_t max_N, int64_t max_M,
+                                 int vectorized, int32_t* path, void* workspace,
+                                 int64_t workspace_bytes, void* stream);
+/* ---- on-device transduction loss around the DTW kernel (csrc/dtwloss.cu) --------
+ * Replaces the per-utterance loop of transduction_model.py:98-157 for a whole batch, ragged shapes
+ * included.  Utterance u owns rows [pred_row, pred_row + Tp) of the flattened (rows_total, F)
+ * predictions / (rows_total, NP) phoneme logits (decollate_tensor order, data_utils.py:169-178) and
+ * rows [tgt_row, tgt_row + Tg) of the concatenated targets (sum Tg, F) / target phonemes (int64).
+ * The table is built by the caller (ascending pred_row) and lives in device memory. */
+typedef struct ssb_utt {
+  int64_t pred_row;   /* first row of the utterance in the flattened prediction tensors */
+  int64_t tgt_row;    /* first row in the concatenated target tensors */
+  int64_t cost_off;   /* silent: float offset of its (Tp x pitch) cost matrix from cost_base */
+  int32_t Tp, Tg;     /* predicted frames, target frames (voiced: Tp == Tg) */
+  int32_t pitch;      /* silent: floats between consecutive cost rows (>= Tg) */
+  int32_t silent;     /* 1: DTW-aligned (transduction_model.py:115-128), 0: frame-synchronous (:138-145) */
+  int32_t pair;       /* silent: row of `path` / index in the ragged DTW batch; voiced: -1 */
+  int32_t reserved_;
+} ssb_utt_t;
+/* cost[p, t] = ||pred[p] - tgt[t]||_2 + w * (logsumexp(phon[p]) - phon[p, tgt_phone[t]]) for every
+ * silent utterance (transduction_model.py:116-124), written at cost_base + cost_off. */
+SSB_API int ssb_dtw_cost_batch(const float* pred, const float* phon, const float* tgt,
+                               const int64_t* tgt_phone, const ssb_utt_t* table_dev, int64_t n_utt,
+                               int64_t max_Tp, int64_t max_Tg, int64_t F, int64_t NP, float w,
+                               float* cost_base, void* stream);
+/* Per row of the flattened predictions: row_loss = its share of the batch loss (silent: the sum
+ * over the target frames the path aligned to it of cost[p, t], :128; voiced: ||y - pred + eps|| +
+ * w * CE, :141-145; rows outside every utterance: 0) and the gradient of the SUMMED loss with
+ * respect to that row of pred / phon.  path: (n_silent, path_pitch) int32 from
+ * ssb_dtw_align_ragged (may be NULL when no utterance is silent). */
+SSB_API int ssb_dtw_loss_rows(const float* pred, const float* phon, const float* tgt,
+                              const int64_t* tgt_phone, const ssb_utt_t* table_dev, int64_t n_utt,
+                              const int32_t* path, int64_t path_pitch, int64_t rows_total, int64_t F,
+                              int64_t NP, float w, float pairwise_eps, float* row_loss,
+                              float* grad_pred, float* grad_phon, void* stream);
 /* float64 variant (align.py:6 follows the caller's dtype: a float64 matrix is accumulated and
  * compared in float64).  `dtw` (same strides as `cost`) is required: it is output and workspace.
  * Any positive strides.  Interface parity only - the training path passes fp32. */

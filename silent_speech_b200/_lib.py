@@ -49,6 +49,19 @@ class TcOperand(ctypes.Structure):
                 ("batch_div", c_i32), ("reserved_", c_i32), ("batch_stride_hi", c_i64)]
 
 
+class DtwPair(ctypes.Structure):
+    """ssb_dtw_pair_t"""
+    _fields_ = [("cost_off", c_i64), ("dirs_off", c_i64), ("pitch", c_i64), ("N", c_i32),
+                ("M", c_i32), ("nbands", c_i32), ("nch", c_i32)]
+
+
+class Utt(ctypes.Structure):
+    """ssb_utt_t"""
+    _fields_ = [("pred_row", c_i64), ("tgt_row", c_i64), ("cost_off", c_i64), ("Tp", c_i32),
+                ("Tg", c_i32), ("pitch", c_i32), ("silent", c_i32), ("pair", c_i32),
+                ("reserved_", c_i32)]
+
+
 _PT = ctypes.POINTER(TcOperand)
 _PG = ctypes.POINTER(Gather)
 _PE = ctypes.POINTER(Epilogue)
@@ -67,6 +80,14 @@ _SIGNATURES = {
                                                c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_dtw_time_warp_batch_f64": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                                    c_ptr, c_ptr, c_ptr]),
+    "ssb_dtw_ragged_plan": (c_i64, [c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "ssb_dtw_align_ragged": (ctypes.c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, ctypes.c_int, c_ptr,
+                                            c_ptr, c_i64, c_ptr]),
+    "ssb_dtw_cost_batch": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64,
+                                          c_i64, c_i64, c_f32, c_ptr, c_ptr]),
+    "ssb_dtw_loss_rows": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64,
+                                         c_i64, c_i64, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr,
+                                         c_ptr]),
     "ssb_mel_num_frames": (c_i64, [c_i64, ctypes.c_int, ctypes.c_int]),
     "ssb_mel_fwd": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_f32, c_ptr,
@@ -122,7 +143,8 @@ _SIGNATURES = {
 
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
 _KERNELS_PER_CALL = {
-    "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_dtw_time_warp_batch_f64": 1, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
+    "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_dtw_time_warp_batch_f64": 1, "ssb_dtw_align_ragged": 2, "ssb_dtw_cost_batch": 1,
+    "ssb_dtw_loss_rows": 1, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
     "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 1, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
@@ -181,7 +203,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 200      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 201      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):
@@ -194,7 +216,7 @@ def _check_abi(lib):
                            f"rebuild (python -m silent_speech_b200.build --force)")
     lib.ssb_sizeof.restype = c_i64
     lib.ssb_sizeof.argtypes = [ctypes.c_int]
-    for which, cls in enumerate((Gather, Scatter, Epilogue, TcOperand)):
+    for which, cls in enumerate((Gather, Scatter, Epilogue, TcOperand, DtwPair, Utt)):
         if lib.ssb_sizeof(which) != ctypes.sizeof(cls):
             raise SSBError(-4, f"struct layout mismatch for {cls.__name__}: library "
                                f"{lib.ssb_sizeof(which)} B, ctypes {ctypes.sizeof(cls)} B")

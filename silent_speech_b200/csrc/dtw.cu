@@ -44,6 +44,9 @@ struct DtwParams {
   const float* cost;
   float* dtw_out;  // nullable
   uint32_t* dirs;
+  // ragged batches (ssb_dtw_align_ragged): per-pair geometry; Ny/Nx/nbands/nch below then hold the
+  // MAXIMA over the batch (shared-memory sizing) and pair_stride/pitch/dirs_pair_words are unused
+  const ssb_dtw_pair_t* table;
   int64_t pair_stride;
   int64_t pitch;
   int64_t dirs_pair_words;
@@ -57,7 +60,7 @@ struct DtwParams {
 // words are stored step-major:  dirs[(band*nch + chunk)*32 + lane]  (uint4 = the lane's 4 rows)
 // so that every chunk ends with one coalesced 512 B store per warp.
 
-template <bool Y_IS_I, bool VEC, bool WRITE_DTW>
+template <bool Y_IS_I, bool VEC, bool WRITE_DTW, bool RAGGED>
 __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -69,26 +72,32 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
   const uint32_t ring_u32 = ssb::smem_u32(wbase) + lane * 16;
   const int g8 = lane & ~7;
   const float INF = CUDART_INF_F;
-  const int Nx = p.Nx;
-  const int64_t pitch = p.pitch;
   // chunks in which every lane is inside [1, Nx) and every prefetch is in range
   const int steady_lo = 32 / CH;
-  const int steady_hi = (Nx - CH - PF) / CH;  // inclusive; may be < steady_lo
 
   for (int pair = blockIdx.x * warps_per_cta + warp; pair < p.npairs;
        pair += gridDim.x * warps_per_cta) {
+    int Nx = p.Nx, Ny = p.Ny, nbands = p.nbands, nch = p.nch;
+    int64_t pitch = p.pitch;
     const float* cost = p.cost + (int64_t)pair * p.pair_stride;
     float* dout = WRITE_DTW ? p.dtw_out + (int64_t)pair * p.pair_stride : nullptr;
     uint4* dirs = reinterpret_cast<uint4*>(p.dirs + (int64_t)pair * p.dirs_pair_words);
+    if constexpr (RAGGED) {   // this pair's own geometry (Y_IS_I: Ny = N, Nx = M)
+      const ssb_dtw_pair_t t = p.table[pair];
+      Ny = t.N; Nx = t.M; nbands = t.nbands; nch = t.nch; pitch = t.pitch;
+      cost = p.cost + t.cost_off;
+      dirs = reinterpret_cast<uint4*>(p.dirs + t.dirs_off);
+    }
+    const int steady_hi = (Nx - CH - PF) / CH;  // inclusive; may be < steady_lo
 
-    for (int band = 0; band < p.nbands; ++band) {
+    for (int band = 0; band < nbands; ++band) {
       const int y0 = band * BAND + lane * R;
       const bool row0 = (y0 == 0);
-      const int rows_valid = min(max(p.Ny - y0, 0), R);
+      const int rows_valid = min(max(Ny - y0, 0), R);
       const int y0_ld = rows_valid > 0 ? y0 : 0;  // keep the address legal for idle lanes
       const int ld_bytes = rows_valid * 4;
       const bool rd_bnd = (band > 0) && (lane == 0);
-      const bool wr_bnd = (band + 1 < p.nbands) && (lane == 31);
+      const bool wr_bnd = (band + 1 < nbands) && (lane == 31);
 
       float v[R];
       uint32_t pk[R];
@@ -193,7 +202,7 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
       }
 
 #pragma unroll 1
-      for (int c = 0; c < p.nch; ++c) {
+      for (int c = 0; c < nch; ++c) {
         const int s0 = c * CH;
         if (c >= steady_lo && c <= steady_hi) {
           // ---- steady chunk: no range checks, running addresses --------------------
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
             ssb::cp_async_commit();
           }
         }
-        dirs[((int64_t)band * p.nch + c) * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dirs[((int64_t)band * nch + c) * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       ssb::cp_async_wait<0>();
       __syncwarp();  // bnd[] written by lane 31 is read by lane 0 in the next band
@@ -248,11 +257,18 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
 template <bool Y_IS_I>
 __global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t dirs_pair_words,
                                      int nch, int N, int M, int npairs,
-                                     int32_t* __restrict__ path) {
+                                     int32_t* __restrict__ path,
+                                     const ssb_dtw_pair_t* __restrict__ table) {
   const int pair = blockIdx.x * blockDim.x + threadIdx.x;
   if (pair >= npairs) return;
   const uint32_t* d = dirs + (int64_t)pair * dirs_pair_words;
-  int32_t* out = path + (int64_t)pair * N;
+  int32_t* out = path + (int64_t)pair * N;    // ragged: rows are padded to the batch maximum N
+  if (table != nullptr) {
+    const ssb_dtw_pair_t t = table[pair];
+    d = dirs + t.dirs_off;
+    for (int rr = t.N; rr < N; ++rr) out[rr] = 0;   // padding rows
+    N = t.N; M = t.M; nch = t.nch;
+  }
   int i = N - 1, j = M - 1;
   int64_t cur_idx = -1;
   uint32_t cur_word = 0;
@@ -306,9 +322,9 @@ int make_geometry(int64_t N, int64_t M, int64_t stride_i, int64_t stride_j, Geom
   return SSB_OK;
 }
 
-template <bool Y_IS_I, bool VEC, bool WRITE_DTW>
+template <bool Y_IS_I, bool VEC, bool WRITE_DTW, bool RAGGED = false>
 int launch_fill(const DtwParams& p, cudaStream_t st) {
-  auto kern = dtw_fill_kernel<Y_IS_I, VEC, WRITE_DTW>;
+  auto kern = dtw_fill_kernel<Y_IS_I, VEC, WRITE_DTW, RAGGED>;
   const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
   const int per_warp = RING_BYTES + bnd_bytes;
   int warps = 4;
@@ -350,6 +366,7 @@ int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64
   p.cost = cost;
   p.dtw_out = dtw;
   p.dirs = (uint32_t*)workspace;
+  p.table = nullptr;
   p.pair_stride = pair_stride;
   p.pitch = g.pitch;
   p.dirs_pair_words = g.dirs_pair_words;
@@ -376,11 +393,25 @@ int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64
   const int grid = (int)((npairs + threads - 1) / threads);
   if (g.y_is_i)
     dtw_backtrace_kernel<true><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nch, (int)N,
-                                                         (int)M, (int)npairs, path);
+                                                         (int)M, (int)npairs, path, nullptr);
   else
     dtw_backtrace_kernel<false><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nch,
-                                                          (int)N, (int)M, (int)npairs, path);
+                                                          (int)N, (int)M, (int)npairs, path, nullptr);
   SSB_LAUNCH_CHECK("dtw_backtrace_kernel");
+  return SSB_OK;
+}
+
+// ---- ragged batches --------------------------------------------------------------------------
+// One launch aligns pairs of DIFFERENT shapes (every silent utterance of a real SizeAwareSampler
+// batch has its own (T_target, T_pred), transduction_model.py:111-128).  Matrices are stored like
+// the reference's costs tensor, (M = T_pred rows) x (N = T_target columns) row-major with a row
+// pitch, and aligned as its `.T` view (stride_i == 1): DTW rows i = target frames.
+int plan_pair(int64_t N, int64_t M, int64_t pitch, ssb_dtw_pair_t* t) {
+  Geometry g;
+  if (int rc = make_geometry(N, M, 1, M == 1 ? 1 : pitch, &g)) return rc;
+  SSB_REQUIRE(g.y_is_i, "dtw ragged: internal orientation error");
+  t->N = (int32_t)N; t->M = (int32_t)M; t->pitch = pitch;
+  t->nbands = g.nbands; t->nch = g.nch;
   return SSB_OK;
 }
 
@@ -484,6 +515,71 @@ int ssb_dtw_time_warp_batch(const float* cost, int64_t npairs, int64_t pair_stri
   SSB_REQUIRE(dtw != nullptr, "dtw: null dtw output");
   return run(cost, npairs, pair_stride, N, M, stride_i, stride_j, dtw, path, workspace,
              workspace_bytes, stream);
+}
+
+int64_t ssb_dtw_ragged_plan(int64_t npairs, const int64_t* N, const int64_t* M,
+                            const int64_t* cost_off, const int64_t* pitch,
+                            ssb_dtw_pair_t* table_out, int64_t* max_dims_out) {
+  if (npairs < 0 || (npairs > 0 && (!N || !M || !cost_off || !pitch || !table_out))) {
+    ssb::set_error("dtw ragged plan: null pointer / bad npairs");
+    return SSB_ERR_ARG;
+  }
+  int64_t words = 0, maxN = 0, maxM = 0;
+  for (int64_t i = 0; i < npairs; ++i) {
+    ssb_dtw_pair_t* t = table_out + i;
+    if (N[i] < 1 || M[i] < 1 || pitch[i] < N[i] || cost_off[i] < 0) {
+      ssb::set_error("dtw ragged plan: pair %lld has N=%lld M=%lld pitch=%lld off=%lld",
+                     (long long)i, (long long)N[i], (long long)M[i], (long long)pitch[i],
+                     (long long)cost_off[i]);
+      return SSB_ERR_ARG;
+    }
+    if (plan_pair(N[i], M[i], pitch[i], t)) return SSB_ERR_ARG;
+    t->cost_off = cost_off[i];
+    t->dirs_off = words;
+    words += (int64_t)t->nbands * t->nch * BAND;
+    maxN = N[i] > maxN ? N[i] : maxN;
+    maxM = M[i] > maxM ? M[i] : maxM;
+  }
+  if (max_dims_out) { max_dims_out[0] = maxN; max_dims_out[1] = maxM; }
+  const int64_t b = words * 4;
+  return b > 16 ? b : 16;
+}
+
+int ssb_dtw_align_ragged(const float* cost_base, int64_t npairs, const ssb_dtw_pair_t* table_dev,
+                         int64_t max_N, int64_t max_M, int vectorized, int32_t* path,
+                         void* workspace, int64_t workspace_bytes, void* stream) {
+  SSB_REQUIRE(npairs >= 0 && npairs < (1LL << 31), "dtw: bad npairs %lld", (long long)npairs);
+  if (npairs == 0) return SSB_OK;
+  SSB_REQUIRE(cost_base && table_dev && path && workspace, "dtw ragged: null pointer");
+  SSB_REQUIRE(max_N >= 1 && max_M >= 1 && max_N < (1 << 24) && max_M < (1 << 24),
+              "dtw ragged: bad maxima %lld x %lld", (long long)max_N, (long long)max_M);
+  SSB_REQUIRE(((uintptr_t)workspace & 15) == 0, "dtw: workspace must be 16 B aligned");
+  SSB_REQUIRE(!vectorized || ((uintptr_t)cost_base & 15) == 0,
+              "dtw ragged: vectorized loads need a 16 B aligned base");
+  (void)workspace_bytes;   // sized by ssb_dtw_ragged_plan; the table is trusted (caller-built)
+  cudaStream_t st = (cudaStream_t)stream;
+  DtwParams p;
+  p.cost = cost_base;
+  p.dtw_out = nullptr;
+  p.dirs = (uint32_t*)workspace;
+  p.table = table_dev;
+  p.pair_stride = 0;
+  p.pitch = 0;
+  p.dirs_pair_words = 0;
+  p.Ny = (int)max_N;
+  p.Nx = (int)max_M;
+  p.nbands = (int)((max_N + BAND - 1) / BAND);
+  p.nch = (int)((max_M + 30) / CH + 1);
+  p.npairs = (int)npairs;
+  int rc = vectorized ? launch_fill<true, true, false, true>(p, st)
+                      : launch_fill<true, false, false, true>(p, st);
+  if (rc) return rc;
+  const int threads = 64;
+  const int grid = (int)((npairs + threads - 1) / threads);
+  dtw_backtrace_kernel<true><<<grid, threads, 0, st>>>(p.dirs, 0, p.nch, (int)max_N, (int)max_M,
+                                                       (int)npairs, path, table_dev);
+  SSB_LAUNCH_CHECK("dtw_backtrace_kernel");
+  return SSB_OK;
 }
 
 }  // extern "C"

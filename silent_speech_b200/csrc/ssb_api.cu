@@ -50,6 +50,8 @@ int64_t ssb_sizeof(int which) {
     case 1: return (int64_t)sizeof(ssb_scatter_t);
     case 2: return (int64_t)sizeof(ssb_epilogue_t);
     case 3: return (int64_t)sizeof(ssb_tc_operand_t);
+    case 4: return (int64_t)sizeof(ssb_dtw_pair_t);
+    case 5: return (int64_t)sizeof(ssb_utt_t);
     default: return -1;
   }
 }

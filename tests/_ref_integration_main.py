@@ -87,10 +87,17 @@ def main():
     for it in range(2):
         saved = tm.align_from_distances
         tm.align_from_distances = ref_align.align_from_distances   # pure-reference CPU pass
+        # architecture.py:64-68 shifts x_raw IN PLACE between overlapping slices; ATen's CPU copy
+        # splits that across intra-op threads and the chunk boundaries then read already-shifted
+        # samples (16 of 89 600 elements here, run-to-run different).  One thread = the intended
+        # shift, which is what the drop-in implements.
+        nthreads = torch.get_num_threads()
+        torch.set_num_threads(1)
         try:
             lr_, gr, pr = step_body(ref_model, optim_ref, "cpu", it)
         finally:
             tm.align_from_distances = saved
+            torch.set_num_threads(nthreads)
         lo, go, po = step_body(ours, optim_our, "cuda", it)
         losses_ref.append(lr_)
         losses_our.append(lo)
@@ -112,6 +119,9 @@ def main():
     perr = 0.0
     osd = ours.state_dict()
     for k, v in ref_model.state_dict().items():
+        if k.startswith("conv_blocks") and k.endswith(("conv1.bias", "conv2.bias",
+                                                       "residual_path.bias")):
+            continue              # zero-gradient parameters: Adam turns rounding noise into +-lr steps
         if v.is_floating_point():
             a, b = osd[k].detach().cpu().double(), v.double()
             perr = max(perr, ((a - b).norm() / (b.norm() + 1e-30)).item())

@@ -36,7 +36,8 @@ def test_struct_mirrors_match_the_compiled_layouts():
     the descriptor structs are checked against sizeof() as compiled (also at every load())."""
     import ctypes
     lib = _lib.load()
-    for which, cls in enumerate((_lib.Gather, _lib.Scatter, _lib.Epilogue, _lib.TcOperand)):
+    for which, cls in enumerate((_lib.Gather, _lib.Scatter, _lib.Epilogue, _lib.TcOperand,
+                                 _lib.DtwPair, _lib.Utt)):
         assert lib.ssb_sizeof(which) == ctypes.sizeof(cls), cls.__name__
     assert lib.ssb_sizeof(99) == -1
 
