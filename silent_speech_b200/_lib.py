@@ -145,7 +145,7 @@ _SIGNATURES = {
 _KERNELS_PER_CALL = {
     "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_dtw_time_warp_batch_f64": 1, "ssb_dtw_align_ragged": 2, "ssb_dtw_cost_batch": 1,
     "ssb_dtw_loss_rows": 1, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
-    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 1, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
+    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 3, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
     "ssb_split_bf16": 1, "ssb_split_bf16_t": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,

@@ -74,6 +74,72 @@ def align_batch(cost, return_dtw=False):
     return path
 
 
+class RaggedPlan:
+    """Host-side plan of ONE launch over pairs of different shapes (ssb_dtw_ragged_plan): matrix
+    p is (M_p = T_pred rows) x (N_p = T_target columns) row-major with pitch_p, at float offset
+    cost_off_p of one buffer, aligned as its `.T` view like transduction_model.py:126 does."""
+
+    def __init__(self, N, M, cost_off, pitch, device):
+        import ctypes
+        lib = _lib.load()
+        n = len(N)
+        arr = lambda v: (ctypes.c_int64 * max(n, 1))(*[int(x) for x in v])
+        table = (_lib.DtwPair * max(n, 1))()
+        dims = (ctypes.c_int64 * 2)()
+        ws = lib.ssb_dtw_ragged_plan(n, arr(N), arr(M), arr(cost_off), arr(pitch), table, dims)
+        if ws < 0:
+            raise _lib.SSBError(ws, _lib.last_error())
+        self.npairs, self.workspace_bytes = n, int(ws)
+        self.max_N, self.max_M = int(dims[0]), int(dims[1])
+        self.vectorized = all(int(o) % 4 == 0 for o in cost_off) and all(int(q) % 4 == 0 for q in pitch)
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8)
+        self.table_host = raw.pin_memory() if torch.cuda.is_available() else raw   # kept alive: an
+        self.table = self.table_host.to(device, non_blocking=True)   # async H2D may be captured
+
+    def run(self, cost_base):
+        """cost_base: 1-D CUDA fp32 buffer holding every matrix.  -> (npairs, max_N) int32 paths
+        (rows >= N_p are 0)."""
+        lib = _lib.load()
+        _lib.require_cuda(cost_base, "cost")
+        path = torch.empty((self.npairs, max(self.max_N, 1)), dtype=torch.int32, device=cost_base.device)
+        if self.npairs == 0:
+            return path
+        ws = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=cost_base.device)
+        with torch.cuda.device(cost_base.device):
+            _lib.check(lib.ssb_dtw_align_ragged(cost_base.data_ptr(), self.npairs, self.table.data_ptr(),
+                                                self.max_N, self.max_M,
+                                                int(self.vectorized and cost_base.data_ptr() % 16 == 0),
+                                                path.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _lib.current_stream()))
+        return path
+
+
+def align_ragged(costs):
+    """Align a list of cost matrices of DIFFERENT shapes in one launch.  costs[p]: CUDA fp32
+    (T_pred_p, T_target_p) tensor exactly as transduction_model.py:116-124 builds `costs`; the
+    DTW runs on its transpose (:126).  Returns a list of int32 CUDA tensors, path_p[t] = predicted
+    frame aligned to target frame t (align.py:16-34 semantics)."""
+    if not costs:
+        return []
+    dev = costs[0].device
+    N, M, off, pitch, flat = [], [], [], [], []
+    cur = 0
+    for c in costs:
+        _lib.require_cuda(c, "cost")
+        if c.dtype != torch.float32 or c.dim() != 2:
+            raise TypeError("align_ragged: 2-D float32 matrices")
+        Tp, Tg = c.shape
+        q = (Tg + 3) // 4 * 4
+        buf = torch.zeros((Tp, q), dtype=torch.float32, device=dev)
+        buf[:, :Tg] = c
+        N.append(Tg), M.append(Tp), off.append(cur), pitch.append(q)
+        flat.append(buf.view(-1))
+        cur += Tp * q
+    plan = RaggedPlan(N, M, off, pitch, dev)
+    path = plan.run(torch.cat(flat))
+    return [path[i, :N[i]] for i in range(len(costs))]
+
+
 def _to_device(a):
     a = np.asarray(a)
     if a.ndim != 2:

@@ -2,17 +2,20 @@
 //
 // Replaces recognition_model.py:96-101:  F.log_softmax(pred, 2) -> pad_sequence ->
 // F.ctc_loss(pred, y, lengths, text_int_lengths, blank=n_chars)  and its autograd backward.
-// One CTA per utterance, one thread per position s of the blank-extended target l'
-// (S = 2L + 1 <= 1024).  The recursion over time is sequential (T = 750 at cfg-5) and latency
-// bound; everything that is parallel (row log-sum-exp, the S states, the C classes) is spread
-// over the CTA:
-//   phase 1  lse[t] = logsumexp_c logits[t, c]                      (one warp per row)
-//   phase 2  alpha_t(s) in log space, stored to the workspace        (1 barrier per step)
-//   phase 3  nll = -logsumexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
-//   phase 4  beta_t(s) backwards in time; per step the class sums
-//              occ_t(c) = sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - lp_t(c) + nll)   (<= 1)
-//            go through shared-memory atomics and
-//              d nll / d logits[t, c] = softmax_t(c) - occ_t(c)      (0 for t >= input length)
+// Three launches (S = 2L + 1 <= 1024 states of the blank-extended target l'):
+//   ctc_lp_kernel     parallel over frames: lse[t] = logsumexp_c logits[t, c] and the table
+//                     lp[t][s] = logits[t, l'_s] - lse[t]
+//   ctc_recur_kernel  the only sequential part (T = 750 frames at cfg-5): ONE WARP per
+//                     (utterance, direction) - alpha forwards and beta backwards run concurrently
+//                     on different SMs - with the states in registers, neighbours by shuffle and
+//                     the lp rows prefetched 8 frames ahead: no block barrier, no shared memory,
+//                     no dependent global load on the chain.  (Round 1 walked alpha then beta in
+//                     one CTA with two block barriers and an L2 round trip per frame: 1.84 ms at
+//                     cfg-5 against 0.64 ms for ATen's log_softmax + ctc_loss forward.)
+//                     nll = -logsumexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
+//   ctc_grad_kernel   parallel over frames: occ_t(c) = sum_{s: l'_s = c} exp(alpha_t(s) +
+//                     beta_t(s) - lp_t(s) + nll) (<= 1) through shared-memory atomics and
+//                     d nll / d logits[t, c] = softmax_t(c) - occ_t(c)   (0 for t >= input length)
 // fp32 throughout (torch's ctc_loss also runs its log-space recursion in the input dtype).
 #include "ssb_common.cuh"
 #include <math_constants.h>
@@ -35,160 +38,245 @@ struct CtcParams {
   const int64_t* targets;         // (N, Lmax)
   const int64_t* in_len;          // (N)
   const int64_t* tgt_len;         // (N)
-  int T, C, Lmax, blank, Sp;      // Sp = padded row length of the alpha workspace
+  int T, C, Lmax, blank, Sp;      // Sp = 32 * KS: row pitch of the per-frame state tables
   int mean_reduction;             // gradient scaled by 1 / (N * max(L, 1))
   int N;
-  float* alpha;                   // workspace (N, T, Sp)
+  // workspace tables
+  float* lp;                      // (N, T, Sp)  log-softmax of frame t at the label of state s
+  float* alpha;                   // (N, T, Sp)  alpha_t(s) relative to zoff[t]
+  float* beta;                    // (N, T, Sp)  beta_t(s) relative to yoff[t]
+  float* lse;                     // (N, T)
+  double* zoff;                   // (N, T)
+  double* yoff;                   // (N, T)
+  double* nlld;                   // (N)
   float* nll;                     // (N)
   float* grad;                    // (N, T, C) or null
 };
 
-// block-wide max of v over the threads with `active`; every thread gets the result.
-// wm: [32] floats of shared memory.  Two barriers.
-__device__ __forceinline__ float block_max(float v, float* wm) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = ssb::warp_max(v);
-  if (lane == 0) wm[warp] = v;
-  __syncthreads();
-  float m = lane < nw ? wm[lane] : -CUDART_INF_F;
-  m = ssb::warp_max(m);
-  __syncthreads();
-  return m;
-}
-
 constexpr int RENORM = 8;   // steps between renormalisations of the log-space recursions
 
-__global__ void ctc_fused_kernel(const CtcParams p) {
-  extern __shared__ double smem_d[];
-  const int n = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+__device__ __forceinline__ int ext_label(const int64_t* tg, int s, int blank) {
+  return (s & 1) ? (int)__ldg(tg + (s >> 1)) : blank;
+}
+
+// ---- phase 1 (parallel over frames): lse[t] and lp[t][s] -------------------------------------
+__global__ void __launch_bounds__(256) ctc_lp_kernel(const CtcParams p) {
+  const int n = blockIdx.y, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int L = (int)min((int64_t)p.Lmax, max((int64_t)0, p.tgt_len[n]));
   const int S = 2 * L + 1;
   const int Tn = (int)min((int64_t)p.T, max((int64_t)0, p.in_len[n]));
-  const int Cp = (p.C + 31) / 32 * 32;
-  // Log-space values drift by ~log(1/C) per frame: after 750 frames |alpha| ~ 2500, where one
-  // fp32 ulp is 2.4e-4 and the occupancies exp(alpha + beta + nll) lose 3 digits.  Both
-  // recursions are therefore kept RELATIVE to a running offset (zoff[t], accumulated in double
-  // and bumped to the current maximum every RENORM frames), so the stored values stay O(10).
-  double* zoff = smem_d;                          // [T] offset of the stored alpha_t
-  float* lse = reinterpret_cast<float*>(zoff + p.T);   // [T]
-  float* buf = lse + p.T;                         // [2][Sp + 4]
-  float* occ = buf + 2 * (p.Sp + 4);              // [2][Cp]
-  float* wm = occ + 2 * Cp;                       // [32]
-  const int bstride = p.Sp + 4;
-  const float* X = p.logits + (int64_t)n * p.T * p.C;
-  float* A = p.alpha + (int64_t)n * p.T * p.Sp;
+  if (t >= Tn) return;
+  const float* x = p.logits + ((int64_t)n * p.T + t) * p.C;
+  float m = -CUDART_INF_F;
+  for (int c = lane; c < p.C; c += 32) m = fmaxf(m, __ldg(x + c));
+  m = ssb::warp_max(m);
+  float sum = 0.f;
+  for (int c = lane; c < p.C; c += 32) sum += expf(__ldg(x + c) - m);
+  sum = ssb::warp_sum(sum);
+  const float lse = m + logf(sum);
+  if (lane == 0) p.lse[(int64_t)n * p.T + t] = lse;
+  const int64_t* tg = p.targets + (int64_t)n * p.Lmax;
+  float* row = p.lp + ((int64_t)n * p.T + t) * p.Sp;
+  for (int s = lane; s < p.Sp; s += 32)
+    row[s] = s < S ? __ldg(x + ext_label(tg, s, p.blank)) - lse : 0.f;
+}
+
+// ---- phase 2 (sequential over frames): one WARP per (utterance, direction) ---------------------
+// Lane l keeps states l*KS .. l*KS + KS-1 of the blank-extended target in registers; the two
+// neighbours a step needs from the adjacent lane come by shuffle, so a frame costs no block
+// barrier and no shared memory.  The lp rows are prefetched PFD frames ahead into registers (the
+// recursion would otherwise pay one L2 round trip per frame).  Log-space values drift by
+// ~log(1/C) per frame (|alpha| ~ 2500 after 750 frames, one fp32 ulp = 2.4e-4 there), so both
+// recursions are kept RELATIVE to a running offset, accumulated in double and bumped to the
+// current maximum every RENORM frames; the stored values stay O(10).
+template <int KS>
+__global__ void __launch_bounds__(32) ctc_recur_kernel(const CtcParams p) {
+  constexpr int PFD = KS <= 8 ? 8 : (KS <= 16 ? 4 : 2);
+  const int n = blockIdx.x, lane = threadIdx.x;
+  const bool is_beta = blockIdx.y != 0;
+  const int L = (int)min((int64_t)p.Lmax, max((int64_t)0, p.tgt_len[n]));
+  const int S = 2 * L + 1;
+  const int Tn = (int)min((int64_t)p.T, max((int64_t)0, p.in_len[n]));
   const float NEG = -CUDART_INF_F;
-
-  // labels of the extended sequence
-  int label = p.blank;
-  bool skip_in = false, skip_out = false;         // may come from s-2 / may go to s+2
-  if (tid < S && (tid & 1)) {
-    const int64_t* tg = p.targets + (int64_t)n * p.Lmax;
-    label = (int)tg[tid >> 1];
-    skip_in = tid >= 3 && label != (int)tg[(tid >> 1) - 1];
-    skip_out = tid + 2 < S && label != (int)tg[(tid >> 1) + 1];
+  const int64_t* tg = p.targets + (int64_t)n * p.Lmax;
+  const float* LP = p.lp + (int64_t)n * p.T * p.Sp + lane * KS;
+  float* OUT = (is_beta ? p.beta : p.alpha) + (int64_t)n * p.T * p.Sp + lane * KS;
+  double* OFF = (is_beta ? p.yoff : p.zoff) + (int64_t)n * p.T;
+  if (Tn == 0) {
+    if (!is_beta && lane == 0) { p.nll[n] = CUDART_INF_F; p.nlld[n] = (double)CUDART_INF_F; }
+    return;
   }
-  // phase 1: row log-sum-exp
-  for (int t = warp; t < Tn; t += nwarps) {
-    float m = NEG;
-    for (int c = lane; c < p.C; c += 32) m = fmaxf(m, X[(int64_t)t * p.C + c]);
-    m = ssb::warp_max(m);
-    float sum = 0.f;
-    for (int c = lane; c < p.C; c += 32) sum += expf(X[(int64_t)t * p.C + c] - m);
-    sum = ssb::warp_sum(sum);
-    if (lane == 0) lse[t] = m + logf(sum);
-  }
-  for (int i = tid; i < 2 * bstride; i += nthr) buf[i] = NEG;
-  for (int i = tid; i < 2 * Cp; i += nthr) occ[i] = 0.f;
-  __syncthreads();
-
-  double nll = (double)CUDART_INF_F;
-  if (Tn > 0) {
-    // phase 2: alpha (states s at index s + 2: two -inf pads in front)
-    double Z = 0.0;
-    if (tid < S) {
-      const float a0 = tid < 2 ? X[label] - lse[0] : NEG;
-      buf[tid + 2] = a0;
-      A[tid] = a0;
-    }
-    if (tid == 0) zoff[0] = 0.0;
-    __syncthreads();
-    for (int t = 1; t < Tn; ++t) {
-      const float* prev = buf + ((t - 1) & 1) * bstride;
-      float* cur = buf + (t & 1) * bstride;
-      float a = NEG;
-      if (tid < S)
-        a = lse3(prev[tid + 2], prev[tid + 1], skip_in ? prev[tid] : NEG) +
-            (X[(int64_t)t * p.C + label] - lse[t]);
-      if (t % RENORM == 0) {
-        const float m = block_max(a, wm);
-        if (m > NEG) { a -= m; Z += (double)m; }
-      }
-      if (tid < S) {
-        cur[tid + 2] = a;
-        A[(int64_t)t * p.Sp + tid] = a;
-      }
-      if (tid == 0) zoff[t] = Z;
-      __syncthreads();
-    }
-    // phase 3
-    const float* last = buf + ((Tn - 1) & 1) * bstride;
-    const float tail = lse2(last[S - 1 + 2], S >= 2 ? last[S - 2 + 2] : NEG);
-    nll = tail > NEG ? -(Z + (double)tail) : (double)CUDART_INF_F;
-  }
-  __syncthreads();
-  if (tid == 0) p.nll[n] = (float)nll;
-  if (!p.grad) return;
-  float* G = p.grad + (int64_t)n * p.T * p.C;
-  for (int i = Tn * p.C + tid; i < p.T * p.C; i += nthr) G[i] = 0.f;   // padding frames
-  if (Tn == 0) return;
-  const bool feasible = nll < (double)CUDART_INF_F;
-  const float scale = p.mean_reduction ? 1.f / ((float)p.N * (float)max(L, 1)) : 1.f;
-  // phase 4: beta (states at index s: two -inf pads BEHIND), class occupancies, gradient
-  for (int i = tid; i < 2 * bstride; i += nthr) buf[i] = NEG;
-  __syncthreads();
-  double Y = 0.0;
-  for (int t = Tn - 1; t >= 0; --t) {
-    const float* nxt = buf + ((t + 1) & 1) * bstride;
-    float* cur = buf + (t & 1) * bstride;
-    float* oc = occ + (t & 1) * Cp;
-    float b = NEG, lp = 0.f;
-    if (tid < S) {
-      lp = X[(int64_t)t * p.C + label] - lse[t];
-      if (t == Tn - 1) b = tid >= S - 2 ? lp : NEG;
-      else b = lse3(nxt[tid], nxt[tid + 1], skip_out ? nxt[tid + 2] : NEG) + lp;
-    }
-    if (t % RENORM == 0) {
-      const float m = block_max(b, wm);
-      if (m > NEG) { b -= m; Y += (double)m; }
-    }
-    if (tid < S) {
-      cur[tid] = b;
-      if (feasible) {
-        // alpha_t(s) beta_t(s) / (y_t(l'_s) p(l|x)) with the offsets put back in double
-        const float off = (float)(zoff[t] + Y + nll);
-        const float v = A[(int64_t)t * p.Sp + tid] + b - lp + off;
-        if (v > -80.f) atomicAdd(oc + label, expf(fminf(v, 0.f)));
+  // which states may take the skip transition (from s-2 for alpha, to s+2 for beta)
+  uint32_t skip = 0, valid = 0;
+#pragma unroll
+  for (int i = 0; i < KS; ++i) {
+    const int s = lane * KS + i;
+    if (s < S) {
+      valid |= 1u << i;
+      if (s & 1) {
+        const int lab = (int)__ldg(tg + (s >> 1));
+        if (!is_beta && s >= 3 && lab != (int)__ldg(tg + (s >> 1) - 1)) skip |= 1u << i;
+        if (is_beta && s + 2 < S && lab != (int)__ldg(tg + (s >> 1) + 1)) skip |= 1u << i;
       }
     }
-    __syncthreads();
-    if (tid < p.C) {
-      const float sm = expf(X[(int64_t)t * p.C + tid] - lse[t]);
-      G[(int64_t)t * p.C + tid] = feasible ? (sm - oc[tid]) * scale : 0.f;
-      oc[tid] = 0.f;   // reused at step t - 2, after the barrier of step t - 1
+  }
+  const int t0 = is_beta ? Tn - 1 : 0, dt = is_beta ? -1 : 1;
+  float pf[PFD][KS];
+#pragma unroll
+  for (int d = 0; d < PFD; ++d) {
+    const int t = t0 + dt * d;
+    const bool ok = t >= 0 && t < Tn;
+#pragma unroll
+    for (int i = 0; i < KS; ++i) pf[d][i] = ok ? LP[(int64_t)t * p.Sp + i] : 0.f;
+  }
+  float a[KS];
+#pragma unroll
+  for (int i = 0; i < KS; ++i) a[i] = NEG;
+  double Z = 0.0;
+  // The frame loop is unrolled by the prefetch depth so that ring slot d is a fixed set of
+  // registers: a slot is consumed, then immediately refilled with the row PFD frames ahead, and
+  // nothing touches those registers until their turn comes round again (a rotating copy would
+  // stall every frame on the load issued the frame before).
+  for (int k0 = 0; k0 < Tn; k0 += PFD) {
+#pragma unroll
+    for (int d = 0; d < PFD; ++d) {
+      const int k = k0 + d;
+      if (k >= Tn) break;
+      const int t = t0 + dt * k;
+      float lp[KS];
+#pragma unroll
+      for (int i = 0; i < KS; ++i) lp[i] = pf[d][i];
+      {
+        const int tn = t + dt * PFD;
+        if (tn >= 0 && tn < Tn) {
+#pragma unroll
+          for (int i = 0; i < KS; ++i) pf[d][i] = LP[(int64_t)tn * p.Sp + i];
+        }
+      }
+      float nv[KS];
+      if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < KS; ++i) {
+          const int s = lane * KS + i;
+          const bool on = is_beta ? (s < S && s >= S - 2) : (s < 2 && s < S);
+          nv[i] = on ? lp[i] : NEG;
+        }
+      } else {
+        // neighbours held by the adjacent lane: n1 = one state away, n2 = two states away
+        float n1, n2;
+        if (!is_beta) {      // states lane*KS - 1 and lane*KS - 2
+          n1 = __shfl_up_sync(0xffffffffu, a[KS - 1], 1);
+          n2 = KS >= 2 ? __shfl_up_sync(0xffffffffu, a[KS >= 2 ? KS - 2 : 0], 1)
+                       : __shfl_up_sync(0xffffffffu, a[0], 2);
+          if (lane == 0) { n1 = NEG; n2 = NEG; }
+          if (KS == 1 && lane == 1) n2 = NEG;
+        } else {             // states (lane+1)*KS and (lane+1)*KS + 1
+          n1 = __shfl_down_sync(0xffffffffu, a[0], 1);
+          n2 = KS >= 2 ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
+                       : __shfl_down_sync(0xffffffffu, a[0], 2);
+          if (lane == 31) { n1 = NEG; n2 = NEG; }
+          if (KS == 1 && lane == 30) n2 = NEG;
+        }
+#pragma unroll
+        for (int i = 0; i < KS; ++i) {
+          float x1, x2;
+          if (!is_beta) {
+            x1 = i >= 1 ? a[i >= 1 ? i - 1 : 0] : n1;
+            x2 = i >= 2 ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? n1 : n2);
+          } else {
+            x1 = i + 1 < KS ? a[i + 1 < KS ? i + 1 : 0] : n1;
+            x2 = i + 2 < KS ? a[i + 2 < KS ? i + 2 : 0] : (i + 1 < KS ? n1 : n2);
+          }
+          const float v = lse3(a[i], x1, ((skip >> i) & 1u) ? x2 : NEG) + lp[i];
+          nv[i] = ((valid >> i) & 1u) ? v : NEG;
+        }
+      }
+      if (t % RENORM == 0 && (is_beta || k > 0)) {
+        float m = NEG;
+#pragma unroll
+        for (int i = 0; i < KS; ++i) m = fmaxf(m, nv[i]);
+        m = ssb::warp_max(m);
+        if (m > NEG) {
+#pragma unroll
+          for (int i = 0; i < KS; ++i) nv[i] -= m;
+          Z += (double)m;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < KS; ++i) {
+        a[i] = nv[i];
+        OUT[(int64_t)t * p.Sp + i] = nv[i];
+      }
+      if (lane == 0) OFF[t] = Z;
     }
+  }
+  if (!is_beta) {   // nll = -logsumexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
+    float e1 = NEG, e2 = NEG;
+#pragma unroll
+    for (int i = 0; i < KS; ++i) {
+      const int s = lane * KS + i;
+      if (s == S - 1) e1 = a[i];
+      if (s == S - 2) e2 = a[i];
+    }
+    e1 = ssb::warp_max(e1);
+    e2 = ssb::warp_max(e2);
+    const float tail = lse2(e1, e2);
+    const double nll = tail > NEG ? -(Z + (double)tail) : (double)CUDART_INF_F;
+    if (lane == 0) { p.nll[n] = (float)nll; p.nlld[n] = nll; }
   }
 }
+
+// ---- phase 3 (parallel over frames): class occupancies and the gradient -----------------------
+//   occ_t(c) = sum_{s: l'_s = c} exp(alpha_t(s) + beta_t(s) - lp_t(s) + nll)   (<= 1)
+//   d nll / d logits[t, c] = softmax_t(c) - occ_t(c)      (0 for t >= input length)
+__global__ void __launch_bounds__(128) ctc_grad_kernel(const CtcParams p) {
+  extern __shared__ float occ[];
+  const int n = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+  const int L = (int)min((int64_t)p.Lmax, max((int64_t)0, p.tgt_len[n]));
+  const int S = 2 * L + 1;
+  const int Tn = (int)min((int64_t)p.T, max((int64_t)0, p.in_len[n]));
+  float* G = p.grad + ((int64_t)n * p.T + t) * p.C;
+  const double nll = p.nlld[n];
+  const bool feasible = nll < (double)CUDART_INF_F;
+  if (t >= Tn || !feasible) {
+    for (int c = tid; c < p.C; c += blockDim.x) G[c] = 0.f;
+    return;
+  }
+  for (int c = tid; c < p.C; c += blockDim.x) occ[c] = 0.f;
+  __syncthreads();
+  const int64_t row = (int64_t)n * p.T + t;
+  const float off = (float)(p.zoff[row] + p.yoff[row] + nll);
+  const int64_t* tg = p.targets + (int64_t)n * p.Lmax;
+  for (int s = tid; s < S; s += blockDim.x) {
+    const float v = p.alpha[row * p.Sp + s] + p.beta[row * p.Sp + s] - p.lp[row * p.Sp + s] + off;
+    if (v > -80.f) atomicAdd(occ + ext_label(tg, s, p.blank), expf(fminf(v, 0.f)));
+  }
+  __syncthreads();
+  const float scale = p.mean_reduction ? 1.f / ((float)p.N * (float)max(L, 1)) : 1.f;
+  const float lse = p.lse[row];
+  const float* x = p.logits + row * p.C;
+  for (int c = tid; c < p.C; c += blockDim.x) G[c] = (expf(__ldg(x + c) - lse) - occ[c]) * scale;
+}
+
+int ks_for(int64_t Lmax) {
+  const int64_t need = (2 * Lmax + 1 + 31) / 32;
+  int ks = 1;
+  while (ks < need) ks <<= 1;
+  return ks;   // 1, 2, 4, 8, 16, 32
+}
+
+int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
 
 }  // namespace
 
 extern "C" {
 
 int64_t ssb_ctc_workspace_bytes(int64_t N, int64_t T, int64_t Lmax) {
-  if (N < 0 || T < 0 || Lmax < 0) return SSB_ERR_ARG;
-  const int64_t Sp = (2 * Lmax + 1 + 31) / 32 * 32;
-  return N * T * Sp * 4;
+  if (N < 0 || T < 0 || Lmax < 0 || 2 * Lmax + 1 > 1024) return SSB_ERR_ARG;
+  const int64_t Sp = 32 * ks_for(Lmax);
+  return 3 * align256(N * T * Sp * 4) + align256(N * T * 4) + 2 * align256(N * T * 8) +
+         align256(N * 8) + 256;
 }
 
 int ssb_ctc_loss_fused(const float* logits, int64_t N, int64_t T, int64_t C, const int64_t* targets,
@@ -199,30 +287,49 @@ int ssb_ctc_loss_fused(const float* logits, int64_t N, int64_t T, int64_t C, con
   SSB_REQUIRE(logits && input_lengths && target_lengths && nll && workspace,
               "ctc_loss_fused: null argument");
   SSB_REQUIRE(targets || Lmax == 0, "ctc_loss_fused: null targets");
-  SSB_REQUIRE(N > 0 && T > 0 && C > 0 && C <= 1024 && blank >= 0 && blank < C,
+  SSB_REQUIRE(N > 0 && N <= 65535 && T > 0 && C > 0 && C <= 1024 && blank >= 0 && blank < C,
               "ctc_loss_fused: N=%lld T=%lld C=%lld blank=%lld", (long long)N, (long long)T,
               (long long)C, (long long)blank);
   SSB_REQUIRE(2 * Lmax + 1 <= 1024, "ctc_loss_fused: targets longer than 511 symbols (Lmax=%lld)",
               (long long)Lmax);
   SSB_REQUIRE(workspace_bytes >= ssb_ctc_workspace_bytes(N, T, Lmax),
               "ctc_loss_fused: workspace too small");
+  SSB_REQUIRE(((uintptr_t)workspace & 255) == 0, "ctc_loss_fused: workspace must be 256 B aligned");
+  static const int64_t dummy_target = 0;   // Lmax == 0: never dereferenced (no odd state exists)
+  (void)dummy_target;
+  const int ks = ks_for(Lmax);
   CtcParams p;
   p.logits = logits; p.targets = targets; p.in_len = input_lengths; p.tgt_len = target_lengths;
   p.T = (int)T; p.C = (int)C; p.Lmax = (int)Lmax; p.blank = (int)blank;
-  p.Sp = (int)((2 * Lmax + 1 + 31) / 32 * 32);
+  p.Sp = 32 * ks;
   p.mean_reduction = mean_reduction; p.N = (int)N;
-  p.alpha = (float*)workspace; p.nll = nll; p.grad = grad_logits;
-  int threads = p.Sp;
-  const int cpad = (int)((C + 31) / 32 * 32);
-  if (threads < cpad) threads = cpad;
-  if (threads < 128) threads = 128;
-  const size_t smem = (size_t)T * 8 + ((size_t)T + 2 * (p.Sp + 4) + 2 * cpad + 32) * 4;
-  SSB_REQUIRE(smem <= 200 * 1024, "ctc_loss_fused: T=%lld too long for shared memory", (long long)T);
-  if (smem > 48 * 1024)
-    SSB_CUDA(cudaFuncSetAttribute(ctc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-  ctc_fused_kernel<<<(unsigned)N, threads, smem, (cudaStream_t)stream>>>(p);
-  SSB_LAUNCH_CHECK("ctc_fused");
+  char* w = (char*)workspace;
+  const int64_t tab = align256(N * T * p.Sp * 4);
+  p.lp = (float*)w; w += tab;
+  p.alpha = (float*)w; w += tab;
+  p.beta = (float*)w; w += tab;
+  p.lse = (float*)w; w += align256(N * T * 4);
+  p.zoff = (double*)w; w += align256(N * T * 8);
+  p.yoff = (double*)w; w += align256(N * T * 8);
+  p.nlld = (double*)w;
+  p.nll = nll; p.grad = grad_logits;
+  cudaStream_t st = (cudaStream_t)stream;
+  ctc_lp_kernel<<<dim3((unsigned)((T + 7) / 8), (unsigned)N), 256, 0, st>>>(p);
+  SSB_LAUNCH_CHECK("ctc_lp_kernel");
+  const dim3 rgrid((unsigned)N, grad_logits ? 2u : 1u);   // alpha only when no gradient is wanted
+  switch (ks) {
+    case 1: ctc_recur_kernel<1><<<rgrid, 32, 0, st>>>(p); break;
+    case 2: ctc_recur_kernel<2><<<rgrid, 32, 0, st>>>(p); break;
+    case 4: ctc_recur_kernel<4><<<rgrid, 32, 0, st>>>(p); break;
+    case 8: ctc_recur_kernel<8><<<rgrid, 32, 0, st>>>(p); break;
+    case 16: ctc_recur_kernel<16><<<rgrid, 32, 0, st>>>(p); break;
+    default: ctc_recur_kernel<32><<<rgrid, 32, 0, st>>>(p); break;
+  }
+  SSB_LAUNCH_CHECK("ctc_recur_kernel");
+  if (grad_logits) {
+    ctc_grad_kernel<<<dim3((unsigned)T, (unsigned)N), 128, (size_t)C * 4, st>>>(p);
+    SSB_LAUNCH_CHECK("ctc_grad_kernel");
+  }
   return SSB_OK;
 }
 
