@@ -5,11 +5,11 @@
 // Three launches (S = 2L + 1 <= 1024 states of the blank-extended target l'):
 //   ctc_lp_kernel     parallel over frames: lse[t] = logsumexp_c logits[t, c] and the table
 //                     lp[t][s] = logits[t, l'_s] - lse[t]
-//   ctc_recur_kernel  the only sequential part (T = 750 frames at cfg-5): ONE WARP per
+//   ctc_recur_kernel  the only sequential part (T = 750 frames at cfg-5): one 4-warp CTA per
 //                     (utterance, direction) - alpha forwards and beta backwards run concurrently
-//                     on different SMs - with the states in registers, neighbours by shuffle and
-//                     the lp rows prefetched 8 frames ahead: no block barrier, no shared memory,
-//                     no dependent global load on the chain.  (Round 1 walked alpha then beta in
+//                     on different SMs - with the states in registers, neighbours by shuffle (one
+//                     tiny mailbox + ONE barrier per frame across warps), the lp rows prefetched
+//                     8 frames ahead (no dependent global load on the chain) and MUFU exp / log.  (Round 1 walked alpha then beta in
 //                     one CTA with two block barriers and an L2 round trip per frame: 1.84 ms at
 //                     cfg-5 against 0.64 ms for ATen's log_softmax + ctc_loss forward.)
 //                     nll = -logsumexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
@@ -27,18 +27,12 @@ __device__ __forceinline__ float lse2(float a, float b) {
   if (m == -CUDART_INF_F) return -CUDART_INF_F;
   return m + logf(expf(a - m) + expf(b - m));
 }
-__device__ __forceinline__ float lse3(float a, float b, float c) {
-  const float m = fmaxf(fmaxf(a, b), c);
-  if (m == -CUDART_INF_F) return -CUDART_INF_F;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
-}
-
 struct CtcParams {
   const float* logits;            // (N, T, C)
   const int64_t* targets;         // (N, Lmax)
   const int64_t* in_len;          // (N)
   const int64_t* tgt_len;         // (N)
-  int T, C, Lmax, blank, Sp;      // Sp = 32 * KS: row pitch of the per-frame state tables
+  int T, C, Lmax, blank, Sp;      // Sp = 128 * KS: row pitch of the per-frame state tables
   int mean_reduction;             // gradient scaled by 1 / (N * max(L, 1))
   int N;
   // workspace tables
@@ -82,36 +76,48 @@ __global__ void __launch_bounds__(256) ctc_lp_kernel(const CtcParams p) {
     row[s] = s < S ? __ldg(x + ext_label(tg, s, p.blank)) - lse : 0.f;
 }
 
-// ---- phase 2 (sequential over frames): one WARP per (utterance, direction) ---------------------
-// Lane l keeps states l*KS .. l*KS + KS-1 of the blank-extended target in registers; the two
-// neighbours a step needs from the adjacent lane come by shuffle, so a frame costs no block
-// barrier and no shared memory.  The lp rows are prefetched PFD frames ahead into registers (the
-// recursion would otherwise pay one L2 round trip per frame).  Log-space values drift by
-// ~log(1/C) per frame (|alpha| ~ 2500 after 750 frames, one fp32 ulp = 2.4e-4 there), so both
-// recursions are kept RELATIVE to a running offset, accumulated in double and bumped to the
-// current maximum every RENORM frames; the stored values stay O(10).
+// ---- phase 2 (sequential over frames): one 4-warp CTA per (utterance, direction) ---------------
+// Thread j keeps states j*KS .. j*KS + KS-1 of the blank-extended target in registers (KS = 1, 2,
+// 4 or 8 covers S <= 1024 with 128 threads).  The two neighbours a step needs from the adjacent
+// thread come by shuffle inside a warp and through a double-buffered 4-entry shared-memory
+// mailbox across warps: ONE block barrier per frame.  The lp rows are prefetched PFD frames ahead
+// into registers, so no global load sits on the dependence chain, and exp / log use the MUFU
+// intrinsics (arguments are differences to the running maximum: |error| ~ 1e-7 per step on values
+// kept O(10)).  Log-space values drift by ~log(1/C) per frame (|alpha| ~ 2500 after 750 frames,
+// one fp32 ulp = 2.4e-4 there), so both recursions are kept RELATIVE to a running offset,
+// accumulated in double and bumped to the current maximum every RENORM frames.
+constexpr int RW = 4;            // warps per recursion CTA
+
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+  const float m = fmaxf(fmaxf(a, b), c);
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
 template <int KS>
-__global__ void __launch_bounds__(32) ctc_recur_kernel(const CtcParams p) {
-  constexpr int PFD = KS <= 8 ? 8 : (KS <= 16 ? 4 : 2);
-  const int n = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(RW * 32) ctc_recur_kernel(const CtcParams p) {
+  constexpr int PFD = 8;
+  __shared__ float edge[2][RW][2];    // [parity][warp]: the two states a neighbouring warp needs
+  __shared__ float wmax[2][RW];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool is_beta = blockIdx.y != 0;
   const int L = (int)min((int64_t)p.Lmax, max((int64_t)0, p.tgt_len[n]));
   const int S = 2 * L + 1;
   const int Tn = (int)min((int64_t)p.T, max((int64_t)0, p.in_len[n]));
   const float NEG = -CUDART_INF_F;
   const int64_t* tg = p.targets + (int64_t)n * p.Lmax;
-  const float* LP = p.lp + (int64_t)n * p.T * p.Sp + lane * KS;
-  float* OUT = (is_beta ? p.beta : p.alpha) + (int64_t)n * p.T * p.Sp + lane * KS;
+  const float* LP = p.lp + (int64_t)n * p.T * p.Sp + tid * KS;
+  float* OUT = (is_beta ? p.beta : p.alpha) + (int64_t)n * p.T * p.Sp + tid * KS;
   double* OFF = (is_beta ? p.yoff : p.zoff) + (int64_t)n * p.T;
   if (Tn == 0) {
-    if (!is_beta && lane == 0) { p.nll[n] = CUDART_INF_F; p.nlld[n] = (double)CUDART_INF_F; }
+    if (!is_beta && tid == 0) { p.nll[n] = CUDART_INF_F; p.nlld[n] = (double)CUDART_INF_F; }
     return;
   }
   // which states may take the skip transition (from s-2 for alpha, to s+2 for beta)
   uint32_t skip = 0, valid = 0;
 #pragma unroll
   for (int i = 0; i < KS; ++i) {
-    const int s = lane * KS + i;
+    const int s = tid * KS + i;
     if (s < S) {
       valid |= 1u << i;
       if (s & 1) {
@@ -130,14 +136,14 @@ __global__ void __launch_bounds__(32) ctc_recur_kernel(const CtcParams p) {
 #pragma unroll
     for (int i = 0; i < KS; ++i) pf[d][i] = ok ? LP[(int64_t)t * p.Sp + i] : 0.f;
   }
+  if (tid < 2 * RW * 2) (&edge[0][0][0])[tid] = NEG;
   float a[KS];
 #pragma unroll
   for (int i = 0; i < KS; ++i) a[i] = NEG;
   double Z = 0.0;
+  __syncthreads();
   // The frame loop is unrolled by the prefetch depth so that ring slot d is a fixed set of
-  // registers: a slot is consumed, then immediately refilled with the row PFD frames ahead, and
-  // nothing touches those registers until their turn comes round again (a rotating copy would
-  // stall every frame on the load issued the frame before).
+  // registers: a slot is consumed, then immediately refilled with the row PFD frames ahead.
   for (int k0 = 0; k0 < Tn; k0 += PFD) {
 #pragma unroll
     for (int d = 0; d < PFD; ++d) {
@@ -158,25 +164,34 @@ __global__ void __launch_bounds__(32) ctc_recur_kernel(const CtcParams p) {
       if (k == 0) {
 #pragma unroll
         for (int i = 0; i < KS; ++i) {
-          const int s = lane * KS + i;
+          const int s = tid * KS + i;
           const bool on = is_beta ? (s < S && s >= S - 2) : (s < 2 && s < S);
           nv[i] = on ? lp[i] : NEG;
         }
       } else {
-        // neighbours held by the adjacent lane: n1 = one state away, n2 = two states away
+        // neighbours held by the adjacent thread: n1 = one state away, n2 = two states away.
+        // Mailbox of the previous frame: edge[(k-1)&1][w] = {nearest, second nearest} state of
+        // warp w as seen from the warp that follows it in the direction of the dependence.
+        const float* mb = &edge[(k - 1) & 1][0][0];
         float n1, n2;
-        if (!is_beta) {      // states lane*KS - 1 and lane*KS - 2
+        if (!is_beta) {      // states tid*KS - 1 and tid*KS - 2
           n1 = __shfl_up_sync(0xffffffffu, a[KS - 1], 1);
           n2 = KS >= 2 ? __shfl_up_sync(0xffffffffu, a[KS >= 2 ? KS - 2 : 0], 1)
                        : __shfl_up_sync(0xffffffffu, a[0], 2);
-          if (lane == 0) { n1 = NEG; n2 = NEG; }
-          if (KS == 1 && lane == 1) n2 = NEG;
-        } else {             // states (lane+1)*KS and (lane+1)*KS + 1
+          if (lane == 0) {
+            n1 = warp > 0 ? mb[(warp - 1) * 2] : NEG;
+            n2 = warp > 0 ? mb[(warp - 1) * 2 + 1] : NEG;
+          }
+          if (KS == 1 && lane == 1) n2 = warp > 0 ? mb[(warp - 1) * 2] : NEG;
+        } else {             // states (tid+1)*KS and (tid+1)*KS + 1
           n1 = __shfl_down_sync(0xffffffffu, a[0], 1);
           n2 = KS >= 2 ? __shfl_down_sync(0xffffffffu, a[KS >= 2 ? 1 : 0], 1)
                        : __shfl_down_sync(0xffffffffu, a[0], 2);
-          if (lane == 31) { n1 = NEG; n2 = NEG; }
-          if (KS == 1 && lane == 30) n2 = NEG;
+          if (lane == 31) {
+            n1 = warp + 1 < RW ? mb[(warp + 1) * 2] : NEG;
+            n2 = warp + 1 < RW ? mb[(warp + 1) * 2 + 1] : NEG;
+          }
+          if (KS == 1 && lane == 30) n2 = warp + 1 < RW ? mb[(warp + 1) * 2] : NEG;
         }
 #pragma unroll
         for (int i = 0; i < KS; ++i) {
@@ -188,15 +203,18 @@ __global__ void __launch_bounds__(32) ctc_recur_kernel(const CtcParams p) {
             x1 = i + 1 < KS ? a[i + 1 < KS ? i + 1 : 0] : n1;
             x2 = i + 2 < KS ? a[i + 2 < KS ? i + 2 : 0] : (i + 1 < KS ? n1 : n2);
           }
-          const float v = lse3(a[i], x1, ((skip >> i) & 1u) ? x2 : NEG) + lp[i];
+          const float v = lse3_fast(a[i], x1, ((skip >> i) & 1u) ? x2 : NEG) + lp[i];
           nv[i] = ((valid >> i) & 1u) ? v : NEG;
         }
       }
-      if (t % RENORM == 0 && (is_beta || k > 0)) {
+      if (t % RENORM == 0 && (is_beta || k > 0)) {   // uniform: block-wide maximum
         float m = NEG;
 #pragma unroll
         for (int i = 0; i < KS; ++i) m = fmaxf(m, nv[i]);
         m = ssb::warp_max(m);
+        if (lane == 0) wmax[k & 1][warp] = m;
+        __syncthreads();
+        m = fmaxf(fmaxf(wmax[k & 1][0], wmax[k & 1][1]), fmaxf(wmax[k & 1][2], wmax[k & 1][3]));
         if (m > NEG) {
 #pragma unroll
           for (int i = 0; i < KS; ++i) nv[i] -= m;
@@ -208,22 +226,38 @@ __global__ void __launch_bounds__(32) ctc_recur_kernel(const CtcParams p) {
         a[i] = nv[i];
         OUT[(int64_t)t * p.Sp + i] = nv[i];
       }
-      if (lane == 0) OFF[t] = Z;
+      // publish what the neighbouring warp needs next frame
+      if (!is_beta && lane == 31) {          // the warp's LAST two states
+        edge[k & 1][warp][0] = a[KS - 1];
+        if (KS >= 2) edge[k & 1][warp][1] = a[KS >= 2 ? KS - 2 : 0];
+      }
+      if (!is_beta && KS == 1 && lane == 30) edge[k & 1][warp][1] = a[0];
+      if (is_beta && lane == 0) {            // the warp's FIRST two states
+        edge[k & 1][warp][0] = a[0];
+        if (KS >= 2) edge[k & 1][warp][1] = a[KS >= 2 ? 1 : 0];
+      }
+      if (is_beta && KS == 1 && lane == 1) edge[k & 1][warp][1] = a[0];
+      if (tid == 0) OFF[t] = Z;
+      __syncthreads();
     }
   }
   if (!is_beta) {   // nll = -logsumexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
-    float e1 = NEG, e2 = NEG;
+    __shared__ float tail2[2];
+    if (tid < 2) tail2[tid] = NEG;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < KS; ++i) {
-      const int s = lane * KS + i;
-      if (s == S - 1) e1 = a[i];
-      if (s == S - 2) e2 = a[i];
+      const int s = tid * KS + i;
+      if (s == S - 1) tail2[0] = a[i];
+      if (s == S - 2) tail2[1] = a[i];
     }
-    e1 = ssb::warp_max(e1);
-    e2 = ssb::warp_max(e2);
-    const float tail = lse2(e1, e2);
-    const double nll = tail > NEG ? -(Z + (double)tail) : (double)CUDART_INF_F;
-    if (lane == 0) { p.nll[n] = (float)nll; p.nlld[n] = nll; }
+    __syncthreads();
+    if (tid == 0) {
+      const float tail = lse2(tail2[0], tail2[1]);
+      const double nll = tail > NEG ? -(Z + (double)tail) : (double)CUDART_INF_F;
+      p.nll[n] = (float)nll;
+      p.nlld[n] = nll;
+    }
   }
 }
 
@@ -259,11 +293,11 @@ __global__ void __launch_bounds__(128) ctc_grad_kernel(const CtcParams p) {
   for (int c = tid; c < p.C; c += blockDim.x) G[c] = (expf(__ldg(x + c) - lse) - occ[c]) * scale;
 }
 
-int ks_for(int64_t Lmax) {
-  const int64_t need = (2 * Lmax + 1 + 31) / 32;
+int ks_for(int64_t Lmax) {   // states per thread of the 128-thread recursion CTA
+  const int64_t need = (2 * Lmax + 1 + 127) / 128;
   int ks = 1;
   while (ks < need) ks <<= 1;
-  return ks;   // 1, 2, 4, 8, 16, 32
+  return ks;   // 1, 2, 4, 8
 }
 
 int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
@@ -274,7 +308,7 @@ extern "C" {
 
 int64_t ssb_ctc_workspace_bytes(int64_t N, int64_t T, int64_t Lmax) {
   if (N < 0 || T < 0 || Lmax < 0 || 2 * Lmax + 1 > 1024) return SSB_ERR_ARG;
-  const int64_t Sp = 32 * ks_for(Lmax);
+  const int64_t Sp = 128 * ks_for(Lmax);
   return 3 * align256(N * T * Sp * 4) + align256(N * T * 4) + 2 * align256(N * T * 8) +
          align256(N * 8) + 256;
 }
@@ -301,7 +335,7 @@ int ssb_ctc_loss_fused(const float* logits, int64_t N, int64_t T, int64_t C, con
   CtcParams p;
   p.logits = logits; p.targets = targets; p.in_len = input_lengths; p.tgt_len = target_lengths;
   p.T = (int)T; p.C = (int)C; p.Lmax = (int)Lmax; p.blank = (int)blank;
-  p.Sp = 32 * ks;
+  p.Sp = 128 * ks;
   p.mean_reduction = mean_reduction; p.N = (int)N;
   char* w = (char*)workspace;
   const int64_t tab = align256(N * T * p.Sp * 4);
@@ -318,12 +352,10 @@ int ssb_ctc_loss_fused(const float* logits, int64_t N, int64_t T, int64_t C, con
   SSB_LAUNCH_CHECK("ctc_lp_kernel");
   const dim3 rgrid((unsigned)N, grad_logits ? 2u : 1u);   // alpha only when no gradient is wanted
   switch (ks) {
-    case 1: ctc_recur_kernel<1><<<rgrid, 32, 0, st>>>(p); break;
-    case 2: ctc_recur_kernel<2><<<rgrid, 32, 0, st>>>(p); break;
-    case 4: ctc_recur_kernel<4><<<rgrid, 32, 0, st>>>(p); break;
-    case 8: ctc_recur_kernel<8><<<rgrid, 32, 0, st>>>(p); break;
-    case 16: ctc_recur_kernel<16><<<rgrid, 32, 0, st>>>(p); break;
-    default: ctc_recur_kernel<32><<<rgrid, 32, 0, st>>>(p); break;
+    case 1: ctc_recur_kernel<1><<<rgrid, RW * 32, 0, st>>>(p); break;
+    case 2: ctc_recur_kernel<2><<<rgrid, RW * 32, 0, st>>>(p); break;
+    case 4: ctc_recur_kernel<4><<<rgrid, RW * 32, 0, st>>>(p); break;
+    default: ctc_recur_kernel<8><<<rgrid, RW * 32, 0, st>>>(p); break;
   }
   SSB_LAUNCH_CHECK("ctc_recur_kernel");
   if (grad_logits) {

@@ -94,6 +94,8 @@ def test_fused_loss_launches_only_library_kernels():
     from torch.profiler import ProfilerActivity, profile
     from silent_speech_b200.losses import dtw_loss
     batch = _ragged_batch(seed=11)
+    for k in ('audio_features', 'phonemes'):               # targets already on the device
+        batch[k] = [t.cuda() for t in batch[k]]
     pred, phon = _preds_for(batch, 3)
     pg, qg = pred.cuda().requires_grad_(True), phon.cuda().requires_grad_(True)
     dtw_loss(pg, qg, batch)[0].backward()                  # warm-up: plan tables, lazy init
@@ -107,7 +109,7 @@ def test_fused_loss_launches_only_library_kernels():
     ours = [n for n in names if any(k in n for k in ("dtw_cost", "dtw_fill", "dtw_backtrace",
                                                      "dtw_loss_rows"))]
     assert len(ours) == 4, names
-    assert len(names) <= 24, names
+    assert len(names) <= 16, names                          # + cat x2, sum, div, backward scaling
 
 
 def test_voiced_only_and_silent_only_batches():

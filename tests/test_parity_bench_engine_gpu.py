@@ -23,10 +23,25 @@ from silent_speech_b200.read_emg import synthetic_batch
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# measured on B200 (round 2): worst parameter 2.6e-3 ... see DESIGN.md; asserted at <= 2x measured
-OUT_TOL = 2e-4
-GRAD_TOL = 2e-2        # TIGHTENED below per family once measured
-GRAD_TOL_BY_FAMILY = {}
+# Measured on B200 (round 2, gpurun_out/parity_cfg1_backward.json -> DESIGN.md section 2), rel-L2
+# vs the fp64 oracle; bounds are <= 2x the measured worst of each group:
+#   outputs                       1.9e-5
+#   heads (w_out, w_aux)          2.0e-5
+#   attention, norms, linear2, w_raw_in   <= 2.0e-3
+#   linear1 (feeds the FFN ReLU)  <= 5.2e-3
+#   conv stack (3 ReLUs deep)     <= 7.4e-3
+# The pattern is the ReLU-kink effect: a forward perturbation delta flips ~delta of the masks and
+# moves the gradients below by ~sqrt(delta); the same test prints the fp32 CPU oracle's own error
+# against fp64 (the floor any fp32 implementation has) next to ours.
+OUT_TOL = 4e-5
+GRAD_TOL_GROUPS = (("w_out", 4e-5), ("w_aux", 4e-5), ("conv_blocks", 1.5e-2), ("linear1", 1.1e-2),
+                   ("", 4e-3))
+
+
+def _grad_tol(family):
+    for key, tol in GRAD_TOL_GROUPS:
+        if key in family:
+            return tol
 
 
 def _flags(D, NL, p):
@@ -82,15 +97,28 @@ def test_cfg1_width_forward_backward_parity_tensor_cores():
         f = _family(k)
         per_family[f] = max(per_family.get(f, 0.0), e)
     worst = max(per_param.items(), key=lambda kv: kv[1])
+    # the floor: the reference formulation itself in fp32 (CPU oracle) against fp64
+    sd32 = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k
+                else v.clone()) for k, v in sd0.items()}
+    random.seed(2)
+    op32, oa32 = om.model_forward(sd32, x.clone(), training=True, dropout_p=0.0)
+    ((op32 * gp).sum() + (oa32 * ga).sum()).backward()
+    floor = {}
+    for k in per_param:
+        f = _family(k)
+        floor[f] = max(floor.get(f, 0.0), rel(sd32[k].grad, sd[k].grad))
     rec = {"config": "768/6, B=2, L=4000 (T=500), dropout 0, default engine vs fp64 oracle",
-           "outputs_rel_l2": out_err, "worst_grad": worst, "grad_rel_l2_by_family": per_family}
+           "outputs_rel_l2": out_err, "worst_grad": worst, "grad_rel_l2_by_family": per_family,
+           "fp32_cpu_oracle_vs_fp64": {"outputs": rel(op32.detach(), op.detach()),
+                                       "worst_grad": max(floor.items(), key=lambda kv: kv[1]),
+                                       "grad_rel_l2_by_family": floor}}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "parity_cfg1_backward.json"), "w") as f:
         json.dump(rec, f, indent=1, sort_keys=True)
     print(json.dumps(rec, indent=1, sort_keys=True))
     assert out_err["pred"] < OUT_TOL and out_err["aux"] < OUT_TOL, out_err
     for f, e in per_family.items():
-        assert e < GRAD_TOL_BY_FAMILY.get(f, GRAD_TOL), (f, e)
+        assert e < _grad_tol(f), (f, e)
 
 
 def _clone_batch(b):

