@@ -39,10 +39,11 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 201
+#define SSB_ABI_VERSION 202
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
- * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t;
+ * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
+ * 6: ssb_prep_entry_t;
  * -1 otherwise), so a foreign-language
  * binding can verify its mirror of the layouts at load time. */
 SSB_API int64_t ssb_sizeof(int which);
@@ -374,6 +375,29 @@ SSB_API int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, co
                        int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW, float drop_p,
                        uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
                        void* stream);
+
+/* ---- weight operand preparation (csrc/prep.cu) -----------------------------------------------
+ * One launch writes the bf16 hi/lo split planes of every parameter in every layout the tensor-core
+ * GEMMs of a step consume (replaces the per-use `.t().contiguous()` / cat / split passes over
+ * nn.Linear, nn.Conv1d and the attention projection weights: architecture.py:18-24,51-59,
+ * transformer.py:32-34,71-78).  Entry = a strided 2-D view of one fp32 parameter,
+ *   view(r, c) = src[(r / RL) * s_rhi + (r % RL) * s_rlo + (c / CL) * s_chi + (c % CL) * s_clo],
+ * written as planes to dst_n[r * ld_n + c] (hi; lo at + plane_n elements) and / or transposed to
+ * dst_t[c * ld_t + r] (lo at + plane_t).  ssb_prep_plan (HOST) fills tile0 / tiles_c and returns
+ * the total tile count (negative on error); the caller uploads the table. */
+typedef struct ssb_prep_entry {
+  const float* src;
+  void* dst_n;            /* bf16, nullable */
+  void* dst_t;            /* bf16, nullable */
+  int64_t plane_n, plane_t;
+  int64_t s_rhi, s_rlo, s_chi, s_clo;
+  int32_t rows, cols, RL, CL;
+  int32_t ld_n, ld_t;
+  int32_t tile0, tiles_c; /* filled by ssb_prep_plan */
+} ssb_prep_entry_t;
+SSB_API int64_t ssb_prep_plan(ssb_prep_entry_t* table_host, int64_t n_entries);
+SSB_API int ssb_prep_planes(const ssb_prep_entry_t* table_dev, int64_t n_entries,
+                            int64_t total_tiles, void* stream);
 
 /* ---- fused log_softmax + CTC loss (csrc/ctc.cu) ------------------------------------------------
  * Replaces recognition_model.py:96-101: F.log_softmax(pred, 2) -> pad_sequence ->

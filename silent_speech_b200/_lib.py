@@ -62,6 +62,14 @@ class Utt(ctypes.Structure):
                 ("reserved_", c_i32)]
 
 
+class PrepEntry(ctypes.Structure):
+    """ssb_prep_entry_t"""
+    _fields_ = [("src", c_ptr), ("dst_n", c_ptr), ("dst_t", c_ptr), ("plane_n", c_i64),
+                ("plane_t", c_i64), ("s_rhi", c_i64), ("s_rlo", c_i64), ("s_chi", c_i64),
+                ("s_clo", c_i64), ("rows", c_i32), ("cols", c_i32), ("RL", c_i32), ("CL", c_i32),
+                ("ld_n", c_i32), ("ld_t", c_i32), ("tile0", c_i32), ("tiles_c", c_i32)]
+
+
 _PT = ctypes.POINTER(TcOperand)
 _PG = ctypes.POINTER(Gather)
 _PE = ctypes.POINTER(Epilogue)
@@ -88,6 +96,8 @@ _SIGNATURES = {
     "ssb_dtw_loss_rows": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64,
                                          c_i64, c_i64, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr,
                                          c_ptr]),
+    "ssb_prep_plan": (c_i64, [c_ptr, c_i64]),
+    "ssb_prep_planes": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_ptr]),
     "ssb_mel_num_frames": (c_i64, [c_i64, ctypes.c_int, ctypes.c_int]),
     "ssb_mel_fwd": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_f32, c_ptr,
@@ -144,7 +154,7 @@ _SIGNATURES = {
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
 _KERNELS_PER_CALL = {
     "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_dtw_time_warp_batch_f64": 1, "ssb_dtw_align_ragged": 2, "ssb_dtw_cost_batch": 1,
-    "ssb_dtw_loss_rows": 1, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
+    "ssb_dtw_loss_rows": 1, "ssb_prep_planes": 1, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
     "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 3, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
@@ -203,7 +213,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 201      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 202      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):
@@ -216,7 +226,7 @@ def _check_abi(lib):
                            f"rebuild (python -m silent_speech_b200.build --force)")
     lib.ssb_sizeof.restype = c_i64
     lib.ssb_sizeof.argtypes = [ctypes.c_int]
-    for which, cls in enumerate((Gather, Scatter, Epilogue, TcOperand, DtwPair, Utt)):
+    for which, cls in enumerate((Gather, Scatter, Epilogue, TcOperand, DtwPair, Utt, PrepEntry)):
         if lib.ssb_sizeof(which) != ctypes.sizeof(cls):
             raise SSBError(-4, f"struct layout mismatch for {cls.__name__}: library "
                                f"{lib.ssb_sizeof(which)} B, ctypes {ctypes.sizeof(cls)} B")

@@ -9,6 +9,7 @@ Data flow (channels-last, no NCL transposes): x_raw (B, L, 8) -> 3 x ResBlock as
 GEMMs + fused BatchNorm/ReLU/residual kernels -> (B*T, D) tokens -> w_raw_in -> N encoder
 layers (transformer.py mirror) -> output heads.
 """
+import os
 import random
 
 import torch
@@ -17,6 +18,7 @@ from absl import flags
 
 from . import functional as F_
 from .transformer import TransformerEncoder, TransformerEncoderLayer
+from .weights import WeightPlanes
 
 FLAGS = flags.FLAGS
 for _define, _name, _default, _help in (
@@ -66,18 +68,18 @@ class ResBlock(nn.Module):
             bn.num_batches_tracked += 1
         return bn.weight, bn.bias, bn.running_mean, bn.running_var
 
-    def forward_cl(self, x):
-        """x: (B, L, Cin) channels-last -> (B, Lout, Cout)."""
+    def forward_cl(self, x, wp=None):
+        """x: (B, L, Cin) channels-last -> (B, Lout, Cout).  wp: the model's WeightPlanes arena."""
         if self.residual_path is None:
             raise NotImplementedError("identity residual is never instantiated by the reference "
                                       "(architecture.py:46-50) and is not built")
         tr = self.training
-        c1 = F_.conv1d_cl(x, _conv_weight(self.conv1), self.conv1.bias, 3, self.stride)
+        c1 = F_.conv1d_w(x, self.conv1, wp, 3, self.stride, lambda: _conv_weight(self.conv1))
         h1 = F_.bn_act(c1, *self._bn_args(self.bn1), training=tr, relu=True,
                        momentum=self.bn1.momentum, eps=self.bn1.eps)
-        c2 = F_.conv1d_cl(h1, _conv_weight(self.conv2), self.conv2.bias, 3, 1)
-        cr = F_.conv1d_cl(x, _conv_weight(self.residual_path), self.residual_path.bias, 1,
-                          self.stride)
+        c2 = F_.conv1d_w(h1, self.conv2, wp, 3, 1, lambda: _conv_weight(self.conv2))
+        cr = F_.conv1d_w(x, self.residual_path, wp, 1, self.stride,
+                         lambda: _conv_weight(self.residual_path))
         ga, ba, rma, rva = self._bn_args(self.bn2)
         gb, bb, rmb, rvb = self._bn_args(self.res_norm)
         return F_.bn_act(c2, ga, ba, rma, rva, tr, True, cr, gb, bb, rmb, rvb,
@@ -113,6 +115,17 @@ class Model(nn.Module):
         # reference.  A 0-d int64 device tensor: the shift is read from it at execution time
         # (training.GraphedTrainStep draws it on the host and fills the cell before each replay).
         self.shift_source = None
+        self._wp = None     # WeightPlanes arena, created at the first CUDA forward
+
+    def weight_planes(self, device):
+        """Every weight's tensor-core operand layouts, made current by one launch (weights.py).
+        SSB_WPLANES=0 falls back to deriving them per use (round-1 path, A/B testing)."""
+        if device.type != "cuda" or not F_._tc_enabled() or os.environ.get("SSB_WPLANES", "1") == "0":
+            return None
+        if self._wp is None or self._wp.model is not self:
+            self._wp = WeightPlanes(self)
+        self._wp.refresh()
+        return self._wp
 
     def forward(self, x_feat, x_raw, session_ids):
         # x_raw is (batch, time, electrode); x_feat and session_ids are ignored, as in the
@@ -126,13 +139,14 @@ class Model(nn.Module):
                     x_raw[:, :-r, :] = x_raw[:, r:, :].clone()
                     x_raw[:, -r:, :] = 0
         x = x_raw.to(torch.float32).contiguous()
+        wp = self.weight_planes(x.device)
         for blk in self.conv_blocks:
-            x = blk.forward_cl(x)
+            x = blk.forward_cl(x, wp)
         B, T, D = x.shape
-        x2 = F_.linear(x.view(B * T, D), self.w_raw_in.weight.t().contiguous(), self.w_raw_in.bias)
-        x2 = self.transformer.forward_tokens(x2, B, T)
-        out = F_.linear(x2, self.w_out.weight.t().contiguous(), self.w_out.bias).view(B, T, -1)
+        x2 = F_.linear_w(x.view(B * T, D), self.w_raw_in, wp)
+        x2 = self.transformer.forward_tokens(x2, B, T, wp)
+        out = F_.linear_w(x2, self.w_out, wp).view(B, T, -1)
         if self.has_aux_out:
-            aux = F_.linear(x2, self.w_aux.weight.t().contiguous(), self.w_aux.bias).view(B, T, -1)
+            aux = F_.linear_w(x2, self.w_aux, wp).view(B, T, -1)
             return out, aux
         return out

@@ -52,6 +52,7 @@ int64_t ssb_sizeof(int which) {
     case 3: return (int64_t)sizeof(ssb_tc_operand_t);
     case 4: return (int64_t)sizeof(ssb_dtw_pair_t);
     case 5: return (int64_t)sizeof(ssb_utt_t);
+    case 6: return (int64_t)sizeof(ssb_prep_entry_t);
     default: return -1;
   }
 }

@@ -409,27 +409,29 @@ class _FFNNativeFn(torch.autograd.Function):
     parameter layout (dW^T = dy^T x) - straight into the gradient bucket when one is registered."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2, p, seed, site):
+    def forward(ctx, x, w1, b1, w2, b2, p, seed, site, w1f=None, w1t=None, w2f=None, w2t=None):
+        """w1f / w2f: [F][K] / [N][F] planes of the weights as they lie, w1t / w2t: planes of their
+        transposes (WeightPlanes arena); None -> derived here with a split pass."""
         _chk(x, "x"), _chk(w1, "w1"), _chk(w2, "w2")
         M, K = x.shape
         F_, N = w1.shape[0], w2.shape[0]
         dev = x.device
         xp = planes_of(x)
         hp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
-        gemm_tc_kmajor(tc_operand_plain(xp, M, K), split_planes(w1), F_, K,
+        gemm_tc_kmajor(tc_operand_plain(xp, M, K), w1f if w1f is not None else split_planes(w1), F_, K,
                        _epi(_scatter_plain(None, M, F_), bias=b1, relu=1, drop_p=p, seed=seed,
                             site=site, planes_out=hp))
         y = torch.empty((M, N), dtype=_f32, device=dev)
-        gemm_tc_kmajor(tc_operand_plain(hp, M, F_), split_planes(w2), N, F_,
+        gemm_tc_kmajor(tc_operand_plain(hp, M, F_), w2f if w2f is not None else split_planes(w2), N, F_,
                        _epi(_scatter_plain(y.data_ptr(), M, N), bias=b2))
-        ctx.save_for_backward(w1, w2, xp, hp)
+        ctx.save_for_backward(w1, w2, xp, hp, w1t, w2t)
         ctx.p = p
         ctx.sinks = tuple(_sink(t) for t in (w1, b1, w2, b2))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        w1, w2, xp, hp = ctx.saved_tensors
+        w1, w2, xp, hp, w1t, w2t = ctx.saved_tensors
         s_w1, s_b1, s_w2, s_b2 = ctx.sinks
         dy = dy.contiguous()
         M, K = xp.shape[1:]
@@ -441,34 +443,183 @@ class _FFNNativeFn(torch.autograd.Function):
         gemm_tc_wgrad(tc_operand_plain(dyp, M, N), hp, F_, N, dW2, accumulate=s_w2 is not None)
         db2 = colsum(dy, out=s_b2, accumulate=s_b2 is not None)
         dhp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
-        gemm_tc_kmajor(tc_operand_plain(dyp, M, N), split_planes_t(w2), F_, N,
+        gemm_tc_kmajor(tc_operand_plain(dyp, M, N), w2t if w2t is not None else split_planes_t(w2), F_, N,
                        _epi(_scatter_plain(None, M, F_), mask_planes=hp[0], mask_scale=scale,
                             planes_out=dhp))
         dW1 = s_w1 if s_w1 is not None else torch.empty_like(w1)          # (F, K) = dh^T x
         gemm_tc_wgrad(tc_operand_plain(dhp, M, F_), xp, K, F_, dW1, accumulate=s_w1 is not None)
         db1 = colsum_planes(dhp, out=s_b1, accumulate=s_b1 is not None)
         dx = torch.empty((M, K), dtype=_f32, device=dev)
-        gemm_tc_kmajor(tc_operand_plain(dhp, M, F_), split_planes_t(w1), K, F_,
+        gemm_tc_kmajor(tc_operand_plain(dhp, M, F_), w1t if w1t is not None else split_planes_t(w1), K, F_,
                        _epi(_scatter_plain(dx.data_ptr(), M, K)))
         return (dx, None if s_w1 is not None else dW1, None if s_b1 is not None else db1,
                 None if s_w2 is not None else dW2, None if s_b2 is not None else db2,
-                None, None, None)
+                None, None, None, None, None, None, None)
 
 
-def ffn_native(x2d, w1, b1, w2, b2, p=0.0, seed=0, site=0):
-    """FFN on nn.Linear-layout weights (linear1.weight (F, K), linear2.weight (N, F))."""
+def ffn_native(x2d, w1, b1, w2, b2, p=0.0, seed=0, site=0, wp=None):
+    """FFN on nn.Linear-layout weights (linear1.weight (F, K), linear2.weight (N, F)); `wp`: the
+    model's WeightPlanes arena (weight operands without per-use split passes)."""
     M, K = x2d.shape
     F_, N = w1.shape[0], w2.shape[0]
     ok = (_tc_fwd_ok(M, F_, K) and _tc_fwd_ok(M, N, F_) and _tc_fwd_ok(M, K, F_)
           and _tc_fwd_ok(M, F_, N) and _tc_wgrad_ok(M, F_, N) and _tc_wgrad_ok(M, K, F_)
           and K % 8 == 0 and b1 is not None and b2 is not None)
     if ok:
-        return _FFNNativeFn.apply(x2d, w1, b1, w2, b2, float(p), int(seed), int(site))
+        pl = [None] * 4
+        if wp is not None:
+            pl = [wp.get(w1, "f"), wp.get(w1, "b"), wp.get(w2, "f"), wp.get(w2, "b")]
+            if any(t is None for t in pl):
+                pl = [None] * 4
+        return _FFNNativeFn.apply(x2d, w1, b1, w2, b2, float(p), int(seed), int(site), *pl)
     return ffn(x2d, w1.t().contiguous(), b1, w2.t().contiguous(), b2, p, seed, site)
 
 
 def ffn(x2d, W1g, b1, W2g, b2, p=0.0, seed=0, site=0):
     return _FFNFn.apply(x2d, W1g, b1, W2g, b2, float(p), int(seed), int(site))
+
+
+# ------------------------------------------------------------------------------------------
+# Weight-plane variants: the same ops on the PARAMETERS themselves (reference shapes), with every
+# weight operand layout taken from the model's WeightPlanes arena (weights.py, csrc/prep.cu: one
+# launch per step) instead of `.t().contiguous()` / cat / split passes per use, and with weight
+# gradients written straight into the gradient bucket where the GEMM can produce the parameter's
+# own layout.
+# ------------------------------------------------------------------------------------------
+class _LinearWFn(torch.autograd.Function):
+    """y = x @ weight^T + bias on an nn.Linear-layout weight (N, K).  wf: [N][K] planes (forward
+    operand), wb: [K][N] planes (data-gradient operand); both required."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, wf, wb):
+        _chk(x, "x")
+        M, K = x.shape
+        N = weight.shape[0]
+        y = torch.empty((M, N), dtype=_f32, device=x.device)
+        xp = planes_of(x)
+        gemm_tc_kmajor(tc_operand_plain(xp, M, K), wf, N, K,
+                       _epi(_scatter_plain(y.data_ptr(), M, N), bias=bias))
+        native = K % 8 == 0 and N % 128 == 0          # dW^T = dy^T x in parameter layout
+        ctx.save_for_backward(x, weight, wb, xp if ctx.needs_input_grad[1] else None)
+        ctx.native = native
+        ctx.sink_w = _sink(weight) if native else None
+        ctx.sink_b = _sink(bias) if bias is not None else None
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, wb, xp = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, K = x.shape
+        N = weight.shape[0]
+        dx = dW = db = None
+        dyp = planes_of(dy)
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            gemm_tc_kmajor(tc_operand_plain(dyp, M, N), wb, K, N, _epi(_scatter_plain(dx.data_ptr(), M, K)))
+        if ctx.needs_input_grad[1]:
+            if ctx.native:
+                dW = ctx.sink_w if ctx.sink_w is not None else torch.empty_like(weight)
+                gemm_tc_wgrad(tc_operand_plain(dyp, M, N), xp, K, N, dW, accumulate=ctx.sink_w is not None)
+                if ctx.sink_w is not None:
+                    dW = None
+            elif _tc_wgrad_ok(M, N, K):
+                dWg = torch.empty((K, N), dtype=_f32, device=x.device)
+                gemm_tc_wgrad(tc_operand_plain(xp, M, K), dyp, N, K, dWg)
+                dW = dWg.t()
+            else:
+                dWg = torch.empty((K, N), dtype=_f32, device=x.device)
+                gemm_tn(_gather_plain(x.data_ptr(), M, K, K), dy, dWg, M, N, K)
+                dW = dWg.t()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if ctx.sink_b is not None:
+                colsum(dy, out=ctx.sink_b, accumulate=True)
+            else:
+                db = colsum(dy)
+        return dx, dW, db, None, None
+
+
+def linear_w(x2d, lin, wp):
+    """nn.Linear `lin` applied to token-major x2d through the WeightPlanes arena `wp` when its
+    shape is tensor-core eligible both ways; otherwise the round-1 path."""
+    w = lin.weight
+    N, K = w.shape
+    wf = wp.get(w, "f") if wp is not None else None
+    wb = wp.get(w, "b") if wp is not None else None
+    M = x2d.shape[0]
+    if wf is not None and wb is not None and _tc_fwd_ok(M, N, K) and _tc_fwd_ok(M, K, N):
+        return _LinearWFn.apply(x2d, w, lin.bias, wf, wb)
+    return linear(x2d, w.t().contiguous(), lin.bias)
+
+
+class _QKVFn(torch.autograd.Function):
+    """qkv = x @ [Wq | Wk | Wv] for the per-head weights w_j (H, D, dh) of transformer.py:71-74
+    (no bias).  wf: [3D][D] planes, wb: [D][3D] planes of the fused matrix."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, wf, wb):
+        _chk(x, "x")
+        M, D = x.shape
+        y = torch.empty((M, 3 * D), dtype=_f32, device=x.device)
+        xp = planes_of(x)
+        gemm_tc_kmajor(tc_operand_plain(xp, M, D), wf, 3 * D, D, _epi(_scatter_plain(y.data_ptr(), M, 3 * D)))
+        ctx.save_for_backward(xp, wb)
+        ctx.wshape = tuple(wq.shape)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, wb = ctx.saved_tensors
+        H, D, dh = ctx.wshape
+        dy = dy.contiguous()
+        M = dy.shape[0]
+        dyp = planes_of(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, D), dtype=_f32, device=dy.device)
+            gemm_tc_kmajor(tc_operand_plain(dyp, M, 3 * D), wb, D, 3 * D,
+                           _epi(_scatter_plain(dx.data_ptr(), M, D)))
+        dWg = torch.empty((D, 3 * D), dtype=_f32, device=dy.device)
+        gemm_tc_wgrad(tc_operand_plain(xp, M, D), dyp, 3 * D, D, dWg)
+        # column (j, h, a) of dWg is d w_j[h, :, a]
+        g = [dWg[:, j * D:(j + 1) * D].view(D, H, dh).permute(1, 0, 2) for j in range(3)]
+        return dx, g[0], g[1], g[2], None, None
+
+
+class _OutProjFn(torch.autograd.Function):
+    """y = o @ Wo with w_o (H, dh, D) = the GEMM-layout matrix [K][N] (transformer.py:111).
+    wf: [N][K] planes, wb: [K][N] planes.  dWo comes out of the GEMM in the parameter's layout."""
+
+    @staticmethod
+    def forward(ctx, o, w_o, wf, wb):
+        _chk(o, "o")
+        M, K = o.shape
+        N = w_o.shape[2]
+        y = torch.empty((M, N), dtype=_f32, device=o.device)
+        op = planes_of(o)
+        gemm_tc_kmajor(tc_operand_plain(op, M, K), wf, N, K, _epi(_scatter_plain(y.data_ptr(), M, N)))
+        ctx.save_for_backward(op, wb, w_o)
+        ctx.sink = _sink(w_o)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        op, wb, w_o = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, N = dy.shape
+        K = op.shape[2]
+        dyp = planes_of(dy)
+        do = None
+        if ctx.needs_input_grad[0]:
+            do = torch.empty((M, K), dtype=_f32, device=dy.device)
+            gemm_tc_kmajor(tc_operand_plain(dyp, M, N), wb, K, N, _epi(_scatter_plain(do.data_ptr(), M, K)))
+        if ctx.sink is not None:
+            gemm_tc_wgrad(tc_operand_plain(op, M, K), dyp, N, K, ctx.sink.view(K, N), accumulate=True)
+            return do, None, None, None
+        dW = torch.empty((K, N), dtype=_f32, device=dy.device)
+        gemm_tc_wgrad(tc_operand_plain(op, M, K), dyp, N, K, dW)
+        return do, dW.view_as(w_o), None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -568,6 +719,90 @@ class _ConvFn(torch.autograd.Function):
 
 def conv1d_cl(x, Wg, bias, ksize, stride):
     return _ConvFn.apply(x, Wg, bias, ksize, stride)
+
+
+class _ConvWFn(torch.autograd.Function):
+    """_ConvFn on the nn.Conv1d parameter itself (Cout, Cin, k) with arena operands: wf =
+    [Cout][(tap, ci)] planes; wd = per-tap-subset data-gradient planes [Cin][(j, co)] in the
+    order the backward uses them (k3 s1: (2,1,0); k3 s2: (1,), (2,0); k1 s2: (0,))."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, ksize, stride, wf, wd0, wd1):
+        _chk(x, "x")
+        B, L, Cin = x.shape
+        Cout = weight.shape[0]
+        Lout = (L - 1) // stride + 1
+        y = torch.empty((B, Lout, Cout), dtype=_f32, device=x.device)
+        off = -1 if ksize == 3 else 0
+        xp = planes_of(x)
+        gemm_tc_kmajor(tc_operand_conv(xp, B, L, Cin, Lout, stride, 1, off), wf, Cout, ksize * Cin,
+                       _epi(Scatter(y.data_ptr(), Lout * Cout, Lout, Cout, 1, 0), bias=bias))
+        ctx.save_for_backward(x, xp if ctx.needs_input_grad[1] else None, wd0, wd1)
+        ctx.cfg = (ksize, stride, bias is not None, tuple(weight.shape))
+        ctx.sink_b = _sink(bias) if bias is not None else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, xp, wd0, wd1 = ctx.saved_tensors
+        ksize, stride, has_bias, wshape = ctx.cfg
+        Cout, Cin, _ = wshape
+        dy = dy.contiguous()
+        B, L, _ = x.shape
+        Lout = dy.shape[1]
+        M = B * Lout
+        K = ksize * Cin
+        off = -1 if ksize == 3 else 0
+        dyp = planes_of(dy)
+        dx = dW = db = None
+        if ctx.needs_input_grad[1]:
+            dWg = torch.empty((K, Cout), dtype=_f32, device=x.device)
+            xpl = xp if xp is not None else planes_of(x)
+            gemm_tc_wgrad(tc_operand_conv(xpl, B, L, Cin, Lout, stride, 1, off), dyp, Cout, K, dWg)
+            dW = dWg.view(ksize, Cin, Cout).permute(2, 1, 0)       # -> (Cout, Cin, k)
+        if has_bias and ctx.needs_input_grad[2]:
+            if ctx.sink_b is not None:
+                colsum(dy.view(M, Cout), out=ctx.sink_b, accumulate=True)
+            else:
+                db = colsum(dy.view(M, Cout))
+        if ctx.needs_input_grad[0]:
+            def run(rows, taps, tap_off, planes, d_t, d_off, dst):
+                gemm_tc_kmajor(tc_operand_conv(dyp, B, Lout, Cout, rows, 1, 1, tap_off), planes, Cin,
+                               taps * Cout, _epi(Scatter(dst.data_ptr(), L * Cin, rows, Cin, d_t, d_off)))
+            if ksize == 3 and stride == 1:
+                dx = torch.empty_like(x)
+                run(L, 3, -1, wd0, 1, 0, dx)
+            elif ksize == 3 and stride == 2:
+                dx = torch.empty_like(x)
+                ne, no = (L + 1) // 2, L // 2
+                run(ne, 1, 0, wd0, 2, 0, dx)             # even rows: dy[t] . W_1^T
+                if no > 0:
+                    run(no, 2, 0, wd1, 2, 1, dx)         # odd rows: dy[t] . W_2^T + dy[t+1] . W_0^T
+            else:
+                dx = torch.zeros_like(x)
+                run((L + 1) // 2, 1, 0, wd0, 2, 0, dx)
+        return dx, dW, db, None, None, None, None, None
+
+
+_CONV_TAPMAPS = {(3, 1): [(2, 1, 0)], (3, 2): [(1,), (2, 0)], (1, 2): [(0,)]}
+
+
+def conv1d_w(x, conv, wp, ksize, stride, gemm_weight):
+    """nn.Conv1d `conv` on channels-last x through the WeightPlanes arena `wp` when eligible;
+    `gemm_weight()` lazily builds the (k*Cin, Cout) matrix of the round-1 path otherwise."""
+    w = conv.weight
+    Cout, Cin, _ = w.shape
+    B, L, _ = x.shape
+    Lout = (L - 1) // stride + 1
+    wf = wp.get(w, "conv_f") if wp is not None else None
+    tms = _CONV_TAPMAPS.get((ksize, stride), [])
+    wd = [wp.get(w, ("conv_d", tm)) for tm in tms] if wp is not None else []
+    ok = (wf is not None and wd and all(d is not None for d in wd)
+          and _tc_fwd_ok(B * Lout, Cout, ksize * Cin, Cin) and _tc_wgrad_ok(B * Lout, Cout, ksize * Cin, Cin)
+          and _tc_fwd_ok(B * L // max(stride, 1), Cin, Cout, Cout))
+    if ok:
+        return _ConvWFn.apply(x, w, conv.bias, ksize, stride, wf, wd[0], wd[1] if len(wd) > 1 else None)
+    return conv1d_cl(x, gemm_weight(), conv.bias, ksize, stride)
 
 
 # ------------------------------------------------------------------------------------------

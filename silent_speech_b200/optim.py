@@ -12,6 +12,7 @@ captured CUDA graph.  It is a `torch.optim.Optimizer`, so `ReduceLROnPlateau`
 import torch
 
 from . import _lib
+from . import weights
 
 
 class FlatAdamW(torch.optim.Optimizer):
@@ -61,6 +62,7 @@ class FlatAdamW(torch.optim.Optimizer):
             self.exp_avg_sq.data_ptr(), self.flat_param.numel(), self.lr_cell.data_ptr(),
             self.step_cell.data_ptr(), g['betas'][0], g['betas'][1], g['eps'], g['weight_decay'],
             self.grad_scale, _lib.current_stream()))
+        weights.bump_epoch()     # parameters were written through raw pointers: planes are stale
         return loss
 
     def state_dict(self):

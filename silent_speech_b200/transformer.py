@@ -92,14 +92,24 @@ class MultiHeadAttention(nn.Module):
         blocks = [w.permute(1, 0, 2).reshape(D, D) for w in (self.w_q, self.w_k, self.w_v)]
         return torch.cat(blocks, dim=1)
 
-    def forward_tokens(self, x2d, B, T, seed=0, site=0):
-        """x2d: (B*T, D) token-major -> attention output (B*T, D) (before residual/LN)."""
+    def forward_tokens(self, x2d, B, T, seed=0, site=0, wp=None):
+        """x2d: (B*T, D) token-major -> attention output (B*T, D) (before residual/LN).
+        wp: the model's WeightPlanes arena (fused QKV / out-projection operands)."""
         H, dh, D = self.n_head, self.d_qkv, self.d_model
         p = self.dropout.p if self.training else 0.0
-        qkv = F_.linear(x2d, self.qkv_weight(), None)
+        M = x2d.shape[0]
+        qf = wp.get(self, "qkv_f") if wp is not None else None
+        arena = (qf is not None and F_._tc_fwd_ok(M, 3 * D, D) and F_._tc_fwd_ok(M, D, 3 * D)
+                 and F_._tc_wgrad_ok(M, 3 * D, D) and F_._tc_wgrad_ok(M, D, D))
+        if arena:
+            qkv = F_._QKVFn.apply(x2d, self.w_q, self.w_k, self.w_v, qf, wp.get(self, "qkv_b"))
+        else:
+            qkv = F_.linear(x2d, self.qkv_weight(), None)
         W = self.relative_positional.max_relative_pos - 1
         o = F_.band_attention(qkv, self.relative_positional.padded_table(), B, T, H, dh, W, p, seed,
                               site)
+        if arena:
+            return F_._OutProjFn.apply(o, self.w_o, wp.get(self.w_o, "f"), wp.get(self.w_o, "b"))
         return F_.linear(o, self.w_o.reshape(D, D), None)
 
     def forward(self, x):
@@ -128,15 +138,15 @@ class TransformerEncoderLayer(nn.Module):
         self.dropout2 = nn.Dropout(dropout)
         self.activation = nn.ReLU()
 
-    def forward_tokens(self, x2d, B, T, seed=0, site0=0):
+    def forward_tokens(self, x2d, B, T, seed=0, site0=0, wp=None):
         """x2d: (B*T, D) -> (B*T, D).  Dropout sites site0 .. site0+3 (probs, attn-out, ffn, ffn-out)."""
         tr = self.training
-        a = self.self_attn.forward_tokens(x2d, B, T, seed, site0)
+        a = self.self_attn.forward_tokens(x2d, B, T, seed, site0, wp)
         x1 = F_.add_dropout_layernorm(x2d, a, self.norm1.weight, self.norm1.bias,
                                       self.dropout1.p if tr else 0.0, seed, site0 + 1,
                                       self.norm1.eps)
         f = F_.ffn_native(x1, self.linear1.weight, self.linear1.bias, self.linear2.weight,
-                          self.linear2.bias, self.dropout.p if tr else 0.0, seed, site0 + 2)
+                          self.linear2.bias, self.dropout.p if tr else 0.0, seed, site0 + 2, wp)
         return F_.add_dropout_layernorm(x1, f, self.norm2.weight, self.norm2.bias,
                                         self.dropout2.p if tr else 0.0, seed, site0 + 3,
                                         self.norm2.eps)
@@ -161,12 +171,12 @@ class TransformerEncoder(nn.Module):
         # "gradients of layers >= i are complete" hooks on the layer inputs through it
         self.layer_input_hook = None
 
-    def forward_tokens(self, x2d, B, T):
+    def forward_tokens(self, x2d, B, T, wp=None):
         seed = _fresh_seed() if self.training else 0
         for i, layer in enumerate(self.layers):
             if self.layer_input_hook is not None:
                 self.layer_input_hook(i, x2d)
-            x2d = layer.forward_tokens(x2d, B, T, seed, 4 * i)
+            x2d = layer.forward_tokens(x2d, B, T, seed, 4 * i, wp)
         return x2d
 
     def forward(self, src, mask=None, src_key_padding_mask=None, is_causal=None):
