@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 202
+#define SSB_ABI_VERSION 203
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -249,11 +249,22 @@ SSB_API int ssb_bn_apply(const float* x, const float* mean, const float* scale, 
                          const float* beta2, int relu, int64_t rows, int64_t C, float* y,
                          void* y_planes, void* stream);
 /* BatchNorm backward through an optional ReLU mask (dz = dy * (mask_src > 0)).
- * workspace >= ssb_col_partials_bytes(rows, C) + 8*C bytes. */
+ * accumulate != 0: dgamma / dbeta are ADDED to (they point into a gradient bucket).
+ * workspace >= ssb_col_partials_bytes(rows, C) + 12*C bytes. */
 SSB_API int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const float* mean,
                        const float* rstd, const float* gamma, int training, int64_t rows,
                        int64_t C, float* dx, void* dx_planes, float* dgamma, float* dbeta,
-                       void* workspace, int64_t workspace_bytes, void* stream);
+                       int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+/* The two normalised branches of a ResBlock output, relu(bn2(c2) + res_norm(cr))
+ * (architecture.py:37-40), share dz: one call reads dy and the mask once per pass and produces
+ * both input gradients and both pairs of parameter gradients.  Same workspace rule. */
+SSB_API int ssb_bn_bwd2(const float* dy, const float* mask_src, const float* xa, const float* mean_a,
+                        const float* rstd_a, const float* gamma_a, const float* xb,
+                        const float* mean_b, const float* rstd_b, const float* gamma_b,
+                        int training, int64_t rows, int64_t C, float* dxa, void* dxa_planes,
+                        float* dxb, void* dxb_planes, float* dgamma_a, float* dbeta_a,
+                        float* dgamma_b, float* dbeta_b, int accumulate, void* workspace,
+                        int64_t workspace_bytes, void* stream);
 /* z = res + dropout(branch); y = LayerNorm(z)*gamma + beta   (transformer.py:55-56,58-59) */
 SSB_API int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const float* gamma,
                                    const float* beta, int64_t rows, int64_t D, float eps,
@@ -265,8 +276,8 @@ SSB_API int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float*
                                    const float* rstd, const float* gamma, int64_t rows, int64_t D,
                                    float drop_p, uint64_t seed, uint32_t site, float* d_res,
                                    float* d_branch, void* d_branch_planes, float* dgamma,
-                                   float* dbeta, void* workspace, int64_t workspace_bytes,
-                                   void* stream);
+                                   float* dbeta, int accumulate, void* workspace,
+                                   int64_t workspace_bytes, void* stream);
 
 /* ---- banded relative-position attention ------------------------------------------
  * Replaces transformer.py:99-110 (logits, softmax, dropout, PV) with the relative-position

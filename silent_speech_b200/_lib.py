@@ -138,13 +138,15 @@ _SIGNATURES = {
     "ssb_bn_apply": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64,
                              c_i64, c_ptr, c_ptr, c_ptr]),
     "ssb_bn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_i64, c_i64, c_ptr,
-                           c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+                           c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
+    "ssb_bn_bwd2": (c_int, [c_ptr] * 10 + [c_int, c_i64, c_i64] + [c_ptr] * 8 + [c_int, c_ptr, c_i64,
+                                                                                c_ptr]),
     "ssb_add_dropout_ln_fwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_f32,
                                        c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "ssb_add_dropout_ln_bwd_workspace_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_add_dropout_ln_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32,
-                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                       c_i64, c_ptr]),
+                                       c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int,
+                                       c_ptr, c_i64, c_ptr]),
     "ssb_band_attn_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
     "ssb_band_attn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
@@ -155,8 +157,8 @@ _SIGNATURES = {
 _KERNELS_PER_CALL = {
     "ssb_dtw_align_batch": 2, "ssb_dtw_time_warp_batch": 2, "ssb_dtw_time_warp_batch_f64": 1, "ssb_dtw_align_ragged": 2, "ssb_dtw_cost_batch": 1,
     "ssb_dtw_loss_rows": 1, "ssb_prep_planes": 1, "ssb_mel_fwd": 1, "ssb_gemm_nn": 1,
-    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 3, "ssb_bn_stats": 4, "ssb_bn_apply": 1,
-    "ssb_bn_bwd": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
+    "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 3, "ssb_bn_stats": 2, "ssb_bn_apply": 1,
+    "ssb_bn_bwd": 3, "ssb_bn_bwd2": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
     "ssb_split_bf16": 1, "ssb_split_bf16_t": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,
     "ssb_gemm_tc_batched_tn": 1, "ssb_pad_split_heads": 1, "ssb_transpose_split_heads": 1,
@@ -213,7 +215,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 202      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 203      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):

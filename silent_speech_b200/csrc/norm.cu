@@ -31,9 +31,6 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* planes, int64_t pla
 }
 
 // ---- column partial sums -------------------------------------------------------------
-// MODE 0: sum((x-mean)^2)                         (BatchNorm variance, second pass: the two-pass
-//         form is immune to the cancellation of E[x^2]-mean^2 on near-constant channels, where
-//         a one-pass or shifted one-pass variance lost up to 1e-2 against torch's stable one)
 // MODE 1: sum(x)                                  (bias gradient)
 // MODE 2: sum(dz), sum(dz * xhat)   dz = dy * (mask_src > 0 if mask_src)   (BatchNorm backward)
 // block = 32 column-lanes (float4 each -> 128 columns) x 8 row-lanes
@@ -55,15 +52,8 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
       mu = *reinterpret_cast<const float4*>(mean + c);
       rs = *reinterpret_cast<const float4*>(rstd + c);
     }
-    float4 kk = s0;
-    if (MODE == 0) kk = *reinterpret_cast<const float4*>(mean + c);
     for (int64_t r = r0 + rl; r < r1; r += 8) {
-      if (MODE == 0) {
-        float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
-        v.x -= kk.x; v.y -= kk.y; v.z -= kk.z; v.w -= kk.w;
-        s0.x = fmaf(v.x, v.x, s0.x); s0.y = fmaf(v.y, v.y, s0.y);
-        s0.z = fmaf(v.z, v.z, s0.z); s0.w = fmaf(v.w, v.w, s0.w);
-      } else if (MODE == 1) {
+      if (MODE == 1) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ld + c));
         s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
       } else {
@@ -93,6 +83,48 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
     if (rl == 0 || MODE == 2)
       *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 2 + rl) * C + c) = a;
   }
+}
+
+// Single-pass BatchNorm statistics.  Per 256-row chunk and column the CTA accumulates SHIFTED
+// sums  s = sum(x - k),  q = sum((x - k)^2)  with k = the chunk's own first sample of that column:
+// x - k is then O(std) even when |mean| >> std, so  M2_chunk = q - s^2/n  does not cancel (the
+// round-1 attempt shifted by one GLOBAL value and lost 1e-2 on near-constant channels; it then
+// fell back to two passes over x).  The finalize kernel merges the per-chunk (n, mean, M2)
+// triples in fp64 (Chan et al.'s parallel variance), so the tensor is read ONCE.
+// partials: [nchunks][3][C] = s, q, k.
+__global__ void __launch_bounds__(256)
+bn_chunk_stats_kernel(const float* __restrict__ x, int64_t rows, int C,
+                      float* __restrict__ partials) {
+  __shared__ float4 red[2][8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cl) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * RCH;
+  const int64_t r1 = min(rows, r0 + RCH);
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, kk = s0;
+  if (c < C) {
+    kk = __ldg(reinterpret_cast<const float4*>(x + r0 * C + c));
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C + c));
+      v.x -= kk.x; v.y -= kk.y; v.z -= kk.z; v.w -= kk.w;
+      s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
+      s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y);
+      s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
+    }
+  }
+  red[0][rl][cl] = s0;
+  red[1][rl][cl] = s1;
+  __syncthreads();
+  if (rl < 2 && c < C) {
+    float4 a = red[rl][0][cl];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 b = red[rl][i][cl];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 3 + rl) * C + c) = a;
+  }
+  if (rl == 2 && c < C)
+    *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 3 + 2) * C + c) = kk;
 }
 
 // column sums of a tensor held as bf16 split planes (x = hi + lo): 32 column-lanes x 8 columns
@@ -170,29 +202,54 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
   out[c] = (accumulate ? out[c] : 0.f) + (float)s;
 }
 
-// training, pass 1: mean[c] = sum(x) / count
-__global__ void bn_mean_kernel(const float* __restrict__ partials, int nchunks, int C, double count,
-                               float* __restrict__ mean) {
+// merge of the per-chunk (n, mean, M2) triples -> mean, rstd, scale, shift + running statistics
+__global__ void bn_merge_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+                                         int64_t rows, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* running_mean,
+                                         float* running_var, float momentum, float eps,
+                                         float* __restrict__ mean, float* __restrict__ rstd,
+                                         float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double sh[FIN_LANES][32];
+  __shared__ double mu_sh[32];
   const int c = blockIdx.x * 32 + threadIdx.x;
-  double s, unused;
-  if (!chunk_sums(partials, nchunks, C, 2, c, s, unused)) return;
-  mean[c] = (float)(s / count);
-}
-
-// training, pass 2: centred sum of squares -> (rstd, scale, shift) + running-stat update
-// (biased variance normalises, unbiased variance feeds running_var; nn.BatchNorm1d semantics)
-__global__ void bn_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
-                                   double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean,
-                                   float* running_var, float momentum, float eps,
-                                   const float* __restrict__ mean, float* __restrict__ rstd,
-                                   float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  double m2, unused;
-  if (!chunk_sums(partials, nchunks, C, 2, c, m2, unused)) return;
-  const double mu = (double)mean[c];
+  const double count = (double)rows;
+  // pass 1: global mean = sum_i n_i * mean_i / N,  mean_i = k_i + s_i / n_i
+  double a = 0.0;
+  if (c < C)
+    for (int k = threadIdx.y; k < nchunks; k += FIN_LANES) {
+      const double n = (double)min((int64_t)RCH, rows - (int64_t)k * RCH);
+      a += n * (double)partials[((int64_t)k * 3 + 2) * C + c] + (double)partials[((int64_t)k * 3) * C + c];
+    }
+  sh[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int y = 0; y < FIN_LANES; ++y) t += sh[y][threadIdx.x];
+    mu_sh[threadIdx.x] = t / count;
+  }
+  __syncthreads();
+  const double mu = mu_sh[threadIdx.x];
+  // pass 2: M2 = sum_i [ (q_i - s_i^2 / n_i) + n_i * (mean_i - mu)^2 ]
+  double b = 0.0;
+  if (c < C)
+    for (int k = threadIdx.y; k < nchunks; k += FIN_LANES) {
+      const double n = (double)min((int64_t)RCH, rows - (int64_t)k * RCH);
+      const double si = (double)partials[((int64_t)k * 3) * C + c];
+      const double qi = (double)partials[((int64_t)k * 3 + 1) * C + c];
+      const double d = (double)partials[((int64_t)k * 3 + 2) * C + c] + si / n - mu;
+      b += fmax(qi - si * si / n, 0.0) + n * d * d;
+    }
+  __syncthreads();
+  sh[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  double m2 = 0.0;
+#pragma unroll
+  for (int y = 0; y < FIN_LANES; ++y) m2 += sh[y][threadIdx.x];
   const double var = m2 / count;
   const float r = (float)(1.0 / sqrt(var + (double)eps));
+  mean[c] = (float)mu;
   rstd[c] = r;
   const float sc = gamma[c] * r;
   scale[c] = sc;
@@ -256,14 +313,14 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
 
 // BatchNorm backward, finalize: sums -> dgamma, dbeta and the two per-channel means
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
-                                       double count, float* __restrict__ dgamma,
+                                       double count, int accumulate, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ m_dz,
                                        float* __restrict__ m_dzx) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, sx;
   if (!chunk_sums(partials, nchunks, C, 2, c, s, sx)) return;
-  dbeta[c] = (float)s;
-  dgamma[c] = (float)sx;
+  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s;
+  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sx;
   m_dz[c] = (float)(s / count);
   m_dzx[c] = (float)(sx / count);
 }
@@ -300,6 +357,144 @@ bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask
     o.w = ga.w * rs.w * (g.w - a.w - (v.w - mu.w) * rs.w * bq.w);
     reinterpret_cast<float4*>(dx)[i] = o;
     if (dx_planes) store_planes4(dx_planes, 4 * n4, i, o);
+  }
+}
+
+// ---- two-branch BatchNorm backward (ResBlock output: relu(bn2(c2) + res_norm(cr))) -----------
+// Both branches receive the SAME dz = dy * (y > 0): one pass reads dy and y once for the four
+// column sums, one pass reads them once more and writes both input gradients.
+__global__ void __launch_bounds__(256)
+bn2_bwd_partials_kernel(const float* __restrict__ dy, const float* __restrict__ mask_src,
+                        const float* __restrict__ xa, const float* __restrict__ mean_a,
+                        const float* __restrict__ rstd_a, const float* __restrict__ xb,
+                        const float* __restrict__ mean_b, const float* __restrict__ rstd_b,
+                        int64_t rows, int C, float* __restrict__ partials /* [nchunks][3][C] */) {
+  __shared__ float4 red[3][8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cl) * 4;
+  const int64_t r0 = (int64_t)blockIdx.y * RCH;
+  const int64_t r1 = min(rows, r0 + RCH);
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0;
+  if (c < C) {
+    const float4 ma = *reinterpret_cast<const float4*>(mean_a + c), ra = *reinterpret_cast<const float4*>(rstd_a + c);
+    const float4 mb = *reinterpret_cast<const float4*>(mean_b + c), rb = *reinterpret_cast<const float4*>(rstd_b + c);
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * C + c));
+      if (mask_src) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src + r * C + c));
+        g.x = m.x > 0.f ? g.x : 0.f; g.y = m.y > 0.f ? g.y : 0.f;
+        g.z = m.z > 0.f ? g.z : 0.f; g.w = m.w > 0.f ? g.w : 0.f;
+      }
+      const float4 va = __ldg(reinterpret_cast<const float4*>(xa + r * C + c));
+      const float4 vb = __ldg(reinterpret_cast<const float4*>(xb + r * C + c));
+      s0.x += g.x; s0.y += g.y; s0.z += g.z; s0.w += g.w;
+      s1.x = fmaf(g.x, (va.x - ma.x) * ra.x, s1.x); s1.y = fmaf(g.y, (va.y - ma.y) * ra.y, s1.y);
+      s1.z = fmaf(g.z, (va.z - ma.z) * ra.z, s1.z); s1.w = fmaf(g.w, (va.w - ma.w) * ra.w, s1.w);
+      s2.x = fmaf(g.x, (vb.x - mb.x) * rb.x, s2.x); s2.y = fmaf(g.y, (vb.y - mb.y) * rb.y, s2.y);
+      s2.z = fmaf(g.z, (vb.z - mb.z) * rb.z, s2.z); s2.w = fmaf(g.w, (vb.w - mb.w) * rb.w, s2.w);
+    }
+  }
+  red[0][rl][cl] = s0;
+  red[1][rl][cl] = s1;
+  red[2][rl][cl] = s2;
+  __syncthreads();
+  if (rl < 3 && c < C) {
+    float4 a = red[rl][0][cl];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+      const float4 b = red[rl][i][cl];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 3 + rl) * C + c) = a;
+  }
+}
+
+__global__ void bn2_bwd_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+                                        double count, int accumulate, float* __restrict__ dgamma_a,
+                                        float* __restrict__ dbeta_a, float* __restrict__ dgamma_b,
+                                        float* __restrict__ dbeta_b, float* __restrict__ m_dz,
+                                        float* __restrict__ m_dzx_a, float* __restrict__ m_dzx_b) {
+  __shared__ double sh[3][FIN_LANES][32];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0, b = 0.0, d = 0.0;
+  if (c < C)
+    for (int k = threadIdx.y; k < nchunks; k += FIN_LANES) {
+      a += (double)partials[((int64_t)k * 3) * C + c];
+      b += (double)partials[((int64_t)k * 3 + 1) * C + c];
+      d += (double)partials[((int64_t)k * 3 + 2) * C + c];
+    }
+  sh[0][threadIdx.y][threadIdx.x] = a;
+  sh[1][threadIdx.y][threadIdx.x] = b;
+  sh[2][threadIdx.y][threadIdx.x] = d;
+  __syncthreads();
+  if (threadIdx.y != 0 || c >= C) return;
+  double s = 0.0, sa = 0.0, sb = 0.0;
+#pragma unroll
+  for (int y = 0; y < FIN_LANES; ++y) {
+    s += sh[0][y][threadIdx.x];
+    sa += sh[1][y][threadIdx.x];
+    sb += sh[2][y][threadIdx.x];
+  }
+  dbeta_a[c] = (accumulate ? dbeta_a[c] : 0.f) + (float)s;
+  dbeta_b[c] = (accumulate ? dbeta_b[c] : 0.f) + (float)s;
+  dgamma_a[c] = (accumulate ? dgamma_a[c] : 0.f) + (float)sa;
+  dgamma_b[c] = (accumulate ? dgamma_b[c] : 0.f) + (float)sb;
+  m_dz[c] = (float)(s / count);
+  m_dzx_a[c] = (float)(sa / count);
+  m_dzx_b[c] = (float)(sb / count);
+}
+
+__global__ void __launch_bounds__(256)
+bn2_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ mask_src,
+                     const float* __restrict__ xa, const float* __restrict__ mean_a,
+                     const float* __restrict__ rstd_a, const float* __restrict__ gamma_a,
+                     const float* __restrict__ xb, const float* __restrict__ mean_b,
+                     const float* __restrict__ rstd_b, const float* __restrict__ gamma_b,
+                     const float* __restrict__ m_dz, const float* __restrict__ m_dzx_a,
+                     const float* __restrict__ m_dzx_b, int training, int64_t n4, int C4,
+                     float* __restrict__ dxa, __nv_bfloat16* __restrict__ dxa_planes,
+                     float* __restrict__ dxb, __nv_bfloat16* __restrict__ dxb_planes) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+    if (mask_src) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mask_src) + i);
+      g.x = m.x > 0.f ? g.x : 0.f; g.y = m.y > 0.f ? g.y : 0.f;
+      g.z = m.z > 0.f ? g.z : 0.f; g.w = m.w > 0.f ? g.w : 0.f;
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), qa = a, qb = a;
+    if (training) {
+      a = *reinterpret_cast<const float4*>(m_dz + c);
+      qa = *reinterpret_cast<const float4*>(m_dzx_a + c);
+      qb = *reinterpret_cast<const float4*>(m_dzx_b + c);
+    }
+    {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xa) + i);
+      const float4 mu = *reinterpret_cast<const float4*>(mean_a + c);
+      const float4 rs = *reinterpret_cast<const float4*>(rstd_a + c);
+      const float4 ga = *reinterpret_cast<const float4*>(gamma_a + c);
+      float4 o;
+      o.x = ga.x * rs.x * (g.x - a.x - (v.x - mu.x) * rs.x * qa.x);
+      o.y = ga.y * rs.y * (g.y - a.y - (v.y - mu.y) * rs.y * qa.y);
+      o.z = ga.z * rs.z * (g.z - a.z - (v.z - mu.z) * rs.z * qa.z);
+      o.w = ga.w * rs.w * (g.w - a.w - (v.w - mu.w) * rs.w * qa.w);
+      reinterpret_cast<float4*>(dxa)[i] = o;
+      if (dxa_planes) store_planes4(dxa_planes, 4 * n4, i, o);
+    }
+    {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xb) + i);
+      const float4 mu = *reinterpret_cast<const float4*>(mean_b + c);
+      const float4 rs = *reinterpret_cast<const float4*>(rstd_b + c);
+      const float4 ga = *reinterpret_cast<const float4*>(gamma_b + c);
+      float4 o;
+      o.x = ga.x * rs.x * (g.x - a.x - (v.x - mu.x) * rs.x * qb.x);
+      o.y = ga.y * rs.y * (g.y - a.y - (v.y - mu.y) * rs.y * qb.y);
+      o.z = ga.z * rs.z * (g.z - a.z - (v.z - mu.z) * rs.z * qb.z);
+      o.w = ga.w * rs.w * (g.w - a.w - (v.w - mu.w) * rs.w * qb.w);
+      reinterpret_cast<float4*>(dxb)[i] = o;
+      if (dxb_planes) store_planes4(dxb_planes, 4 * n4, i, o);
+    }
   }
 }
 
@@ -469,13 +664,13 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
 }
 
 __global__ void ln_param_grad_finalize_kernel(const float* __restrict__ partials, int nblk, int D,
-                                              float* __restrict__ dgamma,
+                                              int accumulate, float* __restrict__ dgamma,
                                               float* __restrict__ dbeta) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double a, b;
   if (!chunk_sums(partials, nblk, D, 2, c, a, b)) return;
-  dgamma[c] = (float)a;
-  dbeta[c] = (float)b;
+  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)a;
+  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)b;
 }
 
 int check_rows_c(const void* p, int64_t rows, int64_t C, const char* what) {
@@ -499,7 +694,7 @@ extern "C" {
 
 int64_t ssb_col_partials_bytes(int64_t rows, int64_t C) {
   if (rows < 0 || C < 0) return SSB_ERR_ARG;
-  return (int64_t)nchunks_for(rows > 0 ? rows : 1) * 2 * C * 4;
+  return (int64_t)nchunks_for(rows > 0 ? rows : 1) * 3 * C * 4;   // up to 3 slots per chunk
 }
 
 int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumulate,
@@ -560,17 +755,11 @@ int ssb_bn_stats(const float* x, int64_t rows, int64_t C, const float* gamma, co
               "bn_stats: workspace too small");
   const int nch = nchunks_for(rows);
   dim3 grid(cb, (unsigned)nch);
-  col_partials_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
-                                               (int)C, (float*)workspace);
-  SSB_LAUNCH_CHECK("col_partials<1>");
-  bn_mean_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, mean);
-  SSB_LAUNCH_CHECK("bn_mean");
-  col_partials_kernel<0><<<grid, 256, 0, st>>>(x, nullptr, nullptr, mean, nullptr, rows, (int)C,
-                                               (int)C, (float*)workspace);
-  SSB_LAUNCH_CHECK("col_partials<0>");
-  bn_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, (double)rows, gamma,
-                                         beta, running_mean, running_var, momentum, eps, mean,
-                                         rstd, scale, shift);
+  bn_chunk_stats_kernel<<<grid, 256, 0, st>>>(x, rows, (int)C, (float*)workspace);
+  SSB_LAUNCH_CHECK("bn_chunk_stats");
+  bn_merge_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, rows, gamma,
+                                                   beta, running_mean, running_var, momentum, eps,
+                                                   mean, rstd, scale, shift);
   SSB_LAUNCH_CHECK("bn_finalize");
   return SSB_OK;
 }
@@ -593,24 +782,24 @@ int ssb_bn_apply(const float* x, const float* mean, const float* scale, const fl
 
 int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const float* mean,
                const float* rstd, const float* gamma, int training, int64_t rows, int64_t C,
-               float* dx, void* dx_planes, float* dgamma, float* dbeta, void* workspace,
-               int64_t workspace_bytes, void* stream) {
+               float* dx, void* dx_planes, float* dgamma, float* dbeta, int accumulate,
+               void* workspace, int64_t workspace_bytes, void* stream) {
   if (int rc = check_rows_c(x, rows, C, "bn_bwd")) return rc;
   SSB_REQUIRE(dy && mean && rstd && gamma && dx && dgamma && dbeta, "bn_bwd: null pointer");
-  const int64_t need = ssb_col_partials_bytes(rows, C) + 2 * C * 4;
+  const int64_t need = ssb_col_partials_bytes(rows, C) + 3 * C * 4;
   SSB_REQUIRE(workspace && workspace_bytes >= need, "bn_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int nch = nchunks_for(rows);
   const unsigned cb = (unsigned)((C + 127) / 128);
   float* partials = (float*)workspace;
-  float* m_dz = partials + (int64_t)nch * 2 * C;
+  float* m_dz = partials + (int64_t)nch * 3 * C;
   float* m_dzx = m_dz + C;
   dim3 grid(cb, (unsigned)nch);
   col_partials_kernel<2><<<grid, 256, 0, st>>>(x, dy, mask_src, mean, rstd, rows, (int)C, (int)C,
                                                partials);
   SSB_LAUNCH_CHECK("col_partials<2>");
-  bn_bwd_finalize_kernel<<<FIN_GRID(C), 0, st>>>(partials, nch, (int)C, (double)rows, dgamma, dbeta,
-                                             m_dz, m_dzx);
+  bn_bwd_finalize_kernel<<<FIN_GRID(C), 0, st>>>(partials, nch, (int)C, (double)rows, accumulate,
+                                             dgamma, dbeta, m_dz, m_dzx);
   SSB_LAUNCH_CHECK("bn_bwd_finalize");
   const int64_t n4 = rows * C / 4;
   const int64_t blocks = (n4 + 255) / 256;
@@ -619,6 +808,43 @@ int ssb_bn_bwd(const float* dy, const float* mask_src, const float* x, const flo
                                           training ? m_dz : nullptr, training ? m_dzx : nullptr,
                                           n4, (int)(C / 4), dx, (__nv_bfloat16*)dx_planes);
   SSB_LAUNCH_CHECK("bn_bwd_apply");
+  return SSB_OK;
+}
+
+int ssb_bn_bwd2(const float* dy, const float* mask_src, const float* xa, const float* mean_a,
+                const float* rstd_a, const float* gamma_a, const float* xb, const float* mean_b,
+                const float* rstd_b, const float* gamma_b, int training, int64_t rows, int64_t C,
+                float* dxa, void* dxa_planes, float* dxb, void* dxb_planes, float* dgamma_a,
+                float* dbeta_a, float* dgamma_b, float* dbeta_b, int accumulate, void* workspace,
+                int64_t workspace_bytes, void* stream) {
+  if (int rc = check_rows_c(xa, rows, C, "bn_bwd2")) return rc;
+  if (int rc = check_rows_c(xb, rows, C, "bn_bwd2")) return rc;
+  SSB_REQUIRE(dy && mean_a && rstd_a && gamma_a && mean_b && rstd_b && gamma_b && dxa && dxb &&
+                  dgamma_a && dbeta_a && dgamma_b && dbeta_b,
+              "bn_bwd2: null pointer");
+  const int64_t need = ssb_col_partials_bytes(rows, C) + 3 * C * 4;
+  SSB_REQUIRE(workspace && workspace_bytes >= need, "bn_bwd2: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nch = nchunks_for(rows);
+  const unsigned cb = (unsigned)((C + 127) / 128);
+  float* partials = (float*)workspace;
+  float* m_dz = partials + (int64_t)nch * 3 * C;
+  float* m_a = m_dz + C;
+  float* m_b = m_a + C;
+  bn2_bwd_partials_kernel<<<dim3(cb, (unsigned)nch), 256, 0, st>>>(
+      dy, mask_src, xa, mean_a, rstd_a, xb, mean_b, rstd_b, rows, (int)C, partials);
+  SSB_LAUNCH_CHECK("bn2_bwd_partials");
+  bn2_bwd_finalize_kernel<<<FIN_GRID(C), 0, st>>>(partials, nch, (int)C, (double)rows, accumulate,
+                                                  dgamma_a, dbeta_a, dgamma_b, dbeta_b, m_dz, m_a, m_b);
+  SSB_LAUNCH_CHECK("bn2_bwd_finalize");
+  const int64_t n4 = rows * C / 4;
+  const int64_t blocks = (n4 + 255) / 256;
+  const int g2 = (int)(blocks < 148 * 16 ? blocks : 148 * 16);
+  bn2_bwd_apply_kernel<<<g2, 256, 0, st>>>(dy, mask_src, xa, mean_a, rstd_a, gamma_a, xb, mean_b,
+                                           rstd_b, gamma_b, m_dz, m_a, m_b, training, n4,
+                                           (int)(C / 4), dxa, (__nv_bfloat16*)dxa_planes, dxb,
+                                           (__nv_bfloat16*)dxb_planes);
+  SSB_LAUNCH_CHECK("bn2_bwd_apply");
   return SSB_OK;
 }
 
@@ -648,8 +874,8 @@ int64_t ssb_add_dropout_ln_bwd_workspace_bytes(int64_t rows, int64_t D) {
 int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, const float* rstd,
                            const float* gamma, int64_t rows, int64_t D, float drop_p,
                            uint64_t seed, uint32_t site, float* d_res, float* d_branch,
-                           void* d_branch_planes, float* dgamma, float* dbeta, void* workspace,
-                           int64_t workspace_bytes, void* stream) {
+                           void* d_branch_planes, float* dgamma, float* dbeta, int accumulate,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
   if (int rc = check_rows_c(dy, rows, D, "add_dropout_ln_bwd")) return rc;
   SSB_REQUIRE(D <= 1024, "add_dropout_ln_bwd: D=%lld > 1024 not built", (long long)D);
   SSB_REQUIRE(z && mean && rstd && gamma && d_res && d_branch && dgamma && dbeta,
@@ -672,7 +898,7 @@ int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, c
 #undef SSB_LN_BWD
   SSB_LAUNCH_CHECK("add_ln_bwd");
   ln_param_grad_finalize_kernel<<<FIN_GRID(D), 0, st>>>((const float*)workspace, nblk, (int)D,
-                                                        dgamma, dbeta);
+                                                        accumulate, dgamma, dbeta);
   SSB_LAUNCH_CHECK("ln_param_grad_finalize");
   return SSB_OK;
 }

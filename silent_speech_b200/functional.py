@@ -823,22 +823,51 @@ def _bn_stats(x2, gamma, beta, rm, rv, training, momentum, eps):
     return buf
 
 
-def _bn_bwd(dy2, mask_src, x2, stats, gamma, training):
+def _bn_bwd(dy2, mask_src, x2, stats, gamma, training, sinks=(None, None)):
+    """sinks: gradient-bucket views of (gamma, beta): the finalize kernel adds into them and None
+    is returned in their place."""
     lib = _lib.load()
     rows, C = x2.shape
     dev = x2.device
     dx = torch.empty_like(x2)
     dxp = (torch.empty((2, rows, C), dtype=torch.bfloat16, device=dev)
            if _want_planes(rows, C) else None)
-    dg = torch.empty(C, dtype=_f32, device=dev)
-    db = torch.empty(C, dtype=_f32, device=dev)
-    ws = _ws(lib.ssb_col_partials_bytes(rows, C) + 8 * C, dev)
+    sunk = sinks[0] is not None and sinks[1] is not None
+    dg = sinks[0] if sunk else torch.empty(C, dtype=_f32, device=dev)
+    db = sinks[1] if sunk else torch.empty(C, dtype=_f32, device=dev)
+    ws = _ws(lib.ssb_col_partials_bytes(rows, C) + 12 * C, dev)
     _lib.check(lib.ssb_bn_bwd(dy2.data_ptr(), mask_src.data_ptr() if mask_src is not None else None,
                               x2.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
                               gamma.data_ptr(), int(training), rows, C, dx.data_ptr(),
                               dxp.data_ptr() if dxp is not None else None,
-                              dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-    return dx, dg, db, dxp
+                              dg.data_ptr(), db.data_ptr(), int(sunk), ws.data_ptr(), ws.numel(),
+                              _stream()))
+    return dx, (None if sunk else dg), (None if sunk else db), dxp
+
+
+def _bn_bwd2(dy2, mask_src, xa2, sa, ga, xb2, sb, gb, training, sinks):
+    """Both normalised branches of a ResBlock output in one pair of passes (ssb_bn_bwd2).
+    sinks: bucket views of (gamma_a, beta_a, gamma_b, beta_b) or Nones."""
+    lib = _lib.load()
+    rows, C = xa2.shape
+    dev = xa2.device
+    dxa, dxb = torch.empty_like(xa2), torch.empty_like(xb2)
+    pl = _want_planes(rows, C)
+    dxap = torch.empty((2, rows, C), dtype=torch.bfloat16, device=dev) if pl else None
+    dxbp = torch.empty((2, rows, C), dtype=torch.bfloat16, device=dev) if pl else None
+    sunk = all(t is not None for t in sinks)
+    pg = list(sinks) if sunk else [torch.empty(C, dtype=_f32, device=dev) for _ in range(4)]
+    ws = _ws(lib.ssb_col_partials_bytes(rows, C) + 12 * C, dev)
+    _lib.check(lib.ssb_bn_bwd2(
+        dy2.data_ptr(), mask_src.data_ptr() if mask_src is not None else None,
+        xa2.data_ptr(), sa[0].data_ptr(), sa[1].data_ptr(), ga.data_ptr(),
+        xb2.data_ptr(), sb[0].data_ptr(), sb[1].data_ptr(), gb.data_ptr(), int(training), rows, C,
+        dxa.data_ptr(), dxap.data_ptr() if pl else None, dxb.data_ptr(),
+        dxbp.data_ptr() if pl else None, pg[0].data_ptr(), pg[1].data_ptr(), pg[2].data_ptr(),
+        pg[3].data_ptr(), int(sunk), ws.data_ptr(), ws.numel(), _stream()))
+    if sunk:
+        pg = [None] * 4
+    return dxa, dxap, dxb, dxbp, pg
 
 
 class _BNActFn(torch.autograd.Function):
@@ -872,6 +901,8 @@ class _BNActFn(torch.autograd.Function):
         if yp is not None:
             attach_planes(y, yp)     # the next convolution's operand, written by this kernel
         ctx.training, ctx.relu, ctx.two = training, relu, xb is not None
+        ctx.sinks = (_sink(ga), _sink(ba), _sink(gb) if xb is not None else None,
+                     _sink(bb) if xb is not None else None)
         if ctx.two:
             ctx.save_for_backward(xa, ga, sa, y, xb, gb, sb)
         else:
@@ -891,13 +922,14 @@ class _BNActFn(torch.autograd.Function):
         def shaped(d, dp, like):     # gradient of a convolution output + its operand planes
             d = d.view_as(like)
             return attach_planes(d, dp.view((2,) + tuple(like.shape))) if dp is not None else d
-        dxa, dga, dba, dxap = _bn_bwd(dy2, mask, xa.view(-1, C), sa, ga, ctx.training)
-        dxb = dgb = dbb = None
         if ctx.two:
-            dxb, dgb, dbb, dxbp = _bn_bwd(dy2, mask, xb.view(-1, C), sb, gb, ctx.training)
-            dxb = shaped(dxb, dxbp, xb)
-        return (shaped(dxa, dxap, xa), dga, dba, None, None, dxb, dgb, dbb, None, None, None, None,
-                None, None)
+            dxa, dxap, dxb, dxbp, (dga, dba, dgb, dbb) = _bn_bwd2(
+                dy2, mask, xa.view(-1, C), sa, ga, xb.view(-1, C), sb, gb, ctx.training, ctx.sinks)
+            return (shaped(dxa, dxap, xa), dga, dba, None, None, shaped(dxb, dxbp, xb), dgb, dbb,
+                    None, None, None, None, None, None)
+        dxa, dga, dba, dxap = _bn_bwd(dy2, mask, xa.view(-1, C), sa, ga, ctx.training, ctx.sinks[:2])
+        return (shaped(dxa, dxap, xa), dga, dba, None, None, None, None, None, None, None, None,
+                None, None, None)
 
 
 def bn_act(xa, ga, ba, rma, rva, training, relu, xb=None, gb=None, bb=None, rmb=None, rvb=None,
@@ -932,6 +964,7 @@ class _AddDropLNFn(torch.autograd.Function):
         if need_bwd:
             ctx.save_for_backward(z, stat, gamma)
         ctx.cfg = (p, seed, site)
+        ctx.sinks = (_sink(gamma), _sink(beta))
         return y
 
     @staticmethod
@@ -946,17 +979,18 @@ class _AddDropLNFn(torch.autograd.Function):
         d_branch = torch.empty_like(z)
         dbp = (torch.empty((2, rows, D), dtype=torch.bfloat16, device=dev)
                if _want_planes(rows, D) else None)
-        dg = torch.empty(D, dtype=_f32, device=dev)
-        db = torch.empty(D, dtype=_f32, device=dev)
+        sunk = ctx.sinks[0] is not None and ctx.sinks[1] is not None
+        dg = ctx.sinks[0] if sunk else torch.empty(D, dtype=_f32, device=dev)
+        db = ctx.sinks[1] if sunk else torch.empty(D, dtype=_f32, device=dev)
         ws = _ws(lib.ssb_add_dropout_ln_bwd_workspace_bytes(rows, D), dev)
         _lib.check(lib.ssb_add_dropout_ln_bwd(
             dy.data_ptr(), z.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(), gamma.data_ptr(),
             rows, D, p, seed & 0xFFFFFFFFFFFFFFFF, site, d_res.data_ptr(), d_branch.data_ptr(),
             dbp.data_ptr() if dbp is not None else None,
-            dg.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+            dg.data_ptr(), db.data_ptr(), int(sunk), ws.data_ptr(), ws.numel(), _stream()))
         if dbp is not None:
             attach_planes(d_branch, dbp)   # dy operand of the branch's backward GEMMs
-        return d_res, d_branch, dg, db, None, None, None, None
+        return (d_res, d_branch, None if sunk else dg, None if sunk else db, None, None, None, None)
 
 
 def add_dropout_layernorm(res, branch, gamma, beta, p=0.0, seed=0, site=0, eps=1e-5):
