@@ -194,7 +194,8 @@ __device__ __forceinline__ bool chunk_sums(const float* __restrict__ partials, i
   return true;
 }
 
-__global__ void colsum_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+__global__ void __launch_bounds__(32 * FIN_LANES)
+colsum_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
                                        float* __restrict__ out, int accumulate) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, unused;
@@ -203,7 +204,8 @@ __global__ void colsum_finalize_kernel(const float* __restrict__ partials, int n
 }
 
 // merge of the per-chunk (n, mean, M2) triples -> mean, rstd, scale, shift + running statistics
-__global__ void bn_merge_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+__global__ void __launch_bounds__(32 * FIN_LANES)
+bn_merge_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
                                          int64_t rows, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float* running_mean,
                                          float* running_var, float momentum, float eps,
@@ -312,7 +314,8 @@ bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
 }
 
 // BatchNorm backward, finalize: sums -> dgamma, dbeta and the two per-channel means
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+__global__ void __launch_bounds__(32 * FIN_LANES)
+bn_bwd_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
                                        double count, int accumulate, float* __restrict__ dgamma,
                                        float* __restrict__ dbeta, float* __restrict__ m_dz,
                                        float* __restrict__ m_dzx) {
@@ -409,7 +412,8 @@ bn2_bwd_partials_kernel(const float* __restrict__ dy, const float* __restrict__ 
   }
 }
 
-__global__ void bn2_bwd_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+__global__ void __launch_bounds__(32 * FIN_LANES)
+bn2_bwd_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
                                         double count, int accumulate, float* __restrict__ dgamma_a,
                                         float* __restrict__ dbeta_a, float* __restrict__ dgamma_b,
                                         float* __restrict__ dbeta_b, float* __restrict__ m_dz,
@@ -663,7 +667,8 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
   }
 }
 
-__global__ void ln_param_grad_finalize_kernel(const float* __restrict__ partials, int nblk, int D,
+__global__ void __launch_bounds__(32 * FIN_LANES)
+ln_param_grad_finalize_kernel(const float* __restrict__ partials, int nblk, int D,
                                               int accumulate, float* __restrict__ dgamma,
                                               float* __restrict__ dbeta) {
   const int c = blockIdx.x * 32 + threadIdx.x;
