@@ -85,46 +85,64 @@ col_partials_kernel(const float* __restrict__ x, const float* __restrict__ dy,
   }
 }
 
-// Single-pass BatchNorm statistics.  Per 256-row chunk and column the CTA accumulates SHIFTED
-// sums  s = sum(x - k),  q = sum((x - k)^2)  with k = the chunk's own first sample of that column:
-// x - k is then O(std) even when |mean| >> std, so  M2_chunk = q - s^2/n  does not cancel (the
-// round-1 attempt shifted by one GLOBAL value and lost 1e-2 on near-constant channels; it then
-// fell back to two passes over x).  The finalize kernel merges the per-chunk (n, mean, M2)
-// triples in fp64 (Chan et al.'s parallel variance), so the tensor is read ONCE.
-// partials: [nchunks][3][C] = s, q, k.
+// Single-pass BatchNorm statistics.  Every thread runs Welford's update over its 32 rows of a
+// 256-row chunk (mean and centred sum of squares M2 updated per sample: no E[x^2] - mean^2
+// cancellation, whatever |mean| / std is), the 8 row-lanes of a column are merged with Chan et
+// al.'s pairwise formula in fp64, and the finalize kernel merges the per-chunk (n, mean, M2)
+// triples the same way: the tensor is read ONCE.  (Round 1 read it twice - mean, then centred
+// squares - after a shifted one-pass sum had lost 1e-2 on near-constant channels.)
+// partials: [nchunks][3][C] = chunk mean, chunk M2, (unused).
 __global__ void __launch_bounds__(256)
 bn_chunk_stats_kernel(const float* __restrict__ x, int64_t rows, int C,
                       float* __restrict__ partials) {
   __shared__ float4 red[2][8][32];
+  __shared__ int cnt[8];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + cl) * 4;
   const int64_t r0 = (int64_t)blockIdx.y * RCH;
   const int64_t r1 = min(rows, r0 + RCH);
-  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, kk = s0;
+  float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), m2 = mu;
+  int n = 0;
   if (c < C) {
-    kk = __ldg(reinterpret_cast<const float4*>(x + r0 * C + c));
     for (int64_t r = r0 + rl; r < r1; r += 8) {
-      float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C + c));
-      v.x -= kk.x; v.y -= kk.y; v.z -= kk.z; v.w -= kk.w;
-      s0.x += v.x; s0.y += v.y; s0.z += v.z; s0.w += v.w;
-      s1.x = fmaf(v.x, v.x, s1.x); s1.y = fmaf(v.y, v.y, s1.y);
-      s1.z = fmaf(v.z, v.z, s1.z); s1.w = fmaf(v.w, v.w, s1.w);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C + c));
+      ++n;
+      const float inv = __frcp_rn((float)n);
+      float d;
+      d = v.x - mu.x; mu.x = fmaf(d, inv, mu.x); m2.x = fmaf(d, v.x - mu.x, m2.x);
+      d = v.y - mu.y; mu.y = fmaf(d, inv, mu.y); m2.y = fmaf(d, v.y - mu.y, m2.y);
+      d = v.z - mu.z; mu.z = fmaf(d, inv, mu.z); m2.z = fmaf(d, v.z - mu.z, m2.z);
+      d = v.w - mu.w; mu.w = fmaf(d, inv, mu.w); m2.w = fmaf(d, v.w - mu.w, m2.w);
     }
+  } else {
+    for (int64_t r = r0 + rl; r < r1; r += 8) ++n;
   }
-  red[0][rl][cl] = s0;
-  red[1][rl][cl] = s1;
+  red[0][rl][cl] = mu;
+  red[1][rl][cl] = m2;
+  if (cl == 0) cnt[rl] = n;
   __syncthreads();
-  if (rl < 2 && c < C) {
-    float4 a = red[rl][0][cl];
+  if (rl == 0 && c < C) {
+    double na = 0.0, ma[4] = {0, 0, 0, 0}, qa[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      const float4 b = red[rl][i][cl];
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    for (int i = 0; i < 8; ++i) {
+      const double nb = (double)cnt[i];
+      if (nb == 0.0) continue;
+      const float4 mb4 = red[0][i][cl], qb4 = red[1][i][cl];
+      const double mb[4] = {mb4.x, mb4.y, mb4.z, mb4.w}, qb[4] = {qb4.x, qb4.y, qb4.z, qb4.w};
+      const double nn = na + nb;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double dlt = mb[j] - ma[j];
+        ma[j] += dlt * (nb / nn);
+        qa[j] += qb[j] + dlt * dlt * (na * nb / nn);
+      }
+      na = nn;
     }
-    *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 3 + rl) * C + c) = a;
+    *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 3) * C + c) =
+        make_float4((float)ma[0], (float)ma[1], (float)ma[2], (float)ma[3]);
+    *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 3 + 1) * C + c) =
+        make_float4((float)qa[0], (float)qa[1], (float)qa[2], (float)qa[3]);
   }
-  if (rl == 2 && c < C)
-    *reinterpret_cast<float4*>(partials + ((int64_t)blockIdx.y * 3 + 2) * C + c) = kk;
 }
 
 // column sums of a tensor held as bf16 split planes (x = hi + lo): 32 column-lanes x 8 columns
@@ -215,12 +233,12 @@ bn_merge_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
   __shared__ double mu_sh[32];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const double count = (double)rows;
-  // pass 1: global mean = sum_i n_i * mean_i / N,  mean_i = k_i + s_i / n_i
+  // pass 1: global mean = sum_i n_i * mean_i / N
   double a = 0.0;
   if (c < C)
     for (int k = threadIdx.y; k < nchunks; k += FIN_LANES) {
       const double n = (double)min((int64_t)RCH, rows - (int64_t)k * RCH);
-      a += n * (double)partials[((int64_t)k * 3 + 2) * C + c] + (double)partials[((int64_t)k * 3) * C + c];
+      a += n * (double)partials[((int64_t)k * 3) * C + c];
     }
   sh[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
@@ -232,15 +250,13 @@ bn_merge_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
   }
   __syncthreads();
   const double mu = mu_sh[threadIdx.x];
-  // pass 2: M2 = sum_i [ (q_i - s_i^2 / n_i) + n_i * (mean_i - mu)^2 ]
+  // pass 2: M2 = sum_i [ M2_i + n_i * (mean_i - mu)^2 ]
   double b = 0.0;
   if (c < C)
     for (int k = threadIdx.y; k < nchunks; k += FIN_LANES) {
       const double n = (double)min((int64_t)RCH, rows - (int64_t)k * RCH);
-      const double si = (double)partials[((int64_t)k * 3) * C + c];
-      const double qi = (double)partials[((int64_t)k * 3 + 1) * C + c];
-      const double d = (double)partials[((int64_t)k * 3 + 2) * C + c] + si / n - mu;
-      b += fmax(qi - si * si / n, 0.0) + n * d * d;
+      const double d = (double)partials[((int64_t)k * 3) * C + c] - mu;
+      b += (double)partials[((int64_t)k * 3 + 1) * C + c] + n * d * d;
     }
   __syncthreads();
   sh[threadIdx.y][threadIdx.x] = b;

@@ -1241,6 +1241,71 @@ def _const_planes(E, key, make):
     return planes
 
 
+def _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, need_bwd=True):
+    """Fused band attention forward on fp32 qkv (M, 3D).  Returns (O, saved-for-backward)."""
+    lib = _lib.load()
+    M, D3 = qkv.shape
+    D = H * dh
+    BH = B * H
+    RW = (2 * W + 1 + 3) // 4 * 4
+    dev = qkv.device
+    bf = torch.bfloat16
+    st = _stream()
+    qkvp = torch.empty((2, M, 3 * H, _HP), dtype=bf, device=dev)
+    _lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, D3, 0, 3 * H, dh, qkvp.data_ptr(), st))
+    ep = _const_planes(E, ("fwd", W, dh, RW), lambda: torch.nn.functional.pad(
+        E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
+    ld_qkv = 3 * H * _HP
+    q_op = _op(qkvp, 0, M * ld_qkv, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
+    R = torch.empty((BH, T, RW), dtype=_f32, device=dev)
+    e_op = _op(ep, 0, H * RW * _HP, H, RW, _HP, _HP, RW * _HP)
+    _tc_batched(q_op, e_op, 2, RW, _HP, _epi(_bscatter(R, 0, T, RW, T * RW, H * T * RW)))
+    O = torch.empty((M, D), dtype=_f32, device=dev)
+    stats = torch.empty((2, BH, T), dtype=_f32, device=dev)
+    _lib.check(lib.ssb_attn_fused_fwd(qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p,
+                                      seed & 0xFFFFFFFFFFFFFFFF, site, O.data_ptr(),
+                                      stats[0].data_ptr(), stats[1].data_ptr(), st))
+    return O, ((qkvp, R, stats, O, E) if need_bwd else None)
+
+
+def _fused_attn_bwd(saved, cfg, dO):
+    """-> dqkv (M, 3D) fp32 (content + positional parts; no gradient for E: SURVEY.md F3)."""
+    lib = _lib.load()
+    qkvp, R, stats, O, E = saved
+    B, T, H, dh, W, p, seed, site, RW = cfg
+    dO = dO.contiguous()
+    M, D = O.shape
+    D3 = 3 * D
+    BH = B * H
+    dev = O.device
+    bf = torch.bfloat16
+    st = _stream()
+    dop = torch.empty((2, M, H, _HP), dtype=bf, device=dev)
+    _lib.check(lib.ssb_pad_split_heads(dO.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), st))
+    delta = torch.empty((BH, T), dtype=_f32, device=dev)
+    _lib.check(lib.ssb_attn_delta(O.data_ptr(), dO.data_ptr(), B, T, H, dh, delta.data_ptr(), st))
+    dqkv = torch.empty((M, D3), dtype=_f32, device=dev)
+    dqkv[:, :D].zero_()                                  # content dQ arrives by red.global.add
+    # band-layout dS: the kernel overwrites exactly the in-band, in-sequence entries - the same
+    # set every call for a given geometry - and everything else must read 0.  One persistent
+    # buffer per geometry, zeroed once, replaces a 131 MB fill per layer and step (backward
+    # passes of successive layers are stream-ordered, so they can share it).
+    dsb = _band_scratch((B, T, H, W, _RWP, dev))
+    _lib.check(lib.ssb_attn_fused_bwd(qkvp.data_ptr(), dop.data_ptr(), R.data_ptr(),
+                                      stats[0].data_ptr(), stats[1].data_ptr(),
+                                      delta.data_ptr(), B, T, H, dh, W, RW, p,
+                                      seed & 0xFFFFFFFFFFFFFFFF, site, dqkv.data_ptr(),
+                                      dsb.data_ptr(), _RWP, st))
+    # positional part: dQ += dS_band E
+    etp = _const_planes(E, ("bwd", W, dh), lambda: torch.nn.functional.pad(    # (2, H, 128, RWP)
+        E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2).contiguous())
+    dsb_op = _op(dsb, 0, M * H * _RWP, BH, T, _RWP, H * _RWP, _RWP, H, T * H * _RWP)
+    et_op = _op(etp, 0, H * _HP * _RWP, H, _HP, _RWP, _RWP, _HP * _RWP)
+    _tc_batched(dsb_op, et_op, 2, dh, _RWP,
+                _epi(_bscatter(dqkv, 0, T, D3, dh, T * D3), accumulate=1))
+    return dqkv
+
+
 class _FusedAttnFn(torch.autograd.Function):
     """Fused band attention (csrc/attn_fused.cu): S, P, dP and dS never leave the SM.  Around the
     two fused kernels only the positional GEMMs with E remain: R = Q E^T before the forward and
@@ -1248,70 +1313,193 @@ class _FusedAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, qkv, E, B, T, H, dh, W, p, seed, site):
-        lib = _lib.load()
         _chk(qkv, "qkv")
-        M, D3 = qkv.shape
-        D = H * dh
-        BH = B * H
-        RW = (2 * W + 1 + 3) // 4 * 4
-        dev = qkv.device
-        bf = torch.bfloat16
-        st = _stream()
-        qkvp = torch.empty((2, M, 3 * H, _HP), dtype=bf, device=dev)
-        _lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, D3, 0, 3 * H, dh, qkvp.data_ptr(), st))
-        ep = _const_planes(E, ("fwd", W, dh, RW), lambda: torch.nn.functional.pad(
-            E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
-        ld_qkv = 3 * H * _HP
-        q_op = _op(qkvp, 0, M * ld_qkv, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
-        R = torch.empty((BH, T, RW), dtype=_f32, device=dev)
-        e_op = _op(ep, 0, H * RW * _HP, H, RW, _HP, _HP, RW * _HP)
-        _tc_batched(q_op, e_op, 2, RW, _HP, _epi(_bscatter(R, 0, T, RW, T * RW, H * T * RW)))
-        O = torch.empty((M, D), dtype=_f32, device=dev)
-        stats = torch.empty((2, BH, T), dtype=_f32, device=dev)
-        _lib.check(lib.ssb_attn_fused_fwd(qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p,
-                                          seed & 0xFFFFFFFFFFFFFFFF, site, O.data_ptr(),
-                                          stats[0].data_ptr(), stats[1].data_ptr(), st))
-        if ctx.needs_input_grad[0]:
-            ctx.save_for_backward(qkvp, R, stats, O, E)
-        ctx.cfg = (B, T, H, dh, W, p, seed, site, RW)
+        O, saved = _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, ctx.needs_input_grad[0])
+        if saved is not None:
+            ctx.save_for_backward(*saved)
+        ctx.cfg = (B, T, H, dh, W, p, seed, site, (2 * W + 1 + 3) // 4 * 4)
         return O
 
     @staticmethod
     def backward(ctx, dO):
-        lib = _lib.load()
-        qkvp, R, stats, O, E = ctx.saved_tensors
-        B, T, H, dh, W, p, seed, site, RW = ctx.cfg
-        dO = dO.contiguous()
-        M, D = O.shape
-        D3 = 3 * D
-        BH = B * H
-        dev = O.device
-        bf = torch.bfloat16
-        st = _stream()
-        dop = torch.empty((2, M, H, _HP), dtype=bf, device=dev)
-        _lib.check(lib.ssb_pad_split_heads(dO.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), st))
-        delta = torch.empty((BH, T), dtype=_f32, device=dev)
-        _lib.check(lib.ssb_attn_delta(O.data_ptr(), dO.data_ptr(), B, T, H, dh, delta.data_ptr(), st))
-        dqkv = torch.empty((M, D3), dtype=_f32, device=dev)
-        dqkv[:, :D].zero_()                                  # content dQ arrives by red.global.add
-        # band-layout dS: the kernel overwrites exactly the in-band, in-sequence entries - the same
-        # set every call for a given geometry - and everything else must read 0.  One persistent
-        # buffer per geometry, zeroed once, replaces a 131 MB fill per layer and step (backward
-        # passes of successive layers are stream-ordered, so they can share it).
-        dsb = _band_scratch((B, T, H, W, _RWP, dev))
-        _lib.check(lib.ssb_attn_fused_bwd(qkvp.data_ptr(), dop.data_ptr(), R.data_ptr(),
-                                          stats[0].data_ptr(), stats[1].data_ptr(),
-                                          delta.data_ptr(), B, T, H, dh, W, RW, p,
-                                          seed & 0xFFFFFFFFFFFFFFFF, site, dqkv.data_ptr(),
-                                          dsb.data_ptr(), _RWP, st))
-        # positional part: dQ += dS_band E
-        etp = _const_planes(E, ("bwd", W, dh), lambda: torch.nn.functional.pad(    # (2, H, 128, RWP)
-            E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2).contiguous())
-        dsb_op = _op(dsb, 0, M * H * _RWP, BH, T, _RWP, H * _RWP, _RWP, H, T * H * _RWP)
-        et_op = _op(etp, 0, H * _HP * _RWP, H, _HP, _RWP, _RWP, _HP * _RWP)
-        _tc_batched(dsb_op, et_op, 2, dh, _RWP,
-                    _epi(_bscatter(dqkv, 0, T, D3, dh, T * D3), accumulate=1))
+        dqkv = _fused_attn_bwd(ctx.saved_tensors, ctx.cfg, dO)
         return dqkv, None, None, None, None, None, None, None, None, None
+
+
+def _ln_fwd(res, branch, gamma, beta, p, seed, site, eps, need_bwd=True):
+    """z = res + dropout(branch); y = LayerNorm(z).  -> y (planes attached), z, stat."""
+    lib = _lib.load()
+    rows, D = res.shape
+    dev = res.device
+    y = torch.empty_like(res)
+    yp = torch.empty((2, rows, D), dtype=torch.bfloat16, device=dev) if _want_planes(rows, D) else None
+    z = torch.empty_like(res) if need_bwd else None
+    stat = torch.empty((2, rows), dtype=_f32, device=dev) if need_bwd else None
+    _lib.check(lib.ssb_add_dropout_ln_fwd(
+        res.data_ptr(), branch.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, D, eps, p,
+        seed & 0xFFFFFFFFFFFFFFFF, site, z.data_ptr() if need_bwd else None, y.data_ptr(),
+        stat[0].data_ptr() if need_bwd else None, stat[1].data_ptr() if need_bwd else None,
+        yp.data_ptr() if yp is not None else None, _stream()))
+    if yp is not None:
+        attach_planes(y, yp)
+    return y, z, stat
+
+
+def _ln_bwd(dy, z, stat, gamma, p, seed, site, sinks):
+    """-> d_res, d_branch, d_branch planes (or None), dgamma, dbeta (None when sunk)."""
+    lib = _lib.load()
+    dy = dy.contiguous()
+    rows, D = z.shape
+    dev = z.device
+    d_res = torch.empty_like(z)
+    d_branch = torch.empty_like(z)
+    dbp = torch.empty((2, rows, D), dtype=torch.bfloat16, device=dev) if _want_planes(rows, D) else None
+    sunk = sinks[0] is not None and sinks[1] is not None
+    dg = sinks[0] if sunk else torch.empty(D, dtype=_f32, device=dev)
+    db = sinks[1] if sunk else torch.empty(D, dtype=_f32, device=dev)
+    ws = _ws(lib.ssb_add_dropout_ln_bwd_workspace_bytes(rows, D), dev)
+    _lib.check(lib.ssb_add_dropout_ln_bwd(
+        dy.data_ptr(), z.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(), gamma.data_ptr(),
+        rows, D, p, seed & 0xFFFFFFFFFFFFFFFF, site, d_res.data_ptr(), d_branch.data_ptr(),
+        dbp.data_ptr() if dbp is not None else None, dg.data_ptr(), db.data_ptr(), int(sunk),
+        ws.data_ptr(), ws.numel(), _stream()))
+    return d_res, d_branch, dbp, (None if sunk else dg), (None if sunk else db)
+
+
+class _AttnBlockFn(torch.autograd.Function):
+    """x1 = LayerNorm(x + dropout(Attention(x) Wo))   transformer.py:54-56 as ONE autograd node:
+    fused QKV GEMM -> fused band attention -> out-projection -> add + dropout + LayerNorm.  The
+    backward hands the residual gradient from the LayerNorm kernel to the QKV data-gradient GEMM's
+    epilogue (accumulate), so the two gradients of x are never summed by a separate pass, and
+    writes dWo and the LayerNorm parameter gradients straight into the gradient bucket."""
+
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, w_o, E, gamma, beta, B, T, W, p_attn, p_res, seed, site, eps,
+                qf, qb, of, ob):
+        _chk(x, "x")
+        H, D, dh = wq.shape
+        M = x.shape[0]
+        need_bwd = any(ctx.needs_input_grad[:8])
+        xp = planes_of(x)
+        qkv = torch.empty((M, 3 * D), dtype=_f32, device=x.device)
+        gemm_tc_kmajor(tc_operand_plain(xp, M, D), qf, 3 * D, D,
+                       _epi(_scatter_plain(qkv.data_ptr(), M, 3 * D)))
+        O, att = _fused_attn_fwd(qkv, E, B, T, H, dh, W, p_attn, seed, site, need_bwd)
+        del qkv
+        op = split_planes(O)
+        a = torch.empty((M, D), dtype=_f32, device=x.device)
+        gemm_tc_kmajor(tc_operand_plain(op, M, D), of, D, D, _epi(_scatter_plain(a.data_ptr(), M, D)))
+        y, z, stat = _ln_fwd(x, a, gamma, beta, p_res, seed, site + 1, eps, need_bwd)
+        if need_bwd:
+            ctx.save_for_backward(xp, op, z, stat, gamma, qb, ob, w_o, *att)
+        ctx.cfg = (B, T, H, dh, W, p_attn, seed, site, (2 * W + 1 + 3) // 4 * 4)
+        ctx.p_res = p_res
+        ctx.sinks = (_sink(gamma), _sink(beta), _sink(w_o))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, op, z, stat, gamma, qb, ob, w_o = ctx.saved_tensors[:8]
+        att = ctx.saved_tensors[8:]
+        B, T, H, dh, W, p_attn, seed, site, RW = ctx.cfg
+        D = H * dh
+        M = z.shape[0]
+        dev = z.device
+        s_g, s_b, s_wo = ctx.sinks
+        d_res, d_a, d_ap, dg, db = _ln_bwd(dy, z, stat, gamma, ctx.p_res, seed, site + 1, (s_g, s_b))
+        if d_ap is None:
+            d_ap = split_planes(d_a)
+        # out-projection: dO = d_a Wo^T, dWo = O^T d_a (parameter layout = GEMM layout)
+        dO = torch.empty((M, D), dtype=_f32, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(d_ap, M, D), ob, D, D, _epi(_scatter_plain(dO.data_ptr(), M, D)))
+        if s_wo is not None:
+            gemm_tc_wgrad(tc_operand_plain(op, M, D), d_ap, D, D, s_wo.view(D, D), accumulate=True)
+            dWo = None
+        else:
+            dWo = torch.empty((D, D), dtype=_f32, device=dev)
+            gemm_tc_wgrad(tc_operand_plain(op, M, D), d_ap, D, D, dWo)
+            dWo = dWo.view_as(w_o)
+        del d_a, d_ap
+        dqkv = _fused_attn_bwd(att, ctx.cfg, dO)
+        dqp = split_planes(dqkv)
+        del dqkv
+        # x receives d_res (through the LayerNorm) + dqkv Wqkv^T: accumulated by the GEMM epilogue
+        gemm_tc_kmajor(tc_operand_plain(dqp, M, 3 * D), qb, D, 3 * D,
+                       _epi(_scatter_plain(d_res.data_ptr(), M, D), accumulate=1))
+        dWg = torch.empty((D, 3 * D), dtype=_f32, device=dev)
+        gemm_tc_wgrad(tc_operand_plain(xp, M, D), dqp, 3 * D, D, dWg)
+        g = [dWg[:, j * D:(j + 1) * D].view(D, H, dh).permute(1, 0, 2) for j in range(3)]
+        return (d_res, g[0], g[1], g[2], dWo, None, dg, db) + (None,) * 12
+
+
+class _FFNBlockFn(torch.autograd.Function):
+    """y = LayerNorm(x + dropout(FFN(x)))   transformer.py:57-59 as ONE autograd node.  The hidden
+    activation and its gradient exist only as operand planes (see _FFNNativeFn); in the backward
+    the residual gradient from the LayerNorm kernel is the accumulator of the last data-gradient
+    GEMM, and every parameter gradient lands in the gradient bucket when one is registered."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, beta, p_ffn, p_res, seed, site, eps, w1f, w1t, w2f, w2t):
+        _chk(x, "x")
+        M, K = x.shape
+        F_ = w1.shape[0]
+        dev = x.device
+        need_bwd = any(ctx.needs_input_grad[:7])
+        xp = planes_of(x)
+        hp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(xp, M, K), w1f, F_, K,
+                       _epi(_scatter_plain(None, M, F_), bias=b1, relu=1, drop_p=p_ffn, seed=seed,
+                            site=site, planes_out=hp))
+        f = torch.empty((M, K), dtype=_f32, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(hp, M, F_), w2f, K, F_, _epi(_scatter_plain(f.data_ptr(), M, K), bias=b2))
+        y, z, stat = _ln_fwd(x, f, gamma, beta, p_res, seed, site + 1, eps, need_bwd)
+        if need_bwd:
+            ctx.save_for_backward(xp, hp, z, stat, gamma, w1t, w2t, w1, w2)
+        ctx.cfg = (p_ffn, p_res, seed, site)
+        ctx.sinks = tuple(_sink(t) for t in (w1, b1, w2, b2, gamma, beta))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, hp, z, stat, gamma, w1t, w2t, w1, w2 = ctx.saved_tensors
+        p_ffn, p_res, seed, site = ctx.cfg
+        s_w1, s_b1, s_w2, s_b2, s_g, s_b = ctx.sinks
+        M, K = z.shape
+        F_ = hp.shape[2]
+        dev = z.device
+        scale = 1.0 / (1.0 - p_ffn) if p_ffn > 0 else 1.0
+        d_res, d_f, d_fp, dg, db = _ln_bwd(dy, z, stat, gamma, p_res, seed, site + 1, (s_g, s_b))
+        if d_fp is None:
+            d_fp = split_planes(d_f)
+        dW2 = s_w2 if s_w2 is not None else torch.empty_like(w2)          # (K, F) = d_f^T h
+        gemm_tc_wgrad(tc_operand_plain(d_fp, M, K), hp, F_, K, dW2, accumulate=s_w2 is not None)
+        db2 = colsum(d_f, out=s_b2, accumulate=s_b2 is not None)
+        dhp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
+        gemm_tc_kmajor(tc_operand_plain(d_fp, M, K), w2t, F_, K,
+                       _epi(_scatter_plain(None, M, F_), mask_planes=hp[0], mask_scale=scale,
+                            planes_out=dhp))
+        dW1 = s_w1 if s_w1 is not None else torch.empty_like(w1)          # (F, K) = dh^T x
+        gemm_tc_wgrad(tc_operand_plain(dhp, M, F_), xp, K, F_, dW1, accumulate=s_w1 is not None)
+        db1 = colsum_planes(dhp, out=s_b1, accumulate=s_b1 is not None)
+        # x receives d_res (through the LayerNorm) + dh W1: accumulated by the GEMM epilogue
+        gemm_tc_kmajor(tc_operand_plain(dhp, M, F_), w1t, K, F_,
+                       _epi(_scatter_plain(d_res.data_ptr(), M, K), accumulate=1))
+        return (d_res, None if s_w1 is not None else dW1, None if s_b1 is not None else db1,
+                None if s_w2 is not None else dW2, None if s_b2 is not None else db2, dg, db) + \
+            (None,) * 9
+
+
+def attn_block_ok(M, B, T, H, dh, W, D):
+    """Shapes for which _AttnBlockFn's kernels all apply (else the composition of single ops)."""
+    return (_fused_attn_ok(B, T, H, dh, W) and _tc_fwd_ok(M, 3 * D, D) and _tc_fwd_ok(M, D, 3 * D)
+            and _tc_wgrad_ok(M, 3 * D, D) and _tc_wgrad_ok(M, D, D) and _want_planes(M, D)
+            and os.environ.get("SSB_BLOCKS", "1") != "0")
+
+
+def ffn_block_ok(M, K, F_):
+    return (_tc_fwd_ok(M, F_, K) and _tc_fwd_ok(M, K, F_) and _tc_wgrad_ok(M, F_, K)
+            and _tc_wgrad_ok(M, K, F_) and K % 8 == 0 and _want_planes(M, K)
+            and os.environ.get("SSB_BLOCKS", "1") != "0")
 
 
 def _fused_attn_ok(B, T, H, dh, W):

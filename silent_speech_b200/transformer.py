@@ -139,17 +139,39 @@ class TransformerEncoderLayer(nn.Module):
         self.activation = nn.ReLU()
 
     def forward_tokens(self, x2d, B, T, seed=0, site0=0, wp=None):
-        """x2d: (B*T, D) -> (B*T, D).  Dropout sites site0 .. site0+3 (probs, attn-out, ffn, ffn-out)."""
+        """x2d: (B*T, D) -> (B*T, D).  Dropout sites site0 .. site0+3 (probs, attn-out, ffn, ffn-out).
+        With the WeightPlanes arena and tensor-core eligible shapes each half of the layer is ONE
+        autograd node (functional._AttnBlockFn / _FFNBlockFn); otherwise the single ops compose."""
         tr = self.training
-        a = self.self_attn.forward_tokens(x2d, B, T, seed, site0, wp)
-        x1 = F_.add_dropout_layernorm(x2d, a, self.norm1.weight, self.norm1.bias,
-                                      self.dropout1.p if tr else 0.0, seed, site0 + 1,
-                                      self.norm1.eps)
-        f = F_.ffn_native(x1, self.linear1.weight, self.linear1.bias, self.linear2.weight,
-                          self.linear2.bias, self.dropout.p if tr else 0.0, seed, site0 + 2, wp)
-        return F_.add_dropout_layernorm(x1, f, self.norm2.weight, self.norm2.bias,
-                                        self.dropout2.p if tr else 0.0, seed, site0 + 3,
-                                        self.norm2.eps)
+        at = self.self_attn
+        H, dh, D = at.n_head, at.d_qkv, at.d_model
+        M = x2d.shape[0]
+        W = at.relative_positional.max_relative_pos - 1
+        p_attn = at.dropout.p if tr else 0.0
+        p1 = self.dropout1.p if tr else 0.0
+        qf = wp.get(at, "qkv_f") if wp is not None else None
+        if qf is not None and F_.attn_block_ok(M, B, T, H, dh, W, D):
+            x1 = F_._AttnBlockFn.apply(
+                x2d, at.w_q, at.w_k, at.w_v, at.w_o, at.relative_positional.padded_table(),
+                self.norm1.weight, self.norm1.bias, int(B), int(T), int(W), float(p_attn), float(p1),
+                int(seed), int(site0), float(self.norm1.eps), qf, wp.get(at, "qkv_b"),
+                wp.get(at.w_o, "f"), wp.get(at.w_o, "b"))
+        else:
+            a = at.forward_tokens(x2d, B, T, seed, site0, wp)
+            x1 = F_.add_dropout_layernorm(x2d, a, self.norm1.weight, self.norm1.bias, p1, seed,
+                                          site0 + 1, self.norm1.eps)
+        p_ffn = self.dropout.p if tr else 0.0
+        p2 = self.dropout2.p if tr else 0.0
+        w1, w2 = self.linear1.weight, self.linear2.weight
+        pl = ([wp.get(w1, "f"), wp.get(w1, "b"), wp.get(w2, "f"), wp.get(w2, "b")]
+              if wp is not None else [None])
+        if all(t is not None for t in pl) and F_.ffn_block_ok(M, D, w1.shape[0]):
+            return F_._FFNBlockFn.apply(x1, w1, self.linear1.bias, w2, self.linear2.bias,
+                                        self.norm2.weight, self.norm2.bias, float(p_ffn), float(p2),
+                                        int(seed), int(site0 + 2), float(self.norm2.eps), *pl)
+        f = F_.ffn_native(x1, w1, self.linear1.bias, w2, self.linear2.bias, p_ffn, seed, site0 + 2, wp)
+        return F_.add_dropout_layernorm(x1, f, self.norm2.weight, self.norm2.bias, p2, seed,
+                                        site0 + 3, self.norm2.eps)
 
     def forward(self, src, src_mask=None, src_key_padding_mask=None, is_causal=False):
         T, B, D = src.shape

@@ -22,8 +22,9 @@ def _model(D, NL):
     return A.Model(112, 80, 48).cuda().train()
 
 
-def _run(m, x, monkeypatch, wplanes):
+def _run(m, x, monkeypatch, wplanes, blocks=False):
     monkeypatch.setenv("SSB_WPLANES", "1" if wplanes else "0")
+    monkeypatch.setenv("SSB_BLOCKS", "1" if blocks else "0")
     m.zero_grad(set_to_none=True)
     random.seed(3)
     pred, aux = m(None, x.clone(), None)
@@ -39,11 +40,14 @@ def test_arena_equals_per_use_derivation(D, NL, L, monkeypatch):
     p0, a0, g0 = _run(m, x, monkeypatch, False)
     p1, a1, g1 = _run(m, x, monkeypatch, True)
     assert m._wp is not None and m._wp.n_entries > 10
-    assert torch.equal(p0, p1) and torch.equal(a0, a1)
-    assert set(g0) == set(g1)
-    for k in g0:
-        d = (g0[k] - g1[k]).norm() / (g0[k].norm() + 1e-30)
-        assert d < 2e-6, (k, d.item())
+    # ... and with each half of an encoder layer as one autograd node (_AttnBlockFn / _FFNBlockFn)
+    p2, a2, g2 = _run(m, x, monkeypatch, True, blocks=True)
+    for p_, a_, g_ in ((p1, a1, g1), (p2, a2, g2)):
+        assert torch.equal(p0, p_) and torch.equal(a0, a_)
+        assert set(g0) == set(g_)
+        for k in g0:
+            d = (g0[k] - g_[k]).norm() / (g0[k].norm() + 1e-30)
+            assert d < 2e-6, (k, d.item())
 
 
 def test_arena_follows_optimizer_steps_and_checkpoint_loads(monkeypatch):
