@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 203
+#define SSB_ABI_VERSION 205
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -372,12 +372,18 @@ SSB_API int ssb_attn_ds_bwd(const float* P, const float* dP, int64_t B, int64_t 
  *   O          : fp32 (B*T, H*dh);  stat_m / stat_linv : fp32 (B*H, T) row max and 1 / sum exp
  * dh in {32, 64, 96}, W <= 99, RW <= 200 (RW % 4 == 0).  Dropout keys as everywhere else
  * (seed, site, element), identical masks in forward and backward. */
+/* head_stride / do_head_stride: elements between consecutive heads in the plane tensors: 128 (or
+ * 0) = heads zero-padded to 128 columns (ssb_pad_split_heads); dh = PACKED, i.e. the plain split
+ * planes of the (B*T, 3*H*dh) projection / (B*T, H*dh) output gradient exactly as a GEMM epilogue
+ * writes them (`planes_out`), so no re-layout pass runs between the GEMM and the attention kernel. */
 SSB_API int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_t T, int64_t H,
                        int64_t dh, int64_t W, int64_t RW, float drop_p, uint64_t seed, uint32_t site,
-                       float* O, float* stat_m, float* stat_linv, void* stream);
+                       float* O, float* stat_m, float* stat_linv, int64_t head_stride, void* stream);
 /* delta[b*H+h, q] = sum_d dO * O over the head's dh columns */
+/* zero_out (nullable): additionally clears H*dh floats of every row of a (B*T, zero_ld) matrix -
+ * the content-dQ accumulator of ssb_attn_fused_bwd - in the same pass. */
 SSB_API int ssb_attn_delta(const float* O, const float* dO, int64_t B, int64_t T, int64_t H, int64_t dh,
-                   float* delta, void* stream);
+                   float* delta, float* zero_out, int64_t zero_ld, void* stream);
 /* dqkv (B*T, 3*H*dh): the dQ third must be zero on entry (content part is accumulated with
  * red.global.add), dK / dV thirds are overwritten.  dSband_planes: bf16 (2, B*T, H, RWp), zero on
  * entry; receives dS in band layout for the positional part of dQ (a tensor-core GEMM with E). */
@@ -385,7 +391,7 @@ SSB_API int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, co
                        const float* stat_m, const float* stat_linv, const float* delta, int64_t B,
                        int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW, float drop_p,
                        uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
-                       void* stream);
+                       int64_t head_stride, int64_t do_head_stride, void* stream);
 
 /* ---- weight operand preparation (csrc/prep.cu) -----------------------------------------------
  * One launch writes the bf16 hi/lo split planes of every parameter in every layout the tensor-core

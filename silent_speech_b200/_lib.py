@@ -119,11 +119,11 @@ _SIGNATURES = {
     "ssb_attn_ds_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
                                 c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
     "ssb_attn_fused_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
-                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "ssb_attn_delta": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr]),
+                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "ssb_attn_delta": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_attn_fused_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64,
                                    c_i64, c_i64, c_i64, c_f32, c_u64, c_u32, c_ptr, c_ptr, c_i64,
-                                   c_ptr]),
+                                   c_i64, c_i64, c_ptr]),
     "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_split_bf16_t": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
@@ -215,7 +215,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 203      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 205      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):

@@ -74,12 +74,13 @@ class ResBlock(nn.Module):
             raise NotImplementedError("identity residual is never instantiated by the reference "
                                       "(architecture.py:46-50) and is not built")
         tr = self.training
-        c1 = F_.conv1d_w(x, self.conv1, wp, 3, self.stride, lambda: _conv_weight(self.conv1))
+        # every convolution here feeds a BatchNorm: in training mode its bias gradient is exactly 0
+        c1 = F_.conv1d_w(x, self.conv1, wp, 3, self.stride, lambda: _conv_weight(self.conv1), tr)
         h1 = F_.bn_act(c1, *self._bn_args(self.bn1), training=tr, relu=True,
                        momentum=self.bn1.momentum, eps=self.bn1.eps)
-        c2 = F_.conv1d_w(h1, self.conv2, wp, 3, 1, lambda: _conv_weight(self.conv2))
+        c2 = F_.conv1d_w(h1, self.conv2, wp, 3, 1, lambda: _conv_weight(self.conv2), tr)
         cr = F_.conv1d_w(x, self.residual_path, wp, 1, self.stride,
-                         lambda: _conv_weight(self.residual_path))
+                         lambda: _conv_weight(self.residual_path), tr)
         ga, ba, rma, rva = self._bn_args(self.bn2)
         gb, bb, rmb, rvb = self._bn_args(self.res_norm)
         return F_.bn_act(c2, ga, ba, rma, rva, tr, True, cr, gb, bb, rmb, rvb,

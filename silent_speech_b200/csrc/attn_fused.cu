@@ -875,11 +875,15 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 constexpr int DELTA_MAXV = 8;   // float4 per lane: H * dh <= 1024
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const float* __restrict__ O, const float* __restrict__ dO, int64_t rows, int T, int H,
-                  int dh, float* __restrict__ delta) {
+                  int dh, float* __restrict__ delta, float* __restrict__ zero_out, int64_t zero_ld) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int D = H * dh, nv = D >> 2, hv = dh >> 2;   // float4 per row / per head
+  if (zero_out) {   // the content-dQ accumulator the fused backward adds into (red.global.add)
+    float4* z = reinterpret_cast<float4*>(zero_out + row * zero_ld);
+    for (int v = lane; v < nv; v += 32) z[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   const float4* a = reinterpret_cast<const float4*>(O + row * (int64_t)D);
   const float4* g = reinterpret_cast<const float4*>(dO + row * (int64_t)D);
   float part[DELTA_MAXV];
@@ -947,16 +951,21 @@ int get_enc(EncodeTiledFn* out) {
   return SSB_OK;
 }
 
-// head planes (2, B*T, G, 128) bf16: dims (d, t, head, batch, plane); box (32 d, box_rows t)
+// head planes (2, B*T, G, hs) bf16, hs = head stride in elements (128: heads zero-padded to 128
+// columns; dh: packed, i.e. the plain split planes of a (B*T, G*dh) matrix as a GEMM epilogue
+// writes them).  dims (d, t, head, batch, plane); box (32 d, box_rows t): only the first dh
+// columns of a head are ever addressed.
 int head_map(CUtensorMap* map, const void* planes, int64_t B, int64_t T, int64_t G, int64_t g0,
-             int64_t H, int box_rows) {
+             int64_t H, int box_rows, int64_t hs, int64_t dh) {
   EncodeTiledFn enc = nullptr;
   if (int rc = get_enc(&enc)) return rc;
-  const __nv_bfloat16* basep = (const __nv_bfloat16*)planes + g0 * 128;
+  SSB_REQUIRE(hs >= dh && hs % 8 == 0, "attn_fused: head stride %lld (dh %lld) must be a multiple of 8",
+              (long long)hs, (long long)dh);
+  const __nv_bfloat16* basep = (const __nv_bfloat16*)planes + g0 * hs;
   SSB_REQUIRE(((uintptr_t)basep & 15) == 0, "attn_fused: planes must be 16 B aligned");
-  const int64_t ld = G * 128;
-  cuuint64_t dims[5] = {128, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)B, 2};
-  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, 256, (cuuint64_t)(T * ld) * 2,
+  const int64_t ld = G * hs;
+  cuuint64_t dims[5] = {(cuuint64_t)dh, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)B, 2};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)hs * 2, (cuuint64_t)(T * ld) * 2,
                            (cuuint64_t)(B * T * ld) * 2};
   cuuint32_t box[5] = {DB, (cuuint32_t)box_rows, 1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -1017,16 +1026,17 @@ extern "C" {
 
 int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_t T, int64_t H,
                        int64_t dh, int64_t W, int64_t RW, float drop_p, uint64_t seed, uint32_t site,
-                       float* O, float* stat_m, float* stat_linv, void* stream) {
+                       float* O, float* stat_m, float* stat_linv, int64_t head_stride, void* stream) {
+  const int64_t hs = head_stride > 0 ? head_stride : 128;
   FusedParams p = {};
   if (int rc = fill(&p, B, T, H, dh, W, RW, drop_p, seed, site)) return rc;
   SSB_REQUIRE(qkv_planes && R && O && stat_m && stat_linv, "attn_fused_fwd: null pointer");
   SSB_REQUIRE(((uintptr_t)O & 15) == 0, "attn_fused_fwd: O must be 16 B aligned");
   p.O = O; p.stat_m = stat_m; p.stat_linv = stat_linv;
   CUtensorMap mq, mk, mv, mr;
-  if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, QT)) return rc;
-  if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, CH)) return rc;
-  if (int rc = head_map(&mv, qkv_planes, B, T, 3 * H, 2 * H, H, CH)) return rc;
+  if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, QT, hs, dh)) return rc;
+  if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, CH, hs, dh)) return rc;
+  if (int rc = head_map(&mv, qkv_planes, B, T, 3 * H, 2 * H, H, CH, hs, dh)) return rc;
   if (int rc = r_map(&mr, R, B * H, T, RW, (int)RW, QT)) return rc;
   const int smem = FWD_SMEM_BYTES;
   if (int rc = set_smem(attn_fused_fwd_kernel, smem)) return rc;
@@ -1037,11 +1047,14 @@ int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_
 }
 
 int ssb_attn_delta(const float* O, const float* dO, int64_t B, int64_t T, int64_t H, int64_t dh,
-                   float* delta, void* stream) {
+                   float* delta, float* zero_out, int64_t zero_ld, void* stream) {
   SSB_REQUIRE(O && dO && delta && B >= 1 && T >= 1 && H >= 1 && dh >= 1, "attn_delta: bad arguments");
-  if (dh % 4 == 0 && H * dh <= 128 * DELTA_MAXV && (((uintptr_t)O | (uintptr_t)dO) & 15) == 0) {
+  const bool vec = dh % 4 == 0 && H * dh <= 128 * DELTA_MAXV && (((uintptr_t)O | (uintptr_t)dO) & 15) == 0;
+  SSB_REQUIRE(!zero_out || (vec && zero_ld % 4 == 0 && ((uintptr_t)zero_out & 15) == 0),
+              "attn_delta: zero_out needs the vector path (dh %% 4 == 0, 16 B aligned rows)");
+  if (vec) {
     attn_delta_kernel<<<(unsigned)((B * T + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-        O, dO, B * T, (int)T, (int)H, (int)dh, delta);
+        O, dO, B * T, (int)T, (int)H, (int)dh, delta, zero_out, zero_ld);
   } else {
     const int64_t warps = B * T * H;
     attn_delta_scalar_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
@@ -1055,7 +1068,9 @@ int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const floa
                        const float* stat_m, const float* stat_linv, const float* delta, int64_t B,
                        int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW, float drop_p,
                        uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
-                       void* stream) {
+                       int64_t head_stride, int64_t do_head_stride, void* stream) {
+  const int64_t hs = head_stride > 0 ? head_stride : 128;
+  const int64_t dhs = do_head_stride > 0 ? do_head_stride : 128;
   FusedParams p = {};
   if (int rc = fill(&p, B, T, H, dh, W, RW, drop_p, seed, site)) return rc;
   SSB_REQUIRE(qkv_planes && dO_planes && R && stat_m && stat_linv && delta && dqkv && dSband_planes,
@@ -1064,10 +1079,10 @@ int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const floa
   p.stat_m = const_cast<float*>(stat_m); p.stat_linv = const_cast<float*>(stat_linv);
   p.delta = delta; p.dqkv = dqkv; p.dsb = (__nv_bfloat16*)dSband_planes; p.RWp = (int)RWp;
   CUtensorMap mq, mk, mv, mdo, mr;
-  if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, CH)) return rc;
-  if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, QT)) return rc;
-  if (int rc = head_map(&mv, qkv_planes, B, T, 3 * H, 2 * H, H, QT)) return rc;
-  if (int rc = head_map(&mdo, dO_planes, B, T, H, 0, H, CH)) return rc;
+  if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, CH, hs, dh)) return rc;
+  if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, QT, hs, dh)) return rc;
+  if (int rc = head_map(&mv, qkv_planes, B, T, 3 * H, 2 * H, H, QT, hs, dh)) return rc;
+  if (int rc = head_map(&mdo, dO_planes, B, T, H, 0, H, CH, dhs, dh)) return rc;
   if (int rc = r_map(&mr, R, B * H, T, RW, RBOX, CH)) return rc;
   const int smem = BWD_SMEM_BYTES;
   if (int rc = set_smem(attn_fused_bwd_kernel, smem)) return rc;

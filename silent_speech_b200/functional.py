@@ -727,7 +727,7 @@ class _ConvWFn(torch.autograd.Function):
     order the backward uses them (k3 s1: (2,1,0); k3 s2: (1,), (2,0); k1 s2: (0,))."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, ksize, stride, wf, wd0, wd1):
+    def forward(ctx, x, weight, bias, ksize, stride, wf, wd0, wd1, zero_bias_grad=False):
         _chk(x, "x")
         B, L, Cin = x.shape
         Cout = weight.shape[0]
@@ -738,8 +738,11 @@ class _ConvWFn(torch.autograd.Function):
         gemm_tc_kmajor(tc_operand_conv(xp, B, L, Cin, Lout, stride, 1, off), wf, Cout, ksize * Cin,
                        _epi(Scatter(y.data_ptr(), Lout * Cout, Lout, Cout, 1, 0), bias=bias))
         ctx.save_for_backward(x, xp if ctx.needs_input_grad[1] else None, wd0, wd1)
-        ctx.cfg = (ksize, stride, bias is not None, tuple(weight.shape))
+        # a bias in front of a TRAINING-mode BatchNorm has an exactly zero gradient (the batch
+        # mean absorbs it): the caller says so and the column sum of dy is skipped
+        ctx.cfg = (ksize, stride, bias is not None and not zero_bias_grad, tuple(weight.shape))
         ctx.sink_b = _sink(bias) if bias is not None else None
+        ctx.zero_b = bias is not None and zero_bias_grad
         return y
 
     @staticmethod
@@ -765,6 +768,8 @@ class _ConvWFn(torch.autograd.Function):
                 colsum(dy.view(M, Cout), out=ctx.sink_b, accumulate=True)
             else:
                 db = colsum(dy.view(M, Cout))
+        elif ctx.zero_b and ctx.needs_input_grad[2] and ctx.sink_b is None:
+            db = torch.zeros(Cout, dtype=_f32, device=x.device)   # exact zero; a bucket already holds it
         if ctx.needs_input_grad[0]:
             def run(rows, taps, tap_off, planes, d_t, d_off, dst):
                 gemm_tc_kmajor(tc_operand_conv(dyp, B, Lout, Cout, rows, 1, 1, tap_off), planes, Cin,
@@ -781,15 +786,16 @@ class _ConvWFn(torch.autograd.Function):
             else:
                 dx = torch.zeros_like(x)
                 run((L + 1) // 2, 1, 0, wd0, 2, 0, dx)
-        return dx, dW, db, None, None, None, None, None
+        return dx, dW, db, None, None, None, None, None, None
 
 
 _CONV_TAPMAPS = {(3, 1): [(2, 1, 0)], (3, 2): [(1,), (2, 0)], (1, 2): [(0,)]}
 
 
-def conv1d_w(x, conv, wp, ksize, stride, gemm_weight):
+def conv1d_w(x, conv, wp, ksize, stride, gemm_weight, zero_bias_grad=False):
     """nn.Conv1d `conv` on channels-last x through the WeightPlanes arena `wp` when eligible;
-    `gemm_weight()` lazily builds the (k*Cin, Cout) matrix of the round-1 path otherwise."""
+    `gemm_weight()` lazily builds the (k*Cin, Cout) matrix of the round-1 path otherwise.
+    zero_bias_grad: the output feeds a training-mode BatchNorm and nothing else."""
     w = conv.weight
     Cout, Cin, _ = w.shape
     B, L, _ = x.shape
@@ -801,7 +807,8 @@ def conv1d_w(x, conv, wp, ksize, stride, gemm_weight):
           and _tc_fwd_ok(B * Lout, Cout, ksize * Cin, Cin) and _tc_wgrad_ok(B * Lout, Cout, ksize * Cin, Cin)
           and _tc_fwd_ok(B * L // max(stride, 1), Cin, Cout, Cout))
     if ok:
-        return _ConvWFn.apply(x, w, conv.bias, ksize, stride, wf, wd[0], wd[1] if len(wd) > 1 else None)
+        return _ConvWFn.apply(x, w, conv.bias, ksize, stride, wf, wd[0], wd[1] if len(wd) > 1 else None,
+                              bool(zero_bias_grad))
     return conv1d_cl(x, gemm_weight(), conv.bias, ksize, stride)
 
 
@@ -1241,22 +1248,31 @@ def _const_planes(E, key, make):
     return planes
 
 
-def _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, need_bwd=True):
-    """Fused band attention forward on fp32 qkv (M, 3D).  Returns (O, saved-for-backward)."""
+def _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, need_bwd=True, packed=None):
+    """Fused band attention forward.  qkv: fp32 (M, 3D), re-laid here into head-padded planes; or
+    packed = (2, M, 3D) split planes straight from the QKV GEMM's epilogue (head stride dh): the
+    kernels' tensor maps only ever address the first dh columns of a head, and the positional
+    GEMM's 128-wide reduction reads the next head's first columns against zero rows of the padded
+    table.  Returns (O, saved-for-backward)."""
     lib = _lib.load()
-    M, D3 = qkv.shape
     D = H * dh
     BH = B * H
     RW = (2 * W + 1 + 3) // 4 * 4
-    dev = qkv.device
     bf = torch.bfloat16
     st = _stream()
-    qkvp = torch.empty((2, M, 3 * H, _HP), dtype=bf, device=dev)
-    _lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, D3, 0, 3 * H, dh, qkvp.data_ptr(), st))
+    if packed is None:
+        M, D3 = qkv.shape
+        dev = qkv.device
+        hs = _HP
+        qkvp = torch.empty((2, M, 3 * H, _HP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, D3, 0, 3 * H, dh, qkvp.data_ptr(), st))
+    else:
+        qkvp, hs = packed, dh
+        M, dev = packed.shape[1], packed.device
     ep = _const_planes(E, ("fwd", W, dh, RW), lambda: torch.nn.functional.pad(
         E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, RW - (2 * W + 1))).contiguous())
-    ld_qkv = 3 * H * _HP
-    q_op = _op(qkvp, 0, M * ld_qkv, BH, T, _HP, ld_qkv, _HP, H, T * ld_qkv)
+    ld_qkv = 3 * H * hs
+    q_op = _op(qkvp, 0, M * ld_qkv, BH, T, _HP, ld_qkv, hs, H, T * ld_qkv)
     R = torch.empty((BH, T, RW), dtype=_f32, device=dev)
     e_op = _op(ep, 0, H * RW * _HP, H, RW, _HP, _HP, RW * _HP)
     _tc_batched(q_op, e_op, 2, RW, _HP, _epi(_bscatter(R, 0, T, RW, T * RW, H * T * RW)))
@@ -1264,12 +1280,13 @@ def _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, need_bwd=True):
     stats = torch.empty((2, BH, T), dtype=_f32, device=dev)
     _lib.check(lib.ssb_attn_fused_fwd(qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p,
                                       seed & 0xFFFFFFFFFFFFFFFF, site, O.data_ptr(),
-                                      stats[0].data_ptr(), stats[1].data_ptr(), st))
+                                      stats[0].data_ptr(), stats[1].data_ptr(), hs, st))
     return O, ((qkvp, R, stats, O, E) if need_bwd else None)
 
 
-def _fused_attn_bwd(saved, cfg, dO):
-    """-> dqkv (M, 3D) fp32 (content + positional parts; no gradient for E: SURVEY.md F3)."""
+def _fused_attn_bwd(saved, cfg, dO, dO_packed=None):
+    """-> dqkv (M, 3D) fp32 (content + positional parts; no gradient for E: SURVEY.md F3).
+    dO_packed: (2, M, D) split planes of dO when its producer already wrote them."""
     lib = _lib.load()
     qkvp, R, stats, O, E = saved
     B, T, H, dh, W, p, seed, site, RW = cfg
@@ -1280,12 +1297,18 @@ def _fused_attn_bwd(saved, cfg, dO):
     dev = O.device
     bf = torch.bfloat16
     st = _stream()
-    dop = torch.empty((2, M, H, _HP), dtype=bf, device=dev)
-    _lib.check(lib.ssb_pad_split_heads(dO.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), st))
+    hs = dh if qkvp.dim() == 3 else _HP          # (2, M, 3D) packed vs (2, M, 3H, 128) padded
+    if dO_packed is not None:
+        dop, dhs = dO_packed, dh
+    else:
+        dhs = _HP
+        dop = torch.empty((2, M, H, _HP), dtype=bf, device=dev)
+        _lib.check(lib.ssb_pad_split_heads(dO.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), st))
     delta = torch.empty((BH, T), dtype=_f32, device=dev)
-    _lib.check(lib.ssb_attn_delta(O.data_ptr(), dO.data_ptr(), B, T, H, dh, delta.data_ptr(), st))
     dqkv = torch.empty((M, D3), dtype=_f32, device=dev)
-    dqkv[:, :D].zero_()                                  # content dQ arrives by red.global.add
+    # content dQ arrives by red.global.add: its columns are cleared by the delta pass
+    _lib.check(lib.ssb_attn_delta(O.data_ptr(), dO.data_ptr(), B, T, H, dh, delta.data_ptr(),
+                                  dqkv.data_ptr(), D3, st))
     # band-layout dS: the kernel overwrites exactly the in-band, in-sequence entries - the same
     # set every call for a given geometry - and everything else must read 0.  One persistent
     # buffer per geometry, zeroed once, replaces a 131 MB fill per layer and step (backward
@@ -1295,7 +1318,7 @@ def _fused_attn_bwd(saved, cfg, dO):
                                       stats[0].data_ptr(), stats[1].data_ptr(),
                                       delta.data_ptr(), B, T, H, dh, W, RW, p,
                                       seed & 0xFFFFFFFFFFFFFFFF, site, dqkv.data_ptr(),
-                                      dsb.data_ptr(), _RWP, st))
+                                      dsb.data_ptr(), _RWP, hs, dhs, st))
     # positional part: dQ += dS_band E
     etp = _const_planes(E, ("bwd", W, dh), lambda: torch.nn.functional.pad(    # (2, H, 128, RWP)
         E[:, :2 * W + 1, :dh], (0, _HP - dh, 0, _RWP - (2 * W + 1))).transpose(1, 2).contiguous())
@@ -1381,11 +1404,12 @@ class _AttnBlockFn(torch.autograd.Function):
         M = x.shape[0]
         need_bwd = any(ctx.needs_input_grad[:8])
         xp = planes_of(x)
-        qkv = torch.empty((M, 3 * D), dtype=_f32, device=x.device)
+        # the projection exists only as packed split planes: the GEMM epilogue writes the operand
+        # format of the attention kernels directly (no fp32 qkv, no head re-layout pass)
+        qkvp = torch.empty((2, M, 3 * D), dtype=torch.bfloat16, device=x.device)
         gemm_tc_kmajor(tc_operand_plain(xp, M, D), qf, 3 * D, D,
-                       _epi(_scatter_plain(qkv.data_ptr(), M, 3 * D)))
-        O, att = _fused_attn_fwd(qkv, E, B, T, H, dh, W, p_attn, seed, site, need_bwd)
-        del qkv
+                       _epi(_scatter_plain(None, M, 3 * D), planes_out=qkvp))
+        O, att = _fused_attn_fwd(None, E, B, T, H, dh, W, p_attn, seed, site, need_bwd, packed=qkvp)
         op = split_planes(O)
         a = torch.empty((M, D), dtype=_f32, device=x.device)
         gemm_tc_kmajor(tc_operand_plain(op, M, D), of, D, D, _epi(_scatter_plain(a.data_ptr(), M, D)))
@@ -1410,8 +1434,10 @@ class _AttnBlockFn(torch.autograd.Function):
         if d_ap is None:
             d_ap = split_planes(d_a)
         # out-projection: dO = d_a Wo^T, dWo = O^T d_a (parameter layout = GEMM layout)
-        dO = torch.empty((M, D), dtype=_f32, device=dev)
-        gemm_tc_kmajor(tc_operand_plain(d_ap, M, D), ob, D, D, _epi(_scatter_plain(dO.data_ptr(), M, D)))
+        dO = torch.empty((M, D), dtype=_f32, device=dev)           # fp32 for delta = rowsum(O . dO)
+        dOp = torch.empty((2, M, D), dtype=torch.bfloat16, device=dev)   # packed operand of the bwd
+        gemm_tc_kmajor(tc_operand_plain(d_ap, M, D), ob, D, D,
+                       _epi(_scatter_plain(dO.data_ptr(), M, D), planes_out=dOp))
         if s_wo is not None:
             gemm_tc_wgrad(tc_operand_plain(op, M, D), d_ap, D, D, s_wo.view(D, D), accumulate=True)
             dWo = None
@@ -1420,7 +1446,7 @@ class _AttnBlockFn(torch.autograd.Function):
             gemm_tc_wgrad(tc_operand_plain(op, M, D), d_ap, D, D, dWo)
             dWo = dWo.view_as(w_o)
         del d_a, d_ap
-        dqkv = _fused_attn_bwd(att, ctx.cfg, dO)
+        dqkv = _fused_attn_bwd(att, ctx.cfg, dO, dO_packed=dOp)
         dqp = split_planes(dqkv)
         del dqkv
         # x receives d_res (through the LayerNorm) + dqkv Wqkv^T: accumulated by the GEMM epilogue

@@ -53,7 +53,7 @@ def main():
             stats = torch.empty(2, BH, T, device="cuda")
             f = lambda: SF._lib.check(lib.ssb_attn_fused_fwd(
                 qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p, 1, 0, O.data_ptr(),
-                stats[0].data_ptr(), stats[1].data_ptr(), SF._stream()))
+                stats[0].data_ptr(), stats[1].data_ptr(), 128, SF._stream()))
             print(f"  attn_fused_fwd_kernel alone: {timeit(f):.0f} us")
             dop = torch.empty((2, M, H, 128), dtype=torch.bfloat16, device="cuda")
             SF._lib.check(lib.ssb_pad_split_heads(go.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), SF._stream()))
@@ -63,7 +63,7 @@ def main():
             g = lambda: SF._lib.check(lib.ssb_attn_fused_bwd(
                 qkvp.data_ptr(), dop.data_ptr(), R.data_ptr(), stats[0].data_ptr(),
                 stats[1].data_ptr(), delta.data_ptr(), B, T, H, dh, W, RW, p, 1, 0,
-                dqkv.data_ptr(), dsb.data_ptr(), 256, SF._stream()))
+                dqkv.data_ptr(), dsb.data_ptr(), 256, 128, 128, SF._stream()))
             print(f"  attn_fused_bwd_kernel alone: {timeit(g):.0f} us")
 
 
