@@ -46,6 +46,11 @@ def test_arena_equals_per_use_derivation(D, NL, L, monkeypatch):
         assert torch.equal(p0, p_) and torch.equal(a0, a_)
         assert set(g0) == set(g_)
         for k in g0:
+            if k.startswith("conv_blocks") and k.endswith(("conv1.bias", "conv2.bias", "residual_path.bias")):
+                # analytically zero in front of a training BatchNorm: rounding noise on the per-use
+                # path, an exact zero (column sum skipped) on the arena path
+                assert g0[k].abs().max() < 1e-4 and g_[k].abs().max() < 1e-4
+                continue
             d = (g0[k] - g_[k]).norm() / (g0[k].norm() + 1e-30)
             assert d < 2e-6, (k, d.item())
 
