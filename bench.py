@@ -531,7 +531,7 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def dp_check(model, bucket, batch, frames, task, world, rank):
+def dp_check(model, bucket, batch, frames, task, world, rank, check_overlap=False):
     """On-hardware correctness of the data-parallel exchange (N > 1).  One extra (untimed)
     forward + backward per arm on each rank's own utterances, same dropout seed and shift:
       * plain: per-rank checksums of the LOCAL gradients, then one all-reduce of the whole bucket;
@@ -564,15 +564,18 @@ def dp_check(model, bucket, batch, frames, task, world, rank):
     sums, abss = gather(local_sum), gather(local_abs)
     red_bits = gather(bits(plain))
     red_sum = plain.double().sum().item()
-    fwd_bwd(OverlappedAllReduce(bucket))
-    ov_diff = ((bucket.flat - plain).double().norm() / (plain.double().norm() + 1e-30)).item()
-    ov_bits = gather(bits(bucket.flat))
+    if check_overlap:
+        fwd_bwd(OverlappedAllReduce(bucket))
+        ov_diff = ((bucket.flat - plain).double().norm() / (plain.double().norm() + 1e-30)).item()
+        ov_bits = gather(bits(bucket.flat))
+    else:
+        ov_diff, ov_bits = 0.0, red_bits
     pbits = gather(sum(bits(p.data.view(-1)) for p in model.parameters()))
     ov_diffs = gather(ov_diff)
     return {"ranks": world,
             "reduced_bucket_identical_on_all_ranks": len(set(red_bits)) == 1 and len(set(ov_bits)) == 1,
             "sum_of_reduced_vs_sum_of_local": abs(red_sum - sum(sums)) / (sum(abss) + 1e-30),
-            "overlapped_vs_plain_rel_l2": max(ov_diffs),
+            "overlapped_vs_plain_rel_l2": max(ov_diffs) if check_overlap else None,
             "params_identical_on_all_ranks_after_timed_steps": len(set(pbits)) == 1,
             "ok": bool(len(set(red_bits)) == 1 and len(set(ov_bits)) == 1 and len(set(pbits)) == 1
                        and abs(red_sum - sum(sums)) <= 1e-5 * sum(abss) and max(ov_diffs) < 1e-5)}
@@ -629,7 +632,7 @@ def run_ours(args):
 
     # the public training call: eager step, or (default) the same step with forward + loss +
     # backward (+ the overlapped gradient all-reduce at N > 1) replayed as one CUDA graph
-    overlap = world > 1 and not args.no_overlap and accumulate == 1
+    overlap = world > 1 and args.overlap and not args.no_overlap and accumulate == 1
     graphed = None if args.eager else GraphedTrainStep(model, optim, "cuda", frames, bucket, task=task,
                                                        accumulate=accumulate, blank=N_CHARS,
                                                        overlap=overlap)
@@ -682,7 +685,7 @@ def run_ours(args):
             "step_tflops": wl["gflop"] * value / world / 1e3,
             "clocks": clk.summary()}
     if world > 1:
-        chk = dp_check(model, bucket, host_batch, frames, task, world, rank)
+        chk = dp_check(model, bucket, host_batch, frames, task, world, rank, check_overlap=overlap)
         if rank == 0:
             line["dp_check"] = chk
     if rank == 0:
@@ -748,8 +751,11 @@ def main():
     ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
                     help="--impl reference: run the unmodified reference on the host or on cuda:0")
     ap.add_argument("--tf32", action="store_true", help="--ref-device cuda: allow TF32")
-    ap.add_argument("--no-overlap", action="store_true",
-                    help="N > 1: one all-reduce after backward instead of the overlapped segments")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1 (EXPERIMENTAL): issue the gradient all-reduce in segments from backward "
+                         "hooks on a side stream, captured inside the step graph.  Default: one "
+                         "all-reduce of the flat bucket after the replay (measured: +0.3 ms/step at N=2)")
+    ap.add_argument("--no-overlap", action="store_true", help="(default behaviour; kept for scripts)")
     ap.add_argument("--no-torch-leg", action="store_true",
                     help="skip the informational reference-on-B200 (stock PyTorch) leg")
     ap.add_argument("--roofline-only", action="store_true",
