@@ -313,40 +313,49 @@ def dtw_side_metric(peaks, world, rank, with_cpu):
     return out
 
 
-def mel_side_metric(peaks, with_cpu):
-    """log-mel of 32 x 10 s clips at 22.05 kHz; 1344 B/frame algorithmic."""
-    from silent_speech_b200 import data_utils as du
-    y = (torch.rand(32, 220500, device="cuda") * 2 - 1) * 0.5
-    f = lambda: du.mel_spectrogram(y, 1024, 80, 22050, 256, 1024, 0, 8000)
-    ms = timed(f, 10, 3, 1) / 10       # public call: includes the reference's range check (a host read)
-    frames = 32 * 861
-    # the kernel alone through the C ABI (what the roofline is about)
+def mel_side_metric(peaks, with_cpu, clocks_mhz=1965.0):
+    """log-mel on 1024 clips x 10 s at 22.05 kHz - enough frames (882 k) to
+    fill the machine; the 32-clip geometry of round 1 finished in 6 us at HBM speed and measured
+    launch + tail.  Algorithmic work per frame: 1344 B of HBM traffic, ~27.5 kFLOP fp32."""
     from silent_speech_b200 import _lib
+    from silent_speech_b200 import data_utils as du
+    B, S, F = 1024, 220500, 861
+    y = (torch.rand(B, S, device="cuda") * 2 - 1) * 0.5
+    f = lambda: du.mel_spectrogram(y, 1024, 80, 22050, 256, 1024, 0, 8000)
+    ms = timed(f, 5, 3, 1) / 5         # public call (range check rides in the kernel)
+    du.flush_range_warnings(block=True)
+    frames = B * F
     lib = _lib.load()
     basis, begin, end = du._basis_for(22050, 1024, 80, 0, 8000, y.device)
-    out_k = torch.empty(32, 80, 861, device="cuda")
+    out_k = torch.empty(B, 80, F, device="cuda")
 
     def k():
-        _lib.check(lib.ssb_mel_fwd(y.data_ptr(), 32, 220500, y.stride(0), 1024, 256, 1024,
+        _lib.check(lib.ssb_mel_fwd(y.data_ptr(), B, S, y.stride(0), 1024, 256, 1024,
                                    basis.data_ptr(), begin.data_ptr(), end.data_ptr(), 80, 1e-5,
-                                   out_k.data_ptr(), _lib.current_stream()))
-    ms_k = timed(k, 20, 3, 1) / 20
+                                   out_k.data_ptr(), None, _lib.current_stream()))
+    ms_k = timed(k, 5, 3, 1) / 5       # 1.2 GB in + out per launch: far beyond L2
     gbs = 1344.0 * frames / ms_k / 1e6
-    out = {"metric": "mel kframes/s (32 clips x 10 s)", "value": frames / ms, "ms": ms,
+    tfl = 27.5e3 * frames / ms_k / 1e9
+    fp32_peak = 148 * 128 * 2 * clocks_mhz * 1e6 / 1e12      # FMA lanes x 2 flop x clock
+    out = {"metric": "mel kframes/s (1024 clips x 10 s)", "value": frames / ms, "ms": ms,
            "kernel_ms": ms_k, "kernel_kframes_per_s": frames / ms_k,
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_frame": 1344,
-                        "note": "kernel time; fp32 16x16x4 register FFT + sparse mel: compute / "
-                                "shared-memory bound at this size (37 MB of algorithmic traffic), "
-                                "not HBM-bound"}}
+                        "traffic": ncu_traffic("mel"),
+                        "fp32": {"achieved_tflops": tfl, "peak_tflops": fp32_peak,
+                                 "frac": tfl / fp32_peak, "flop_per_frame": 27.5e3,
+                                 "peak_source": f"148 SMs x 128 FMA lanes x 2 x {clocks_mhz:.0f} MHz (nominal)"},
+                        "limiter": "neither roof: ncu (profiles/r2_mel.txt) shows the L1/TEX pipe "
+                                   "(shared-memory exchanges of the 16x16x4 FFT + twiddle loads) "
+                                   "85 % busy, DRAM traffic = algorithmic"}}
     if with_cpu:
         from oracle import mel as omel
         yh = y[:4].cpu().numpy()
         t0 = time.perf_counter()
         omel.mel_spectrogram(yh)
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": 4 * 861 / dt / 1e3, "unit": "kframes/s", "cores": 1,
-                               "kind": "port", "sample": "4 of the 32 clips (numpy)"}
+        out["cpu_baseline"] = {"value": 4 * F / dt / 1e3, "unit": "kframes/s", "cores": 1,
+                               "kind": "port", "sample": "4 of the 1024 clips (numpy)"}
     return out
 
 

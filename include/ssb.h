@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 205
+#define SSB_ABI_VERSION 206
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -159,10 +159,14 @@ SSB_API int ssb_dtw_time_warp_batch_f64(const double* cost, int64_t npairs, int6
  * Built for n_fft == win == 1024 (the reference's only configuration, data_utils.py:79).
  */
 SSB_API int64_t ssb_mel_num_frames(int64_t S, int n_fft, int hop);
+/* range_cell (nullable): two device uint32 words, initialised to 0 by the caller, that receive
+ * order-preserving keys of -min(y) and max(y) over every sample the kernel reads (the reference
+ * prints a warning when y leaves [-1, 1], data_utils.py:40-43): key(f) = f >= 0 ? bits | 2^31 :
+ * ~bits.  Lets the caller test the range without a separate reduction pass. */
 SSB_API int ssb_mel_fwd(const float* y, int64_t B, int64_t S, int64_t y_stride, int n_fft, int hop,
                         int win, const float* mel_basis, const int32_t* tap_begin,
                         const int32_t* tap_end, int num_mels, float clip_val, float* out,
-                        void* stream);
+                        void* range_cell, void* stream);
 
 /* ---- dense contractions with gathered operands ------------------------------
  * Replaces nn.Linear (architecture.py:51,55,59; transformer.py:32,34), the three

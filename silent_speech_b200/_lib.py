@@ -101,7 +101,7 @@ _SIGNATURES = {
     "ssb_mel_num_frames": (c_i64, [c_i64, ctypes.c_int, ctypes.c_int]),
     "ssb_mel_fwd": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int,
                                    ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_f32, c_ptr,
-                                   c_ptr]),
+                                   c_ptr, c_ptr]),
     "ssb_gemm_nn": (c_int, [_PG, c_ptr, c_i64, _PE, c_i64, c_i64, c_i64, c_ptr]),
     "ssb_gemm_nt": (c_int, [_PG, c_ptr, c_i64, c_i64, c_int, c_int, c_int, _PE, c_i64, c_i64,
                             c_i64, c_ptr]),
@@ -215,7 +215,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 205      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 206      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(THREADS)
 mel_kernel(const float* __restrict__ y, int64_t y_stride, int S, int hop, int pad, int frames,
            const float* __restrict__ basis, const int* __restrict__ tap_begin,
            const int* __restrict__ tap_end, int num_mels, float clip_val,
-           float* __restrict__ out) {
+           float* __restrict__ out, unsigned int* __restrict__ range_cell) {
   __shared__ __align__(16) float2 ex1[2][16 * ROW];   // step 1 -> 2a exchange; later the spectrum
   __shared__ __align__(16) float2 ex2[2][16 * ROW];   // step 2a -> 2b exchange
   __shared__ float mag[FRAMES_PER_CTA][NBINS + 3];
@@ -78,6 +78,7 @@ mel_kernel(const float* __restrict__ y, int64_t y_stride, int S, int hop, int pa
   float2* s1 = ex1[g];
   float2* s2 = ex2[g];
   float2 v[16];
+  float smin = 3.4e38f, smax = -3.4e38f;   // range of the samples this thread touches (data_utils.py:40-43)
 
   // step 1: thread m = t takes samples k = 64*n1 + m (windowed, reflect-padded load:
   // data_utils.py:51,54; frame f covers n = f*hop - pad + k), 16-point DFT over n1,
@@ -92,7 +93,20 @@ mel_kernel(const float* __restrict__ y, int64_t y_stride, int S, int hop, int pa
     nb = nb < 0 ? -nb : (nb >= S ? 2 * (S - 1) - nb : nb);
     const float a = has_a ? __ldg(yb + n0) : 0.f;
     const float c = has_b ? __ldg(yb + nb) : 0.f;
+    smin = fminf(smin, fminf(a, c));
+    smax = fmaxf(smax, fmaxf(a, c));
     v[n1] = make_float2(w * a, w * c);
+  }
+  if (range_cell) {
+    // order-preserving float -> uint map, so the range check of the reference (min < -1 / max > 1
+    // warnings) costs two atomics per warp here instead of a separate reduction and a host read
+    smin = ssb::warp_max(-smin);   // = -min
+    smax = ssb::warp_max(smax);
+    if ((tid & 31) == 0) {
+      auto key = [](float f) { const unsigned int u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+      atomicMax(range_cell, key(smin));       // cell 0: -min
+      atomicMax(range_cell + 1, key(smax));   // cell 1: max
+    }
   }
   dft16(v);
 #pragma unroll
@@ -191,7 +205,7 @@ int64_t ssb_mel_num_frames(int64_t S, int n_fft, int hop) {
 int ssb_mel_fwd(const float* y, int64_t B, int64_t S, int64_t y_stride, int n_fft, int hop,
                 int win, const float* mel_basis, const int32_t* tap_begin,
                 const int32_t* tap_end, int num_mels, float clip_val, float* out,
-                void* stream) {
+                void* range_cell, void* stream) {
   SSB_REQUIRE(n_fft == NFFT && win == NFFT,
               "mel: only n_fft = win_size = 1024 is built (the reference's only call, "
               "data_utils.py:79); got n_fft=%d win=%d", n_fft, win);
@@ -211,7 +225,8 @@ int ssb_mel_fwd(const float* y, int64_t B, int64_t S, int64_t y_stride, int n_ff
   if (int rc = ensure_twiddles(st)) return rc;
   dim3 grid((unsigned)((frames + FRAMES_PER_CTA - 1) / FRAMES_PER_CTA), (unsigned)B);
   mel_kernel<<<grid, THREADS, 0, st>>>(y, y_stride, (int)S, hop, pad, (int)frames, mel_basis,
-                                       tap_begin, tap_end, num_mels, clip_val, out);
+                                       tap_begin, tap_end, num_mels, clip_val, out,
+                                       (unsigned int*)range_cell);
   SSB_LAUNCH_CHECK("mel_kernel");
   return SSB_OK;
 }

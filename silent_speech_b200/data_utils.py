@@ -112,13 +112,7 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     _lib.require_cuda(y, "y")
     if y.dim() != 2:
         raise ValueError("y must be (batch, samples)")
-    # data_utils.py:40-43 warns about samples outside [-1, 1]; one fused reduction and one
-    # host read instead of up to four reductions with a sync each
-    lo, hi = torch.stack(torch.aminmax(y)).tolist()
-    if lo < -1.:
-        print('min value is ', lo)
-    if hi > 1.:
-        print('max value is ', hi)
+    flush_range_warnings()          # report finished checks of earlier calls (never blocks)
     lib = _lib.load()
     y = y.to(torch.float32)
     if y.stride(1) != 1:
@@ -129,11 +123,48 @@ def mel_spectrogram(y, n_fft, num_mels, sampling_rate, hop_size, win_size, fmin,
     if frames < 0:
         raise _lib.SSBError(frames, "mel_spectrogram: bad sizes")
     out = torch.empty((B, num_mels, frames), dtype=torch.float32, device=y.device)
+    # data_utils.py:40-43 prints a warning when samples leave [-1, 1].  The kernel tracks min / max
+    # of what it reads (two atomics per warp); the two words come back by an asynchronous copy and
+    # are reported by flush_range_warnings() - at the next call, or right after the caller's own
+    # synchronisation (load_audio's .cpu()) - instead of a reduction pass + host read per call.
+    cell = torch.zeros(2, dtype=torch.int32, device=y.device)
     with torch.cuda.device(y.device):
         _lib.check(lib.ssb_mel_fwd(y.data_ptr(), B, S, y.stride(0), n_fft, hop_size, win_size,
                                    basis.data_ptr(), begin.data_ptr(), end.data_ptr(), num_mels,
-                                   1e-5, out.data_ptr(), _lib.current_stream()))
+                                   1e-5, out.data_ptr(), cell.data_ptr(), _lib.current_stream()))
+        if B and frames and not torch.cuda.is_current_stream_capturing():
+            host = torch.empty(2, dtype=torch.int32).pin_memory()
+            host.copy_(cell, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            _pending_range.append((host, ev))
     return out
+
+
+_pending_range = []
+
+
+def _key_to_float(k):
+    k = int(k) & 0xFFFFFFFF
+    bits = (k & 0x7FFFFFFF) if (k & 0x80000000) else (~k & 0xFFFFFFFF)
+    return float(np.array([bits], dtype=np.uint32).view(np.float32)[0])
+
+
+def flush_range_warnings(block=False):
+    """Print the reference's out-of-range warnings (data_utils.py:40-43) for every finished
+    mel_spectrogram call; block=True waits for the outstanding ones."""
+    keep = []
+    for host, ev in _pending_range:
+        if not block and not ev.query():
+            keep.append((host, ev))
+            continue
+        ev.synchronize()
+        lo, hi = -_key_to_float(host[0]), _key_to_float(host[1])
+        if lo < -1.:
+            print('min value is ', lo)
+        if hi > 1.:
+            print('max value is ', hi)
+    _pending_range[:] = keep
 
 
 # ---------------------------------------------------------------------------------------
@@ -264,6 +295,7 @@ def load_audio(filename, start=None, end=None, max_frames=None, renormalize_volu
     y = torch.tensor(audio, dtype=torch.float32).unsqueeze(0).cuda()
     mspec = mel_spectrogram(y, 1024, 80, 22050, 256, 1024, 0, 8000, center=False)
     mspec = mspec.squeeze(0).T.cpu().numpy()
+    flush_range_warnings(block=True)      # the copy above already synchronised: no extra wait
     if max_frames is not None and mspec.shape[0] > max_frames:
         mspec = mspec[:max_frames, :]
     return mspec

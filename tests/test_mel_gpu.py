@@ -60,3 +60,18 @@ def test_edge_cases():
         du.mel_spectrogram(torch.zeros(1, 4000), 1024, 80, 22050, 256, 1024, 0, 8000)  # CPU tensor
     with pytest.raises(Exception):
         du.mel_spectrogram(y, 512, 80, 22050, 128, 512, 0, 8000)                        # not built
+
+
+def test_out_of_range_warning_is_reported_without_a_blocking_check(capsys):
+    """data_utils.py:40-43 prints 'min value is' / 'max value is' for samples outside [-1, 1]; here
+    the kernel tracks the range and the report comes from flush_range_warnings()."""
+    y = torch.zeros(2, 4096, device="cuda")
+    y[0, 100] = -1.75
+    y[1, 3000] = 2.5
+    du.mel_spectrogram(y, 1024, 80, 22050, 256, 1024, 0, 8000)
+    du.flush_range_warnings(block=True)
+    out = capsys.readouterr().out
+    assert "min value is  -1.75" in out and "max value is  2.5" in out
+    du.mel_spectrogram(y.clamp(-1, 1), 1024, 80, 22050, 256, 1024, 0, 8000)
+    du.flush_range_warnings(block=True)
+    assert capsys.readouterr().out == ""

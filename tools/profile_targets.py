@@ -28,7 +28,7 @@ def mel(n):
     for _ in range(n):
         _lib.check(lib.ssb_mel_fwd(y.data_ptr(), B, 220500, y.stride(0), 1024, 256, 1024,
                                    basis.data_ptr(), begin.data_ptr(), end.data_ptr(), 80, 1e-5,
-                                   out.data_ptr(), _lib.current_stream()))
+                                   out.data_ptr(), None, _lib.current_stream()))
 
 
 def attn(n):
