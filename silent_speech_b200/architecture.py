@@ -146,8 +146,15 @@ class Model(nn.Module):
         B, T, D = x.shape
         x2 = F_.linear_w(x.view(B * T, D), self.w_raw_in, wp)
         x2 = self.transformer.forward_tokens(x2, B, T, wp)
-        out = F_.linear_w(x2, self.w_out, wp).view(B, T, -1)
         if self.has_aux_out:
+            hf = wp.get(self, "heads_f") if wp is not None else None
+            M, N = B * T, self.w_out.out_features + self.w_aux.out_features
+            if (hf is not None and F_._tc_fwd_ok(M, N, D) and F_._tc_fwd_ok(M, D, N)
+                    and F_._tc_wgrad_ok(M, N, D)):
+                out, aux = F_._HeadsFn.apply(x2, self.w_out.weight, self.w_out.bias, self.w_aux.weight,
+                                             self.w_aux.bias, hf, wp.get(self, "heads_b"))
+                return out.view(B, T, -1), aux.view(B, T, -1)
+            out = F_.linear_w(x2, self.w_out, wp).view(B, T, -1)
             aux = F_.linear_w(x2, self.w_aux, wp).view(B, T, -1)
             return out, aux
-        return out
+        return F_.linear_w(x2, self.w_out, wp).view(B, T, -1)

@@ -104,15 +104,25 @@ bn_chunk_stats_kernel(const float* __restrict__ x, int64_t rows, int C,
   float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), m2 = mu;
   int n = 0;
   if (c < C) {
-    for (int64_t r = r0 + rl; r < r1; r += 8) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C + c));
-      ++n;
-      const float inv = __frcp_rn((float)n);
-      float d;
-      d = v.x - mu.x; mu.x = fmaf(d, inv, mu.x); m2.x = fmaf(d, v.x - mu.x, m2.x);
-      d = v.y - mu.y; mu.y = fmaf(d, inv, mu.y); m2.y = fmaf(d, v.y - mu.y, m2.y);
-      d = v.z - mu.z; mu.z = fmaf(d, inv, mu.z); m2.z = fmaf(d, v.z - mu.z, m2.z);
-      d = v.w - mu.w; mu.w = fmaf(d, inv, mu.w); m2.w = fmaf(d, v.w - mu.w, m2.w);
+    // four independent 16 B loads in flight per thread before the (serial) Welford updates
+    for (int64_t r = r0 + rl; r < r1; r += 32) {
+      float4 v4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        v4[j] = (r + 8 * j < r1) ? __ldg(reinterpret_cast<const float4*>(x + (r + 8 * j) * C + c))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r + 8 * j >= r1) break;
+        const float4 v = v4[j];
+        ++n;
+        const float inv = __frcp_rn((float)n);
+        float d;
+        d = v.x - mu.x; mu.x = fmaf(d, inv, mu.x); m2.x = fmaf(d, v.x - mu.x, m2.x);
+        d = v.y - mu.y; mu.y = fmaf(d, inv, mu.y); m2.y = fmaf(d, v.y - mu.y, m2.y);
+        d = v.z - mu.z; mu.z = fmaf(d, inv, mu.z); m2.z = fmaf(d, v.z - mu.z, m2.z);
+        d = v.w - mu.w; mu.w = fmaf(d, inv, mu.w); m2.w = fmaf(d, v.w - mu.w, m2.w);
+      }
     }
   } else {
     for (int64_t r = r0 + rl; r < r1; r += 8) ++n;

@@ -553,6 +553,43 @@ def linear_w(x2d, lin, wp):
     return linear(x2d, w.t().contiguous(), lin.bias)
 
 
+class _HeadsFn(torch.autograd.Function):
+    """(w_out(x), w_aux(x)) of architecture.py:81-84 as ONE GEMM on the stacked weight (N1 + N2
+    outputs; 80 + 48 = 128 in the transduction model), so that forward, data gradient and weight
+    gradient all run on the tensor cores.  hf: [N1+N2][K] planes, hb: [K][N1+N2] planes."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, hf, hb):
+        _chk(x, "x")
+        M, K = x.shape
+        N1, N2 = w1.shape[0], w2.shape[0]
+        N = N1 + N2
+        bias = torch.cat([b1, b2])
+        y = torch.empty((M, N), dtype=_f32, device=x.device)
+        xp = planes_of(x)
+        gemm_tc_kmajor(tc_operand_plain(xp, M, K), hf, N, K, _epi(_scatter_plain(y.data_ptr(), M, N), bias=bias))
+        ctx.save_for_backward(xp, hb)
+        ctx.split = (N1, N2)
+        return y[:, :N1].contiguous(), y[:, N1:].contiguous()
+
+    @staticmethod
+    def backward(ctx, d1, d2):
+        xp, hb = ctx.saved_tensors
+        N1, N2 = ctx.split
+        N = N1 + N2
+        M, K = xp.shape[1:]
+        dy = torch.cat([d1, d2], dim=1)
+        dyp = split_planes(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=_f32, device=dy.device)
+            gemm_tc_kmajor(tc_operand_plain(dyp, M, N), hb, K, N, _epi(_scatter_plain(dx.data_ptr(), M, K)))
+        dWg = torch.empty((K, N), dtype=_f32, device=dy.device)
+        gemm_tc_wgrad(tc_operand_plain(xp, M, K), dyp, N, K, dWg)
+        db = colsum(dy)
+        return dx, dWg[:, :N1].t(), db[:N1], dWg[:, N1:].t(), db[N1:], None, None
+
+
 class _QKVFn(torch.autograd.Function):
     """qkv = x @ [Wq | Wk | Wv] for the per-head weights w_j (H, D, dh) of transformer.py:71-74
     (no bias).  wf: [3D][D] planes, wb: [D][3D] planes of the fused matrix."""

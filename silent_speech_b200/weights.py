@@ -52,6 +52,13 @@ class WeightPlanes:
         lin(m.w_out.weight)
         if getattr(m, "has_aux_out", False):
             lin(m.w_aux.weight)
+            # both heads as ONE matrix (rows: w_out, then w_aux): 80 + 48 = 128 outputs make the
+            # forward, data-gradient and weight-gradient GEMMs tensor-core eligible together
+            n1, n2, K = m.w_out.weight.shape[0], m.w_aux.weight.shape[0], m.w_out.weight.shape[1]
+            if _ok(n1 + n2, K) and _ok(K, n1 + n2) and n1 % 8 == 0:
+                for w, r0 in ((m.w_out.weight, 0), (m.w_aux.weight, n1)):
+                    out.append(dict(p=w, rows=w.shape[0], cols=K, RL=w.shape[0], CL=K, s=(0, K, 0, 1),
+                                    kn="heads_f", kt="heads_b", group=m, stack=(r0, n1 + n2)))
         for layer in m.transformer.layers:
             lin(layer.linear1.weight)
             lin(layer.linear2.weight)
@@ -104,12 +111,13 @@ class WeightPlanes:
         for sp in specs:
             p, R, C = sp["p"], sp["rows"], sp["cols"]
             parts, part = sp.get("parts", 1), sp.get("part", 0)
+            r_off, r_tot = sp.get("stack", (part * R, R * parts))   # row offset / rows of the stack
             owner = id(sp.get("group", p))
             dn = dt_ = None
             if sp["kn"] is not None:     # as read: parts stack along rows
-                dn = (block((owner, sp["kn"]), R * parts, C), part * R * C, C)
+                dn = (block((owner, sp["kn"]), r_tot, C), r_off * C, C)
             if sp["kt"] is not None:     # transposed (C x R): parts stack along columns
-                dt_ = (block((owner, sp["kt"]), C, R * parts), part * R, R * parts)
+                dt_ = (block((owner, sp["kt"]), C, r_tot), r_off, r_tot)
             plan.append((sp, dn, dt_))
         self.arena = torch.zeros(max(total, 64), dtype=torch.bfloat16, device=dev)
         base = self.arena.data_ptr()

@@ -72,6 +72,9 @@ def test_every_layout_matches_the_torch_derivation():
         check(lin.weight, "b", lin.weight.t())
     check(m.w_out.weight, "f", m.w_out.weight)          # 80-wide head: forward operand only
     assert wp.get(m.w_out.weight, "b") is None
+    stacked = torch.cat([m.w_out.weight, m.w_aux.weight], 0)     # both heads as one 128-wide matrix
+    check(m, "heads_f", stacked)
+    check(m, "heads_b", stacked.t())
     D = 128
     for layer in m.transformer.layers:
         at = layer.self_attn
