@@ -51,8 +51,10 @@ def test_arena_equals_per_use_derivation(D, NL, L, monkeypatch):
                 # path, an exact zero (column sum skipped) on the arena path
                 assert g0[k].abs().max() < 1e-4 and g_[k].abs().max() < 1e-4
                 continue
+            # same arithmetic, different summation orders (split-K atomics; the stacked heads'
+            # data gradient is one K = 128 GEMM instead of two CUDA-core GEMMs and an add)
             d = (g0[k] - g_[k]).norm() / (g0[k].norm() + 1e-30)
-            assert d < 2e-6, (k, d.item())
+            assert d < 5e-5, (k, d.item())
 
 
 def test_arena_follows_optimizer_steps_and_checkpoint_loads(monkeypatch):
