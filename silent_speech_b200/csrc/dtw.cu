@@ -8,25 +8,36 @@
 // x == DTW column j (Y_IS_I); for a C-ordered matrix y == j and x == i.  The recurrence is
 // symmetric under that swap, only the tie-break order changes, so one kernel serves both.
 //
-// Work decomposition.  One warp owns one (pair) at a time and walks it in bands of
-// BAND = 32 lanes x R strip-rows.  Inside a band lane l owns strip rows [y0, y0+R) and, at
-// step s, computes sweep column x = s - l (a systolic skew of one column per lane): the
-// value of the row above comes from lane l-1 by one shuffle per step, the diagonal is the
-// previous shuffle result, the left neighbour is the lane's own register.  Each cell does
-// exactly one fp32 add (cost + min3), so the result is bit-identical to the reference's
-// sequential loop.  The band's bottom row is parked in shared memory (Nx floats, updated in
-// place 31 columns behind the read position) and feeds lane 0 of the next band.
+// Work decomposition.  A pair is cut into bands of BAND = 32 lanes x R strip-rows; one warp
+// sweeps one band.  Inside a band lane l owns strip rows [y0, y0+R) and, at step s, computes
+// sweep column x = s - l (a systolic skew of one column per lane): the value of the row above
+// comes from lane l-1 by one shuffle per step, the diagonal is the previous shuffle result, the
+// left neighbour is the lane's own register.  Each cell does exactly one fp32 add
+// (cost + min3), so the result is bit-identical to the reference's sequential loop.
+//
+// Band pipeline.  The W warps of a CTA take the bands of the CTA's pairs round-robin (band
+// instance g -> warp g % W) and run them CONCURRENTLY: the bottom row of band b is parked in the
+// producing warp's shared-memory boundary buffer and read by the warp sweeping band b+1, which
+// follows three 16-step chunks behind (progress words in shared memory, one update per chunk).
+// Two things come from that: (1) a lone pair finishes in (nch + 3 (nbands-1)) chunk times instead
+// of nch * nbands -- the 16-pair training batch is latency-bound; (2) the 128 B lines that
+// straddle a band boundary (pitch 600 floats: three columns of four start off a line boundary)
+// are requested by the two neighbouring warps within ~1 us of each other, so the second request
+// hits L2 instead of fetching the line from DRAM again (r2 capture of the one-warp-per-pair
+// kernel: DRAM read 1.198x algorithmic; the model "every band-column fetch rounds out to 128 B
+// lines" gives 1.200x).
 //
 // HBM traffic.  Cost tiles stream global->shared with cp.async: at step s lane l = 8g+q
 // copies ITS OWN 16 B (its R=4 rows) of column s-8g+PF, so every group of 8 lanes fetches
 // one full 128 B line, each lane only ever reads shared memory it filled itself (no
-// cross-lane visibility hazards), and the per-lane ring is RING=32 columns deep
-// (PF=24 columns of prefetch + 8 of intra-group skew): 16 KB of shared memory per warp.
-// Cost is read exactly once: 4 B/cell algorithmic, plus 0.29 B/cell of direction codes
+// cross-lane visibility hazards), and the per-lane ring is RING=16 columns deep
+// (PF=8 columns of prefetch + 8 of intra-group skew): 8 KB of shared memory per warp.
+// Cost is read exactly once: 4 B/cell algorithmic, plus 0.28 B/cell of direction codes
 // written in the skewed (step-major) order so that every 16 steps a warp stores one
 // coalesced 512 B row of packed codes.
 #include "ssb_common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 #include <type_traits>
 
 namespace {
@@ -51,6 +62,7 @@ struct DtwParams {
   int64_t pitch;
   int64_t dirs_pair_words;
   int Ny, Nx, nbands, nch, npairs;
+  int flags;   // experiment switches: 1 = L2 eviction hints, 2 = L2 prefetch one chunk ahead
 };
 
 // Direction codes: 2 raw predicate bits per cell: bit0 = "second candidate (i,j-1) < first
@@ -60,23 +72,76 @@ struct DtwParams {
 // words are stored step-major:  dirs[(band*nch + chunk)*32 + lane]  (uint4 = the lane's 4 rows)
 // so that every chunk ends with one coalesced 512 B store per warp.
 
+constexpr int MAX_WARPS = 8;    // band-pipeline width (warps per CTA)
+constexpr int PROG_SHIFT = 12;  // progress word = (band instance of the warp << 12) + chunks done
+constexpr int LAG = 3;          // chunks the consumer of a boundary row stays behind its producer:
+                                // chunk c reads bnd[16c .. 16c+15], written at steps <= 16c+15+31
+
+// spin until the progress word of another warp of this CTA reaches `need` (`seen` caches the last
+// value read, so a consumer that is far enough behind does not touch shared memory at all)
+__device__ __forceinline__ void wait_progress(const volatile uint32_t* word, uint32_t need,
+                                              uint32_t& seen) {
+  if (seen >= need) return;
+  uint32_t v = *word;
+  while (v < need) {
+    __nanosleep(32);
+    v = *word;
+  }
+  seen = v;
+  __threadfence_block();   // the boundary values published before `word` are visible from here on
+}
+
 template <bool Y_IS_I, bool VEC, bool WRITE_DTW, bool RAGGED>
-__global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
+__global__ void __launch_bounds__(MAX_WARPS * 32) dtw_fill_kernel(const DtwParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps_per_cta = blockDim.x >> 5;
+  const int W = blockDim.x >> 5;
   const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
-  unsigned char* wbase = smem + (size_t)warp * (RING_BYTES + bnd_bytes);
+  const int per_warp = RING_BYTES + bnd_bytes;
+  unsigned char* wbase = smem + (size_t)warp * per_warp;
   const unsigned char* ring_lane = wbase + lane * 16;  // this lane's 16 B slot of every column
-  float* bnd = reinterpret_cast<float*>(wbase + RING_BYTES);
+  const int pwarp = (warp + W - 1) % W, cwarp = (warp + 1) % W;   // producer / consumer neighbours
+  float* bnd_out = reinterpret_cast<float*>(wbase + RING_BYTES);                      // this band's bottom row
+  const float* bnd_in = reinterpret_cast<const float*>(smem + (size_t)pwarp * per_warp + RING_BYTES);
+  volatile uint32_t* prog = reinterpret_cast<volatile uint32_t*>(smem + (size_t)W * per_warp);
+  // a row of +inf stands in for the boundary above band 0, so the top-row read needs no predicate
+  float* inf_row = reinterpret_cast<float*>(smem + (size_t)W * per_warp + 64);
   const uint32_t ring_u32 = ssb::smem_u32(wbase) + lane * 16;
   const int g8 = lane & ~7;
   const float INF = CUDART_INF_F;
   // chunks in which every lane is inside [1, Nx) and every prefetch is in range
   const int steady_lo = 32 / CH;
+  // steady chunks start at a multiple of RING = CH steps, so step u of a chunk writes ring slot
+  // (u + PF - g8) % RING: slot u for the lane groups with g8 % 16 == 8, else slot (u + 8) % 16.
+  // Two per-lane bases turn that into immediate offsets (wr_a for u < 8, wr_b for u >= 8).
+  static_assert(RING == 16 && CH == 16 && PF == 8, "write-slot bases assume RING = CH = 16, PF = 8");
+  const uint32_t wr_a = ring_u32 + ((g8 & 8) ? 0u : 8u * 512u);
+  const uint32_t wr_b = ring_u32 - ((g8 & 8) ? 0u : 8u * 512u);
+  const bool lane0 = (lane == 0);
+  // L2 policy of this lane's cost loads: the 128 B lines at the two ends of a band's 512 B column
+  // segment are shared with the neighbouring band (read by another warp ~48 columns later), the
+  // middle of the segment is dead after this read
+  const bool use_hint = (p.flags & 1) != 0;
+  uint64_t policy = 0;
+  if (use_hint) {
+    if ((lane >> 3) == 0 || (lane >> 3) == 3)
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+    else
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  }
+  const bool use_l2pf = (p.flags & 2) != 0;
 
-  for (int pair = blockIdx.x * warps_per_cta + warp; pair < p.npairs;
-       pair += gridDim.x * warps_per_cta) {
+  if (threadIdx.x < W) prog[threadIdx.x] = 0u;
+  for (int x = threadIdx.x; x < bnd_bytes / 4; x += blockDim.x) inf_row[x] = INF;
+  __syncthreads();
+
+  int turn = 0;             // (band instance counter of the CTA) % W
+  uint32_t k = 0;           // band instances this warp has swept
+  uint32_t seen_p = 0, seen_c = 0;
+  bool prev_wrote = false;  // this warp's previous instance parked a boundary row ...
+  int prev_nch = 0;         // ... of this many chunks
+
+  for (int pair = blockIdx.x; pair < p.npairs; pair += gridDim.x) {
     int Nx = p.Nx, Ny = p.Ny, nbands = p.nbands, nch = p.nch;
     int64_t pitch = p.pitch;
     const float* cost = p.cost + (int64_t)pair * p.pair_stride;
@@ -89,23 +154,53 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
       dirs = reinterpret_cast<uint4*>(p.dirs + t.dirs_off);
     }
     const int steady_hi = (Nx - CH - PF) / CH;  // inclusive; may be < steady_lo
+    const bool pitch_fits = pitch < (1LL << 30);   // steady chunks address columns as base + u * pitch_bytes
+    const uint32_t pitch_bytes = (uint32_t)pitch * 4u;
 
     for (int band = 0; band < nbands; ++band) {
+      const bool mine = (turn == warp);
+      turn = (turn + 1 == W) ? 0 : turn + 1;
+      if (!mine) continue;
+
       const int y0 = band * BAND + lane * R;
       const bool row0 = (y0 == 0);
       const int rows_valid = min(max(Ny - y0, 0), R);
       const int y0_ld = rows_valid > 0 ? y0 : 0;  // keep the address legal for idle lanes
       const int ld_bytes = rows_valid * 4;
-      const bool rd_bnd = (band > 0) && (lane == 0);
-      const bool wr_bnd = (band + 1 < nbands) && (lane == 31);
+      const bool has_in = band > 0, has_out = band + 1 < nbands;
+      const bool wr_bnd = has_out && (lane == 31);
+      const float* top = has_in ? bnd_in : inf_row;   // the row above this band, by column
+      // progress words this instance waits on: the producer of its top boundary (the previous band
+      // instance, swept by warp - 1) and the reader of the row this warp parked last time
+      const uint32_t p_base = (warp == 0 ? k - 1 : k) << PROG_SHIFT;
+      const uint32_t c_base = (warp == W - 1 ? k : k - 1) << PROG_SHIFT;
+      const bool guard_out = has_out && prev_wrote;
 
       float v[R];
-      uint32_t pk[R];
+      float pa[R];        // direction codes of the current 8 steps (2 bits each, as a float)
+      uint32_t pk[R];     // ... of the first 8 steps of the chunk
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         v[r] = INF;  // column x = 0 of the DTW table
+        pa[r] = 0.f;
         pk[r] = 0u;
       }
+      // code bookkeeping around the 4 steps of quad `quad` (compile-time under the unrolled loops)
+      auto codes_begin = [&](int quad) {
+        if (quad == 0 || quad == 2) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) pa[r] = 0.f;
+        }
+      };
+      auto codes_end = [&](int quad) {
+        if (quad == 1) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) pk[r] = __float2uint_rn(pa[r]);
+        } else if (quad == 3) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) pk[r] = pk[r] * 65536u + __float2uint_rn(pa[r]);
+        }
+      };
       if (row0) v[0] = 0.f;  // dtw[0,0]
       if (WRITE_DTW) {
 #pragma unroll
@@ -116,7 +211,12 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
 
       auto prefetch = [&](uint32_t dst, const float* src) {
         if (VEC) {
-          ssb::cp_async_16(dst, src, ld_bytes);
+          if (use_hint)
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst),
+                         "l"(src), "r"(ld_bytes), "l"(policy)
+                         : "memory");
+          else
+            ssb::cp_async_16(dst, src, ld_bytes);
         } else {
 #pragma unroll
           for (int r = 0; r < R; ++r)
@@ -135,23 +235,22 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
           const float first = Y_IS_I ? upc : old;
           const float second = Y_IS_I ? old : upc;
           float nv;
-          // Inline PTX pins the shape ptxas emits per cell: FSETP FSEL FSETP FSEL FADD SEL SEL
-          // IMAD.  (Left to itself it rewrites the packing into 4 LOP3 bit-inserts per cell, or
-          // parks the predicates with P2R and replays them at the end of the chunk.)
+          // The half-rate ALU pipe (compare / select / min) bounds this kernel, so the cell is
+          // written for it: FSET x2 + FMNMX x2 there, FADD + 2 FFMA on the FMA pipe (r2 run with
+          // FSETP FSEL SEL x2 = 6 half-rate instructions per cell: ALU pipe 68 % busy, issue 62 %).
+          // The two predicates arrive as 1.0f / 0.0f and the 2-bit codes of 8 steps are packed in
+          // a float (exact: < 4^8), converted twice per chunk.
           asm("{\n\t"
-              ".reg .pred p1, p2;\n\t"
-              ".reg .f32 m1, m;\n\t"
-              ".reg .u32 c;\n\t"
-              "setp.lt.f32 p1, %3, %2;\n\t"
-              "selp.f32 m1, %3, %2, p1;\n\t"
-              "selp.u32 c, 1, 0, p1;\n\t"
-              "setp.lt.f32 p2, %4, m1;\n\t"
-              "selp.f32 m, %4, m1, p2;\n\t"
-              "selp.u32 c, 2, c, p2;\n\t"
+              ".reg .f32 m1, m, r1, r2;\n\t"
+              "set.lt.f32.f32 r1, %3, %2;\n\t"
+              "min.f32 m1, %2, %3;\n\t"
+              "set.lt.f32.f32 r2, %4, m1;\n\t"
+              "min.f32 m, m1, %4;\n\t"
               "add.rn.f32 %0, %5, m;\n\t"
-              "mad.lo.u32 %1, %1, 4, c;\n\t"
+              "fma.rn.f32 r1, r2, 0f40000000, r1;\n\t"
+              "fma.rn.f32 %1, %1, 0f40800000, r1;\n\t"
               "}"
-              : "=f"(nv), "+r"(pk[r])
+              : "=f"(nv), "+f"(pa[r])
               : "f"(first), "f"(second), "f"(upp), "f"(cc[r]));
           upp = old;
           upc = nv;
@@ -176,16 +275,16 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
           prefetch(ring_u32 + ((xl << 9) & RING_MASK), cost + ((int64_t)xl * pitch + y0_ld));
         const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
         float bval = INF;
-        if (rd_bnd && s >= 1 && s < Nx) bval = bnd[s];
+        if (lane0 && s >= 1 && s < Nx) bval = top[s];
         diag_in = up_in;
-        up_in = (lane == 0) ? bval : t;
+        up_in = lane0 ? bval : t;
         const int x = s - lane;
         if (x >= 1 && x < Nx) {
           cells(*reinterpret_cast<const float4*>(ring_lane + ((x << 9) & RING_MASK)), x);
-          if (wr_bnd) bnd[x] = v[R - 1];
+          if (wr_bnd) bnd_out[x] = v[R - 1];
         } else {
 #pragma unroll
-          for (int r = 0; r < R; ++r) pk[r] <<= 2;
+          for (int r = 0; r < R; ++r) pa[r] *= 4.f;   // code 0
         }
       };
 
@@ -204,48 +303,79 @@ __global__ void __launch_bounds__(128) dtw_fill_kernel(const DtwParams p) {
 #pragma unroll 1
       for (int c = 0; c < nch; ++c) {
         const int s0 = c * CH;
-        if (c >= steady_lo && c <= steady_hi) {
+        // chunk c reads bnd_in[s0 .. s0+15]: the producer wrote them by the end of its chunk c+2;
+        // it writes bnd_out[s0-31 .. s0-16]: their previous contents were read by the consumer of
+        // this warp's previous instance in its chunks <= c-1
+        if (has_in) wait_progress(prog + pwarp, p_base + (uint32_t)min(c + LAG, nch), seen_p);
+        if (guard_out) wait_progress(prog + cwarp, c_base + (uint32_t)min(c, prev_nch), seen_c);
+        if (use_l2pf) {
+          // pull the 16 columns this warp starts to copy one chunk from now into L2 (64 lines of
+          // 128 B: two per lane), so the cp.async ring only has to cover the L2 latency
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int line = lane * 2 + i, col = s0 + CH + PF + (line >> 2);
+            if (col >= 1 && col < Nx && band * BAND + (line & 3) * 32 < Ny)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(cost + ((int64_t)col * pitch + band * BAND +
+                                                                    (line & 3) * 32)));
+          }
+        }
+        if (c >= steady_lo && c <= steady_hi && pitch_fits) {
           // ---- steady chunk: no range checks, running addresses --------------------
-          const float* src = cost + ((int64_t)(s0 - g8 + PF) * pitch + y0_ld);
-          uint32_t wr_off = (uint32_t)((s0 - g8 + PF) << 9) & RING_MASK;
-          uint32_t rd_off = (uint32_t)((s0 - lane) << 9) & RING_MASK;
-          const float* bnd_rd = bnd + s0;         // lane 0 reads  bnd[s]
-          float* bnd_wr = bnd + (s0 - lane);      // lane 31 writes bnd[x]
+          // column u of the chunk at src0 + u * pitch_bytes (one IMAD.WIDE); the ring read slot
+          // lives in the top 4 bits of rd_hi, so "+1 (mod 16)" is one add and the offset one IMAD.HI
+          const uint64_t src0 = reinterpret_cast<uint64_t>(cost + ((int64_t)(s0 - g8 + PF) * pitch + y0_ld));
+          uint32_t rd_hi = (uint32_t)(s0 - lane) << 28;
+          const float* top_rd = top + s0;             // every lane reads top[s] (lane 0 uses it)
+          float* bnd_wr = bnd_out + (s0 - lane);      // lane 31 writes bnd[x]
 #pragma unroll
           for (int quad = 0; quad < CH / 4; ++quad) {
             // columns consumed in steps 4k..4k+3 were issued in group <= k - PF/4
             ssb::cp_async_wait<PF / 4 - 1>();
+            codes_begin(quad);
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4) {
               const int u = quad * 4 + u4;
-              prefetch(ring_u32 + wr_off, src);
-              src += pitch;
-              wr_off = (wr_off + 512u) & RING_MASK;
+              prefetch((u < 8 ? wr_a : wr_b) + (uint32_t)u * 512u,
+                       reinterpret_cast<const float*>(src0 + (uint64_t)(uint32_t)u * (uint64_t)pitch_bytes));
               const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
-              float bval = INF;
-              if (rd_bnd) bval = bnd_rd[u];
+              const float bval = top_rd[u];
               diag_in = up_in;
-              up_in = (lane == 0) ? bval : t;
-              const float4 c4 = *reinterpret_cast<const float4*>(ring_lane + rd_off);
-              rd_off = (rd_off + 512u) & RING_MASK;
+              up_in = lane0 ? bval : t;
+              float4 c4;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w)
+                           : "r"(ring_u32 + __umulhi(rd_hi, (uint32_t)RING_BYTES)));
+              rd_hi += 1u << 28;
               cells(c4, s0 + u - lane);
               if (wr_bnd) bnd_wr[u] = v[R - 1];
             }
+            codes_end(quad);
             ssb::cp_async_commit();
           }
         } else {
 #pragma unroll
           for (int quad = 0; quad < CH / 4; ++quad) {
             ssb::cp_async_wait<PF / 4 - 1>();
+            codes_begin(quad);
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4) step_general(s0 + quad * 4 + u4);
+            codes_end(quad);
             ssb::cp_async_commit();
           }
         }
         dirs[((int64_t)band * nch + c) * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        // publish: lane 31's boundary stores of this chunk, then the progress word
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          prog[warp] = (c + 1 == nch) ? ((k + 1) << PROG_SHIFT) : ((k << PROG_SHIFT) + (uint32_t)(c + 1));
+        }
       }
       ssb::cp_async_wait<0>();
-      __syncwarp();  // bnd[] written by lane 31 is read by lane 0 in the next band
+      __syncwarp();
+      ++k;
+      prev_wrote = has_out;
+      prev_nch = nch;
     }
   }
 }
@@ -296,6 +426,69 @@ __global__ void dtw_backtrace_kernel(const uint32_t* __restrict__ dirs, int64_t 
   for (int rr = lowest - 1; rr >= 0; --rr) out[rr] = 0;
 }
 
+// Small batches (the 16 silent utterances of a training step): one CTA per pair copies the pair's
+// direction words into shared memory with coalesced 16 B loads and one thread walks them there
+// (~25 ns per step instead of an L2 round trip per new word: 120 us -> ~35 us at 600 x 500).
+template <bool Y_IS_I>
+__global__ void __launch_bounds__(256) dtw_backtrace_smem_kernel(
+    const uint32_t* __restrict__ dirs, int64_t dirs_pair_words, int nch, int N, int M, int npairs,
+    int32_t* __restrict__ path, const ssb_dtw_pair_t* __restrict__ table) {
+  extern __shared__ __align__(16) uint32_t sdirs[];
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    const uint32_t* d = dirs + (int64_t)pair * dirs_pair_words;
+    int32_t* out = path + (int64_t)pair * N;    // ragged: rows are padded to the batch maximum N
+    int n = N, m = M, nc = nch;
+    int64_t words = dirs_pair_words;
+    if (table != nullptr) {
+      const ssb_dtw_pair_t t = table[pair];
+      d = dirs + t.dirs_off;
+      n = t.N; m = t.M; nc = t.nch;
+      words = (int64_t)t.nbands * t.nch * BAND;
+    }
+    const uint4* d4 = reinterpret_cast<const uint4*>(d);
+    uint4* s4 = reinterpret_cast<uint4*>(sdirs);
+    for (int64_t w = threadIdx.x; w < words / 4; w += blockDim.x) s4[w] = __ldg(d4 + w);
+    // rows the walk never assigns (and the padding rows of a ragged batch) keep the reference's
+    // initial value 0 (align.py:21)
+    for (int rr = threadIdx.x; rr < N; rr += blockDim.x) out[rr] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int i = n - 1, j = m - 1;
+      while (i > 0 && j > 0) {
+        out[i] = j;
+        const int x = Y_IS_I ? j : i, y = Y_IS_I ? i : j;
+        const int band = y / BAND, l = (y % BAND) / R, r = y % R, s = x + l;
+        const uint32_t word = sdirs[((band * nc + (s / CH)) * 32 + l) * 4 + r];
+        const uint32_t code = (word >> (2 * (CH - 1 - (s % CH)))) & 3u;
+        const bool diag = (code & 2u) != 0u, left = (code & 1u) != 0u;
+        if (diag || !left) --i;  // up or diagonal
+        if (diag || left) --j;   // left or diagonal
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// picks the backtrace variant; `max_words` = direction words of the largest pair
+template <bool Y_IS_I>
+int launch_backtrace(const uint32_t* dirs, int64_t dirs_pair_words, int64_t max_words, int nch, int N,
+                     int M, int npairs, int32_t* path, const ssb_dtw_pair_t* table, cudaStream_t st) {
+  const int64_t smem = max_words * 4;
+  if (npairs <= 2 * ssb::num_sms() && smem <= 200 * 1024) {
+    auto kern = dtw_backtrace_smem_kernel<Y_IS_I>;
+    SSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<npairs, 256, smem, st>>>(dirs, dirs_pair_words, nch, N, M, npairs, path, table);
+    SSB_LAUNCH_CHECK("dtw_backtrace_smem_kernel");
+    return SSB_OK;
+  }
+  const int threads = 64;
+  const int grid = (npairs + threads - 1) / threads;
+  dtw_backtrace_kernel<Y_IS_I><<<grid, threads, 0, st>>>(dirs, dirs_pair_words, nch, N, M, npairs,
+                                                         path, table);
+  SSB_LAUNCH_CHECK("dtw_backtrace_kernel");
+  return SSB_OK;
+}
+
 struct Geometry {
   bool y_is_i;
   int Ny, Nx, nbands, nch;
@@ -323,23 +516,28 @@ int make_geometry(int64_t N, int64_t M, int64_t stride_i, int64_t stride_j, Geom
 }
 
 template <bool Y_IS_I, bool VEC, bool WRITE_DTW, bool RAGGED = false>
-int launch_fill(const DtwParams& p, cudaStream_t st) {
+int launch_fill(const DtwParams& p_in, cudaStream_t st) {
   auto kern = dtw_fill_kernel<Y_IS_I, VEC, WRITE_DTW, RAGGED>;
+  DtwParams p = p_in;
+  static const int env_flags = [] { const char* e = getenv("SSB_DTW_FLAGS"); return e ? atoi(e) : 0; }();
+  p.flags = env_flags;
+  SSB_REQUIRE(p.nch < (1 << PROG_SHIFT), "dtw: sweep extent %d too large", p.Nx);
   const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
   const int per_warp = RING_BYTES + bnd_bytes;
-  int warps = 4;
-  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
-  SSB_REQUIRE(warps * per_warp <= 227 * 1024, "dtw: sweep extent %d too large for shared memory",
+  // pipeline width: one warp per band of a pair (ragged: of the tallest pair), at least 4 warps per
+  // CTA when there are pairs to spare (band instances of consecutive pairs then run side by side)
+  int warps = p.nbands < MAX_WARPS ? p.nbands : MAX_WARPS;
+  if (warps < 4 && p.npairs >= 4 * ssb::num_sms()) warps = 4;
+  while (warps > 1 && warps * per_warp + 64 + bnd_bytes > 100 * 1024) --warps;
+  SSB_REQUIRE(warps * per_warp + 64 + bnd_bytes <= 227 * 1024, "dtw: sweep extent %d too large for shared memory",
               p.Nx);
-  if (p.npairs < 4 * ssb::num_sms()) warps = 1;  // few pairs: spread one warp per CTA
-  const int smem = warps * per_warp;
+  const int smem = warps * per_warp + 64 + bnd_bytes;   // + progress words + the +inf row
   SSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int occ = 0;
   SSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
   if (occ < 1) occ = 1;
-  const int64_t want = ((int64_t)p.npairs + warps - 1) / warps;
   const int64_t cap = (int64_t)ssb::num_sms() * occ;
-  const int grid = (int)(want < cap ? want : cap);
+  const int grid = (int)(p.npairs < cap ? p.npairs : cap);
   kern<<<grid, warps * 32, smem, st>>>(p);
   SSB_LAUNCH_CHECK("dtw_fill_kernel");
   return SSB_OK;
@@ -389,16 +587,11 @@ int run(const float* cost, int64_t npairs, int64_t pair_stride, int64_t N, int64
 #undef SSB_DTW_DISPATCH
   if (rc) return rc;
 
-  const int threads = 64;
-  const int grid = (int)((npairs + threads - 1) / threads);
   if (g.y_is_i)
-    dtw_backtrace_kernel<true><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nch, (int)N,
-                                                         (int)M, (int)npairs, path, nullptr);
-  else
-    dtw_backtrace_kernel<false><<<grid, threads, 0, st>>>(p.dirs, g.dirs_pair_words, g.nch,
-                                                          (int)N, (int)M, (int)npairs, path, nullptr);
-  SSB_LAUNCH_CHECK("dtw_backtrace_kernel");
-  return SSB_OK;
+    return launch_backtrace<true>(p.dirs, g.dirs_pair_words, g.dirs_pair_words, g.nch, (int)N, (int)M,
+                                  (int)npairs, path, nullptr, st);
+  return launch_backtrace<false>(p.dirs, g.dirs_pair_words, g.dirs_pair_words, g.nch, (int)N, (int)M,
+                                 (int)npairs, path, nullptr, st);
 }
 
 // ---- ragged batches --------------------------------------------------------------------------
@@ -574,12 +767,8 @@ int ssb_dtw_align_ragged(const float* cost_base, int64_t npairs, const ssb_dtw_p
   int rc = vectorized ? launch_fill<true, true, false, true>(p, st)
                       : launch_fill<true, false, false, true>(p, st);
   if (rc) return rc;
-  const int threads = 64;
-  const int grid = (int)((npairs + threads - 1) / threads);
-  dtw_backtrace_kernel<true><<<grid, threads, 0, st>>>(p.dirs, 0, p.nch, (int)max_N, (int)max_M,
-                                                       (int)npairs, path, table_dev);
-  SSB_LAUNCH_CHECK("dtw_backtrace_kernel");
-  return SSB_OK;
+  return launch_backtrace<true>(p.dirs, 0, (int64_t)p.nbands * p.nch * BAND, p.nch, (int)max_N,
+                                (int)max_M, (int)npairs, path, table_dev, st);
 }
 
 }  // extern "C"

@@ -285,6 +285,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if constexpr (CTAS == 2) cluster_sync_all();   // the peer's barriers are initialised too
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) may run under the previous kernel's tail; its results are read only from here on
+  ssb::pdl_wait();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr_gen;
 
@@ -876,13 +879,22 @@ int launch_impl(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CTAS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CTAS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CTAS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (ssb::pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CTAS > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   SSB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTAS>, mapA, mapB, p));
   SSB_LAUNCH_CHECK("gemm_tc_kernel");
   return SSB_OK;

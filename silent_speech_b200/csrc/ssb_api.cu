@@ -1,6 +1,7 @@
 // Library-level entry points: version, error string, device query.
 #include "ssb_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 
 namespace ssb {
@@ -24,6 +25,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 static std::atomic<const uint64_t*> g_seed_src{nullptr};
 const uint64_t* seed_source() { return g_seed_src.load(std::memory_order_relaxed); }
 void set_seed_source(const uint64_t* p) { g_seed_src.store(p, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SSB_PDL");
+    return e && e[0] == '1';   // off by default: see ssb_common.cuh
+  }();
+  return on;
+}
 
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;

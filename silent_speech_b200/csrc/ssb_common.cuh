@@ -39,7 +39,17 @@ int num_sms();
 // Philox with seed + *src, so a captured CUDA graph draws fresh masks on every replay.
 const uint64_t* seed_source();
 
+// Programmatic dependent launch (opt-in, SSB_PDL=1): kernels launched with the attribute start
+// their prologue under the previous kernel's tail and call pdl_wait() before touching its results.
+// Measured on the cfg-1 step graph with the attribute on every gemm_tc launch (r2 session 8,
+// two A/B pairs): 24.79 / 24.82 ms with, 24.50 / 24.49 ms without -- the 1-CTA-per-SM persistent
+// kernels gain nothing from an early launch and lose to the dependency wait, so it stays off.
+bool pdl_enabled();
+
 // ---- small device helpers ---------------------------------------------------
+// Blocks until the grids this launch depends on have completed and their writes are visible; a
+// no-op for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

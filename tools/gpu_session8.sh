@@ -1,0 +1,17 @@
+#!/bin/bash
+# DTW ALU-pipe rewrite + PDL A/B on the GEMM launches
+set -u
+O=gpurun_out
+T=${1:-r2s8}
+mkdir -p $O
+export PYTHONUNBUFFERED=1
+( time timeout 900 python -m pytest tests/test_dtw_gpu.py tests/test_fused_loss_gpu.py tests/test_step_gpu.py tests/test_ops_gpu.py -q --maxfail=10 ) > $O/${T}_pytest.log 2>&1
+echo "pytest rc=$?" >> $O/${T}_pytest.log
+timeout 300 python tools/dtw_bench.py 10000 5 > $O/${T}_dtw_bench.json 2> $O/${T}_dtw_bench.err
+timeout 300 python tools/dtw_bench.py 16 20 > $O/${T}_dtw_bench16.json 2>> $O/${T}_dtw_bench.err
+( SSB_PDL=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-torch-leg --no-cpu --no-side ) > $O/${T}_bench_nopdl.json 2> $O/${T}_bench_nopdl.err
+( SSB_PDL=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-torch-leg --no-cpu --no-side ) > $O/${T}_bench_pdl.json 2> $O/${T}_bench_pdl.err
+( SSB_PDL=0 timeout 600 python bench.py --steps 20 --warmup 5 --no-torch-leg --no-cpu --no-side ) > $O/${T}_bench_nopdl2.json 2> $O/${T}_bench_nopdl2.err
+( SSB_PDL=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-torch-leg --no-cpu --no-side ) > $O/${T}_bench_pdl2.json 2> $O/${T}_bench_pdl2.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:dtw_fill -s 1 -c 1 -f -o $O/${T}_dtw python tools/profile_targets.py dtw 2 > $O/${T}_ncu_dtw.log 2>&1
+ls -la $O | grep ${T}
