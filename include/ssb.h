@@ -39,11 +39,11 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 206
+#define SSB_ABI_VERSION 207
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
- * 6: ssb_prep_entry_t;
+ * 6: ssb_prep_entry_t, 7: ssb_emg_rec_t;
  * -1 otherwise), so a foreign-language
  * binding can verify its mirror of the layouts at load time. */
 SSB_API int64_t ssb_sizeof(int which);
@@ -449,6 +449,39 @@ SSB_API int ssb_ctc_loss_fused(const float* logits, int64_t N, int64_t T, int64_
 SSB_API int ssb_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n,
                            const float* lr_cell, int64_t* step_cell, float beta1, float beta2,
                            float eps, float weight_decay, float grad_scale, void* stream);
+
+/* ---- EMG signal conditioning (csrc/emg.cu) ------------------------------
+ * Replaces, for a whole batch of recordings, the per-channel scipy / numpy chain of
+ * read_emg.py:27-45 as load_utterance applies it (read_emg.py:62-67):
+ *   notch_harmonics(x, 60, 1000) -> remove_drift(x, 1000)      = a cascade of scipy.signal.filtfilt
+ *   subsample(x, new_freq, old_freq)                           = np.interp onto a uniform grid
+ * in float64 with the reference's operation order: results are bit-identical to scipy / numpy.
+ * Signals are (rows, C) float64 row-major with the recordings stacked along rows; recording r owns
+ * rows [off, off + n) of the input / filtered arrays and rows [out_off, out_off + n_out) of the
+ * resampled array (out_off dense and ascending).  The table lives in device memory.
+ *
+ * ssb_emg_filtfilt_chain: y = filtfilt_S(... filtfilt_1(x)) per recording and channel (defaults of
+ * scipy.signal.filtfilt: odd extension by 3 * ntaps samples, lfilter_zi initial state).  Stage s is
+ * described by 11 doubles at coef_host + 11 s = { b[0..3], a[0..3] (a[0] == 1), zi[0..2] } and
+ * ntaps_host[s] in {3, 4}; unused entries are ignored.  Coefficients are design-time data computed
+ * by the caller (scipy.signal.iirnotch / butter / lfilter_zi, exactly as the reference does).
+ * min_n = the smallest n of the table (scipy requires n > padlen).  x and y may not alias.
+ * ssb_emg_subsample: out[out_off + i] = np.interp(i * step, arange(n) / old_freq, y) for i < n_out;
+ * step = 1 / new_freq as the host computed it; out is float64, or float32 when out_f32 != 0. */
+typedef struct ssb_emg_rec {
+  int64_t off;        /* first row of the recording in the (rows, C) signal arrays */
+  int64_t out_off;    /* first row in the resampled output */
+  int32_t n;          /* samples */
+  int32_t n_out;      /* resampled samples */
+} ssb_emg_rec_t;
+SSB_API int64_t ssb_emg_filtfilt_workspace_bytes(int64_t rows_total, int64_t n_rec, int C);
+SSB_API int ssb_emg_filtfilt_chain(const double* x, double* y, const ssb_emg_rec_t* table_dev,
+                                   int64_t n_rec, int64_t rows_total, int min_n, int C,
+                                   const double* coef_host, const int32_t* ntaps_host, int n_stages,
+                                   void* workspace, int64_t workspace_bytes, void* stream);
+SSB_API int ssb_emg_subsample(const double* x, const ssb_emg_rec_t* table_dev, int64_t n_rec,
+                              int64_t out_rows_total, int C, double old_freq, double step,
+                              void* out, int out_f32, void* stream);
 
 #ifdef __cplusplus
 }

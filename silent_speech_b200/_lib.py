@@ -70,6 +70,11 @@ class PrepEntry(ctypes.Structure):
                 ("ld_n", c_i32), ("ld_t", c_i32), ("tile0", c_i32), ("tiles_c", c_i32)]
 
 
+class EmgRec(ctypes.Structure):
+    """ssb_emg_rec_t"""
+    _fields_ = [("off", c_i64), ("out_off", c_i64), ("n", c_i32), ("n_out", c_i32)]
+
+
 _PT = ctypes.POINTER(TcOperand)
 _PG = ctypes.POINTER(Gather)
 _PE = ctypes.POINTER(Epilogue)
@@ -151,6 +156,11 @@ _SIGNATURES = {
                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
     "ssb_band_attn_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
                                   c_f32, c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
+    "ssb_emg_filtfilt_workspace_bytes": (c_i64, [c_i64, c_i64, c_int]),
+    "ssb_emg_filtfilt_chain": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr,
+                                       c_int, c_ptr, c_i64, c_ptr]),
+    "ssb_emg_subsample": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, ctypes.c_double, ctypes.c_double,
+                                  c_ptr, c_int, c_ptr]),
 }
 
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
@@ -164,6 +174,7 @@ _KERNELS_PER_CALL = {
     "ssb_gemm_tc_batched_tn": 1, "ssb_pad_split_heads": 1, "ssb_transpose_split_heads": 1,
     "ssb_attn_softmax_fwd": 1, "ssb_attn_ds_bwd": 1,
     "ssb_attn_fused_fwd": 1, "ssb_attn_delta": 1, "ssb_attn_fused_bwd": 1,
+    "ssb_emg_filtfilt_chain": 1, "ssb_emg_subsample": 1,
 }
 launch_count = 0   # running total of libssb kernel launches issued by this process
 
@@ -215,7 +226,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 206      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 207      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):
@@ -228,7 +239,8 @@ def _check_abi(lib):
                            f"rebuild (python -m silent_speech_b200.build --force)")
     lib.ssb_sizeof.restype = c_i64
     lib.ssb_sizeof.argtypes = [ctypes.c_int]
-    for which, cls in enumerate((Gather, Scatter, Epilogue, TcOperand, DtwPair, Utt, PrepEntry)):
+    for which, cls in enumerate((Gather, Scatter, Epilogue, TcOperand, DtwPair, Utt, PrepEntry,
+                                 EmgRec)):
         if lib.ssb_sizeof(which) != ctypes.sizeof(cls):
             raise SSBError(-4, f"struct layout mismatch for {cls.__name__}: library "
                                f"{lib.ssb_sizeof(which)} B, ctypes {ctypes.sizeof(cls)} B")

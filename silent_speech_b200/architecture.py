@@ -62,25 +62,40 @@ class ResBlock(nn.Module):
         else:
             self.residual_path = None
         self.stride = stride
+        self._bump_counters = True
 
     def _bn_args(self, bn):
-        if self.training:
+        if self.training and self._bump_counters:
             bn.num_batches_tracked += 1
         return bn.weight, bn.bias, bn.running_mean, bn.running_var
 
-    def forward_cl(self, x, wp=None):
-        """x: (B, L, Cin) channels-last -> (B, Lout, Cout).  wp: the model's WeightPlanes arena."""
+    def batch_counters(self):
+        return [bn.num_batches_tracked for bn in (self.bn1, self.bn2, getattr(self, "res_norm", None))
+                if bn is not None]
+
+    def forward_cl(self, x, wp=None, bump_counters=True):
+        """x: (B, L, Cin) channels-last -> (B, Lout, Cout).  wp: the model's WeightPlanes arena.
+        bump_counters=False: the caller has already advanced num_batches_tracked (Model does all
+        nine in one launch)."""
+        self._bump_counters = bump_counters
         if self.residual_path is None:
             raise NotImplementedError("identity residual is never instantiated by the reference "
                                       "(architecture.py:46-50) and is not built")
         tr = self.training
         # every convolution here feeds a BatchNorm: in training mode its bias gradient is exactly 0
-        c1 = F_.conv1d_w(x, self.conv1, wp, 3, self.stride, lambda: _conv_weight(self.conv1), tr)
+        # conv1 and residual_path read the same input: one autograd node when x needs a gradient
+        pair = F_.conv_pair_w(x, self.conv1, self.residual_path, wp, tr) if self.stride == 2 else None
+        if pair is not None:
+            c1, cr = pair
+        else:
+            c1 = F_.conv1d_w(x, self.conv1, wp, 3, self.stride, lambda: _conv_weight(self.conv1), tr)
+            cr = None
         h1 = F_.bn_act(c1, *self._bn_args(self.bn1), training=tr, relu=True,
                        momentum=self.bn1.momentum, eps=self.bn1.eps)
         c2 = F_.conv1d_w(h1, self.conv2, wp, 3, 1, lambda: _conv_weight(self.conv2), tr)
-        cr = F_.conv1d_w(x, self.residual_path, wp, 1, self.stride,
-                         lambda: _conv_weight(self.residual_path), tr)
+        if cr is None:
+            cr = F_.conv1d_w(x, self.residual_path, wp, 1, self.stride,
+                             lambda: _conv_weight(self.residual_path), tr)
         ga, ba, rma, rva = self._bn_args(self.bn2)
         gb, bb, rmb, rvb = self._bn_args(self.res_norm)
         return F_.bn_act(c2, ga, ba, rma, rva, tr, True, cr, gb, bb, rmb, rvb,
@@ -141,8 +156,11 @@ class Model(nn.Module):
                     x_raw[:, -r:, :] = 0
         x = x_raw.to(torch.float32).contiguous()
         wp = self.weight_planes(x.device)
+        counters = [c for blk in self.conv_blocks if blk.training for c in blk.batch_counters()]
+        if counters:          # the 9 BatchNorm step counters in one launch instead of nine
+            torch._foreach_add_(counters, 1)
         for blk in self.conv_blocks:
-            x = blk.forward_cl(x, wp)
+            x = blk.forward_cl(x, wp, bump_counters=False)
         B, T, D = x.shape
         x2 = F_.linear_w(x.view(B * T, D), self.w_raw_in, wp)
         x2 = self.transformer.forward_tokens(x2, B, T, wp)

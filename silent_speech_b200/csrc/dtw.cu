@@ -37,7 +37,6 @@
 // coalesced 512 B row of packed codes.
 #include "ssb_common.cuh"
 #include <math_constants.h>
-#include <stdlib.h>
 #include <type_traits>
 
 namespace {
@@ -49,7 +48,7 @@ constexpr int PF = 8;           // prefetch distance (columns); RING - PF >= 8
 constexpr int RING_BYTES = RING * 32 * 16;
 constexpr int RING_MASK = (RING - 1) << 9;  // byte offset of a column inside the ring
 constexpr int CH = 16;          // steps per chunk == 2-bit codes per direction word
-static_assert(PF % 4 == 0 && RING - PF >= 8, "ring geometry");
+static_assert(RING - PF >= 8, "ring geometry");
 
 struct DtwParams {
   const float* cost;
@@ -62,7 +61,6 @@ struct DtwParams {
   int64_t pitch;
   int64_t dirs_pair_words;
   int Ny, Nx, nbands, nch, npairs;
-  int flags;   // experiment switches: 1 = L2 eviction hints, 2 = L2 prefetch one chunk ahead
 };
 
 // Direction codes: 2 raw predicate bits per cell: bit0 = "second candidate (i,j-1) < first
@@ -71,6 +69,10 @@ struct DtwParams {
 // One word packs the 16 steps of a chunk for one strip row (earliest step in the top bits);
 // words are stored step-major:  dirs[(band*nch + chunk)*32 + lane]  (uint4 = the lane's 4 rows)
 // so that every chunk ends with one coalesced 512 B store per warp.
+
+// boundary row of a band: one float per sweep column, plus the 31 + 16 steps past the last column
+// that the edge chunks read (and ignore)
+__host__ __device__ constexpr int bnd_bytes_for(int Nx) { return ((Nx + 48 + 3) & ~3) * 4; }
 
 constexpr int MAX_WARPS = 8;    // band-pipeline width (warps per CTA)
 constexpr int PROG_SHIFT = 12;  // progress word = (band instance of the warp << 12) + chunks done
@@ -92,11 +94,11 @@ __device__ __forceinline__ void wait_progress(const volatile uint32_t* word, uin
 }
 
 template <bool Y_IS_I, bool VEC, bool WRITE_DTW, bool RAGGED>
-__global__ void __launch_bounds__(MAX_WARPS * 32) dtw_fill_kernel(const DtwParams p) {
+__global__ void __launch_bounds__(MAX_WARPS * 32, 3) dtw_fill_kernel(const DtwParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int W = blockDim.x >> 5;
-  const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
+  const int bnd_bytes = bnd_bytes_for(p.Nx);
   const int per_warp = RING_BYTES + bnd_bytes;
   unsigned char* wbase = smem + (size_t)warp * per_warp;
   const unsigned char* ring_lane = wbase + lane * 16;  // this lane's 16 B slot of every column
@@ -118,21 +120,10 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) dtw_fill_kernel(const DtwParam
   const uint32_t wr_a = ring_u32 + ((g8 & 8) ? 0u : 8u * 512u);
   const uint32_t wr_b = ring_u32 - ((g8 & 8) ? 0u : 8u * 512u);
   const bool lane0 = (lane == 0);
-  // L2 policy of this lane's cost loads: the 128 B lines at the two ends of a band's 512 B column
-  // segment are shared with the neighbouring band (read by another warp ~48 columns later), the
-  // middle of the segment is dead after this read
-  const bool use_hint = (p.flags & 1) != 0;
-  uint64_t policy = 0;
-  if (use_hint) {
-    if ((lane >> 3) == 0 || (lane >> 3) == 3)
-      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
-    else
-      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-  }
-  const bool use_l2pf = (p.flags & 2) != 0;
 
   if (threadIdx.x < W) prog[threadIdx.x] = 0u;
   for (int x = threadIdx.x; x < bnd_bytes / 4; x += blockDim.x) inf_row[x] = INF;
+  if (lane == 0) bnd_out[0] = INF;    // column 0 of every boundary row (producers write x >= 1 only)
   __syncthreads();
 
   int turn = 0;             // (band instance counter of the CTA) % W
@@ -211,11 +202,6 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) dtw_fill_kernel(const DtwParam
 
       auto prefetch = [&](uint32_t dst, const float* src) {
         if (VEC) {
-          if (use_hint)
-            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;\n" ::"r"(dst),
-                         "l"(src), "r"(ld_bytes), "l"(policy)
-                         : "memory");
-          else
             ssb::cp_async_16(dst, src, ld_bytes);
         } else {
 #pragma unroll
@@ -273,12 +259,14 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) dtw_fill_kernel(const DtwParam
         const int xl = s - g8 + PF;
         if (xl >= 1 && xl < Nx)
           prefetch(ring_u32 + ((xl << 9) & RING_MASK), cost + ((int64_t)xl * pitch + y0_ld));
+        ssb::cp_async_commit();
         const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
         float bval = INF;
         if (lane0 && s >= 1 && s < Nx) bval = top[s];
         diag_in = up_in;
         up_in = lane0 ? bval : t;
         const int x = s - lane;
+        ssb::cp_async_wait<PF>();   // the column issued PF steps ago (and everything older) has landed
         if (x >= 1 && x < Nx) {
           cells(*reinterpret_cast<const float4*>(ring_lane + ((x << 9) & RING_MASK)), x);
           if (wr_bnd) bnd_out[x] = v[R - 1];
@@ -288,15 +276,23 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) dtw_fill_kernel(const DtwParam
         }
       };
 
-      // prologue: the loads that steps s < 0 would have issued (PF/4 groups of 4 steps)
-#pragma unroll 1
-      for (int gi = 0; gi < PF / 4; ++gi) {
+      if (!WRITE_DTW && VEC) {
+        // edge chunks read columns <= 0 as +inf: every slot of this lane's ring starts out so
+        // (a slot is overwritten by column x + 16 only after the lane has consumed column x)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int xl = 4 * gi + u - g8;
-          if (xl >= 1 && xl < Nx)
-            prefetch(ring_u32 + ((xl << 9) & RING_MASK), cost + ((int64_t)xl * pitch + y0_ld));
-        }
+        for (int sl = 0; sl < RING; ++sl)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(ring_u32 + (uint32_t)sl * 512u),
+                       "f"(INF)
+                       : "memory");
+      }
+      // prologue: the loads that steps s < 0 would have issued.  One commit group per step: a
+      // step waits only for the column issued PF steps earlier, so PF columns (4 KB per warp)
+      // stay in flight instead of 4 .. 8 with one group per four steps.
+#pragma unroll 1
+      for (int u = 0; u < PF; ++u) {
+        const int xl = u - g8;
+        if (xl >= 1 && xl < Nx)
+          prefetch(ring_u32 + ((xl << 9) & RING_MASK), cost + ((int64_t)xl * pitch + y0_ld));
         ssb::cp_async_commit();
       }
 
@@ -308,59 +304,58 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) dtw_fill_kernel(const DtwParam
         // this warp's previous instance in its chunks <= c-1
         if (has_in) wait_progress(prog + pwarp, p_base + (uint32_t)min(c + LAG, nch), seen_p);
         if (guard_out) wait_progress(prog + cwarp, c_base + (uint32_t)min(c, prev_nch), seen_c);
-        if (use_l2pf) {
-          // pull the 16 columns this warp starts to copy one chunk from now into L2 (64 lines of
-          // 128 B: two per lane), so the cp.async ring only has to cover the L2 latency
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int line = lane * 2 + i, col = s0 + CH + PF + (line >> 2);
-            if (col >= 1 && col < Nx && band * BAND + (line & 3) * 32 < Ny)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(cost + ((int64_t)col * pitch + band * BAND +
-                                                                    (line & 3) * 32)));
-          }
-        }
-        if (c >= steady_lo && c <= steady_hi && pitch_fits) {
-          // ---- steady chunk: no range checks, running addresses --------------------
-          // column u of the chunk at src0 + u * pitch_bytes (one IMAD.WIDE); the ring read slot
-          // lives in the top 4 bits of rd_hi, so "+1 (mod 16)" is one add and the offset one IMAD.HI
+        // ---- fast chunk: running addresses, no per-cell range checks -------------------
+        // column u of the chunk at src0 + u * pitch_bytes (one IMAD.WIDE); the ring read slot
+        // lives in the top 4 bits of rd_hi, so the offset of step u is one IMAD.HI.
+        // EDGE (head / tail chunks): lanes outside [1, Nx) run the same cell code on +inf costs
+        // (head: the ring was pre-filled, so column <= 0 stays +inf) or on stale ring contents
+        // (tail: nothing reads those values or codes); only the copies and the boundary store are
+        // predicated.  r2: the fully predicated general step cost 125 instructions against 42.
+        auto fast_chunk = [&](auto edge_tag) {
+          constexpr bool EDGE = decltype(edge_tag)::value;
           const uint64_t src0 = reinterpret_cast<uint64_t>(cost + ((int64_t)(s0 - g8 + PF) * pitch + y0_ld));
-          uint32_t rd_hi = (uint32_t)(s0 - lane) << 28;
+          const uint32_t rd_hi = (uint32_t)(s0 - lane) << 28;
           const float* top_rd = top + s0;             // every lane reads top[s] (lane 0 uses it)
           float* bnd_wr = bnd_out + (s0 - lane);      // lane 31 writes bnd[x]
+          const int pf_lo = 1 - (s0 - g8 + PF), pf_hi = Nx - (s0 - g8 + PF);   // copy column u iff pf_lo <= u < pf_hi
+          const int bw_lo = 1 - (s0 - lane), bw_hi = Nx - (s0 - lane);        // store bnd[x] iff bw_lo <= u < bw_hi
 #pragma unroll
           for (int quad = 0; quad < CH / 4; ++quad) {
-            // columns consumed in steps 4k..4k+3 were issued in group <= k - PF/4
-            ssb::cp_async_wait<PF / 4 - 1>();
             codes_begin(quad);
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4) {
               const int u = quad * 4 + u4;
-              prefetch((u < 8 ? wr_a : wr_b) + (uint32_t)u * 512u,
-                       reinterpret_cast<const float*>(src0 + (uint64_t)(uint32_t)u * (uint64_t)pitch_bytes));
+              if (!EDGE || (u >= pf_lo && u < pf_hi))
+                prefetch((u < 8 ? wr_a : wr_b) + (uint32_t)u * 512u,
+                         reinterpret_cast<const float*>(src0 + (uint64_t)(uint32_t)u * (uint64_t)pitch_bytes));
+              ssb::cp_async_commit();
+              if (EDGE && u == 0 && s0 == 0) continue;   // step 0: every lane is at a column <= 0
               const float t = __shfl_up_sync(0xffffffffu, v[R - 1], 1);
               const float bval = top_rd[u];
               diag_in = up_in;
               up_in = lane0 ? bval : t;
+              ssb::cp_async_wait<PF>();
               float4 c4;
               asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                            : "=f"(c4.x), "=f"(c4.y), "=f"(c4.z), "=f"(c4.w)
-                           : "r"(ring_u32 + __umulhi(rd_hi, (uint32_t)RING_BYTES)));
-              rd_hi += 1u << 28;
+                           : "r"(ring_u32 + __umulhi(rd_hi + ((uint32_t)u << 28), (uint32_t)RING_BYTES)));
               cells(c4, s0 + u - lane);
-              if (wr_bnd) bnd_wr[u] = v[R - 1];
+              if (wr_bnd && (!EDGE || (u >= bw_lo && u < bw_hi))) bnd_wr[u] = v[R - 1];
             }
             codes_end(quad);
-            ssb::cp_async_commit();
           }
+        };
+        if (c >= steady_lo && c <= steady_hi && pitch_fits) {
+          fast_chunk(std::false_type{});
+        } else if (!WRITE_DTW && VEC && pitch_fits) {
+          fast_chunk(std::true_type{});
         } else {
 #pragma unroll
           for (int quad = 0; quad < CH / 4; ++quad) {
-            ssb::cp_async_wait<PF / 4 - 1>();
             codes_begin(quad);
 #pragma unroll
             for (int u4 = 0; u4 < 4; ++u4) step_general(s0 + quad * 4 + u4);
             codes_end(quad);
-            ssb::cp_async_commit();
           }
         }
         dirs[((int64_t)band * nch + c) * 32 + lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -516,13 +511,10 @@ int make_geometry(int64_t N, int64_t M, int64_t stride_i, int64_t stride_j, Geom
 }
 
 template <bool Y_IS_I, bool VEC, bool WRITE_DTW, bool RAGGED = false>
-int launch_fill(const DtwParams& p_in, cudaStream_t st) {
+int launch_fill(const DtwParams& p, cudaStream_t st) {
   auto kern = dtw_fill_kernel<Y_IS_I, VEC, WRITE_DTW, RAGGED>;
-  DtwParams p = p_in;
-  static const int env_flags = [] { const char* e = getenv("SSB_DTW_FLAGS"); return e ? atoi(e) : 0; }();
-  p.flags = env_flags;
   SSB_REQUIRE(p.nch < (1 << PROG_SHIFT), "dtw: sweep extent %d too large", p.Nx);
-  const int bnd_bytes = ((p.Nx + 3) & ~3) * 4;
+  const int bnd_bytes = bnd_bytes_for(p.Nx);
   const int per_warp = RING_BYTES + bnd_bytes;
   // pipeline width: one warp per band of a pair (ragged: of the tallest pair), at least 4 warps per
   // CTA when there are pairs to spare (band instances of consecutive pairs then run side by side)

@@ -62,6 +62,7 @@ int64_t ssb_sizeof(int which) {
     case 4: return (int64_t)sizeof(ssb_dtw_pair_t);
     case 5: return (int64_t)sizeof(ssb_utt_t);
     case 6: return (int64_t)sizeof(ssb_prep_entry_t);
+    case 7: return (int64_t)sizeof(ssb_emg_rec_t);
     default: return -1;
   }
 }

@@ -826,7 +826,108 @@ class _ConvWFn(torch.autograd.Function):
         return dx, dW, db, None, None, None, None, None, None
 
 
+class _ConvPairWFn(torch.autograd.Function):
+    """The two stride-2 convolutions that read a ResBlock's input, conv1 (k3, p1) and
+    residual_path (k1) of architecture.py:18,24, as ONE autograd node: their input gradients land
+    in one buffer (the 1x1 data-gradient GEMM accumulates into the even rows the k3 one wrote)
+    instead of a zero-filled second tensor summed by the autograd engine (a fill and an add over
+    the block input per ResBlock and step).  Operands as in _ConvWFn."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, wr, br, wf1, wd1a, wd1b, wfr, wdr, zero_bias_grad):
+        _chk(x, "x")
+        B, L, Cin = x.shape
+        Cout = w1.shape[0]
+        Lout = (L - 1) // 2 + 1
+        xp = planes_of(x)
+        c1 = torch.empty((B, Lout, Cout), dtype=_f32, device=x.device)
+        cr = torch.empty((B, Lout, Cout), dtype=_f32, device=x.device)
+        gemm_tc_kmajor(tc_operand_conv(xp, B, L, Cin, Lout, 2, 1, -1), wf1, Cout, 3 * Cin,
+                       _epi(Scatter(c1.data_ptr(), Lout * Cout, Lout, Cout, 1, 0), bias=b1))
+        gemm_tc_kmajor(tc_operand_conv(xp, B, L, Cin, Lout, 2, 1, 0), wfr, Cout, Cin,
+                       _epi(Scatter(cr.data_ptr(), Lout * Cout, Lout, Cout, 1, 0), bias=br))
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[3]
+        ctx.save_for_backward(x, xp if need_w else None, wd1a, wd1b, wdr)
+        ctx.cfg = (tuple(w1.shape), bool(zero_bias_grad))
+        ctx.sinks = (_sink(b1), _sink(br))
+        return c1, cr
+
+    @staticmethod
+    def backward(ctx, d1, dr):
+        x, xp, wd1a, wd1b, wdr = ctx.saved_tensors
+        (Cout, Cin, _), zero_b = ctx.cfg
+        d1, dr = d1.contiguous(), dr.contiguous()
+        B, L, _ = x.shape
+        Lout = d1.shape[1]
+        M = B * Lout
+        dev = x.device
+        d1p, drp = planes_of(d1), planes_of(dr)
+        dx = dW1 = dWr = db1 = dbr = None
+        xpl = xp if xp is not None else planes_of(x)
+        if ctx.needs_input_grad[1]:
+            g = torch.empty((3 * Cin, Cout), dtype=_f32, device=dev)
+            gemm_tc_wgrad(tc_operand_conv(xpl, B, L, Cin, Lout, 2, 1, -1), d1p, Cout, 3 * Cin, g)
+            dW1 = g.view(3, Cin, Cout).permute(2, 1, 0)
+        if ctx.needs_input_grad[3]:
+            g = torch.empty((Cin, Cout), dtype=_f32, device=dev)
+            gemm_tc_wgrad(tc_operand_conv(xpl, B, L, Cin, Lout, 2, 1, 0), drp, Cout, Cin, g)
+            dWr = g.view(1, Cin, Cout).permute(2, 1, 0)
+        for need, d, sink, which in ((ctx.needs_input_grad[2], d1, ctx.sinks[0], 0),
+                                     (ctx.needs_input_grad[4], dr, ctx.sinks[1], 1)):
+            if not need:
+                continue
+            if zero_b:       # bias in front of a training-mode BatchNorm: exact zero gradient
+                val = None if sink is not None else torch.zeros(Cout, dtype=_f32, device=dev)
+            elif sink is not None:
+                colsum(d.view(M, Cout), out=sink, accumulate=True)
+                val = None
+            else:
+                val = colsum(d.view(M, Cout))
+            if which == 0:
+                db1 = val
+            else:
+                dbr = val
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+
+            def run(dyp, rows, taps, planes, d_off, acc):
+                gemm_tc_kmajor(tc_operand_conv(dyp, B, Lout, Cout, rows, 1, 1, 0), planes, Cin,
+                               taps * Cout, _epi(Scatter(dx.data_ptr(), L * Cin, rows, Cin, 2, d_off),
+                                                 accumulate=acc))
+            ne, no = (L + 1) // 2, L // 2
+            run(d1p, ne, 1, wd1a, 0, 0)          # even rows: d1[t] . W1_1^T
+            if no > 0:
+                run(d1p, no, 2, wd1b, 1, 0)      # odd rows: d1[t] . W1_2^T + d1[t+1] . W1_0^T
+            run(drp, ne, 1, wdr, 0, 1)           # even rows += dr[t] . Wr^T
+        return dx, dW1, db1, dWr, dbr, None, None, None, None, None, None
+
+
 _CONV_TAPMAPS = {(3, 1): [(2, 1, 0)], (3, 2): [(1,), (2, 0)], (1, 2): [(0,)]}
+
+
+def conv_pair_w(x, conv1, conv_r, wp, zero_bias_grad=False):
+    """(conv1(x), residual_path(x)) for a stride-2 ResBlock through one autograd node, or None when
+    the pair is not eligible (the caller then uses conv1d_w twice)."""
+    if wp is None or not x.requires_grad or os.environ.get("SSB_CONVPAIR", "1") == "0":
+        return None
+    w1, wr = conv1.weight, conv_r.weight
+    if (tuple(w1.shape[2:]) != (3,) or tuple(wr.shape[2:]) != (1,) or conv1.stride != (2,)
+            or conv_r.stride != (2,) or conv1.bias is None or conv_r.bias is None):
+        return None
+    Cout, Cin, _ = w1.shape
+    B, L, _ = x.shape
+    Lout = (L - 1) // 2 + 1
+    wf1, wfr = wp.get(w1, "conv_f"), wp.get(wr, "conv_f")
+    wd1 = [wp.get(w1, ("conv_d", tm)) for tm in _CONV_TAPMAPS[(3, 2)]]
+    wdr = wp.get(wr, ("conv_d", _CONV_TAPMAPS[(1, 2)][0]))
+    ok = (all(t is not None for t in (wf1, wfr, wdr, *wd1))
+          and _tc_fwd_ok(B * Lout, Cout, 3 * Cin, Cin) and _tc_wgrad_ok(B * Lout, Cout, 3 * Cin, Cin)
+          and _tc_fwd_ok(B * Lout, Cout, Cin, Cin) and _tc_wgrad_ok(B * Lout, Cout, Cin, Cin)
+          and _tc_fwd_ok(B * L // 2, Cin, Cout, Cout))
+    if not ok:
+        return None
+    return _ConvPairWFn.apply(x, w1, conv1.bias, wr, conv_r.bias, wf1, wd1[0], wd1[1], wfr, wdr,
+                              bool(zero_bias_grad))
 
 
 def conv1d_w(x, conv, wp, ksize, stride, gemm_weight, zero_bias_grad=False):

@@ -37,7 +37,7 @@ def test_struct_mirrors_match_the_compiled_layouts():
     import ctypes
     lib = _lib.load()
     for which, cls in enumerate((_lib.Gather, _lib.Scatter, _lib.Epilogue, _lib.TcOperand,
-                                 _lib.DtwPair, _lib.Utt, _lib.PrepEntry)):
+                                 _lib.DtwPair, _lib.Utt, _lib.PrepEntry, _lib.EmgRec)):
         assert lib.ssb_sizeof(which) == ctypes.sizeof(cls), cls.__name__
     assert lib.ssb_sizeof(99) == -1
 
