@@ -359,6 +359,39 @@ def mel_side_metric(peaks, with_cpu, clocks_mhz=1965.0):
     return out
 
 
+def emg_side_metric(with_cpu):
+    """EMG signal conditioning (read_emg.py:62-67): 7 notch + 1 high-pass
+    filtfilt passes and the resampling of 256 recordings x 12 s x 8 channels (1 kHz float64), one
+    launch each.  Latency-bound by construction (a float64 recurrence per channel, bit-exact with
+    scipy), so the figure of merit is recordings/s against the host formulation."""
+    import numpy as np
+    from silent_speech_b200 import emg_signal as es
+    R, n = 256, 12000
+    rs = np.random.RandomState(0)
+    x = torch.from_numpy(50.0 * rs.randn(R * n, 8)).cuda()
+    recs = [x[i * n:(i + 1) * n] for i in range(R)]
+    st = es.notch_stages(60, 1000) + es.drift_stages(1000)
+
+    def f():
+        y, offs = es.filtfilt_cascade(recs, st)
+        es.subsample_rows(y, [(o, n) for o in offs], 689.06, 1000, torch.float32)
+    ms = timed(f, 3, 1, 1) / 3
+    out = {"metric": "EMG conditioning recordings/s (256 x 12000 samples x 8 ch, device-resident)",
+           "value": R / ms * 1e3, "ms": ms,
+           "bound": "latency: 16 sequential float64 IIR passes per channel, one thread per channel"}
+    if with_cpu:
+        from oracle import emg as oemg
+        xs = [r.cpu().numpy() for r in recs[:2]]
+        z = np.zeros((0, 8))
+        t0 = time.perf_counter()
+        for a in xs:
+            oemg.condition(z, a, z, rates=(689.06,))
+        dt = (time.perf_counter() - t0) / len(xs)
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "recordings/s", "cores": 1, "kind": "port",
+                               "sample": "2 of the 256 recordings (oracle/emg.py, C inner loops)"}
+    return out
+
+
 WORKLOADS = {
     # name: metric, frames/utterance, algorithmic GFLOP per bs-32 step per GPU (SURVEY.md section 8d)
     "cfg1": {"metric": METRIC, "frames": 500, "gflop": 6229.0},
@@ -707,6 +740,7 @@ def run_ours(args):
             line["dtw"] = side
         if rank == 0 and world == 1:
             line["mel"] = mel_side_metric(peaks, not args.no_cpu)
+            line["emg"] = emg_side_metric(not args.no_cpu)
     if rank == 0 and world == 1 and not args.no_cpu:
         # bounded sample of the same workload on the host cores: the unmodified reference on 4 of
         # the 32 utterances, 1 timed step after 1 warm-up (the full-batch run is --impl reference)

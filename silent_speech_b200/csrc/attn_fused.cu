@@ -42,7 +42,9 @@ constexpr int BLK_BIG = QT * 64;   // bytes of a [128 rows][32 d] block  (8 KB)
 constexpr int BLK_SMALL = CH * 64; // bytes of a [32 rows][32 d] block   (2 KB)
 constexpr int MAX_NDB = 3;       // dh <= 96
 
-constexpr int KST = 3;           // forward: K / V ring depth
+constexpr int KG = 3;            // forward: key chunks per S MMA (N = 32 KG)
+constexpr int KST = 2 * KG;      // forward: K ring depth = two MMA groups
+constexpr int VST = 4;           // forward: V ring depth
 constexpr int NCW = 16;          // element-wise warps: 4 per TMEM lane group (a lone warp per
                                  // scheduler cannot hide its own latencies: 341 / 708 us per layer
                                  // with 4 warps)
@@ -226,17 +228,16 @@ struct FwdSmem {   // byte offsets from the 1024-aligned base
   static constexpr int Q = 0;                                         // 2 planes x ndb x 8 KB
   static constexpr int KRING = Q + 2 * MAX_NDB * BLK_BIG;             // 48 KB
   static constexpr int KSTAGE = 2 * MAX_NDB * BLK_SMALL;              // 12 KB
-  static constexpr int PHASE1_END = KRING + KST * KSTAGE;             // 84 KB
+  static constexpr int PHASE1_END = KRING + KST * KSTAGE;             // 120 KB
   // phase 2 aliases the Q / K region once every S MMA has retired
   static constexpr int VRING = 0;
-  static constexpr int PT = VRING + KST * KSTAGE;                     // P tiles 0..2 (2 planes x 8 KB each)
-  static constexpr int PHASE2_END = PT + 3 * 2 * BLK_BIG;             // 84 KB
+  static constexpr int PT = VRING + VST * KSTAGE;                     // P tiles 0..3 (2 planes x 8 KB each)
+  static constexpr int PHASE2_END = PT + 4 * 2 * BLK_BIG;             // 112 KB
   static constexpr int R = PHASE1_END;                                // 128 x RW fp32 (<= 100 KB)
-  static constexpr int PT3 = R + QT * 200 * 4;                        // P tile 3
-  static constexpr int RED = PT3 + 2 * BLK_BIG;                       // [2][4][128] fp32 max / sum exchange
+  static constexpr int RED = R + QT * 200 * 4;                        // [2][4][128] fp32 max / sum exchange
   static constexpr int BARS = RED + 2 * 4 * QT * 4;
   static constexpr int TOTAL = BARS + 512;
-  static __device__ __forceinline__ int pt(int k) { return k < 3 ? PT + k * 2 * BLK_BIG : PT3; }
+  static __device__ __forceinline__ int pt(int k) { return PT + k * 2 * BLK_BIG; }
 };
 static_assert(FwdSmem::PHASE2_END <= FwdSmem::PHASE1_END, "phase-2 buffers must fit the alias");
 
@@ -250,7 +251,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t bars = base + FwdSmem::BARS;
   const uint32_t bar_q = bars, bar_r = bars + 8, bar_s = bars + 16, bar_o = bars + 24;
   const uint32_t kfull = bars + 32, kempty = kfull + 8 * KST, vfull = kempty + 8 * KST,
-                 vempty = vfull + 8 * KST, pfull = vempty + 8 * KST, pempty = pfull + 32;
+                 vempty = vfull + 8 * VST, pfull = vempty + 8 * VST, pempty = pfull + 32;
   const uint32_t tmem_slot = pempty + 32;
   const uint32_t sready = tmem_slot + 8;   // [11]: S columns of chunk j complete
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -265,11 +266,9 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 
   if (threadIdx.x == NCT) {
     for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);
-    for (int s = 0; s < KST; ++s) {
-      mbar_init(kfull + 8 * s, 1); mbar_init(kempty + 8 * s, 1);
-      mbar_init(vfull + 8 * s, 1); mbar_init(vempty + 8 * s, 1);
-    }
-    for (int s = 0; s < 4; ++s) { mbar_init(pfull + 8 * s, 4); mbar_init(pempty + 8 * s, 1); }
+    for (int s = 0; s < KST; ++s) { mbar_init(kfull + 8 * s, 1); mbar_init(kempty + 8 * s, 1); }
+    for (int s = 0; s < VST; ++s) { mbar_init(vfull + 8 * s, 1); mbar_init(vempty + 8 * s, 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(pfull + 8 * s, NCW); mbar_init(pempty + 8 * s, 1); }
     for (int s = 0; s < 11; ++s) mbar_init(sready + 8 * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -285,66 +284,85 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t tmem_o = tmem + 352;   // O accumulator columns [352, 352 + dh)
 
   if (warp == NCW + 1) {
+    // ---------------- TMA producer ----------------
+    // One lane per (plane, d block): the 2 * ndb copies of an operand tile are issued side by side.
+    // (r2 trace: a single thread needed ~1000 cycles to issue the 6 copies of a chunk, which paced
+    // both the K stream of phase 1 and the V stream behind the last P tiles.)
+    const int pl = lane / ndb, blk = lane - pl * ndb;
+    const bool op = lane < 2 * ndb;
+    if (lane == 0) mbar_expect_tx(bar_q, 2 * ndb * BLK_BIG);
+    __syncwarp();
+    if (op) tma_5d(base + FwdSmem::Q + pl * plane_q + blk * BLK_BIG, &mapQ, bar_q, blk * DB, q0, h, b, pl);
+    // K ring: [plane][d block][KST x 32 rows][64 B] - the rows of consecutive stages are
+    // contiguous inside a (plane, block) slab, so one MMA can take KG chunks as its N = 32 KG
+    auto load_k = [&](int j) {
+      const int s = j % KST;
+      if (lane == 0) mbar_expect_tx(kfull + 8 * s, 2 * ndb * BLK_SMALL);
+      __syncwarp();
+      if (op)
+        tma_5d(base + FwdSmem::KRING + (pl * ndb + blk) * (KST * BLK_SMALL) + s * BLK_SMALL, &mapK,
+               kfull + 8 * s, blk * DB, kw0 + j * CH, h, b, pl);
+    };
+    auto load_v = [&](int j) {
+      const int s = j % VST;
+      if (lane == 0) mbar_expect_tx(vfull + 8 * s, 2 * ndb * BLK_SMALL);
+      __syncwarp();
+      if (op)
+        tma_5d(base + FwdSmem::VRING + s * FwdSmem::KSTAGE + pl * plane_k + blk * BLK_SMALL, &mapV,
+               vfull + 8 * s, blk * DB, kw0 + j * CH, h, b, pl);
+    };
+    for (int j = 0; j < KST && j < nch; ++j) load_k(j);
     if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      mbar_expect_tx(bar_q, 2 * ndb * BLK_BIG);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int blk = 0; blk < ndb; ++blk)
-          tma_5d(base + FwdSmem::Q + pl * plane_q + blk * BLK_BIG, &mapQ, bar_q, blk * DB, q0, h, b, pl);
-      auto load_kv = [&](const CUtensorMap* map, uint32_t ring, uint32_t full, int j) {
-        const int s = j % KST;
-        mbar_expect_tx(full + 8 * s, 2 * ndb * BLK_SMALL);
-        for (int pl = 0; pl < 2; ++pl)
-          for (int blk = 0; blk < ndb; ++blk)
-            tma_5d(ring + s * FwdSmem::KSTAGE + pl * plane_k + blk * BLK_SMALL, map, full + 8 * s,
-                   blk * DB, kw0 + j * CH, h, b, pl);
-      };
-      for (int j = 0; j < KST && j < nch; ++j) load_kv(&mapK, base + FwdSmem::KRING, kfull, j);
       mbar_expect_tx(bar_r, QT * p.RW * 4);
       tma_3d(base + FwdSmem::R, &mapR, bar_r, 0, q0, bh);
-      for (int j = KST; j < nch; ++j) {      // stage j % KST is free when chunk j - KST's MMAs retired
-        mbar_wait(kempty + 8 * (j % KST), (uint32_t)(j / KST - 1) & 1u);
-        load_kv(&mapK, base + FwdSmem::KRING, kfull, j);
-      }
-      // phase 2: the V ring aliases the Q / K region, dead once every S MMA has retired
-      mbar_wait(bar_s, 0);
-      for (int j = 0; j < nch; ++j) {
-        if (j >= KST) mbar_wait(vempty + 8 * (j % KST), (uint32_t)(j / KST - 1) & 1u);
-        load_kv(&mapV, base + FwdSmem::VRING, vfull, j);
-      }
+    }
+    for (int j = KST; j < nch; ++j) {      // stage j % KST is free when chunk j - KST's MMAs retired
+      mbar_wait(kempty + 8 * (j % KST), (uint32_t)(j / KST - 1) & 1u);
+      load_k(j);
+    }
+    // phase 2: the V ring aliases the Q / K region, dead once every S MMA has retired
+    mbar_wait(bar_s, 0);
+    for (int j = 0; j < nch; ++j) {
+      if (j >= VST) mbar_wait(vempty + 8 * (j % VST), (uint32_t)(j / VST - 1) & 1u);
+      load_v(j);
     }
   } else if (warp == NCW) {
     if (lane == 0) {
       // ---------------- MMA issue ----------------
-      // phase 1: S[:, 32 j .. 32 j + 32) = Q K_j^T
-      const uint32_t id_s = idesc(CH, 0, 0);
+      // phase 1: S[:, 32 j .. 32 (j + KG)) = Q [K_j ; .. ; K_j+KG-1]^T, KG chunks per MMA.  An N = 32
+      // MMA costs ~80 cycles, almost all of it re-reading the 4 KB Q operand from shared memory
+      // (r2 trace: 198 of them = 16 k of the CTA's 43 k cycles); N = 96 reads Q a third as often.
       const uint64_t dq_hi = desc64(base + FwdSmem::Q, 16), dq_lo = dadv(dq_hi, plane_q);
+      const uint32_t slab_k = KST * BLK_SMALL, plane_kr = ndb * slab_k;
       mbar_wait(bar_q, 0);
-      for (int j = 0; j < nch; ++j) {
-        const int s = j % KST;
-        mbar_wait(kfull + 8 * s, (uint32_t)(j / KST) & 1u);
+      for (int j = 0; j < nch; j += KG) {
+        const int s = j % KST, g = min(KG, nch - j);
+        for (int u = 0; u < g; ++u) mbar_wait(kfull + 8 * (s + u), (uint32_t)(j / KST) & 1u);
         tc_fence_after();
-        const uint64_t dk_hi = desc64(base + FwdSmem::KRING + s * FwdSmem::KSTAGE, 16);
-        const uint64_t dk_lo = dadv(dk_hi, plane_k);
+        const uint32_t id_s = idesc(g * CH, 0, 0);
+        const uint64_t dk_hi = desc64(base + FwdSmem::KRING + s * BLK_SMALL, 16);
+        const uint64_t dk_lo = dadv(dk_hi, plane_kr);
         const uint32_t d = tmem + (uint32_t)(j * CH);
         uint32_t acc = 0;
         for (int blk = 0; blk < ndb; ++blk)
           for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t oa = blk * BLK_BIG + ks * 32, ob = blk * BLK_SMALL + ks * 32;
+            const uint32_t oa = blk * BLK_BIG + ks * 32, ob = blk * slab_k + ks * 32;
             umma(d, dadv(dq_hi, oa), dadv(dk_hi, ob), id_s, acc);
             umma(d, dadv(dq_hi, oa), dadv(dk_lo, ob), id_s, 1u);
             umma(d, dadv(dq_lo, oa), dadv(dk_hi, ob), id_s, 1u);
             acc = 1u;
           }
-        umma_commit(kempty + 8 * s);
-        umma_commit(sready + 8 * j);        // pass 1 of the softmax may read these 32 columns
+        for (int u = 0; u < g; ++u) {
+          umma_commit(kempty + 8 * (s + u));
+          umma_commit(sready + 8 * (j + u));   // pass 1 of the softmax may read these columns
+        }
       }
       umma_commit(bar_s);
       // phase 2: O += P_j V_j
       const uint32_t id_o = idesc(p.dh, 0, 1);
       for (int j = 0; j < nch; ++j) {
-        const int s = j % KST, pb = j & 3;
-        mbar_wait(vfull + 8 * s, (uint32_t)(j / KST) & 1u);
+        const int s = j % VST, pb = j & 3;
+        mbar_wait(vfull + 8 * s, (uint32_t)(j / VST) & 1u);
         mbar_wait(pfull + 8 * pb, (uint32_t)(j >> 2) & 1u);
         tc_fence_after();
         const uint64_t dp_hi = desc64(base + FwdSmem::pt(pb), 16), dp_lo = dadv(dp_hi, BLK_BIG);
@@ -421,71 +439,67 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     const float mneg = -m * LOG2E;
     float sum = 0.f;
     const int64_t drow = ((int64_t)bh * p.T + q) * p.Tp4;
-    for (int j = cg; j < nch; j += 4) {
+    // Pass 2 walks the chunks IN ORDER with all 16 warps on the same chunk: warp group cg takes
+    // the 8 keys [8 cg, 8 cg + 8) of every chunk = one 16 B piece of the row's P operand.  Tiles
+    // then complete one after the other and the P V MMAs run alongside the element-wise work
+    // (r2 trace: with group cg owning whole chunks cg, cg + 4, .. the first four tiles appeared
+    // together after 6 k cycles and the MMAs trailed the last tile by 3.5 k).
+    for (int j = 0; j < nch; ++j) {
       const int cls = chunk_class(j);
-      const int n = j >> 2;               // n-th use of P tile cg
-      const uint32_t pt = base + FwdSmem::pt(cg);
+      const int n = j >> 2;               // n-th use of P tile j % 4
+      const uint32_t pt = base + FwdSmem::pt(j & 3);
+      const int c0 = j * CH + cg * 8;     // first S column of this thread's piece
+      float e[8];
+      if (cls == 0) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float e[16];
-        if (cls == 0) {
+        for (int c = 0; c < 8; ++c) e[c] = 0.f;
+      } else {
+        uint32_t v[8];
+        tmem_ld8(tlane + (uint32_t)c0, v);
+        tmem_wait_ld();
+        const uint32_t ra = rrow + (uint32_t)(c0 + soff) * 4u;
+        if (cls == 2) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) e[c] = 0.f;
+          for (int c = 0; c < 8; ++c) {
+            const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4));
+            e[c] = ex2(fmaf(y, LOG2E, mneg));
+            sum += e[c];
+          }
         } else {
-          uint32_t v[16];
-          tmem_ld16(tlane + (uint32_t)(j * CH + half * 16), v);
-          tmem_wait_ld();
-          const uint32_t ra = rrow + (uint32_t)(j * CH + half * 16 + soff) * 4u;
-          if (cls == 2) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4));
-              e[c] = ex2(fmaf(y, LOG2E, mneg));
-              sum += e[c];
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const int col = j * CH + half * 16 + c, rel = col + soff;
-              const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4));
-              const bool ok = row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W;
-              e[c] = ok ? ex2(fmaf(y, LOG2E, mneg)) : 0.f;
-              sum += e[c];
-            }
-          }
-          if (p.drop_p > 0.f) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 rnd = ssb::dropout_bits4(
-                  seed, p.site, (uint64_t)(drow + ((kw0 + j * CH + half * 16) >> 2) + g));
-              e[4 * g + 0] = rnd.x >= p.drop_thresh ? e[4 * g + 0] * p.drop_scale : 0.f;
-              e[4 * g + 1] = rnd.y >= p.drop_thresh ? e[4 * g + 1] * p.drop_scale : 0.f;
-              e[4 * g + 2] = rnd.z >= p.drop_thresh ? e[4 * g + 2] * p.drop_scale : 0.f;
-              e[4 * g + 3] = rnd.w >= p.drop_thresh ? e[4 * g + 3] * p.drop_scale : 0.f;
-            }
+          for (int c = 0; c < 8; ++c) {
+            const int col = c0 + c, rel = col + soff;
+            const float y = fmaf(__uint_as_float(v[c]), p.scale, ld_shared_f32(ra + c * 4));
+            const bool ok = row_ok && kw0 + col < p.T && rel >= 0 && rel <= 2 * p.W;
+            e[c] = ok ? ex2(fmaf(y, LOG2E, mneg)) : 0.f;
+            sum += e[c];
           }
         }
-        uint4 hi[2], lo[2];
+        if (p.drop_p > 0.f) {
 #pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          split_pack(e[8 * c2 + 0], e[8 * c2 + 1], hi[c2].x, lo[c2].x);
-          split_pack(e[8 * c2 + 2], e[8 * c2 + 3], hi[c2].y, lo[c2].y);
-          split_pack(e[8 * c2 + 4], e[8 * c2 + 5], hi[c2].z, lo[c2].z);
-          split_pack(e[8 * c2 + 6], e[8 * c2 + 7], hi[c2].w, lo[c2].w);
-        }
-        // only now is the tile needed: the MMAs of chunk j-4 (its previous user) must have retired
-        if (half == 0 && n >= 1) mbar_wait(pempty + 8 * cg, (uint32_t)(n - 1) & 1u);
-#pragma unroll
-        for (int c2 = 0; c2 < 2; ++c2) {
-          const uint32_t off = sw64_off(i, half * 2 + c2);
-          st_shared_v4(pt + off, hi[c2]);
-          st_shared_v4(pt + BLK_BIG + off, lo[c2]);
+          for (int g = 0; g < 2; ++g) {
+            const uint4 rnd = ssb::dropout_bits4(seed, p.site, (uint64_t)(drow + ((kw0 + c0) >> 2) + g));
+            e[4 * g + 0] = rnd.x >= p.drop_thresh ? e[4 * g + 0] * p.drop_scale : 0.f;
+            e[4 * g + 1] = rnd.y >= p.drop_thresh ? e[4 * g + 1] * p.drop_scale : 0.f;
+            e[4 * g + 2] = rnd.z >= p.drop_thresh ? e[4 * g + 2] * p.drop_scale : 0.f;
+            e[4 * g + 3] = rnd.w >= p.drop_thresh ? e[4 * g + 3] * p.drop_scale : 0.f;
+          }
         }
       }
+      uint4 hi, lo;
+      split_pack(e[0], e[1], hi.x, lo.x);
+      split_pack(e[2], e[3], hi.y, lo.y);
+      split_pack(e[4], e[5], hi.z, lo.z);
+      split_pack(e[6], e[7], hi.w, lo.w);
+      // only now is the tile needed: the MMAs of chunk j-4 (its previous user) must have retired
+      if (n >= 1) mbar_wait(pempty + 8 * (j & 3), (uint32_t)(n - 1) & 1u);
+      const uint32_t off = sw64_off(i, cg);
+      st_shared_v4(pt + off, hi);
+      st_shared_v4(pt + BLK_BIG + off, lo);
       fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pfull + 8 * cg);
+      if (lane == 0) mbar_arrive(pfull + 8 * (j & 3));
     }
     red[4 * QT + cg * QT + i] = sum;
     bar_compute();
@@ -498,20 +512,39 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       p.stat_m[(int64_t)bh * p.T + q] = m;
       p.stat_linv[(int64_t)bh * p.T + q] = linv;
     }
-    float* orow = p.O + ((int64_t)b * p.T + q) * (p.H * p.dh) + h * p.dh;
+    // The tile leaves through shared memory (every MMA has retired: the V ring / P tiles are
+    // free): each thread parks its row's columns, then the CTA writes whole 384 B rows with
+    // consecutive lanes on consecutive 16 B.  (r2 trace: one thread per row storing straight to
+    // its own row of O took 5.9 k of the CTA's 43 k cycles - 32 rows per store instruction.)
+    constexpr uint32_t OSTRIDE = (DB * MAX_NDB + 4) * 4;       // 400 B: 8 lanes cover 128 B
+    const uint32_t ost = base + FwdSmem::VRING;
     const int cw = p.dh >> 2;
     for (int c0 = cg * cw; c0 < (cg + 1) * cw; c0 += 8) {
       uint32_t v[8];
       tmem_ld8(tlane + 352 + (uint32_t)c0, v);
       tmem_wait_ld();
-      if (row_ok) {
-        *reinterpret_cast<float4*>(orow + c0) =
-            make_float4(__uint_as_float(v[0]) * linv, __uint_as_float(v[1]) * linv,
-                        __uint_as_float(v[2]) * linv, __uint_as_float(v[3]) * linv);
-        *reinterpret_cast<float4*>(orow + c0 + 4) =
-            make_float4(__uint_as_float(v[4]) * linv, __uint_as_float(v[5]) * linv,
-                        __uint_as_float(v[6]) * linv, __uint_as_float(v[7]) * linv);
-      }
+      const uint32_t dst = ost + (uint32_t)i * OSTRIDE + (uint32_t)c0 * 4u;
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(__uint_as_float(v[0]) * linv),
+                   "f"(__uint_as_float(v[1]) * linv), "f"(__uint_as_float(v[2]) * linv),
+                   "f"(__uint_as_float(v[3]) * linv)
+                   : "memory");
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "f"(__uint_as_float(v[4]) * linv),
+                   "f"(__uint_as_float(v[5]) * linv), "f"(__uint_as_float(v[6]) * linv),
+                   "f"(__uint_as_float(v[7]) * linv)
+                   : "memory");
+    }
+    bar_compute();
+    const int nv4 = p.dh >> 2;
+    float* otile = p.O + ((int64_t)b * p.T + q0) * (p.H * p.dh) + h * p.dh;
+    const int rows_ok = min(QT, p.T - q0);
+    for (int f = threadIdx.x; f < rows_ok * nv4; f += NCT) {
+      const int row = f / nv4, c4 = f - row * nv4;
+      float4 o;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                   : "r"(ost + (uint32_t)row * OSTRIDE + (uint32_t)c4 * 16u)
+                   : "memory");
+      *reinterpret_cast<float4*>(otile + (int64_t)row * (p.H * p.dh) + c4 * 4) = o;
     }
   }
   tc_fence_before();
@@ -586,45 +619,45 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t t_dv = tmem + 128, t_dk = tmem + 256, t_dq = tmem + 384;
 
   if (warp == NCW + 1) {
-    if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      mbar_expect_tx(kv_full, 4 * ndb * BLK_BIG);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int blk = 0; blk < ndb; ++blk) {
-          tma_5d(base + BwdSmem::K + pl * plane_big + blk * BLK_BIG, &mapK, kv_full, blk * DB, k0, h, b, pl);
-          tma_5d(base + BwdSmem::V + pl * plane_big + blk * BLK_BIG, &mapV, kv_full, blk * DB, k0, h, b, pl);
-        }
-      auto load_qd = [&](int j) {
-        const int s = j & 1;
-        const uint32_t dst = base + BwdSmem::QD + s * BwdSmem::QD_STAGE;
-        mbar_expect_tx(qd_full + 8 * s, 4 * ndb * BLK_SMALL);
-        for (int pl = 0; pl < 2; ++pl)
-          for (int blk = 0; blk < ndb; ++blk) {
-            tma_5d(dst + pl * plane_small + blk * BLK_SMALL, &mapQ, qd_full + 8 * s, blk * DB,
-                   qw0 + j * CH, h, b, pl);
-            tma_5d(dst + BwdSmem::QD_HALF + pl * plane_small + blk * BLK_SMALL, &mapDO,
-                   qd_full + 8 * s, blk * DB, qw0 + j * CH, h, b, pl);
-          }
-      };
-      auto load_r = [&](int j) {
-        const int s = j & 1;
+    // ---------------- TMA producer ----------------
+    // One lane per (tensor, plane, d block) copy, issued side by side (see the forward kernel).
+    const int which = lane / (2 * ndb), rem = lane - which * 2 * ndb;   // 0: K / Q_c, 1: V / dO_c
+    const int pl = rem / ndb, blk = rem - pl * ndb;
+    const bool op = lane < 4 * ndb;
+    if (lane == 0) mbar_expect_tx(kv_full, 4 * ndb * BLK_BIG);
+    __syncwarp();
+    if (op)
+      tma_5d(base + (which ? BwdSmem::V : BwdSmem::K) + pl * plane_big + blk * BLK_BIG,
+             which ? &mapV : &mapK, kv_full, blk * DB, k0, h, b, pl);
+    auto load_qd = [&](int j) {
+      const int s = j & 1;
+      const uint32_t dst = base + BwdSmem::QD + s * BwdSmem::QD_STAGE;
+      if (lane == 0) mbar_expect_tx(qd_full + 8 * s, 4 * ndb * BLK_SMALL);
+      __syncwarp();
+      if (op)
+        tma_5d(dst + which * BwdSmem::QD_HALF + pl * plane_small + blk * BLK_SMALL,
+               which ? &mapDO : &mapQ, qd_full + 8 * s, blk * DB, qw0 + j * CH, h, b, pl);
+    };
+    auto load_r = [&](int j) {
+      const int s = j & 1;
+      if (lane == 0) {
         mbar_expect_tx(r_full + 8 * s, BwdSmem::R_STAGE);
         // columns rel0 .. rel0 + 158 of rows q_c .. q_c + 31 (start rounded down to 4 floats: TMA
         // faults on an inner coordinate that is not 16 B aligned); out-of-range parts are zero-filled
         const int rel0 = k0 - (qw0 + j * CH) - (CH - 1) + p.W;
         tma_3d(base + BwdSmem::R + s * BwdSmem::R_STAGE, &mapR, r_full + 8 * s, rel0 & ~3,
                qw0 + j * CH, bh);
-      };
-      load_qd(0);
-      load_r(0);
-      if (nch > 1) { load_qd(1); load_r(1); }
-      for (int j = 0; j + 2 < nch; ++j) {
-        const int s = j & 1;
-        mbar_wait(r_free + 8 * s, (uint32_t)(j >> 1) & 1u);     // threads are done with R stage s
-        load_r(j + 2);
-        mbar_wait(qd_free + 8 * s, (uint32_t)(j >> 1) & 1u);    // dV / dK MMAs of chunk j retired
-        load_qd(j + 2);
       }
+    };
+    load_qd(0);
+    load_r(0);
+    if (nch > 1) { load_qd(1); load_r(1); }
+    for (int j = 0; j + 2 < nch; ++j) {
+      const int s = j & 1;
+      mbar_wait(r_free + 8 * s, (uint32_t)(j >> 1) & 1u);     // threads are done with R stage s
+      load_r(j + 2);
+      mbar_wait(qd_free + 8 * s, (uint32_t)(j >> 1) & 1u);    // dV / dK MMAs of chunk j retired
+      load_qd(j + 2);
     }
   } else if (warp == NCW) {
     if (lane == 0) {
