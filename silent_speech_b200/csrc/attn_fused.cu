@@ -327,7 +327,7 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       load_v(j);
     }
   } else if (warp == NCW) {
-    if (lane == 0) {
+    if (ssb::elect_one()) {
       // ---------------- MMA issue ----------------
       // phase 1: S[:, 32 j .. 32 (j + KG)) = Q [K_j ; .. ; K_j+KG-1]^T, KG chunks per MMA.  An N = 32
       // MMA costs ~80 cycles, almost all of it re-reading the 4 KB Q operand from shared memory
@@ -660,7 +660,7 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       load_qd(j + 2);
     }
   } else if (warp == NCW) {
-    if (lane == 0) {
+    if (ssb::elect_one()) {
       // ---------------- MMA issue ----------------
       const uint32_t id_s = idesc(CH, 0, 0), id_acc = idesc(p.dh, 0, 1), id_dq = idesc(CH, 1, 1);
       // K / V tiles as K-major A operands (S^T, dP^T) and K as the MN-major A operand of dQ^T

@@ -313,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own operand rows) =====================
-    if (lane == 0) {
+    if (ssb::elect_one()) {
       uint32_t it = 0;
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
         int n0, batch, row0, f0, kb_begin, nkb;
@@ -360,7 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && ssb::elect_one()) {
       const uint32_t idesc = make_idesc(p.mn_major, C::BMC);
       uint32_t it = 0, tcount = 0;
       for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {

@@ -50,6 +50,21 @@ bool pdl_enabled();
 // Blocks until the grids this launch depends on have completed and their writes are visible; a
 // no-op for a kernel launched without the programmatic-serialization attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// One elected lane of a CONVERGED warp.  Unlike `lane == 0`, ptxas knows that exactly one thread
+// passes: the tcgen05 / TMA (uniform-datapath) instructions behind it are emitted straight, without
+// the ELECT + BRA.U.ANY "for each active thread" loop it wraps around them under a divergent
+// predicate (8 extra instructions per MMA on the issuing thread).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
