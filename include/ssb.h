@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 207
+#define SSB_ABI_VERSION 208
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -321,6 +321,10 @@ typedef struct {
 SSB_API int ssb_split_bf16(const float* x, int64_t n, void* planes /* bf16 [2][n] */, void* stream);
 /* transposed: planes[p][c][r] = split(x[r][c]) of a row-major (rows, cols) fp32 matrix (both
  * multiples of 8): the W^T operand of an nn.Linear data gradient without an fp32 transpose. */
+/* strided: planes[p][r*ld_out + c] = split(x[r*ld_in + c]) for c < cols (cols % 8 == 0); the lo plane
+ * starts plane_stride elements after the hi plane. */
+SSB_API int ssb_split_bf16_2d(const float* x, int64_t rows, int64_t cols, int64_t ld_in, void* planes,
+                              int64_t ld_out, int64_t plane_stride, void* stream);
 SSB_API int ssb_split_bf16_t(const float* x, int64_t rows, int64_t cols,
                              void* planes /* bf16 [2][cols][rows] */, void* stream);
 /* C[(b,t), n] = epi( sum_k A((b,t), k) * B[n, k] );  B planes: [2][N][K] bf16 (K contiguous).
@@ -382,20 +386,27 @@ SSB_API int ssb_attn_ds_bwd(const float* P, const float* dP, int64_t B, int64_t 
  * writes them (`planes_out`), so no re-layout pass runs between the GEMM and the attention kernel. */
 SSB_API int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_t T, int64_t H,
                        int64_t dh, int64_t W, int64_t RW, float drop_p, uint64_t seed, uint32_t site,
-                       float* O, float* stat_m, float* stat_linv, int64_t head_stride, void* stream);
+                       float* O, void* O_planes, float* stat_m, float* stat_linv, int64_t head_stride,
+                       void* stream);
 /* delta[b*H+h, q] = sum_d dO * O over the head's dh columns */
 /* zero_out (nullable): additionally clears H*dh floats of every row of a (B*T, zero_ld) matrix -
  * the content-dQ accumulator of ssb_attn_fused_bwd - in the same pass. */
 SSB_API int ssb_attn_delta(const float* O, const float* dO, int64_t B, int64_t T, int64_t H, int64_t dh,
                    float* delta, float* zero_out, int64_t zero_ld, void* stream);
-/* dqkv (B*T, 3*H*dh): the dQ third must be zero on entry (content part is accumulated with
- * red.global.add), dK / dV thirds are overwritten.  dSband_planes: bf16 (2, B*T, H, RWp), zero on
- * entry; receives dS in band layout for the positional part of dQ (a tensor-core GEMM with E). */
+/* dqkv: rows dq_ld floats apart; the dQ columns [0, H*dh) must be zero on entry (the content part is
+ * accumulated with red.global.add).  dkv_planes == NULL: dq_ld == 3*H*dh and dK / dV overwrite the
+ * other two thirds of the (B*T, 3*H*dh) buffer.  dkv_planes != NULL: a bf16 (2, B*T, 3*H*dh) planes
+ * buffer whose dK / dV thirds are written instead (the operand format of the QKV data-gradient
+ * GEMM; its dQ third is the caller's to fill, ssb_split_bf16_2d), and dqkv may be (B*T, H*dh).
+ * dSband_planes: bf16 (2, B*T, H, RWp), zero on entry; receives dS in band layout for the positional
+ * part of dQ (a tensor-core GEMM with E).
+ * ssb_attn_fused_fwd: O_planes (nullable) additionally receives O as bf16 (2, B*T, H*dh) planes. */
 SSB_API int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const float* R,
                        const float* stat_m, const float* stat_linv, const float* delta, int64_t B,
                        int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW, float drop_p,
-                       uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
-                       int64_t head_stride, int64_t do_head_stride, void* stream);
+                       uint64_t seed, uint32_t site, float* dqkv, int64_t dq_ld, void* dkv_planes,
+                       void* dSband_planes, int64_t RWp, int64_t head_stride, int64_t do_head_stride,
+                       void* stream);
 
 /* ---- weight operand preparation (csrc/prep.cu) -----------------------------------------------
  * One launch writes the bf16 hi/lo split planes of every parameter in every layout the tensor-core

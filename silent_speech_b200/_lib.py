@@ -124,14 +124,15 @@ _SIGNATURES = {
     "ssb_attn_ds_bwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
                                 c_u64, c_u32, c_ptr, c_ptr, c_ptr]),
     "ssb_attn_fused_fwd": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
-                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+                                   c_u64, c_u32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_attn_delta": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i64, c_ptr]),
     "ssb_attn_fused_bwd": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64,
-                                   c_i64, c_i64, c_i64, c_f32, c_u64, c_u32, c_ptr, c_ptr, c_i64,
-                                   c_i64, c_i64, c_ptr]),
+                                   c_i64, c_i64, c_i64, c_f32, c_u64, c_u32, c_ptr, c_i64, c_ptr,
+                                   c_ptr, c_i64, c_i64, c_i64, c_ptr]),
     "ssb_col_partials_bytes": (c_i64, [c_i64, c_i64]),
     "ssb_colsum": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_int, c_ptr, c_i64, c_ptr]),
     "ssb_split_bf16_t": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "ssb_split_bf16_2d": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr]),
     "ssb_ctc_workspace_bytes": (c_i64, [c_i64, c_i64, c_i64]),
     "ssb_ctc_loss_fused": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
                                    c_int, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
@@ -170,7 +171,7 @@ _KERNELS_PER_CALL = {
     "ssb_gemm_nt": 1, "ssb_gemm_tn": 1, "ssb_colsum": 2, "ssb_colsum_planes": 2, "ssb_adamw_flat": 2, "ssb_ctc_loss_fused": 3, "ssb_bn_stats": 2, "ssb_bn_apply": 1,
     "ssb_bn_bwd": 3, "ssb_bn_bwd2": 3, "ssb_add_dropout_ln_fwd": 1, "ssb_add_dropout_ln_bwd": 2,
     "ssb_band_attn_fwd": 1, "ssb_band_attn_bwd": 2,
-    "ssb_split_bf16": 1, "ssb_split_bf16_t": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,
+    "ssb_split_bf16": 1, "ssb_split_bf16_t": 1, "ssb_split_bf16_2d": 1, "ssb_gemm_tc_kmajor": 1, "ssb_gemm_tc_wgrad": 1, "ssb_gemm_tc_batched": 1,
     "ssb_gemm_tc_batched_tn": 1, "ssb_pad_split_heads": 1, "ssb_transpose_split_heads": 1,
     "ssb_attn_softmax_fwd": 1, "ssb_attn_ds_bwd": 1,
     "ssb_attn_fused_fwd": 1, "ssb_attn_delta": 1, "ssb_attn_fused_bwd": 1,
@@ -226,7 +227,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 207      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 208      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):

@@ -212,11 +212,15 @@ struct FusedParams {
   uint32_t site;
   // forward
   float* O;          // (B*T, H*dh)
+  __nv_bfloat16* O_planes;   // nullable: O also as (2, B*T, H*dh) bf16 hi / lo planes
   float* stat_m;     // (B*H, T) row max of the logits
   float* stat_linv;  // (B*H, T) 1 / sum exp
   // backward
   const float* delta;   // (B*H, T)  sum_d dO * O
-  float* dqkv;          // (B*T, 3*H*dh): dQ accumulated atomically (pre-zeroed), dK / dV stored
+  float* dqkv;          // dQ accumulated atomically (pre-zeroed): rows dq_ld apart; with dkv_planes == NULL
+                        // the buffer is (B*T, 3*H*dh) and dK / dV are stored into its other thirds
+  int64_t dq_ld;
+  __nv_bfloat16* dkv_planes;   // nullable: (2, B*T, 3*H*dh) bf16 planes, dK / dV written to their thirds
   __nv_bfloat16* dsb;   // (2, B*T, H, RWp) band-layout dS planes (pre-zeroed)
   int RWp;
 };
@@ -545,6 +549,14 @@ attn_fused_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                    : "r"(ost + (uint32_t)row * OSTRIDE + (uint32_t)c4 * 16u)
                    : "memory");
       *reinterpret_cast<float4*>(otile + (int64_t)row * (p.H * p.dh) + c4 * 4) = o;
+      if (p.O_planes) {   // the out-projection's operand, written here instead of by a split pass
+        uint2 hi, lo;
+        split_pack(o.x, o.y, hi.x, lo.x);
+        split_pack(o.z, o.w, hi.y, lo.y);
+        __nv_bfloat16* dst = p.O_planes + ((int64_t)b * p.T + q0 + row) * (p.H * p.dh) + h * p.dh + c4 * 4;
+        *reinterpret_cast<uint2*>(dst) = hi;
+        *reinterpret_cast<uint2*>(dst + (int64_t)p.B * p.T * p.H * p.dh) = lo;
+      }
     }
   }
   tc_fence_before();
@@ -759,10 +771,10 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       tmem_wait_ld();
       if (i < p.dh) {
         const int qb = qw0 + j * CH + c8;
-        float* dst = p.dqkv + ((int64_t)b * p.T + qb) * (3 * D) + h * p.dh + i;
+        float* dst = p.dqkv + ((int64_t)b * p.T + qb) * p.dq_ld + h * p.dh + i;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          if (qb + c < p.T) atomicAdd(dst + (int64_t)c * (3 * D), __uint_as_float(v[c]) * p.scale);
+          if (qb + c < p.T) atomicAdd(dst + (int64_t)c * p.dq_ld, __uint_as_float(v[c]) * p.scale);
       }
       tc_fence_before();
       __syncwarp();
@@ -874,23 +886,55 @@ attn_fused_bwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       if (j >= 1) dq_epilogue(j - 1, false);
     }
     dq_epilogue(nch - 1, true);   // also: every MMA of the tile has retired -> dV / dK are complete
-    float* krow = p.dqkv + ((int64_t)b * p.T + k) * (3 * D) + D + h * p.dh;
+    // dK / dV leave through shared memory like the forward's O tile (every MMA has retired: the
+    // K / V / {Q_c, dO_c} buffers are free): rows are parked by their owning threads, then written
+    // out 384 B at a time, as fp32 into dqkv or directly as the operand planes of the QKV
+    // data-gradient GEMM.
+    constexpr uint32_t OSTRIDE = (DB * MAX_NDB + 4) * 4;       // 400 B: 8 lanes cover 128 B
+    constexpr uint32_t OTILE = QT * OSTRIDE;
+    static_assert(2 * OTILE <= BwdSmem::PD, "dK / dV staging must fit the K / V / QD buffers");
+    const uint32_t ost = base + BwdSmem::K;
     const int cw = p.dh >> 2;
     for (int c0 = cg * cw; c0 < (cg + 1) * cw; c0 += 8) {
       uint32_t a[8], g[8];
       tmem_ld8(tlane + 256 + (uint32_t)c0, a);
       tmem_ld8(tlane + 128 + (uint32_t)c0, g);
       tmem_wait_ld();
-      if (key_ok) {
+      const uint32_t dst = ost + (uint32_t)i * OSTRIDE + (uint32_t)c0 * 4u;
 #pragma unroll
-        for (int c = 0; c < 8; c += 4) {
-          *reinterpret_cast<float4*>(krow + c0 + c) =
-              make_float4(__uint_as_float(a[c]) * p.scale, __uint_as_float(a[c + 1]) * p.scale,
-                          __uint_as_float(a[c + 2]) * p.scale, __uint_as_float(a[c + 3]) * p.scale);
-          *reinterpret_cast<float4*>(krow + D + c0 + c) =
-              make_float4(__uint_as_float(g[c]), __uint_as_float(g[c + 1]),
-                          __uint_as_float(g[c + 2]), __uint_as_float(g[c + 3]));
-        }
+      for (int c = 0; c < 8; c += 4) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + c * 4u),
+                     "f"(__uint_as_float(a[c]) * p.scale), "f"(__uint_as_float(a[c + 1]) * p.scale),
+                     "f"(__uint_as_float(a[c + 2]) * p.scale), "f"(__uint_as_float(a[c + 3]) * p.scale)
+                     : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + OTILE + c * 4u),
+                     "f"(__uint_as_float(g[c])), "f"(__uint_as_float(g[c + 1])),
+                     "f"(__uint_as_float(g[c + 2])), "f"(__uint_as_float(g[c + 3]))
+                     : "memory");
+      }
+    }
+    bar_compute();
+    const int nv4 = p.dh >> 2;
+    const int rows_ok = min(QT, p.T - k0);
+    const int per = rows_ok * nv4;
+    const int64_t plane = (int64_t)p.B * p.T * 3 * D;
+    for (int f = threadIdx.x; f < 2 * per; f += NCT) {
+      const int which = f >= per ? 1 : 0;              // 0: dK, 1: dV
+      const int r = f - which * per, row = r / nv4, c4 = r - row * nv4;
+      float4 o;
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                   : "r"(ost + which * OTILE + (uint32_t)row * OSTRIDE + (uint32_t)c4 * 16u)
+                   : "memory");
+      const int64_t e = ((int64_t)b * p.T + k0 + row) * (3 * D) + (1 + which) * D + h * p.dh + c4 * 4;
+      if (p.dkv_planes) {
+        uint2 hi, lo;
+        split_pack(o.x, o.y, hi.x, lo.x);
+        split_pack(o.z, o.w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(p.dkv_planes + e) = hi;
+        *reinterpret_cast<uint2*>(p.dkv_planes + plane + e) = lo;
+      } else {
+        *reinterpret_cast<float4*>(p.dqkv + e) = o;
       }
     }
   }
@@ -1059,13 +1103,15 @@ extern "C" {
 
 int ssb_attn_fused_fwd(const void* qkv_planes, const float* R, int64_t B, int64_t T, int64_t H,
                        int64_t dh, int64_t W, int64_t RW, float drop_p, uint64_t seed, uint32_t site,
-                       float* O, float* stat_m, float* stat_linv, int64_t head_stride, void* stream) {
+                       float* O, void* O_planes, float* stat_m, float* stat_linv, int64_t head_stride,
+                       void* stream) {
   const int64_t hs = head_stride > 0 ? head_stride : 128;
   FusedParams p = {};
   if (int rc = fill(&p, B, T, H, dh, W, RW, drop_p, seed, site)) return rc;
   SSB_REQUIRE(qkv_planes && R && O && stat_m && stat_linv, "attn_fused_fwd: null pointer");
   SSB_REQUIRE(((uintptr_t)O & 15) == 0, "attn_fused_fwd: O must be 16 B aligned");
-  p.O = O; p.stat_m = stat_m; p.stat_linv = stat_linv;
+  SSB_REQUIRE(!O_planes || (((uintptr_t)O_planes & 7) == 0 && dh % 4 == 0), "attn_fused_fwd: O_planes alignment");
+  p.O = O; p.O_planes = (__nv_bfloat16*)O_planes; p.stat_m = stat_m; p.stat_linv = stat_linv;
   CUtensorMap mq, mk, mv, mr;
   if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, QT, hs, dh)) return rc;
   if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, CH, hs, dh)) return rc;
@@ -1100,8 +1146,9 @@ int ssb_attn_delta(const float* O, const float* dO, int64_t B, int64_t T, int64_
 int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const float* R,
                        const float* stat_m, const float* stat_linv, const float* delta, int64_t B,
                        int64_t T, int64_t H, int64_t dh, int64_t W, int64_t RW, float drop_p,
-                       uint64_t seed, uint32_t site, float* dqkv, void* dSband_planes, int64_t RWp,
-                       int64_t head_stride, int64_t do_head_stride, void* stream) {
+                       uint64_t seed, uint32_t site, float* dqkv, int64_t dq_ld, void* dkv_planes,
+                       void* dSband_planes, int64_t RWp, int64_t head_stride, int64_t do_head_stride,
+                       void* stream) {
   const int64_t hs = head_stride > 0 ? head_stride : 128;
   const int64_t dhs = do_head_stride > 0 ? do_head_stride : 128;
   FusedParams p = {};
@@ -1110,7 +1157,12 @@ int ssb_attn_fused_bwd(const void* qkv_planes, const void* dO_planes, const floa
               "attn_fused_bwd: null pointer");
   SSB_REQUIRE(RWp >= 2 * W + 1 && ((uintptr_t)dqkv & 15) == 0, "attn_fused_bwd: bad RWp / alignment");
   p.stat_m = const_cast<float*>(stat_m); p.stat_linv = const_cast<float*>(stat_linv);
-  p.delta = delta; p.dqkv = dqkv; p.dsb = (__nv_bfloat16*)dSband_planes; p.RWp = (int)RWp;
+  SSB_REQUIRE(dkv_planes ? dq_ld >= H * dh : dq_ld == 3 * H * dh,
+              "attn_fused_bwd: dq_ld=%lld (3*H*dh when dK / dV are stored as fp32, >= H*dh with planes)",
+              (long long)dq_ld);
+  SSB_REQUIRE(((uintptr_t)dkv_planes & 7) == 0, "attn_fused_bwd: dkv_planes alignment");
+  p.delta = delta; p.dqkv = dqkv; p.dq_ld = dq_ld; p.dkv_planes = (__nv_bfloat16*)dkv_planes;
+  p.dsb = (__nv_bfloat16*)dSband_planes; p.RWp = (int)RWp;
   CUtensorMap mq, mk, mv, mdo, mr;
   if (int rc = head_map(&mq, qkv_planes, B, T, 3 * H, 0, H, CH, hs, dh)) return rc;
   if (int rc = head_map(&mk, qkv_planes, B, T, 3 * H, H, H, QT, hs, dh)) return rc;

@@ -755,6 +755,30 @@ split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64
   }
 }
 
+// strided variant: the leading `cols` columns of rows `ld_in` apart -> the same columns of planes
+// with rows `ld_out` apart (one third of a (M, 3D) operand: the others are written by their producer)
+__global__ void __launch_bounds__(256)
+split_2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int c8,
+                int64_t ld_in, int64_t ld_out, int64_t plane_stride) {
+  const int64_t n8 = rows * c8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / c8;
+    const int c = (int)(i - r * c8) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x + r * ld_in + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x + r * ld_in + c + 4));
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hi[j] = __float2bfloat16_rn(v[j]);
+      lo[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hi[j]));
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + c) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(out + plane_stride + r * ld_out + c) = *reinterpret_cast<const uint4*>(lo);
+  }
+}
+
 // transposed variant: planes[p][c][r] = split(x[r][c]) for a row-major (rows, cols) matrix: the
 // data-gradient operand W^T of an nn.Linear weight without a transposed fp32 copy.
 // block (32, 8) handles a 64-row x 32-column tile through shared memory; stores are bf16x2.
@@ -952,6 +976,24 @@ int ssb_split_bf16(const float* x, int64_t n, void* planes, void* stream) {
   const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
   split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)planes, n8, n);
   SSB_LAUNCH_CHECK("split_kernel");
+  return SSB_OK;
+}
+
+int ssb_split_bf16_2d(const float* x, int64_t rows, int64_t cols, int64_t ld_in, void* planes,
+                      int64_t ld_out, int64_t plane_stride, void* stream) {
+  if (rows == 0 || cols == 0) return SSB_OK;
+  SSB_REQUIRE(x && planes && rows > 0 && cols > 0 && cols % 8 == 0 && ld_in % 4 == 0 && ld_out % 8 == 0 &&
+                  ld_in >= cols && ld_out >= cols && plane_stride % 8 == 0,
+              "split_bf16_2d: cols=%lld ld_in=%lld ld_out=%lld (cols, ld_out multiples of 8)",
+              (long long)cols, (long long)ld_in, (long long)ld_out);
+  SSB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 15) == 0,
+              "split_bf16_2d: pointers must be 16 B aligned");
+  const int64_t n8 = rows * (cols / 8);
+  const int64_t blocks = (n8 + 255) / 256;
+  const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
+  split_2d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)planes, rows, (int)(cols / 8),
+                                                          ld_in, ld_out, plane_stride);
+  SSB_LAUNCH_CHECK("split_2d_kernel");
   return SSB_OK;
 }
 

@@ -1386,7 +1386,7 @@ def _const_planes(E, key, make):
     return planes
 
 
-def _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, need_bwd=True, packed=None):
+def _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, need_bwd=True, packed=None, o_planes=None):
     """Fused band attention forward.  qkv: fp32 (M, 3D), re-laid here into head-padded planes; or
     packed = (2, M, 3D) split planes straight from the QKV GEMM's epilogue (head stride dh): the
     kernels' tensor maps only ever address the first dh columns of a head, and the positional
@@ -1418,12 +1418,15 @@ def _fused_attn_fwd(qkv, E, B, T, H, dh, W, p, seed, site, need_bwd=True, packed
     stats = torch.empty((2, BH, T), dtype=_f32, device=dev)
     _lib.check(lib.ssb_attn_fused_fwd(qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p,
                                       seed & 0xFFFFFFFFFFFFFFFF, site, O.data_ptr(),
+                                      o_planes.data_ptr() if o_planes is not None else None,
                                       stats[0].data_ptr(), stats[1].data_ptr(), hs, st))
     return O, ((qkvp, R, stats, O, E) if need_bwd else None)
 
 
-def _fused_attn_bwd(saved, cfg, dO, dO_packed=None):
-    """-> dqkv (M, 3D) fp32 (content + positional parts; no gradient for E: SURVEY.md F3).
+def _fused_attn_bwd(saved, cfg, dO, dO_packed=None, planes_out=False):
+    """-> dqkv (M, 3D) fp32 (content + positional parts; no gradient for E: SURVEY.md F3), or with
+    planes_out its (2, M, 3D) bf16 split planes (dK / dV thirds written by the kernel's epilogue,
+    the dQ third split from a (M, D) fp32 accumulator after the positional GEMM).
     dO_packed: (2, M, D) split planes of dO when its producer already wrote them."""
     lib = _lib.load()
     qkvp, R, stats, O, E = saved
@@ -1443,10 +1446,12 @@ def _fused_attn_bwd(saved, cfg, dO, dO_packed=None):
         dop = torch.empty((2, M, H, _HP), dtype=bf, device=dev)
         _lib.check(lib.ssb_pad_split_heads(dO.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), st))
     delta = torch.empty((BH, T), dtype=_f32, device=dev)
-    dqkv = torch.empty((M, D3), dtype=_f32, device=dev)
+    ldq = D if planes_out else D3
+    dqkv = torch.empty((M, ldq), dtype=_f32, device=dev)
+    dqp = torch.empty((2, M, D3), dtype=bf, device=dev) if planes_out else None
     # content dQ arrives by red.global.add: its columns are cleared by the delta pass
     _lib.check(lib.ssb_attn_delta(O.data_ptr(), dO.data_ptr(), B, T, H, dh, delta.data_ptr(),
-                                  dqkv.data_ptr(), D3, st))
+                                  dqkv.data_ptr(), ldq, st))
     # band-layout dS: the kernel overwrites exactly the in-band, in-sequence entries - the same
     # set every call for a given geometry - and everything else must read 0.  One persistent
     # buffer per geometry, zeroed once, replaces a 131 MB fill per layer and step (backward
@@ -1455,7 +1460,8 @@ def _fused_attn_bwd(saved, cfg, dO, dO_packed=None):
     _lib.check(lib.ssb_attn_fused_bwd(qkvp.data_ptr(), dop.data_ptr(), R.data_ptr(),
                                       stats[0].data_ptr(), stats[1].data_ptr(),
                                       delta.data_ptr(), B, T, H, dh, W, RW, p,
-                                      seed & 0xFFFFFFFFFFFFFFFF, site, dqkv.data_ptr(),
+                                      seed & 0xFFFFFFFFFFFFFFFF, site, dqkv.data_ptr(), ldq,
+                                      dqp.data_ptr() if planes_out else None,
                                       dsb.data_ptr(), _RWP, hs, dhs, st))
     # positional part: dQ += dS_band E
     etp = _const_planes(E, ("bwd", W, dh), lambda: torch.nn.functional.pad(    # (2, H, 128, RWP)
@@ -1463,8 +1469,11 @@ def _fused_attn_bwd(saved, cfg, dO, dO_packed=None):
     dsb_op = _op(dsb, 0, M * H * _RWP, BH, T, _RWP, H * _RWP, _RWP, H, T * H * _RWP)
     et_op = _op(etp, 0, H * _HP * _RWP, H, _HP, _RWP, _RWP, _HP * _RWP)
     _tc_batched(dsb_op, et_op, 2, dh, _RWP,
-                _epi(_bscatter(dqkv, 0, T, D3, dh, T * D3), accumulate=1))
-    return dqkv
+                _epi(_bscatter(dqkv, 0, T, ldq, dh, T * ldq), accumulate=1))
+    if not planes_out:
+        return dqkv
+    _lib.check(lib.ssb_split_bf16_2d(dqkv.data_ptr(), M, D, D, dqp.data_ptr(), D3, M * D3, st))
+    return dqp
 
 
 class _FusedAttnFn(torch.autograd.Function):
@@ -1547,8 +1556,9 @@ class _AttnBlockFn(torch.autograd.Function):
         qkvp = torch.empty((2, M, 3 * D), dtype=torch.bfloat16, device=x.device)
         gemm_tc_kmajor(tc_operand_plain(xp, M, D), qf, 3 * D, D,
                        _epi(_scatter_plain(None, M, 3 * D), planes_out=qkvp))
-        O, att = _fused_attn_fwd(None, E, B, T, H, dh, W, p_attn, seed, site, need_bwd, packed=qkvp)
-        op = split_planes(O)
+        op = torch.empty((2, M, D), dtype=torch.bfloat16, device=x.device)   # written by the kernel's epilogue
+        O, att = _fused_attn_fwd(None, E, B, T, H, dh, W, p_attn, seed, site, need_bwd, packed=qkvp,
+                                 o_planes=op)
         a = torch.empty((M, D), dtype=_f32, device=x.device)
         gemm_tc_kmajor(tc_operand_plain(op, M, D), of, D, D, _epi(_scatter_plain(a.data_ptr(), M, D)))
         y, z, stat = _ln_fwd(x, a, gamma, beta, p_res, seed, site + 1, eps, need_bwd)
@@ -1584,9 +1594,7 @@ class _AttnBlockFn(torch.autograd.Function):
             gemm_tc_wgrad(tc_operand_plain(op, M, D), d_ap, D, D, dWo)
             dWo = dWo.view_as(w_o)
         del d_a, d_ap
-        dqkv = _fused_attn_bwd(att, ctx.cfg, dO, dO_packed=dOp)
-        dqp = split_planes(dqkv)
-        del dqkv
+        dqp = _fused_attn_bwd(att, ctx.cfg, dO, dO_packed=dOp, planes_out=True)
         # x receives d_res (through the LayerNorm) + dqkv Wqkv^T: accumulated by the GEMM epilogue
         gemm_tc_kmajor(tc_operand_plain(dqp, M, 3 * D), qb, D, 3 * D,
                        _epi(_scatter_plain(d_res.data_ptr(), M, D), accumulate=1))

@@ -50,20 +50,22 @@ def main():
             SF._lib.check(lib.ssb_pad_split_heads(qkv.data_ptr(), M, 3 * D, 0, 3 * H, dh, qkvp.data_ptr(), SF._stream()))
             R = torch.randn(BH, T, RW, device="cuda")
             O = torch.empty(M, D, device="cuda")
+            Op = torch.empty((2, M, D), dtype=torch.bfloat16, device="cuda")
             stats = torch.empty(2, BH, T, device="cuda")
             f = lambda: SF._lib.check(lib.ssb_attn_fused_fwd(
-                qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p, 1, 0, O.data_ptr(),
+                qkvp.data_ptr(), R.data_ptr(), B, T, H, dh, W, RW, p, 1, 0, O.data_ptr(), Op.data_ptr(),
                 stats[0].data_ptr(), stats[1].data_ptr(), 128, SF._stream()))
             print(f"  attn_fused_fwd_kernel alone: {timeit(f):.0f} us")
             dop = torch.empty((2, M, H, 128), dtype=torch.bfloat16, device="cuda")
             SF._lib.check(lib.ssb_pad_split_heads(go.data_ptr(), M, D, 0, H, dh, dop.data_ptr(), SF._stream()))
             delta = torch.zeros(BH, T, device="cuda")
-            dqkv = torch.zeros(M, 3 * D, device="cuda")
+            dqkv = torch.zeros(M, D, device="cuda")
+            dqp = torch.empty((2, M, 3 * D), dtype=torch.bfloat16, device="cuda")
             dsb = torch.zeros((2, M, H, 256), dtype=torch.bfloat16, device="cuda")
             g = lambda: SF._lib.check(lib.ssb_attn_fused_bwd(
                 qkvp.data_ptr(), dop.data_ptr(), R.data_ptr(), stats[0].data_ptr(),
                 stats[1].data_ptr(), delta.data_ptr(), B, T, H, dh, W, RW, p, 1, 0,
-                dqkv.data_ptr(), dsb.data_ptr(), 256, 128, 128, SF._stream()))
+                dqkv.data_ptr(), D, dqp.data_ptr(), dsb.data_ptr(), 256, 128, 128, SF._stream()))
             print(f"  attn_fused_bwd_kernel alone: {timeit(g):.0f} us")
 
 
