@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 208
+#define SSB_ABI_VERSION 209
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -275,6 +275,8 @@ SSB_API int ssb_add_dropout_ln_fwd(const float* res, const float* branch, const 
                                    float drop_p, uint64_t seed, uint32_t site, float* z_out,
                                    float* y, float* mean, float* rstd, void* y_planes,
                                    void* stream);
+/* backward: d_branch (fp32) may be NULL when d_branch_planes is given (the consumer is a tensor-core
+ * GEMM and nothing reads the fp32 copy). */
 SSB_API int64_t ssb_add_dropout_ln_bwd_workspace_bytes(int64_t rows, int64_t D);
 SSB_API int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean,
                                    const float* rstd, const float* gamma, int64_t rows, int64_t D,
@@ -332,10 +334,13 @@ SSB_API int ssb_split_bf16_t(const float* x, int64_t rows, int64_t cols,
 SSB_API int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N, int64_t K,
                                const ssb_epilogue_t* epi, void* stream);
 /* dW[k, n] (+)= sum_(b,t) X((b,t), k) * G[(b,t), n];  G planes: [2][batches*rows_out][N] bf16.
- * K % 128 == 0, X->C % 128 == 0, N % 8 == 0. */
+ * K % 128 == 0, X->C % 128 == 0, N % 8 == 0.
+ * group_w > 0 (needs accumulate): element (k, n) goes to dW[(n / group_w) * group_stride + k * lddw +
+ * n % group_w] - the fused QKV weight gradient written straight into the (H, D, dh) parameters of
+ * transformer.py:71-75 (group_w = dh, lddw = dh, group_stride = D * dh). */
 SSB_API int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_plane_stride,
-                              int64_t N, int64_t K, float* dW, int64_t lddw, int accumulate,
-                              void* stream);
+                              int64_t N, int64_t K, float* dW, int64_t lddw, int64_t group_w,
+                              int64_t group_stride, int accumulate, void* stream);
 /* Batched forms (attention): one GEMM per batch item b, all in one launch.
  *   C_b[t, n] = epi( sum_k A_b[t, k] * B_b'[n, k] ),   b' = b (b_mode 1), lo(b) (b_mode 2), 0 (b_mode 0)
  *   B: rows = N (L_src), inner = K (C).  Output row (b, t) at

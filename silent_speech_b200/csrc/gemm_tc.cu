@@ -90,6 +90,7 @@ struct TcParams {
   __nv_bfloat16* planes; int64_t planes_stride;   // optional split-plane copy of the result, plain (M, N)
   const __nv_bfloat16* mask_planes;               // mask source given as its bf16 hi plane
   int relu, accumulate, atomic;
+  int grp_w; int64_t grp_stride;                  // weight gradients: output column n -> (n / grp_w) * grp_stride + n % grp_w
   float drop_p, drop_scale; uint32_t drop_thresh; uint64_t seed; const uint64_t* seed_src; uint32_t site;
 };
 
@@ -455,6 +456,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       if (nkb == 0) limit = 0;
       const int64_t row_step = (int64_t)4 * p.out_dt * p.out_ld;
+      // grouped output columns (a fused QKV weight gradient lands in the (H, D, dh) parameters)
+      auto ncol = [&](int n) -> int64_t {
+        return p.grp_w ? (int64_t)(n / p.grp_w) * p.grp_stride + (n % p.grp_w) : (int64_t)n;
+      };
       const uint32_t tmem_d = tmem_base + acc * (uint32_t)BN + ((uint32_t)(lg * 32) << 16);
       const bool group_live = first - rsub < limit;   // warp-uniform: not a pure padding row group
       // Operands the epilogue READS (ReLU/dropout mask source, accumulate target) are fetched for
@@ -502,7 +507,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (p.mask_src)
             side[i] = __ldg(reinterpret_cast<const float4*>(p.mask_src + (grow0 + 4 * i) * p.N + n));
           else
-            side[i] = *reinterpret_cast<const float4*>(orow0 + i * row_step + n);
+            side[i] = *reinterpret_cast<const float4*>(orow0 + i * row_step + ncol(n));
         }
       };
       // bias / ReLU / dropout / mask / accumulate on 4 consecutive outputs starting at element e
@@ -668,7 +673,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < 8; ++i) {
           if (!n_ok || first + 4 * i >= limit) continue;
           float4 r = o[i];
-          float* dst = orow0 + i * row_step + n;
+          float* dst = orow0 + i * row_step + ncol(n);
           if (p.atomic) {
             atomicAdd(reinterpret_cast<float4*>(dst), r);
             continue;
@@ -703,7 +708,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (!n_ok || first + 4 * i >= limit || p.atomic) continue;
-            *reinterpret_cast<float4*>(orow0 + i * row_step + n) = o[i];
+            *reinterpret_cast<float4*>(orow0 + i * row_step + ncol(n)) = o[i];
           }
         }
       }
@@ -1050,13 +1055,17 @@ int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N
 }
 
 int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_plane_stride,
-                      int64_t N, int64_t K, float* dW, int64_t lddw, int accumulate,
-                      void* stream) {
+                      int64_t N, int64_t K, float* dW, int64_t lddw, int64_t group_w,
+                      int64_t group_stride, int accumulate, void* stream) {
   SSB_REQUIRE(X && X->planes && Gplanes && dW, "gemm_tc_wgrad: null operand");
   SSB_REQUIRE(K % BM == 0 && X->C % BM == 0 && K % X->C == 0 && K / X->C <= 3,
               "gemm_tc_wgrad: K=%lld / C=%d must be multiples of 128", (long long)K, X->C);
-  SSB_REQUIRE(N % 8 == 0 && lddw >= N && lddw % 4 == 0 && ((uintptr_t)dW & 15) == 0,
+  SSB_REQUIRE(N % 8 == 0 && lddw % 4 == 0 && ((uintptr_t)dW & 15) == 0 &&
+                  (group_w > 0 ? (group_w % 4 == 0 && N % group_w == 0 && lddw >= group_w &&
+                                  group_stride % 4 == 0 && group_stride >= (K - 1) * lddw + group_w)
+                               : lddw >= N),
               "gemm_tc_wgrad: bad N / dW geometry");
+  SSB_REQUIRE(group_w == 0 || accumulate, "gemm_tc_wgrad: grouped output needs accumulate (no 2-D clear)");
   SSB_REQUIRE(X->batches >= 1 && X->rows_out >= 1 && (X->s_t == 1 || X->s_t == 2),
               "gemm_tc_wgrad: bad X geometry");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1072,6 +1081,7 @@ int ssb_gemm_tc_wgrad(const ssb_tc_operand_t* X, const void* Gplanes, int64_t g_
   p.batch_div = X->batches;
   p.b_mode = 1;
   p.out = dW; p.out_ld = (int)lddw; p.N = (int)N;
+  p.grp_w = (int)group_w; p.grp_stride = group_stride;
   p.out_dt = 1; p.out_doff = 0;   // output row f of dW
   p.a_inner = X->C; p.a_row_step = X->s_t; p.a_tap_step = X->s_tap; p.a_off = X->off;
   p.rows_per_batch = X->rows_out;

@@ -670,7 +670,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z,
           o.z = rnd.z >= drop_thresh ? o.z * drop_scale : 0.f;
           o.w = rnd.w >= drop_thresh ? o.w * drop_scale : 0.f;
         }
-        reinterpret_cast<float4*>(d_branch + row * D)[v] = o;
+        if (d_branch) reinterpret_cast<float4*>(d_branch + row * D)[v] = o;
         if (d_branch_planes) store_planes4(d_branch_planes, rows * D, row * nv + v, o);
       }
     }
@@ -909,7 +909,7 @@ int ssb_add_dropout_ln_bwd(const float* dy, const float* z, const float* mean, c
                            void* workspace, int64_t workspace_bytes, void* stream) {
   if (int rc = check_rows_c(dy, rows, D, "add_dropout_ln_bwd")) return rc;
   SSB_REQUIRE(D <= 1024, "add_dropout_ln_bwd: D=%lld > 1024 not built", (long long)D);
-  SSB_REQUIRE(z && mean && rstd && gamma && d_res && d_branch && dgamma && dbeta,
+  SSB_REQUIRE(z && mean && rstd && gamma && d_res && (d_branch || d_branch_planes) && dgamma && dbeta,
               "add_dropout_ln_bwd: null pointer");
   SSB_REQUIRE(workspace && workspace_bytes >= ssb_add_dropout_ln_bwd_workspace_bytes(rows, D),
               "add_dropout_ln_bwd: workspace too small");

@@ -207,10 +207,12 @@ def gemm_tc_kmajor(opA, Bplanes, N, K, epi):
                                       ctypes.byref(epi), _stream()))
 
 
-def gemm_tc_wgrad(opX, Gplanes, N, K, dW, accumulate=False):
+def gemm_tc_wgrad(opX, Gplanes, N, K, dW, accumulate=False, group=None):
+    """group = (lddw, group_w, group_stride): grouped output columns (ssb.h), dW a raw base tensor."""
     lib = _lib.load()
+    ld, gw, gs = group if group is not None else (dW.stride(0), 0, 0)
     _lib.check(lib.ssb_gemm_tc_wgrad(ctypes.byref(opX), Gplanes.data_ptr(), Gplanes[0].numel(), N,
-                                     K, dW.data_ptr(), dW.stride(0), int(accumulate), _stream()))
+                                     K, dW.data_ptr(), ld, gw, gs, int(accumulate), _stream()))
 
 
 # ------------------------------------------------------------------------------------------
@@ -1515,22 +1517,25 @@ def _ln_fwd(res, branch, gamma, beta, p, seed, site, eps, need_bwd=True):
     return y, z, stat
 
 
-def _ln_bwd(dy, z, stat, gamma, p, seed, site, sinks):
-    """-> d_res, d_branch, d_branch planes (or None), dgamma, dbeta (None when sunk)."""
+def _ln_bwd(dy, z, stat, gamma, p, seed, site, sinks, planes_only=False):
+    """-> d_res, d_branch, d_branch planes (or None), dgamma, dbeta (None when sunk).
+    planes_only: when the planes are produced, skip the fp32 d_branch (returned as None): its only
+    readers are tensor-core GEMMs and a column sum that takes planes as well."""
     lib = _lib.load()
     dy = dy.contiguous()
     rows, D = z.shape
     dev = z.device
     d_res = torch.empty_like(z)
-    d_branch = torch.empty_like(z)
     dbp = torch.empty((2, rows, D), dtype=torch.bfloat16, device=dev) if _want_planes(rows, D) else None
+    d_branch = None if (planes_only and dbp is not None) else torch.empty_like(z)
     sunk = sinks[0] is not None and sinks[1] is not None
     dg = sinks[0] if sunk else torch.empty(D, dtype=_f32, device=dev)
     db = sinks[1] if sunk else torch.empty(D, dtype=_f32, device=dev)
     ws = _ws(lib.ssb_add_dropout_ln_bwd_workspace_bytes(rows, D), dev)
     _lib.check(lib.ssb_add_dropout_ln_bwd(
         dy.data_ptr(), z.data_ptr(), stat[0].data_ptr(), stat[1].data_ptr(), gamma.data_ptr(),
-        rows, D, p, seed & 0xFFFFFFFFFFFFFFFF, site, d_res.data_ptr(), d_branch.data_ptr(),
+        rows, D, p, seed & 0xFFFFFFFFFFFFFFFF, site, d_res.data_ptr(),
+        d_branch.data_ptr() if d_branch is not None else None,
         dbp.data_ptr() if dbp is not None else None, dg.data_ptr(), db.data_ptr(), int(sunk),
         ws.data_ptr(), ws.numel(), _stream()))
     return d_res, d_branch, dbp, (None if sunk else dg), (None if sunk else db)
@@ -1567,6 +1572,13 @@ class _AttnBlockFn(torch.autograd.Function):
         ctx.cfg = (B, T, H, dh, W, p_attn, seed, site, (2 * W + 1 + 3) // 4 * 4)
         ctx.p_res = p_res
         ctx.sinks = (_sink(gamma), _sink(beta), _sink(w_o))
+        # w_q, w_k, w_v gradients as ONE target when their bucket views are adjacent and in order
+        sq, sk, sv = _sink(wq), _sink(wk), _sink(wv)
+        n = wq.numel()
+        ctx.qkv_sink = (sq if (sq is not None and sk is not None and sv is not None
+                               and sq.is_contiguous() and sk.is_contiguous() and sv.is_contiguous()
+                               and sk.data_ptr() == sq.data_ptr() + 4 * n
+                               and sv.data_ptr() == sk.data_ptr() + 4 * n) else None)
         return y
 
     @staticmethod
@@ -1578,7 +1590,8 @@ class _AttnBlockFn(torch.autograd.Function):
         M = z.shape[0]
         dev = z.device
         s_g, s_b, s_wo = ctx.sinks
-        d_res, d_a, d_ap, dg, db = _ln_bwd(dy, z, stat, gamma, ctx.p_res, seed, site + 1, (s_g, s_b))
+        d_res, d_a, d_ap, dg, db = _ln_bwd(dy, z, stat, gamma, ctx.p_res, seed, site + 1, (s_g, s_b),
+                                           planes_only=True)
         if d_ap is None:
             d_ap = split_planes(d_a)
         # out-projection: dO = d_a Wo^T, dWo = O^T d_a (parameter layout = GEMM layout)
@@ -1598,9 +1611,17 @@ class _AttnBlockFn(torch.autograd.Function):
         # x receives d_res (through the LayerNorm) + dqkv Wqkv^T: accumulated by the GEMM epilogue
         gemm_tc_kmajor(tc_operand_plain(dqp, M, 3 * D), qb, D, 3 * D,
                        _epi(_scatter_plain(d_res.data_ptr(), M, D), accumulate=1))
-        dWg = torch.empty((D, 3 * D), dtype=_f32, device=dev)
-        gemm_tc_wgrad(tc_operand_plain(xp, M, D), dqp, 3 * D, D, dWg)
-        g = [dWg[:, j * D:(j + 1) * D].view(D, H, dh).permute(1, 0, 2) for j in range(3)]
+        s_q = ctx.qkv_sink
+        if s_q is not None:
+            # element (d, j H dh + h dh + a) of the fused gradient is grad(w_{q,k,v})[h, d, a], and the
+            # three (H, D, dh) gradients sit back to back in the bucket: one grouped-column scatter
+            gemm_tc_wgrad(tc_operand_plain(xp, M, D), dqp, 3 * D, D, s_q, accumulate=True,
+                          group=(dh, dh, D * dh))
+            g = [None, None, None]
+        else:
+            dWg = torch.empty((D, 3 * D), dtype=_f32, device=dev)
+            gemm_tc_wgrad(tc_operand_plain(xp, M, D), dqp, 3 * D, D, dWg)
+            g = [dWg[:, j * D:(j + 1) * D].view(D, H, dh).permute(1, 0, 2) for j in range(3)]
         return (d_res, g[0], g[1], g[2], dWo, None, dg, db) + (None,) * 12
 
 
@@ -1640,12 +1661,14 @@ class _FFNBlockFn(torch.autograd.Function):
         F_ = hp.shape[2]
         dev = z.device
         scale = 1.0 / (1.0 - p_ffn) if p_ffn > 0 else 1.0
-        d_res, d_f, d_fp, dg, db = _ln_bwd(dy, z, stat, gamma, p_res, seed, site + 1, (s_g, s_b))
+        d_res, d_f, d_fp, dg, db = _ln_bwd(dy, z, stat, gamma, p_res, seed, site + 1, (s_g, s_b),
+                                           planes_only=True)
         if d_fp is None:
             d_fp = split_planes(d_f)
         dW2 = s_w2 if s_w2 is not None else torch.empty_like(w2)          # (K, F) = d_f^T h
         gemm_tc_wgrad(tc_operand_plain(d_fp, M, K), hp, F_, K, dW2, accumulate=s_w2 is not None)
-        db2 = colsum(d_f, out=s_b2, accumulate=s_b2 is not None)
+        db2 = (colsum(d_f, out=s_b2, accumulate=s_b2 is not None) if d_f is not None
+               else colsum_planes(d_fp, out=s_b2, accumulate=s_b2 is not None))
         dhp = torch.empty((2, M, F_), dtype=torch.bfloat16, device=dev)
         gemm_tc_kmajor(tc_operand_plain(d_fp, M, K), w2t, F_, K,
                        _epi(_scatter_plain(None, M, F_), mask_planes=hp[0], mask_scale=scale,
