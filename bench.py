@@ -195,8 +195,8 @@ def ffn_instep_launches():
     functional._FFNNativeFn issues them (operands as split planes, same epilogues):
       ffn1_fwd   h  = dropout(relu(x W1^T + b1))   16000 x 768 -> 3072, Philox dropout, planes out
       ffn2_fwd   y  = h W2^T + b2                  16000 x 3072 -> 768, fp32 out
-      ffn_dgrad  dh = (dy W2) * mask(h) / (1-p)    16000 x 768 -> 3072, mask off h's hi plane,
-                                                   planes out
+      ffn_dgrad  dh = (dy W2) * mask(h) / (1-p)    16000 x 768 -> 3072, 1-bit mask written by
+                                                   ffn1_fwd's epilogue, planes out
     Returns [(name, launch_fn, flops)] plus the tensors that must stay alive."""
     from silent_speech_b200 import functional as SF
     M, K, Fh = BS * FRAMES, D_MODEL, 3072
@@ -211,17 +211,21 @@ def ffn_instep_launches():
     hp = torch.empty((2, M, Fh), dtype=torch.bfloat16, device=dev)
     dhp = torch.empty((2, M, Fh), dtype=torch.bfloat16, device=dev)
     y = torch.empty(M, K, device=dev)
+    bits = os.environ.get("SSB_MASKBITS", "1") != "0"
+    hbits = torch.zeros((M, Fh // 8), dtype=torch.uint8, device=dev) if bits else None
     e1 = SF._epi(SF._scatter_plain(None, M, Fh), bias=b1, relu=1, drop_p=0.2, seed=1234, site=2,
-                 planes_out=hp)
+                 planes_out=hp, mask_bits_out=hbits)
     e2 = SF._epi(SF._scatter_plain(y.data_ptr(), M, K), bias=b2)
-    e3 = SF._epi(SF._scatter_plain(None, M, Fh), mask_planes=hp[0], mask_scale=1.25, planes_out=dhp)
+    e3 = SF._epi(SF._scatter_plain(None, M, Fh), mask_scale=1.25, planes_out=dhp,
+                 mask_planes=None if bits else hp[0], mask_bits=hbits)
     opx, oph, opdy = (SF.tc_operand_plain(xp, M, K), SF.tc_operand_plain(hp, M, Fh),
                       SF.tc_operand_plain(dyp, M, K))
     fl = 2.0 * M * K * Fh
     launches = [("ffn1_fwd(bias+relu+dropout, planes out)", lambda: SF.gemm_tc_kmajor(opx, w1p, Fh, K, e1), fl),
                 ("ffn2_fwd(bias, fp32 out)", lambda: SF.gemm_tc_kmajor(oph, w2p, K, Fh, e2), fl),
-                ("ffn_dgrad(mask planes in, planes out)", lambda: SF.gemm_tc_kmajor(opdy, w2tp, Fh, K, e3), fl)]
-    keep = (x, w1, w2, b1, b2, dy, xp, w1p, w2p, w2tp, dyp, hp, dhp, y, e1, e2, e3, opx, oph, opdy)
+                ("ffn_dgrad(mask bits in, planes out)" if bits else "ffn_dgrad(mask planes in, planes out)",
+                 lambda: SF.gemm_tc_kmajor(opdy, w2tp, Fh, K, e3), fl)]
+    keep = (x, w1, w2, b1, b2, dy, xp, w1p, w2p, w2tp, dyp, hp, dhp, y, e1, e2, e3, opx, oph, opdy, hbits)
     return launches, keep
 
 
@@ -245,6 +249,7 @@ def gemm_roofline(peaks, ms_per_step=None, gflop_step=STEP_GFLOP):
     (`tensor_pipe_frac`).  `step_frac` is the whole training step against the SUSTAINED peak."""
     launches, keep = ffn_instep_launches()
     _M, _K, _F = BS * FRAMES, D_MODEL, 3072
+    _BITS = os.environ.get("SSB_MASKBITS", "1") != "0"
     scratch = torch.empty(64 * 1024 * 1024, device="cuda")   # 256 MB > L2: flushed between launches
     rows, tot_ms, tot_fl = [], 0.0, 0.0
     tr = ncu_traffic("gemm_tc") or {}
@@ -263,10 +268,12 @@ def gemm_roofline(peaks, ms_per_step=None, gflop_step=STEP_GFLOP):
            "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
            "traffic": traffic, "traffic_unit": "B/launch (mean of the 3; ncu capture of these launches: "
                                                "profiles/r2_gemm_tc_instep.txt)",
-           # operands are bf16 hi/lo planes (4 B/element, like fp32); the mask is one bf16 plane
-           "algorithmic_bytes_per_launch": {"ffn1_fwd": 4 * (_M * _K + _F * _K + _M * _F),
-                                            "ffn2_fwd": 4 * (_M * _F + _F * _K + _M * _K),
-                                            "ffn_dgrad": 4 * (_M * _K + _F * _K + _M * _F) + 2 * _M * _F},
+           # operands are bf16 hi/lo planes (4 B/element, like fp32); the mask is 1 bit per element
+           # (written by ffn1_fwd, read by ffn_dgrad), or one bf16 plane with SSB_MASKBITS=0
+           "algorithmic_bytes_per_launch": {
+               "ffn1_fwd": 4 * (_M * _K + _F * _K + _M * _F) + (_M * _F // 8 if _BITS else 0),
+               "ffn2_fwd": 4 * (_M * _F + _F * _K + _M * _K),
+               "ffn_dgrad": 4 * (_M * _K + _F * _K + _M * _F) + (_M * _F // 8 if _BITS else 2 * _M * _F)},
            "mma_per_logical_mma": 3, "tensor_pipe_frac": 3.0 * tf / peak,
            "peak_source": f"{peaks['_source']} cuBLAS bf16 burst (launches timed alone)",
            "launches": rows, "ms_per_launch": tot_ms / len(rows)}

@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 209
+#define SSB_ABI_VERSION 210
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -211,6 +211,10 @@ typedef struct {
   int64_t planes_stride;  /* elements between the hi and lo output planes */
   const void* mask_planes; /* instead of mask_src: bf16 hi plane (M, N) of the mask source
                               (hi = bf16(x) keeps the sign and zero-ness of x) */
+  const void* mask_bits;   /* instead of mask_src: (M, N / 8) bytes, bit n % 8 of byte (m, n / 8) set
+                              where the mask source is > 0 (N % 8 == 0) */
+  void* mask_bits_out;     /* with planes_out: also write that bit mask of the RESULT (the forward
+                              FFN GEMM hands it to the data gradient: 1/16 of the hi plane's bytes) */
 } ssb_epilogue_t;
 
 /* C[m,n] = epi( sum_k A(m,k) * W[k*ldw + n] ) */

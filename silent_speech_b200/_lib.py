@@ -38,7 +38,7 @@ class Epilogue(ctypes.Structure):
     _fields_ = [("out", Scatter), ("bias", c_ptr), ("mask_src", c_ptr), ("mask_scale", c_f32),
                 ("relu", c_i32), ("accumulate", c_i32), ("drop_p", c_f32), ("seed", c_u64),
                 ("site", c_u32), ("planes_out", c_ptr), ("planes_stride", c_i64),
-                ("mask_planes", c_ptr)]
+                ("mask_planes", c_ptr), ("mask_bits", c_ptr), ("mask_bits_out", c_ptr)]
 
 
 class TcOperand(ctypes.Structure):
@@ -228,7 +228,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 209      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 210      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):

@@ -436,7 +436,7 @@ Gather to_gather(const ssb_gather_t* g) {
 
 int fill_epilogue(const ssb_epilogue_t* e, int64_t M, int64_t N, Epilogue* out) {
   SSB_REQUIRE(e && e->out.base, "gemm: null output");
-  SSB_REQUIRE(!e->planes_out && !e->mask_planes,
+  SSB_REQUIRE(!e->planes_out && !e->mask_planes && !e->mask_bits && !e->mask_bits_out,
               "gemm: split-plane epilogue operands exist on the tcgen05 engine only");
   SSB_REQUIRE(e->out.rows_per_batch > 0 && e->out.ld >= N && e->out.ld % 4 == 0 &&
                   e->out.batch_stride % 4 == 0 && ((uintptr_t)e->out.base & 15) == 0,

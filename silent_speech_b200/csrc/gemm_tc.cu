@@ -89,6 +89,8 @@ struct TcParams {
   const float* bias; const float* mask_src; float mask_scale;
   __nv_bfloat16* planes; int64_t planes_stride;   // optional split-plane copy of the result, plain (M, N)
   const __nv_bfloat16* mask_planes;               // mask source given as its bf16 hi plane
+  const uint8_t* mask_bits;                       // mask source given as 1 bit per element ((M, N / 8) bytes)
+  uint8_t* mask_bits_out;                         // forward: bit (m, n) = result(m, n) > 0
   int relu, accumulate, atomic;
   int grp_w; int64_t grp_stride;                  // weight gradients: output column n -> (n / grp_w) * grp_stride + n % grp_w
   float drop_p, drop_scale; uint32_t drop_thresh; uint64_t seed; const uint64_t* seed_src; uint32_t site;
@@ -424,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // "wide" lane map for split-plane epilogue operands: row (i*8 + rsubw), 8 columns per lane, so
     // a lane's share of a bf16 plane row is one 16 B store (the 4-column map made 8 B stores and
     // the plane-emitting FFN GEMMs ran 25 % slower than their fp32-output twins)
-    const bool wide = p.planes != nullptr || p.mask_planes != nullptr;
+    const bool wide = p.planes != nullptr || p.mask_planes != nullptr || p.mask_bits != nullptr;
     const int rsubw = lane >> 2, csubw = (lane & 3) * 8;
     uint32_t tcount = 0;
     for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {
@@ -475,7 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             ((int64_t)firstw * p.out_dt + p.out_doff) * p.out_ld;
       const int64_t row_stepw = (int64_t)8 * p.out_dt * p.out_ld;
       auto prefetch = [&](int c) {
-        if (!(p.mask_src || p.mask_planes || p.accumulate) || !group_live) return;
+        if (!(p.mask_src || p.mask_planes || p.mask_bits || p.accumulate) || !group_live) return;
         if (wide) {
           const int n = n0 + c * 32 + csubw;
           if (n >= p.N) return;
@@ -483,7 +485,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int i = 0; i < 4; ++i) {
             if (firstw + 8 * i >= limit) continue;
             const int64_t e = (groww0 + 8 * i) * p.N + n;
-            if (p.mask_planes) {   // 8 bf16: only sign / zero-ness matter
+            if (p.mask_bits) {     // one byte decides the lane's 8 outputs of this row
+              const uint32_t m = __ldg(p.mask_bits + (e >> 3));
+              side[2 * i] = make_float4((m & 1u) ? 1.f : 0.f, (m & 2u) ? 1.f : 0.f, (m & 4u) ? 1.f : 0.f,
+                                        (m & 8u) ? 1.f : 0.f);
+              side[2 * i + 1] = make_float4((m & 16u) ? 1.f : 0.f, (m & 32u) ? 1.f : 0.f,
+                                            (m & 64u) ? 1.f : 0.f, (m & 128u) ? 1.f : 0.f);
+            } else if (p.mask_planes) {   // 8 bf16: only sign / zero-ness matter
               const uint4 m = __ldg(reinterpret_cast<const uint4*>(p.mask_planes + e));
               side[2 * i] = make_float4(__uint_as_float(m.x << 16), __uint_as_float(m.x & 0xffff0000u),
                                         __uint_as_float(m.y << 16), __uint_as_float(m.y & 0xffff0000u));
@@ -523,7 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           r.z = rnd.z >= p.drop_thresh ? r.z * p.drop_scale : 0.f;
           r.w = rnd.w >= p.drop_thresh ? r.w * p.drop_scale : 0.f;
         }
-        if (p.mask_src || p.mask_planes) {
+        if (p.mask_src || p.mask_planes || p.mask_bits) {
           r.x = sd.x > 0.f ? r.x * p.mask_scale : 0.f;
           r.y = sd.y > 0.f ? r.y * p.mask_scale : 0.f;
           r.z = sd.z > 0.f ? r.z * p.mask_scale : 0.f;
@@ -611,7 +619,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               oB[i].y = (rnd.z >> 16) >= t16 ? oB[i].y * sc : 0.f;
               oB[i].z = (rnd.w & 0xffffu) >= t16 ? oB[i].z * sc : 0.f;
               oB[i].w = (rnd.w >> 16) >= t16 ? oB[i].w * sc : 0.f;
-              if (p.mask_src || p.mask_planes) {
+              if (p.mask_src || p.mask_planes || p.mask_bits) {
                 const float4 sa = side[2 * i], sb = side[2 * i + 1];
                 oA[i].x = sa.x > 0.f ? oA[i].x * p.mask_scale : 0.f; oA[i].y = sa.y > 0.f ? oA[i].y * p.mask_scale : 0.f;
                 oA[i].z = sa.z > 0.f ? oA[i].z * p.mask_scale : 0.f; oA[i].w = sa.w > 0.f ? oA[i].w * p.mask_scale : 0.f;
@@ -634,6 +642,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (!n_ok || firstw + 8 * i >= limit) continue;
               *reinterpret_cast<float4*>(oroww0 + i * row_stepw + n) = oA[i];
               *reinterpret_cast<float4*>(oroww0 + i * row_stepw + n + 4) = oB[i];
+            }
+          }
+          if (p.mask_bits_out) {   // 1 bit per output: what the data gradient needs of this activation
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (!n_ok || firstw + 8 * i >= limit) continue;
+              const uint32_t m = (oA[i].x > 0.f ? 1u : 0u) | (oA[i].y > 0.f ? 2u : 0u) |
+                                 (oA[i].z > 0.f ? 4u : 0u) | (oA[i].w > 0.f ? 8u : 0u) |
+                                 (oB[i].x > 0.f ? 16u : 0u) | (oB[i].y > 0.f ? 32u : 0u) |
+                                 (oB[i].z > 0.f ? 64u : 0u) | (oB[i].w > 0.f ? 128u : 0u);
+              p.mask_bits_out[((groww0 + 8 * i) * p.N + n) >> 3] = (uint8_t)m;
             }
           }
           if (p.planes) {   // x = hi + lo, the operand format of the next GEMM (no split pass)
@@ -945,13 +964,18 @@ int fill_epi(const ssb_epilogue_t* e, int64_t N, TcParams* p) {
   SSB_REQUIRE(N % 4 == 0 && e->out.ld >= N && e->out.ld % 4 == 0 && e->out.batch_stride % 4 == 0 &&
                   ((uintptr_t)e->out.base & 15) == 0,
               "gemm_tc: bad output geometry / alignment");
-  SSB_REQUIRE(!(e->mask_src && e->mask_planes), "gemm_tc: mask_src and mask_planes are exclusive");
+  SSB_REQUIRE(!(e->mask_src && e->mask_planes) && !(e->mask_bits && (e->mask_src || e->mask_planes)),
+              "gemm_tc: mask_src, mask_planes and mask_bits are exclusive");
+  SSB_REQUIRE((!e->mask_bits && !e->mask_bits_out) || N % 8 == 0, "gemm_tc: mask bits need N %% 8 == 0");
+  SSB_REQUIRE(!e->mask_bits_out || e->planes_out, "gemm_tc: mask_bits_out rides on the plane-emitting epilogue");
   SSB_REQUIRE(((uintptr_t)e->planes_out & 15) == 0 && ((uintptr_t)e->mask_planes & 15) == 0 &&
                   e->planes_stride % 8 == 0 && ((!e->planes_out && !e->mask_planes) || N % 8 == 0),
               "gemm_tc: split-plane epilogue operands need 16 B alignment and N %% 8 == 0");
   SSB_REQUIRE(e->out.base || !e->accumulate, "gemm_tc: accumulate needs an fp32 output");
   p->planes = (__nv_bfloat16*)e->planes_out; p->planes_stride = e->planes_stride;
   p->mask_planes = (const __nv_bfloat16*)e->mask_planes;
+  p->mask_bits = (const uint8_t*)e->mask_bits;
+  p->mask_bits_out = (uint8_t*)e->mask_bits_out;
   SSB_REQUIRE(e->drop_p >= 0.f && e->drop_p < 1.f, "gemm_tc: bad dropout p");
   p->out = e->out.base; p->out_batch_stride = e->out.batch_stride; p->out_ld = e->out.ld;
   p->out_batch_stride_hi = e->out.batch_stride_hi;
@@ -1128,7 +1152,8 @@ int ssb_gemm_tc_batched(const ssb_tc_operand_t* A, const ssb_tc_operand_t* B, in
               "gemm_tc_batched: bad geometry");
   TcParams p = {};
   if (int rc = fill_epi(epi, N, &p)) return rc;
-  SSB_REQUIRE(!p.planes && !p.mask_planes, "gemm_tc batched: split-plane epilogue operands unsupported");
+  SSB_REQUIRE(!p.planes && !p.mask_planes && !p.mask_bits && !p.mask_bits_out,
+              "gemm_tc batched: split-plane epilogue operands unsupported");
   SSB_REQUIRE(epi->out.rows_per_batch == A->rows_out, "gemm_tc_batched: rows_per_batch mismatch");
   int64_t a_lo, a_hi, b_lo, b_hi;
   batch_levels(A, &a_lo, &a_hi);
@@ -1164,7 +1189,8 @@ int ssb_gemm_tc_batched_tn(const ssb_tc_operand_t* X, const ssb_tc_operand_t* G,
               "gemm_tc_batched_tn: operand geometry mismatch");
   TcParams p = {};
   if (int rc = fill_epi(epi, N, &p)) return rc;
-  SSB_REQUIRE(!p.planes && !p.mask_planes, "gemm_tc batched: split-plane epilogue operands unsupported");
+  SSB_REQUIRE(!p.planes && !p.mask_planes && !p.mask_bits && !p.mask_bits_out,
+              "gemm_tc batched: split-plane epilogue operands unsupported");
   SSB_REQUIRE(epi->out.rows_per_batch == K, "gemm_tc_batched_tn: output rows_per_batch must be K");
   int64_t x_lo, x_hi, g_lo, g_hi;
   batch_levels(X, &x_lo, &x_hi);
