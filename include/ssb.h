@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 210
+#define SSB_ABI_VERSION 211
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -215,6 +215,11 @@ typedef struct {
                               where the mask source is > 0 (N % 8 == 0) */
   void* mask_bits_out;     /* with planes_out: also write that bit mask of the RESULT (the forward
                               FFN GEMM hands it to the data gradient: 1/16 of the hi plane's bytes) */
+  int32_t planes_lrelu;    /* with planes_out: the PLANE copy is leaky_relu(result, planes_neg_slope)
+                              while the fp32 output (if any) keeps the result itself: the operand of the
+                              next convolution of a HiFi-GAN residual block (hifi_gan/models.py:40-44:
+                              x = x + c2(lrelu(c1(lrelu(x)))) needs x in fp32 and lrelu(x) as operand) */
+  float planes_neg_slope;
 } ssb_epilogue_t;
 
 /* C[m,n] = epi( sum_k A(m,k) * W[k*ldw + n] ) */
@@ -502,6 +507,28 @@ SSB_API int ssb_emg_filtfilt_chain(const double* x, double* y, const ssb_emg_rec
 SSB_API int ssb_emg_subsample(const double* x, const ssb_emg_rec_t* table_dev, int64_t n_rec,
                               int64_t out_rows_total, int C, double old_freq, double step,
                               void* out, int out_f32, void* stream);
+
+/* ---- HiFi-GAN generator inference (csrc/vocoder.cu) ---------------------
+ * Replaces the element-wise ends of hifi_gan/models.py:96-112 (Generator.forward, called by
+ * vocoder.py:28-36); every convolution of the generator runs through ssb_gemm_tc_kmajor with
+ * s_tap = dilation (host side: silent_speech_b200/vocoder.py).  Tensors are channels-last
+ * (rows = samples, C contiguous).
+ *
+ * ssb_voc_mix: v = scale * (a + b + c) over n elements (b, c nullable) - the multi-receptive-field
+ * fusion xs / num_kernels of models.py:101-108.  Written as fp32 to `out` (nullable) and / or as
+ * bf16 split planes (hi at planes, lo plane_stride elements later; nullable) of
+ * leaky_relu(v, neg_slope) when lrelu_on != 0 (models.py:99), of v otherwise.  n % 4 == 0.
+ *
+ * ssb_voc_post: audio[t] = tanh(bias + sum_{tap, ch} w[tap * C + ch] *
+ *     leaky_relu(scale * (a + b + c)[t + tap - taps / 2, ch], neg_slope)), rows outside [0, rows)
+ * reading as zero padding - models.py:109-111 (F.leaky_relu default slope, conv_post with its
+ * single output channel, tanh) fused with the last stage's fusion.  taps odd, taps * C <= 1024. */
+SSB_API int ssb_voc_mix(const float* a, const float* b, const float* c, int64_t n, float scale,
+                        int lrelu_on, float neg_slope, float* out, void* planes,
+                        int64_t plane_stride, void* stream);
+SSB_API int ssb_voc_post(const float* a, const float* b, const float* c, int64_t rows, int64_t C,
+                         int64_t taps, float scale, float neg_slope, const float* w, float bias,
+                         float* audio, void* stream);
 
 #ifdef __cplusplus
 }

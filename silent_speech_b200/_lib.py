@@ -38,7 +38,8 @@ class Epilogue(ctypes.Structure):
     _fields_ = [("out", Scatter), ("bias", c_ptr), ("mask_src", c_ptr), ("mask_scale", c_f32),
                 ("relu", c_i32), ("accumulate", c_i32), ("drop_p", c_f32), ("seed", c_u64),
                 ("site", c_u32), ("planes_out", c_ptr), ("planes_stride", c_i64),
-                ("mask_planes", c_ptr), ("mask_bits", c_ptr), ("mask_bits_out", c_ptr)]
+                ("mask_planes", c_ptr), ("mask_bits", c_ptr), ("mask_bits_out", c_ptr),
+                ("planes_lrelu", c_i32), ("planes_neg_slope", c_f32)]
 
 
 class TcOperand(ctypes.Structure):
@@ -163,6 +164,10 @@ _SIGNATURES = {
                                        c_int, c_ptr, c_i64, c_ptr]),
     "ssb_emg_subsample": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, ctypes.c_double, ctypes.c_double,
                                   c_ptr, c_int, c_ptr]),
+    "ssb_voc_mix": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_int, c_f32, c_ptr, c_ptr, c_i64,
+                            c_ptr]),
+    "ssb_voc_post": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_f32, c_f32, c_ptr, c_f32,
+                             c_ptr, c_ptr]),
 }
 
 # kernels launched by one call of each entry point (used by bench.py's gpu_launches count)
@@ -176,7 +181,7 @@ _KERNELS_PER_CALL = {
     "ssb_gemm_tc_batched_tn": 1, "ssb_pad_split_heads": 1, "ssb_transpose_split_heads": 1,
     "ssb_attn_softmax_fwd": 1, "ssb_attn_ds_bwd": 1,
     "ssb_attn_fused_fwd": 1, "ssb_attn_delta": 1, "ssb_attn_fused_bwd": 1,
-    "ssb_emg_filtfilt_chain": 1, "ssb_emg_subsample": 1,
+    "ssb_emg_filtfilt_chain": 1, "ssb_emg_subsample": 1, "ssb_voc_mix": 1, "ssb_voc_post": 1,
 }
 launch_count = 0   # running total of libssb kernel launches issued by this process
 
@@ -228,7 +233,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 210      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 211      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):

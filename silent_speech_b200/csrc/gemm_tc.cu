@@ -92,6 +92,7 @@ struct TcParams {
   const uint8_t* mask_bits;                       // mask source given as 1 bit per element ((M, N / 8) bytes)
   uint8_t* mask_bits_out;                         // forward: bit (m, n) = result(m, n) > 0
   int relu, accumulate, atomic;
+  int planes_lrelu; float planes_slope;           // plane copy = leaky_relu(result) (fp32 output unchanged)
   int grp_w; int64_t grp_stride;                  // weight gradients: output column n -> (n / grp_w) * grp_stride + n % grp_w
   float drop_p, drop_scale; uint32_t drop_thresh; uint64_t seed; const uint64_t* seed_src; uint32_t site;
 };
@@ -659,7 +660,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               if (!n_ok || firstw + 8 * i >= limit) continue;
-              const float f[8] = {oA[i].x, oA[i].y, oA[i].z, oA[i].w, oB[i].x, oB[i].y, oB[i].z, oB[i].w};
+              float f[8] = {oA[i].x, oA[i].y, oA[i].z, oA[i].w, oB[i].x, oB[i].y, oB[i].z, oB[i].w};
+              if (p.planes_lrelu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.planes_slope;
+              }
               uint32_t hw[4], lw[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -972,6 +977,8 @@ int fill_epi(const ssb_epilogue_t* e, int64_t N, TcParams* p) {
                   e->planes_stride % 8 == 0 && ((!e->planes_out && !e->mask_planes) || N % 8 == 0),
               "gemm_tc: split-plane epilogue operands need 16 B alignment and N %% 8 == 0");
   SSB_REQUIRE(e->out.base || !e->accumulate, "gemm_tc: accumulate needs an fp32 output");
+  SSB_REQUIRE(!e->planes_lrelu || e->planes_out, "gemm_tc: planes_lrelu rides on the plane-emitting epilogue");
+  p->planes_lrelu = e->planes_lrelu; p->planes_slope = e->planes_neg_slope;
   p->planes = (__nv_bfloat16*)e->planes_out; p->planes_stride = e->planes_stride;
   p->mask_planes = (const __nv_bfloat16*)e->mask_planes;
   p->mask_bits = (const uint8_t*)e->mask_bits;
@@ -1044,8 +1051,10 @@ int ssb_split_bf16_t(const float* x, int64_t rows, int64_t cols, void* planes, v
 int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N, int64_t K,
                        const ssb_epilogue_t* epi, void* stream) {
   SSB_REQUIRE(A && A->planes && Bplanes, "gemm_tc: null operand");
-  SSB_REQUIRE(K % BK == 0 && A->C % BK == 0 && K % A->C == 0 && K / A->C <= 3,
-              "gemm_tc: K=%lld / C=%d must be multiples of 64 (K = taps*C, taps <= 3)",
+  // taps: 1 / 3 in the transduction model; HiFi-GAN's dilated k = 3 / 7 / 11 and stride-phase
+  // transposed convolutions (silent_speech_b200/vocoder.py) use up to 16 at tap step = dilation
+  SSB_REQUIRE(K % BK == 0 && A->C % BK == 0 && K % A->C == 0 && K / A->C <= 16,
+              "gemm_tc: K=%lld / C=%d must be multiples of 32 (K = taps*C, taps <= 16)",
               (long long)K, A->C);
   SSB_REQUIRE(A->batches >= 1 && A->rows_out >= 1 && A->L_src >= 1 && (A->s_t == 1 || A->s_t == 2),
               "gemm_tc: bad A geometry");

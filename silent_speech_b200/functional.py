@@ -60,10 +60,12 @@ def _scatter_plain(ptr, M, ld):
 
 
 def _epi(out, bias=None, relu=0, accumulate=0, mask_src=None, mask_scale=1.0, drop_p=0.0, seed=0,
-         site=0, planes_out=None, mask_planes=None, mask_bits=None, mask_bits_out=None):
+         site=0, planes_out=None, mask_planes=None, mask_bits=None, mask_bits_out=None,
+         planes_lrelu=None):
     """ssb_epilogue_t.  planes_out: (2, M, N) bf16 tensor receiving the result as split planes
     (tcgen05 engine); mask_planes: bf16 hi plane (M, N) standing in for mask_src; mask_bits /
-    mask_bits_out: (M, N / 8) uint8 bit masks (result > 0) read / written by the epilogue."""
+    mask_bits_out: (M, N / 8) uint8 bit masks (result > 0) read / written by the epilogue;
+    planes_lrelu: negative slope of a leaky ReLU applied to the plane copy only."""
     return Epilogue(out, bias.data_ptr() if bias is not None else None,
                     mask_src.data_ptr() if mask_src is not None else None, mask_scale, int(relu),
                     int(accumulate), float(drop_p), int(seed) & 0xFFFFFFFFFFFFFFFF, int(site),
@@ -71,7 +73,9 @@ def _epi(out, bias=None, relu=0, accumulate=0, mask_src=None, mask_scale=1.0, dr
                     planes_out[0].numel() if planes_out is not None else 0,
                     mask_planes.data_ptr() if mask_planes is not None else None,
                     mask_bits.data_ptr() if mask_bits is not None else None,
-                    mask_bits_out.data_ptr() if mask_bits_out is not None else None)
+                    mask_bits_out.data_ptr() if mask_bits_out is not None else None,
+                    int(planes_lrelu is not None),
+                    float(planes_lrelu) if planes_lrelu is not None else 0.0)
 
 
 # ------------------------------------------------------------------------------------------

@@ -9,7 +9,9 @@ verbatim copy baseline/_ref), with dropin/ ahead of it on sys.path:
      the CPU with the REFERENCE's Model (architecture.py + transformer.py) and numba align.py
      from the same state_dict and batch: losses, every gradient, parameters after 2 steps;
   2. `transduction_model.test` (:33-55, eval loop with phoneme accuracy + confusion matrix);
-  3. `transduction_model.train_model` (:159-227) for one epoch on the synthetic corpus mirror.
+  3. `transduction_model.train_model` (:159-227) for one epoch on the synthetic corpus mirror;
+  4. `transduction_model.save_output` (:57-71) with the drop-in `Vocoder` (HiFi-GAN on libssb) against
+     the reference's own generator on the CPU.
 Prints one JSON object.
 """
 import json
@@ -152,6 +154,39 @@ def main():
     # two SizeAwareSampler batches (~80 utterances each) were trained on: BatchNorm counted them
     out["train_batches"] = int(state["conv_blocks.0.bn1.num_batches_tracked"])
     out["trained"] = out["train_batches"] >= 1
+    # 4. the reference's save_output (:57-71) with the drop-in Vocoder (vocoder.py:16-36 on libssb):
+    #    model.eval() -> pred -> normaliser inverse -> vocoder -> sf.write, against the reference's own
+    #    HiFi-GAN Generator (CPU) fed the same predicted mel from the same checkpoint file
+    import vocoder as vocoder_mod
+    assert "dropin" in vocoder_mod.__file__ and tm.Vocoder is vocoder_mod.Vocoder
+    from oracle import vocoder as ov
+    vcfg = dict(ov.V1, upsample_initial_channel=128)
+    with open(os.path.join(tmp, "config.json"), "w") as f:
+        json.dump(vcfg, f)
+    ckpt = os.path.join(tmp, "g_00000001")
+    torch.save({"generator": ov.weight_normed_state_dict(ov.formula_state_dict(vcfg))}, ckpt)
+    FLAGS.hifigan_checkpoint = ckpt
+    voc = tm.Vocoder()
+    seen = {}
+
+    def spy(y):
+        seen["mel"] = y.detach().cpu().clone()
+        return voc(y)
+    written = {}
+    tm.sf.write = lambda fn, audio, sr: written.update(fn=fn, audio=np.asarray(audio), sr=sr)
+    tm.save_output(model, dev[0], os.path.join(tmp, "example_output_0.wav"), "cuda", dev.mfcc_norm, spy)
+    models, env = refenv.import_reference("models", "env")
+    gen = models.Generator(env.AttrDict(vcfg))
+    gen.load_state_dict(torch.load(ckpt)["generator"])
+    gen.eval()
+    gen.remove_weight_norm()
+    with torch.no_grad():
+        ref_audio = gen(seen["mel"].T[np.newaxis, :, :]).squeeze().numpy()      # vocoder.py:32-36
+    out["save_output_samples"] = int(written["audio"].shape[0])
+    out["save_output_sr"] = int(written["sr"])
+    out["save_output_frames"] = int(seen["mel"].shape[0])
+    out["vocoder_rel_l2"] = float(np.linalg.norm(written["audio"].astype(np.float64) - ref_audio)
+                                  / np.linalg.norm(ref_audio))
     from silent_speech_b200 import _lib
     out["libssb_launches"] = int(_lib.launch_count)
     print("RESULT " + json.dumps(out))

@@ -45,4 +45,8 @@ def test_unmodified_transduction_model_runs_on_the_dropin():
     assert out["train_model_type"] == "silent_speech_b200.architecture.Model"
     assert out["model_pt_saved"] and out["saved_keys_match_reference"]
     assert out["finite_after_epoch"] and out["trained"]
+    # save_output with the drop-in Vocoder: 256 samples per predicted frame at 22.05 kHz, audio equal to
+    # the reference generator's (bf16x3 convolutions: ~1e-5)
+    assert out["save_output_samples"] == 256 * out["save_output_frames"] and out["save_output_sr"] == 22050
+    assert out["vocoder_rel_l2"] < 1e-4, out["vocoder_rel_l2"]
     assert out["libssb_launches"] > 1000          # the CUDA library did the work
