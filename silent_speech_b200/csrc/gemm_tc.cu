@@ -84,6 +84,8 @@ struct TcParams {
   int batch_div;                                 // batch index -> (lo = b % div, hi = b / div)
   int b_mode;                                    // B batch coords: 0 none, 1 (lo, hi), 2 (lo, 0)
   int tiles_x, tiles_y, splits;                   // persistent tile list
+  int n_mma;                                      // K-major, N < BN: the MMA's N (multiple of 32); the B box
+                                                  // holds n_mma / CTAS rows per CTA.  0: BN
   // epilogue
   float* out; int64_t out_batch_stride, out_batch_stride_hi; int out_ld, out_dt, out_doff;
   const float* bias; const float* mask_src; float mask_scale;
@@ -221,9 +223,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 }
 
 // instruction descriptor (InstrDescriptor): D=f32, A=B=bf16, M=128 (256 for a CTA pair), N=256
-__host__ __device__ constexpr uint32_t make_idesc(int mn_major, int m) {
+__host__ __device__ constexpr uint32_t make_idesc(int mn_major, int m, int n = BN) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(mn_major & 1) << 15) |
-         ((uint32_t)(mn_major & 1) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+         ((uint32_t)(mn_major & 1) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -322,14 +324,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int tile = worker; tile < total_tiles; tile += num_workers) {
         int n0, batch, row0, f0, kb_begin, nkb;
         decode(tile, n0, batch, row0, f0, kb_begin, nkb);
-        const int nb0 = n0 + rank * C::B_ROWS;
+        const int b_rows = p.n_mma ? p.n_mma / CTAS : C::B_ROWS;   // rows of B this CTA stages
+        const int nb0 = n0 + rank * b_rows;
+        const uint32_t stage_tx = p.n_mma ? (uint32_t)(2 * A_PLANE + 2 * b_rows * BK * 2) : (uint32_t)STAGE_BYTES;
         for (int i = 0; i < nkb; ++i, ++it) {
           const int kb = kb_begin + i;
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(empty_bar + 8 * s, ph ^ 1u);
           const uint32_t st = smem_base + s * STAGE_BYTES;
-          if (rank == 0) mbar_expect_tx(full_bar + 8 * s, CTAS * STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(full_bar + 8 * s, CTAS * stage_tx);
           const uint32_t fb = full_bar_lead + 8 * s;
           if (!p.mn_major) {
             const int kk = kb * BK;
@@ -365,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (rank == 0 && ssb::elect_one()) {
-      const uint32_t idesc = make_idesc(p.mn_major, C::BMC);
+      const uint32_t idesc = make_idesc(p.mn_major, C::BMC, p.n_mma ? p.n_mma : BN);
       uint32_t it = 0, tcount = 0;
       for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {
         int n0, batch, row0, f0, kb_begin, nkb;
@@ -914,6 +918,16 @@ int default_ctas() {
   return v;
 }
 
+// N-adaptive MMAs for N < 256 (SSB_TC_NARROW=0 restores full-width MMAs; read once)
+bool narrow_n_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSB_TC_NARROW");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <int CTAS>
 int launch_impl(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, int64_t total,
                 cudaStream_t st) {
@@ -1071,8 +1085,13 @@ int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N
   // a CTA pair covers 256 rows: not worth it when a batch item has no second half tile
   const int ctas = A->rows_out > BM ? default_ctas() : 1;
   const int bmc = BM * ctas;
-  if (int rc = make_map(&mapB, Bplanes, K, N, 1, 1, K, N * K, N * K, N * K, BK, BN / ctas, 1))
+  // narrow outputs (HiFi-GAN's 32 ... 128 channels, the 128-wide output heads): an MMA of N =
+  // round32(N) instead of 256 columns of which most would multiply zero-filled rows of B
+  const int n_mma = N < BN && narrow_n_enabled() ? (int)((N + 31) / 32 * 32) : 0;
+  if (int rc = make_map(&mapB, Bplanes, K, N, 1, 1, K, N * K, N * K, N * K, BK,
+                        (n_mma ? n_mma : BN) / ctas, 1))
     return rc;
+  p.n_mma = n_mma;
   p.batch_div = (int)n_lo;
   p.b_mode = 0;
   p.a_inner = A->C; p.a_row_step = A->s_t; p.a_tap_step = A->s_tap; p.a_off = A->off;

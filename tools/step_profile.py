@@ -66,10 +66,25 @@ def main():
     print(f"# {len(evs)} device activities, busy {tot / 1e3:.2f} ms, span {span / 1e3:.2f} ms")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:args.top]:
         print(f"{v:10.1f} us {100 * v / tot:5.1f}% {cnt[k]:5d}  {k}")
+    # idle time between consecutive activities, attributed to the activity that FOLLOWS the gap
+    # (its launch latency / dependency wait): where the span - busy difference sits
+    gap, gcnt = defaultdict(float), defaultdict(int)
+    for a, b in zip(evs[:-1], evs[1:]):
+        g = b.time_range.start - a.time_range.end
+        if g > 0:
+            gap[short(b.name)] += g
+            gcnt[short(b.name)] += 1
+    gtot = sum(gap.values())
+    print(f"# idle between activities: {gtot / 1e3:.2f} ms; by following kernel:")
+    for k, v in sorted(gap.items(), key=lambda kv: -kv[1])[:15]:
+        print(f"#  gap {v:8.1f} us {100 * v / max(gtot, 1e-9):5.1f}% {gcnt[k]:5d} (avg {v / gcnt[k]:5.2f} us)  {k}")
     if args.seq:
         with open(args.seq, "w") as f:
+            prev_end = None
             for e in evs:
-                f.write(f"{short(e.name)}\t{e.time_range.end - e.time_range.start:.1f}\n")
+                g = 0.0 if prev_end is None else e.time_range.start - prev_end
+                prev_end = e.time_range.end
+                f.write(f"{short(e.name)}\t{e.time_range.end - e.time_range.start:.1f}\t{g:.1f}\n")
 
 
 if __name__ == "__main__":

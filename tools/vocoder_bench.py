@@ -55,8 +55,14 @@ def main():
     x = melc.t()[None].contiguous()
     audio = g(x)[0, 0]
     sd_c = {k: v.cuda() for k, v in sd.items()}
-    ref = ov.generator_forward(sd_c, melc, cfg)
+    torch.backends.cudnn.allow_tf32 = False            # cuDNN convolutions default to TF32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        ref = ov.generator_forward(sd_c, melc, cfg)
+        ref64 = ov.generator_forward({k: v.double() for k, v in sd_c.items()}, melc.double(), cfg)
     err = float((audio - ref).norm() / ref.norm())
+    err64 = float((audio.double() - ref64).norm() / ref64.norm())
+    floor64 = float((ref.double() - ref64).norm() / ref64.norm())
     from silent_speech_b200 import _lib
     n0 = _lib.launch_count
     g(x)
@@ -73,7 +79,8 @@ def main():
     ms_graph = gpu_time(graph.replay)
     gerr = float((ag[0, 0] - ref).norm() / ref.norm())
     res = {"config": "hifi_gan/config_v1.json", "frames": T, "samples": int(audio.numel()),
-           "gflop": flops(cfg, T) / 1e9, "rel_l2_vs_torch_fp32_gpu": err, "rel_l2_graph": gerr,
+           "gflop": flops(cfg, T) / 1e9, "rel_l2_vs_torch_fp32_gpu": err, "rel_l2_vs_torch_fp64_gpu": err64,
+           "torch_fp32_rel_l2_vs_fp64": floor64, "rel_l2_graph": gerr,
            "libssb_ms": ms, "libssb_graph_ms": ms_graph, "libssb_launches": launches,
            "libssb_graph_tflops": flops(cfg, T) / ms_graph / 1e9,
            "libssb_graph_samples_per_s": audio.numel() / ms_graph * 1e3}
@@ -85,7 +92,7 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = True
         res["torch_tf32_gpu_ms"] = gpu_time(lambda: ov.generator_forward(sd_c, melc, cfg))
         tf = ov.generator_forward(sd_c, melc, cfg)
-        res["torch_tf32_rel_l2"] = float((tf - ref).norm() / ref.norm())
+        res["torch_tf32_rel_l2_vs_fp64"] = float((tf.double() - ref64).norm() / ref64.norm())
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         if "--no-cpu" not in sys.argv:
@@ -106,7 +113,7 @@ def main():
         evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
         agg = {}
         for e in evs:
-            k = e.name.split("(")[0][-60:]
+            k = e.name.replace("(anonymous namespace)::", "").replace("void ", "").replace("at::native::", "").split("(")[0][:60]
             a = agg.setdefault(k, [0.0, 0])
             a[0] += e.device_time if hasattr(e, "device_time") else e.cuda_time
             a[1] += 1
