@@ -29,6 +29,10 @@ def main():
     ap.add_argument("--eager", action="store_true")
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--seq", default=None, help="write the kernel sequence (name, us) to this file")
+    ap.add_argument("--steady", type=int, default=0,
+                    help="profile this many back-to-back steps (no host sync between them) and report "
+                         "the LAST one: the host runs ahead as in the bench, so idle time between "
+                         "activities is the GPU's own, not the enqueue latency of a cold step")
     args = ap.parse_args()
     from silent_speech_b200.read_emg import synthetic_batch
     from silent_speech_b200.training import GradientBucket, GraphedTrainStep, train_step
@@ -52,10 +56,19 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        step()
+        for _ in range(max(1, args.steady)):
+            step()
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
+    if args.steady > 1:
+        # a step ends with the fused optimiser kernel: keep what lies between the last two of them
+        ends = [i for i, e in enumerate(evs) if "adamw_flat_kernel" in e.name]
+        assert len(ends) >= 2, "no optimiser kernels found"
+        prev_end = evs[ends[-2]].time_range.end
+        evs = evs[ends[-2] + 1:ends[-1] + 1]
+        print(f"# steady state: step {args.steady} of {args.steady} back-to-back steps; "
+              f"{(evs[0].time_range.start - prev_end):.1f} us idle after the previous step's optimiser kernel")
     agg, cnt = defaultdict(float), defaultdict(int)
     for e in evs:
         d = e.time_range.end - e.time_range.start

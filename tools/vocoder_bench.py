@@ -117,6 +117,9 @@ def main():
             a = agg.setdefault(k, [0.0, 0])
             a[0] += e.device_time if hasattr(e, "device_time") else e.cuda_time
             a[1] += 1
+        evs.sort(key=lambda e: e.time_range.start)
+        res["seq_us"] = [[e.name.replace("(anonymous namespace)::", "").replace("void ", "").split("(")[0][:24],
+                          round(e.time_range.end - e.time_range.start, 1)] for e in evs]
         res["kernels_us"] = {k: [round(v[0], 1), v[1]] for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])}
     print(json.dumps(res))
 
