@@ -399,6 +399,48 @@ def emg_side_metric(with_cpu):
     return out
 
 
+def vocoder_side_metric(with_cpu):
+    """HiFi-GAN generator inference (vocoder.py:28-36 / hifi_gan/models.py:96-112,
+    config_v1, random weights): one 600-frame utterance -> 153 600 samples.  Checked against the oracle
+    formulation run by stock PyTorch on the same GPU in fp32 (TF32 off), which is also the timed
+    stock-torch leg."""
+    from oracle import vocoder as ov      # checker + baseline legs only
+    from silent_speech_b200 import vocoder as sv
+    T, cfg = 600, ov.V1
+    sd = ov.formula_state_dict(cfg)
+    g = sv.Generator(cfg).to("cuda")
+    g.load_state_dict(sd)
+    mel = ov.formula_mel(T).cuda()
+    x = mel.t()[None].contiguous()
+    audio = g(x)[0, 0]
+    ms = timed(lambda: g(x), 5, 3, 1) / 5
+    sd_c = {k: v.cuda() for k, v in sd.items()}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        ref = ov.generator_forward(sd_c, mel, cfg)
+        ms_t = timed(lambda: ov.generator_forward(sd_c, mel, cfg), 3, 2, 1) / 3
+    torch.backends.cudnn.allow_tf32 = tf32
+    gf = 368.46   # 2 * MACs of the generator at 600 frames (tools/vocoder_bench.py flops())
+    out = {"metric": "HiFi-GAN v1 vocoder samples/s (one 600-frame utterance, device-resident mel)",
+           "value": audio.numel() / ms * 1e3, "ms": ms, "samples": int(audio.numel()),
+           "tflops": gf / ms, "rel_l2_vs_torch_fp32": float((audio - ref).norm() / ref.norm()),
+           "stock_torch_fp32_same_gpu_ms": ms_t,
+           "bound": "latency / L2: 77 convolution GEMMs with N = 32 ... 256 output channels"}
+    if with_cpu:
+        Tc = 100
+        mc = ov.formula_mel(Tc)
+        with torch.no_grad():
+            ov.generator_forward(sd, mc, cfg)
+            t0 = time.perf_counter()
+            ov.generator_forward(sd, mc, cfg)
+            dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": Tc * 256 / dt, "unit": "samples/s", "cores": torch.get_num_threads(),
+                               "kind": "port", "sample": "100 of the 600 frames (oracle/vocoder.py = the "
+                                                         "reference's torch modules, fp32)"}
+    return out
+
+
 WORKLOADS = {
     # name: metric, frames/utterance, algorithmic GFLOP per bs-32 step per GPU (SURVEY.md section 8d)
     "cfg1": {"metric": METRIC, "frames": 500, "gflop": 6229.0},
@@ -748,6 +790,7 @@ def run_ours(args):
         if rank == 0 and world == 1:
             line["mel"] = mel_side_metric(peaks, not args.no_cpu)
             line["emg"] = emg_side_metric(not args.no_cpu)
+            line["vocoder"] = vocoder_side_metric(not args.no_cpu)
     if rank == 0 and world == 1 and not args.no_cpu:
         # bounded sample of the same workload on the host cores: the unmodified reference on 4 of
         # the 32 utterances, 1 timed step after 1 warm-up (the full-batch run is --impl reference)

@@ -39,7 +39,7 @@ extern "C" {
 /* ---- library ------------------------------------------------------------ */
 /* Bumped whenever a struct layout or a signature in this header changes; the Python binding
  * (silent_speech_b200/_lib.py ABI_VERSION) refuses to load a library reporting another value. */
-#define SSB_ABI_VERSION 211
+#define SSB_ABI_VERSION 212
 SSB_API int ssb_version(void);               /* == SSB_ABI_VERSION of the header it was built from */
 /* sizeof() of the descriptor structs below as compiled into the library (0: ssb_gather_t,
  * 1: ssb_scatter_t, 2: ssb_epilogue_t, 3: ssb_tc_operand_t, 4: ssb_dtw_pair_t, 5: ssb_utt_t,
@@ -342,6 +342,18 @@ SSB_API int ssb_split_bf16_t(const float* x, int64_t rows, int64_t cols,
  * K % 64 == 0, C % 64 == 0.  epi->out.rows_per_batch must equal A->rows_out. */
 SSB_API int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N, int64_t K,
                                const ssb_epilogue_t* epi, void* stream);
+/* Stream-K remainder for ssb_gemm_tc_kmajor.  With T output tiles on W persistent workers (CTA pairs)
+ * the last wave holds only T mod W tiles; when a workspace is registered, those tiles are cut along K
+ * into equal pieces over the idle workers, the piece holding a tile's last k-block adds the others'
+ * fp32 partial accumulators (through the workspace) and runs the epilogue.  Deterministic (fixed
+ * schedule and summation order per shape); results differ from the classic schedule by fp32
+ * re-association only.  The workspace is caller-owned device memory of
+ * ssb_gemm_tc_streamk_workspace_bytes() bytes, 256 B aligned, ZERO-FILLED once by the caller and left
+ * zero in its flag area by every launch; one per device (the current device at the call), shared by
+ * all ssb_gemm_tc_kmajor launches on that device, which therefore must be stream-ordered with respect
+ * to each other.  NULL detaches (classic schedule).  SSB_STREAMK=0 disables it process-wide. */
+SSB_API int64_t ssb_gemm_tc_streamk_workspace_bytes(void);
+SSB_API int ssb_gemm_tc_set_streamk_workspace(void* workspace, int64_t workspace_bytes);
 /* dW[k, n] (+)= sum_(b,t) X((b,t), k) * G[(b,t), n];  G planes: [2][batches*rows_out][N] bf16.
  * K % 128 == 0, X->C % 128 == 0, N % 8 == 0.
  * group_w > 0 (needs accumulate): element (k, n) goes to dW[(n / group_w) * group_stride + k * lddw +

@@ -114,6 +114,8 @@ _SIGNATURES = {
     "ssb_gemm_tn": (c_int, [_PG, c_ptr, c_i64, c_ptr, c_i64, c_int, c_i64, c_i64, c_i64, c_ptr]),
     "ssb_split_bf16": (c_int, [c_ptr, c_i64, c_ptr, c_ptr]),
     "ssb_gemm_tc_kmajor": (c_int, [_PT, c_ptr, c_i64, c_i64, _PE, c_ptr]),
+    "ssb_gemm_tc_streamk_workspace_bytes": (c_i64, []),
+    "ssb_gemm_tc_set_streamk_workspace": (c_int, [c_ptr, c_i64]),
     "ssb_gemm_tc_wgrad": (c_int, [_PT, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_i64, c_i64, c_int,
                                   c_ptr]),
     "ssb_gemm_tc_batched": (c_int, [_PT, _PT, c_int, c_i64, c_i64, _PE, c_ptr]),
@@ -233,7 +235,7 @@ def load():
     return _lib
 
 
-ABI_VERSION = 211      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
+ABI_VERSION = 212      # include/ssb.h SSB_ABI_VERSION: bumped whenever a struct or signature changes
 
 
 def _check_abi(lib):

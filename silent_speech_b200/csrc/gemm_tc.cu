@@ -84,6 +84,13 @@ struct TcParams {
   int batch_div;                                 // batch index -> (lo = b % div, hi = b / div)
   int b_mode;                                    // B batch coords: 0 none, 1 (lo, hi), 2 (lo, 0)
   int tiles_x, tiles_y, splits;                   // persistent tile list
+  // stream-K remainder (K-major only; see the schedule comment in the kernel): tiles [0, sk_full) are
+  // walked whole, the sk_rem tiles of the last, partial wave are cut along K into pieces shared by
+  // sk_workers workers.  sk_rem == 0: classic schedule.
+  int sk_allow;                                   // host: this launch may use the stream-K remainder
+  int sk_full, sk_rem, sk_workers;
+  float* sk_ws;                                   // [worker][rank][8 warps][4 blocks][32][32] fp32 partials
+  unsigned* sk_flags;                             // [worker][rank][8 warps], 0 between launches
   int n_mma;                                      // K-major, N < BN: the MMA's N (multiple of 32); the B box
                                                   // holds n_mma / CTAS rows per CTA.  0: BN
   // epilogue
@@ -317,13 +324,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   };
 
+  // ---- work items -------------------------------------------------------------------------
+  // Classic schedule: worker w walks tiles w, w + W, ... whole.  With T tiles on W workers the last
+  // wave holds only T mod W tiles while the other workers idle: 189 tiles (16000 x 768 outputs) on
+  // 74 CTA pairs are 2.55 waves of work in 3 waves of time.  Stream-K remainder: the F = T - T mod W
+  // tiles of the full waves stay whole; the R = T mod W remaining tiles are laid end to end along K
+  // (R * num_kb k-blocks) and cut into equal contiguous ranges, one per worker.  A range covers the
+  // END of one tile and / or the START of the next.  The worker whose range holds a tile's last
+  // k-block OWNS the tile: its epilogue adds the other ranges' fp32 partial accumulators (written to
+  // a workspace slot per worker and published through a flag) and then runs the normal epilogue.
+  // Every worker first computes its partial piece (no waiting), then its owner piece, so an owner
+  // only ever waits for work that is being computed at the same time: no chains, and all CTAs of
+  // the persistent grid are resident.  At most 4-5 workers share a tile (sk_workers <= 4 R).
+  constexpr int IT_FULL = 0, IT_PARTIAL = 1, IT_OWNER = 2;
+  auto sk_range = [&](int w, int& u0, int& u1) {
+    const long long U = (long long)p.sk_rem * p.num_kb;
+    u0 = (int)((long long)w * U / p.sk_workers);
+    u1 = (int)((long long)(w + 1) * U / p.sk_workers);
+  };
+  // idx-th work item of this worker: tile, k-block range, role.  false: no more items.
+  auto get_item = [&](int idx, int& tile, int& kb0, int& nk, int& mode) -> bool {
+    const int full = p.sk_rem ? p.sk_full : total_tiles;
+    const int n1 = full > worker ? (full - worker + num_workers - 1) / num_workers : 0;
+    kb0 = -1;            // -1: take the range decode() gives (whole K, or the split of an MN-major tile)
+    nk = 0;
+    mode = IT_FULL;
+    if (idx < n1) { tile = worker + idx * num_workers; return true; }
+    if (!p.sk_rem || worker >= p.sk_workers) return false;
+    int u0, u1;
+    sk_range(worker, u0, u1);
+    if (u0 == u1) return false;
+    const int k = idx - n1;
+    const int ta = u0 / p.num_kb;
+    const int a_last = (ta + 1) * p.num_kb;             // one past the last unit of tile ta
+    const bool has_b = u1 > a_last;
+    if (has_b && k == 0) {                              // head of the next tile: partial, computed first
+      tile = p.sk_full + ta + 1; kb0 = 0; nk = u1 - a_last; mode = IT_PARTIAL;
+      return true;
+    }
+    if (k != (has_b ? 1 : 0)) return false;
+    const int a_end = has_b ? a_last : u1;
+    tile = p.sk_full + ta; kb0 = u0 - ta * p.num_kb; nk = a_end - u0;
+    mode = a_end == a_last ? (kb0 == 0 ? IT_FULL : IT_OWNER) : IT_PARTIAL;
+    return true;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own operand rows) =====================
     if (ssb::elect_one()) {
       uint32_t it = 0;
-      for (int tile = worker; tile < total_tiles; tile += num_workers) {
+      int tile, it_kb0, it_nk, it_mode;
+      for (int idx = 0; get_item(idx, tile, it_kb0, it_nk, it_mode); ++idx) {
         int n0, batch, row0, f0, kb_begin, nkb;
         decode(tile, n0, batch, row0, f0, kb_begin, nkb);
+        if (it_kb0 >= 0) { kb_begin = it_kb0; nkb = it_nk; }
         const int b_rows = p.n_mma ? p.n_mma / CTAS : C::B_ROWS;   // rows of B this CTA stages
         const int nb0 = n0 + rank * b_rows;
         const uint32_t stage_tx = p.n_mma ? (uint32_t)(2 * A_PLANE + 2 * b_rows * BK * 2) : (uint32_t)STAGE_BYTES;
@@ -371,9 +425,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (rank == 0 && ssb::elect_one()) {
       const uint32_t idesc = make_idesc(p.mn_major, C::BMC, p.n_mma ? p.n_mma : BN);
       uint32_t it = 0, tcount = 0;
-      for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {
+      int tile, it_kb0, it_nk, it_mode;
+      for (int idx = 0; get_item(idx, tile, it_kb0, it_nk, it_mode); ++idx, ++tcount) {
         int n0, batch, row0, f0, kb_begin, nkb;
         decode(tile, n0, batch, row0, f0, kb_begin, nkb);
+        if (it_kb0 >= 0) { kb_begin = it_kb0; nkb = it_nk; }
         const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
         mbar_wait(tempty_bar + 8 * acc, aph ^ 1u);      // every epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -434,10 +490,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool wide = p.planes != nullptr || p.mask_planes != nullptr || p.mask_bits != nullptr;
     const int rsubw = lane >> 2, csubw = (lane & 3) * 8;
     uint32_t tcount = 0;
-    for (int tile = worker; tile < total_tiles; tile += num_workers, ++tcount) {
+    int tile, it_kb0, it_nk, it_mode;
+    for (int idx = 0; get_item(idx, tile, it_kb0, it_nk, it_mode); ++idx, ++tcount) {
       int n0, batch, row0, f0, kb_begin, nkb;
       decode(tile, n0, batch, row0, f0, kb_begin, nkb);
+      if (it_kb0 >= 0) { kb_begin = it_kb0; nkb = it_nk; }
       const uint32_t acc = tcount & 1u, aph = (tcount >> 1) & 1u;
+      // stream-K roles: the workers whose partial accumulators this (owner) item has to add
+      int sk_contrib[6], sk_nc = 0;
+      if (it_mode == IT_OWNER) {
+        const int t_first = (tile - p.sk_full) * p.num_kb;      // first unit of this tile
+        for (int w = worker - 1; w >= 0 && sk_nc < 6; --w) {
+          int u0, u1;
+          sk_range(w, u0, u1);
+          if (u1 <= t_first) break;
+          if (u0 != u1) sk_contrib[sk_nc++] = w;
+        }
+      }
+      // this warp's slot of a worker's partial tile / its flag
+      auto sk_slot = [&](int w) -> float* {
+        return p.sk_ws + ((size_t)(w * CTAS + rank) * EPI_WARPS + ew) * (4 * 32 * 32);
+      };
+      auto sk_flag = [&](int w) -> unsigned* { return p.sk_flags + (w * CTAS + rank) * EPI_WARPS + ew; };
       // first row this lane stores (rows advance by 4 per i), its address and global row index
       int first, limit;
       float* orow0;
@@ -546,8 +620,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         return r;
       };
-      prefetch(cpar);
-      if (p.mask_planes != nullptr && !p.mn_major && tile + num_workers < total_tiles) {
+      if (it_mode != IT_PARTIAL) prefetch(cpar);
+      if (p.mask_planes != nullptr && !p.mn_major &&
+          tile + num_workers < (p.sk_rem ? p.sk_full : total_tiles)) {
         // The mask plane of the NEXT tile this CTA will finish is known now: pull its lines into L2
         // while this tile's accumulator is still being produced, so the register prefetch above
         // (one column block ahead) meets L2 latency instead of an HBM round trip.  (ncu, r2: 47 %
@@ -564,12 +639,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       mbar_wait(tfull_bar + 8 * acc, aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (it_mode == IT_OWNER) {
+        // the other pieces of this tile were started at the same time as this one: a short wait
+        if (lane == 0)
+          for (int q = 0; q < sk_nc; ++q) {
+            unsigned f;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(sk_flag(sk_contrib[q])) : "memory");
+              if (!f) __nanosleep(64);
+            } while (!f);
+          }
+        __threadfence();
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int c = cpar; c < BN / 32; c += 2) {
         if (n0 + c * 32 >= p.N) break;    // warp-uniform: nothing to store in this column block
         uint32_t v[32];
         tmem_ld32(tmem_d + (uint32_t)(c * 32), v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (it_mode == IT_PARTIAL) {      // raw accumulator -> this worker's workspace slot (coalesced)
+          float* dst = sk_slot(worker) + (c >> 1) * 1024 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(dst + j * 32, __uint_as_float(v[j]));
+          continue;
+        }
+        if (it_mode == IT_OWNER) {
+          for (int q = 0; q < sk_nc; ++q) {
+            const float* src = sk_slot(sk_contrib[q]) + (c >> 1) * 1024 + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldcg(src + j * 32));
+          }
+        }
         if (!group_live) continue;
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -739,6 +840,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             *reinterpret_cast<float4*>(orow0 + i * row_step + ncol(n)) = o[i];
           }
         }
+      }
+      if (it_mode == IT_PARTIAL) {
+        __threadfence();                  // every lane's partial stores before the flag
+        __syncwarp();
+        if (lane == 0) {
+          unsigned one = 1u;
+          asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sk_flag(worker)), "r"(one) : "memory");
+        }
+      } else if (it_mode == IT_OWNER) {
+        __syncwarp();                     // all lanes have read the partials: re-arm the flags (0 between launches)
+        if (lane == 0)
+          for (int q = 0; q < sk_nc; ++q) *sk_flag(sk_contrib[q]) = 0u;
       }
       // hand the accumulator back to the (leader's) MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -928,6 +1041,49 @@ bool narrow_n_enabled() {
   return v != 0;
 }
 
+// stream-K workspace (ssb_gemm_tc_set_streamk_workspace): caller-owned, one per device
+struct SkWorkspace { void* base; int64_t bytes; };
+SkWorkspace g_sk_ws[64] = {};
+std::mutex g_sk_mutex;
+constexpr int64_t SK_SLOT_BYTES = (int64_t)EPI_WARPS * 4 * 32 * 32 * 4;   // one CTA's raw 128 x 256 accumulator
+constexpr int64_t SK_FLAG_BYTES = 8192;                                    // >= 148 CTAs x 8 warps x 4 B (4736)
+
+inline int64_t sk_workspace_bytes() { return SK_FLAG_BYTES + (int64_t)ssb::num_sms() * SK_SLOT_BYTES; }
+
+bool streamk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SSB_STREAMK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// Fill the stream-K fields for a K-major launch of `total` tiles on `workers` workers (CTAs or CTA
+// pairs); returns the number of workers the grid needs.
+int plan_streamk(TcParams* p, int64_t total, int workers) {
+  p->sk_full = (int)total; p->sk_rem = 0; p->sk_workers = 0; p->sk_ws = nullptr; p->sk_flags = nullptr;
+  const int grid_workers = (int)(total < workers ? total : workers);
+  int dev = 0;
+  if (!streamk_enabled() || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return grid_workers;
+  SkWorkspace ws;
+  {
+    std::lock_guard<std::mutex> lk(g_sk_mutex);
+    ws = g_sk_ws[dev];
+  }
+  const int rem = (int)(total % workers);
+  // worth it when the partial wave leaves a quarter of the machine idle and a piece still holds a
+  // few k-blocks (a piece costs one accumulator round trip through L2 on top of its MMAs)
+  if (!ws.base || ws.bytes < sk_workspace_bytes() || rem == 0 || rem * 4 > workers * 3 || p->num_kb < 16)
+    return grid_workers;
+  p->sk_rem = rem;
+  p->sk_full = (int)(total - rem);
+  p->sk_workers = rem * 4 < workers ? rem * 4 : workers;
+  p->sk_flags = (unsigned*)ws.base;
+  p->sk_ws = (float*)((char*)ws.base + SK_FLAG_BYTES);
+  return grid_workers > p->sk_workers ? grid_workers : p->sk_workers;
+}
+
 template <int CTAS>
 int launch_impl(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams& p, int64_t total,
                 cudaStream_t st) {
@@ -940,7 +1096,13 @@ int launch_impl(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams
     attr_set[dev] = true;
   }
   const int workers = ssb::num_sms() / CTAS;
-  const int grid = (int)(total < workers ? total : workers) * CTAS;
+  int grid = (int)(total < workers ? total : workers) * CTAS;
+  TcParams pk = p;
+  if (p.sk_allow && !p.mn_major && p.splits == 1)
+    grid = plan_streamk(&pk, total, workers) * CTAS;
+  else {
+    pk.sk_full = (int)total; pk.sk_rem = 0;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(THREADS);
@@ -962,7 +1124,7 @@ int launch_impl(const CUtensorMap& mapA, const CUtensorMap& mapB, const TcParams
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  SSB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTAS>, mapA, mapB, p));
+  SSB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<CTAS>, mapA, mapB, pk));
   SSB_LAUNCH_CHECK("gemm_tc_kernel");
   return SSB_OK;
 }
@@ -1062,6 +1224,20 @@ int ssb_split_bf16_t(const float* x, int64_t rows, int64_t cols, void* planes, v
   return SSB_OK;
 }
 
+int64_t ssb_gemm_tc_streamk_workspace_bytes(void) { return sk_workspace_bytes(); }
+
+int ssb_gemm_tc_set_streamk_workspace(void* workspace, int64_t workspace_bytes) {
+  int dev = 0;
+  SSB_CUDA(cudaGetDevice(&dev));
+  SSB_REQUIRE(dev >= 0 && dev < 64, "gemm_tc: device index out of range");
+  SSB_REQUIRE(!workspace || (workspace_bytes >= sk_workspace_bytes() && ((uintptr_t)workspace & 255) == 0),
+              "gemm_tc: stream-K workspace needs %lld bytes, 256 B aligned", (long long)sk_workspace_bytes());
+  std::lock_guard<std::mutex> lk(g_sk_mutex);
+  g_sk_ws[dev].base = workspace;
+  g_sk_ws[dev].bytes = workspace ? workspace_bytes : 0;
+  return SSB_OK;
+}
+
 int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N, int64_t K,
                        const ssb_epilogue_t* epi, void* stream) {
   SSB_REQUIRE(A && A->planes && Bplanes, "gemm_tc: null operand");
@@ -1092,6 +1268,7 @@ int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, int64_t N
                         (n_mma ? n_mma : BN) / ctas, 1))
     return rc;
   p.n_mma = n_mma;
+  p.sk_allow = 1;
   p.batch_div = (int)n_lo;
   p.b_mode = 0;
   p.a_inner = A->C; p.a_row_step = A->s_t; p.a_tap_step = A->s_tap; p.a_off = A->off;

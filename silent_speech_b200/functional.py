@@ -208,8 +208,28 @@ def tc_operand_conv(planes, B, L, C, rows_out, stride, taps_step, off):
                      off)
 
 
+_streamk_ws = {}     # device index -> the registered stream-K workspace (kept alive here)
+
+
+def _ensure_streamk(lib, device):
+    """Register the per-device stream-K workspace of ssb_gemm_tc_kmajor (include/ssb.h) on first use:
+    zero-filled once, owned by this module.  All tcgen05 GEMMs of a device share it, so they must be
+    stream-ordered (they are: one execution stream per process; SSB_STREAMK=0 turns it off)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _streamk_ws or torch.cuda.is_current_stream_capturing():
+        return
+    if os.environ.get("SSB_STREAMK", "1") == "0":
+        _streamk_ws[idx] = None
+        return
+    with torch.cuda.device(idx):
+        ws = torch.zeros(int(lib.ssb_gemm_tc_streamk_workspace_bytes()), dtype=torch.uint8, device=device)
+        _lib.check(lib.ssb_gemm_tc_set_streamk_workspace(ws.data_ptr(), ws.numel()))
+    _streamk_ws[idx] = ws
+
+
 def gemm_tc_kmajor(opA, Bplanes, N, K, epi):
     lib = _lib.load()
+    _ensure_streamk(lib, Bplanes.device)
     _lib.check(lib.ssb_gemm_tc_kmajor(ctypes.byref(opA), Bplanes.data_ptr(), N, K,
                                       ctypes.byref(epi), _stream()))
 

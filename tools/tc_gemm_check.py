@@ -219,7 +219,81 @@ def t_convgrad():
               f"dx {rel(x.grad, xr.grad):.2e} dw {rel(w.grad, wr.grad):.2e} db {rel(b.grad, br.grad):.2e}")
 
 
+def t_streamk():
+    """Stream-K remainder (include/ssb.h ssb_gemm_tc_set_streamk_workspace) against the classic schedule
+    and fp64: plain, accumulate + plane-emitting (wide) epilogues; repeated launches (flag re-arming);
+    timing of both schedules."""
+    from silent_speech_b200 import _lib
+    lib = _lib.load()
+    SF._ensure_streamk(lib, torch.device("cuda", torch.cuda.current_device()))
+    ws = SF._streamk_ws[torch.cuda.current_device()]
+    assert ws is not None, "SSB_STREAMK=0?"
+
+    def attach(on):
+        _lib.check(lib.ssb_gemm_tc_set_streamk_workspace(ws.data_ptr() if on else None, ws.numel() if on else 0))
+
+    def ms(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    shapes = [(16000, 768, 3072), (16000, 3072, 768), (16000, 768, 768), (16000, 2304, 768), (16000, 768, 2304),
+              (32000, 768, 2304), (4800, 256, 768), (4800, 256, 2816), (601, 2048, 1024), (38400, 128, 896),
+              (1000, 768, 768), (333, 80, 768), (24000, 768, 3072), (130, 256, 512)]
+    for (M, N, K) in shapes:
+        x, w, b = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=K ** -0.5), rnd(N, seed=3)
+        xp, wp = SF.split_planes(x), SF.split_planes(w)
+        ref = x.double() @ w.double().t() + b.double()
+        res0 = rnd(M, N, seed=4)
+
+        def run(y, pl, variant):
+            if variant == 0:
+                epi = SF._epi(SF._scatter_plain(y.data_ptr(), M, N), bias=b)
+            else:   # accumulate in place + planes of leaky_relu(result): the wide lane map
+                y.copy_(res0)
+                epi = SF._epi(SF._scatter_plain(y.data_ptr(), M, N), bias=b, accumulate=1, planes_out=pl,
+                              planes_lrelu=0.1)
+            SF.gemm_tc_kmajor(SF.tc_operand_plain(xp, M, K), wp, N, K, epi)
+        out = {}
+        for variant in ((0, 1) if N % 8 == 0 else (0,)):
+            for on in (1, 0, 1):
+                attach(on)
+                y = torch.full((M, N), float("nan"), device=dev)
+                pl = torch.zeros((2, M, N), dtype=torch.bfloat16, device=dev)
+                run(y, pl, variant)
+                torch.cuda.synchronize()
+                want = ref if variant == 0 else ref + res0.double()
+                e = rel(y, want)
+                key = (variant, on)
+                if key in out:
+                    assert torch.equal(out[key][0], y), "stream-K result not reproducible"
+                out[key] = (y, e)
+                if variant == 1:
+                    rec = pl[0].float() + pl[1].float()
+                    lr = torch.where(y > 0, y, y * 0.1)
+                    assert rel(rec, lr) < 1e-4, rel(rec, lr)
+                assert e < 2e-5 and torch.isfinite(y).all(), (M, N, K, variant, on, e)
+        attach(1)
+        y = torch.empty((M, N), device=dev)
+        pl = torch.empty((2, M, N), dtype=torch.bfloat16, device=dev)
+        t1 = ms(lambda: run(y, pl, 0))
+        attach(0)
+        t0 = ms(lambda: run(y, pl, 0))
+        attach(1)
+        d = (out[(0, 1)][0] - out[(0, 0)][0]).abs().max().item()
+        print(f"streamk {M}x{N}x{K}: rel err on {out[(0, 1)][1]:.2e} off {out[(0, 0)][1]:.2e} max|on-off| {d:.2e}  "
+              f"{t1 * 1e3:.1f} us on / {t0 * 1e3:.1f} us off ({t0 / t1:.3f}x)", flush=True)
+    assert int(ws[:8192].max()) == 0, "stream-K flags not re-armed"
+    print("streamk ok")
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
-    {"split": t_split, "kmajor": t_kmajor, "wgrad": t_wgrad, "conv1": lambda: t_conv(1),
+    {"streamk": t_streamk, "split": t_split, "kmajor": t_kmajor, "wgrad": t_wgrad, "conv1": lambda: t_conv(1),
      "conv2": lambda: t_conv(2), "perf": t_perf, "shapes": t_shapes, "ffn": t_ffn, "convgrad": t_convgrad}[what]()
