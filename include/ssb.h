@@ -351,7 +351,9 @@ SSB_API int ssb_gemm_tc_kmajor(const ssb_tc_operand_t* A, const void* Bplanes, i
  * ssb_gemm_tc_streamk_workspace_bytes() bytes, 256 B aligned, ZERO-FILLED once by the caller and left
  * zero in its flag area by every launch; one per device (the current device at the call), shared by
  * all ssb_gemm_tc_kmajor launches on that device, which therefore must be stream-ordered with respect
- * to each other.  NULL detaches (classic schedule).  SSB_STREAMK=0 disables it process-wide. */
+ * to each other.  NULL detaches (classic schedule).  Opt-in: ignored unless SSB_STREAMK=1 is set in the
+ * environment (on B200 the partial exchange costs more than the idle tail it removes for every shape of
+ * the transduction step; csrc/gemm_tc.cu has the numbers). */
 SSB_API int64_t ssb_gemm_tc_streamk_workspace_bytes(void);
 SSB_API int ssb_gemm_tc_set_streamk_workspace(void* workspace, int64_t workspace_bytes);
 /* dW[k, n] (+)= sum_(b,t) X((b,t), k) * G[(b,t), n];  G planes: [2][batches*rows_out][N] bf16.

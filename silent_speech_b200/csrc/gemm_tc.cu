@@ -1041,7 +1041,17 @@ bool narrow_n_enabled() {
   return v != 0;
 }
 
-// stream-K workspace (ssb_gemm_tc_set_streamk_workspace): caller-owned, one per device
+// stream-K workspace (ssb_gemm_tc_set_streamk_workspace): caller-owned, one per device.
+// Measured on B200 (r2 session 25, tools/tc_gemm_check.py streamk; on / off, same process):
+//   16000 x 768 x 3072   162.6 / 162.2 us      16000 x 3072 x 768   196.3 / 175.5 us
+//   16000 x 768 x 768     77.6 /  59.9 us      32000 x 768 x 2304   237.0 / 239.2 us
+//   4800 x 256 x 768      44.3 /  27.8 us      4800 x 256 x 2816     52.2 /  54.7 us
+// cfg-1 step 24.95 / 24.35 ms, vocoder 3.40 / 2.89 ms.  The partial accumulators of a remainder tile
+// are as many bytes as the tile's output per piece (128 KB per CTA written, then read by the owner, at
+// the ~30 - 60 GB/s one SM's 8 epilogue warps pull from L2), all at the end of the kernel: 10 - 30 us
+// of exchange against 0.45 waves (4 - 17 us) of MMAs saved.  It pays only where a tile is long
+// (K >= 2816) and the grid badly underfilled, so it stays opt-in (SSB_STREAMK=1) - bit-reproducible,
+// schedule checked on the CPU (tests/test_streamk_schedule_cpu.py).
 struct SkWorkspace { void* base; int64_t bytes; };
 SkWorkspace g_sk_ws[64] = {};
 std::mutex g_sk_mutex;
@@ -1054,7 +1064,7 @@ bool streamk_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SSB_STREAMK");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured slower on every cfg-1 / vocoder shape (see below)
   }
   return v != 0;
 }

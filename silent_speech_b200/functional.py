@@ -214,11 +214,12 @@ _streamk_ws = {}     # device index -> the registered stream-K workspace (kept a
 def _ensure_streamk(lib, device):
     """Register the per-device stream-K workspace of ssb_gemm_tc_kmajor (include/ssb.h) on first use:
     zero-filled once, owned by this module.  All tcgen05 GEMMs of a device share it, so they must be
-    stream-ordered (they are: one execution stream per process; SSB_STREAMK=0 turns it off)."""
+    stream-ordered (one execution stream per process).  Opt-in (SSB_STREAMK=1): measured slower than
+    the classic schedule on every shape of the cfg-1 step and the vocoder (csrc/gemm_tc.cu)."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     if idx in _streamk_ws or torch.cuda.is_current_stream_capturing():
         return
-    if os.environ.get("SSB_STREAMK", "1") == "0":
+    if os.environ.get("SSB_STREAMK", "0") != "1":
         _streamk_ws[idx] = None
         return
     with torch.cuda.device(idx):

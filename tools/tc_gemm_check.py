@@ -227,7 +227,7 @@ def t_streamk():
     lib = _lib.load()
     SF._ensure_streamk(lib, torch.device("cuda", torch.cuda.current_device()))
     ws = SF._streamk_ws[torch.cuda.current_device()]
-    assert ws is not None, "SSB_STREAMK=0?"
+    assert ws is not None, "run with SSB_STREAMK=1"
 
     def attach(on):
         _lib.check(lib.ssb_gemm_tc_set_streamk_workspace(ws.data_ptr() if on else None, ws.numel() if on else 0))
