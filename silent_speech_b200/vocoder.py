@@ -24,6 +24,7 @@ B200-first layout instead of the reference's NCL convolutions:
   * channel counts are padded to a multiple of 32 (one tensor-core k-block) with zero weights: padded
     channels stay exactly 0 through bias-free zero filters and leaky ReLU.
 """
+import contextlib
 import json
 import math
 import os
@@ -270,6 +271,24 @@ class Generator:
                                     w.data_ptr(), bias, audio.data_ptr(), _stream()))
         return audio
 
+    def _pair_workers(self):
+        """CTA pairs the persistent GEMM runs on (one pair per two SMs)."""
+        if self.device.type != "cuda":
+            return 0
+        if getattr(self, "_nw", None) is None:
+            self._nw = torch.cuda.get_device_properties(self.device).multi_processor_count // 2
+        return self._nw
+
+    def _branch_streams(self, n):
+        """Side streams for the residual branches (SSB_VOC_STREAMS=0: everything on the caller's stream)."""
+        if self.device.type != "cuda" or os.environ.get("SSB_VOC_STREAMS", "1") == "0":
+            return None
+        pool = getattr(self, "_side_streams", None)
+        if pool is None or len(pool) < n:
+            pool = [torch.cuda.Stream(device=self.device) for _ in range(n)]
+            self._side_streams = pool
+        return pool
+
     def forward_one(self, mel):
         """mel (T, num_mels) fp32 on self.device -> audio (T * prod(rates),)."""
         prep = self._prep or self._prepare()
@@ -293,20 +312,32 @@ class Generator:
             xp = fullp.view(2, R * u, C)                              # planes of lrelu(signal)
             x = xf[pad:pad + L]
             branches = [x.clone() for _ in range(nk - 1)]
+            # The residual branches of a stage are independent chains.  Where one GEMM's tiles leave
+            # most CTA pairs idle (the first stage: 4800 rows x 256 channels = 19 tiles for 74 pairs),
+            # the branches run side by side on their own streams; a full grid gains nothing from it.
+            side = self._branch_streams(nk) if -(-L // 256) * -(-C // 256) * nk <= self._pair_workers() else None
+            main = torch.cuda.current_stream() if side else None
             for j, convs in enumerate(prep["blocks"][i]):
                 # branch 0 accumulates into the phase GEMM's output in place, the others into copies
                 dst = (xf, pad) if j == 0 else (branches[j - 1], 0)
                 src = (xp, pad, L)
-                for m, pair in enumerate(convs):
-                    last = m == len(convs) - 1
-                    if len(pair) == 2:                                # ResBlock1: models.py:40-44
-                        hp = self._gemm(pair[0], src, L)
-                        nxt = self._gemm(pair[1], (hp, 0, L), L, out=dst, accumulate=True,
-                                         planes=not last)
-                    else:                                             # ResBlock2: models.py:65-68
-                        nxt = self._gemm(pair[0], src, L, out=dst, accumulate=True, planes=not last)
-                    if not last:
-                        src = (nxt, 0, L)
+                if side:
+                    side[j].wait_stream(main)
+                with (torch.cuda.stream(side[j]) if side else contextlib.nullcontext()):
+                    for m, pair in enumerate(convs):
+                        last = m == len(convs) - 1
+                        if len(pair) == 2:                            # ResBlock1: models.py:40-44
+                            hp = self._gemm(pair[0], src, L)
+                            nxt = self._gemm(pair[1], (hp, 0, L), L, out=dst, accumulate=True,
+                                             planes=not last)
+                        else:                                         # ResBlock2: models.py:65-68
+                            nxt = self._gemm(pair[0], src, L, out=dst, accumulate=True, planes=not last)
+                        if not last:
+                            src = (nxt, 0, L)
+                    del src
+            if side:
+                for st in side[:nk]:
+                    main.wait_stream(st)
             branches.insert(0, x)
             while len(branches) > 3:                                  # more than 3 kernels: pre-sum
                 branches = branches[:-3] + [self._sum([b.contiguous() for b in branches[-3:]])]
