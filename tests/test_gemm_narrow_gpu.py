@@ -30,7 +30,8 @@ def test_narrow_outputs(M, N):
     K = 192
     x, w, b = _rnd(M, K, seed=1), _rnd(N, K, seed=2, scale=K ** -0.5), _rnd(N, seed=3)
     y = torch.full((M, N), float("nan"), device="cuda")
-    SF.gemm_tc_kmajor(SF.tc_operand_plain(SF.split_planes(x), M, K), SF.split_planes(w), N, K,
+    xp, wp = SF.split_planes(x), SF.split_planes(w)     # the operand descriptor holds a raw pointer: keep xp alive
+    SF.gemm_tc_kmajor(SF.tc_operand_plain(xp, M, K), wp, N, K,
                       SF._epi(SF._scatter_plain(y.data_ptr(), M, N), bias=b, relu=1))
     ref = torch.relu(x.double() @ w.double().t() + b.double())
     assert torch.isfinite(y).all() and _rel(y, ref) < 2e-5
