@@ -72,10 +72,24 @@ def gemm(n):
             fn()
 
 
+def thin(n):
+    """first ResBlock at cfg-1 (8-channel EMG in, 768 out, 32 x 4000 samples): the thin-K CUDA-core kernels"""
+    from absl import flags
+    from silent_speech_b200 import architecture
+    if not flags.FLAGS.is_parsed():
+        flags.FLAGS(["x"])
+    blk = architecture.ResBlock(8, 768, 2).cuda().train()
+    x = torch.randn(32, 4000, 8, device="cuda")
+    for _ in range(n):
+        for p_ in blk.parameters():
+            p_.grad = None
+        blk.forward_cl(x).square().mean().backward()
+
+
 if __name__ == "__main__":
     what = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     torch.cuda.set_device(0)
-    {"mel": mel, "attn": attn, "dtw": dtw, "ctc": ctc, "gemm": gemm}[what](n)
+    {"mel": mel, "attn": attn, "dtw": dtw, "ctc": ctc, "gemm": gemm, "thin": thin}[what](n)
     torch.cuda.synchronize()
     print(what, "done")
