@@ -323,7 +323,7 @@ thin_nn_kernel(const Gather ga, const float* __restrict__ W, int ldw, const Epil
     for (int r = rl; r < rend; r += 4) {
       // packed fp32 FMAs (FFMA2, sm_100): two columns per instruction, same rounding as two FFMAs.
       // The kernel is issue-bound (ncu, r2 session 30: 60 M warp instructions, 62 % of them FFMA,
-      // IPC 2.0 at 8 warps per SM), so halving the FMA count is the lever.
+      // IPC 2.0 at 8 warps per SM), so halving the FMA count is the lever: 125.7 -> 113.9 us at cfg-1.
       float2 v01 = make_float2(bias.x, bias.y), v23 = make_float2(bias.z, bias.w);
 #pragma unroll
       for (int q = 0; q < K4; ++q) {
@@ -383,12 +383,12 @@ thin_tn_kernel(const Gather ga, const float* __restrict__ G, int ldg, float* __r
         const float4 a = As[r][q];
         const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {     // packed fp32 FMAs, see thin_nn_kernel
+        for (int j = 0; j < 4; ++j) {
+          // (scalar FFMAs on purpose: the packed form that helps thin_nn_kernel made this kernel,
+          // which waits on its global loads with 96 live accumulators, 50 % slower: 190 -> 285 us)
           float4& c = acc[4 * q + j];
-          const float2 aa = make_float2(av[j], av[j]);
-          const float2 c01 = __ffma2_rn(aa, make_float2(g[i].x, g[i].y), make_float2(c.x, c.y));
-          const float2 c23 = __ffma2_rn(aa, make_float2(g[i].z, g[i].w), make_float2(c.z, c.w));
-          c = make_float4(c01.x, c01.y, c23.x, c23.y);
+          c.x = fmaf(av[j], g[i].x, c.x); c.y = fmaf(av[j], g[i].y, c.y);
+          c.z = fmaf(av[j], g[i].z, c.z); c.w = fmaf(av[j], g[i].w, c.w);
         }
       }
     }
