@@ -13,6 +13,7 @@
 // Output rows go through the same (b, t) -> b*batch_stride + (t*d_t + d_off)*ld map, which
 // lets the stride-2 data gradients write the even / odd input rows directly.
 #include "ssb_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -413,6 +414,103 @@ thin_tn_kernel(const Gather ga, const float* __restrict__ G, int ldg, float* __r
   }
 }
 
+// Weight gradient of a thin reduction with 8 < K <= 32 (the first convolution: K = 3 taps x 8
+// channels, dW (24 x 768) reduced over 64 000 rows).  thin_tn_kernel keeps all K x 4 accumulators
+// AND a 16-row register prefetch of G per thread: 217 registers, 8 warps per SM, 190 us at cfg-1 with
+// the warps waiting on their global loads (ncu, r2 session 30: IPC 1.3, long-scoreboard stalls).
+// Here the K range is split over two thread halves (2 x K4 accumulator float4 per thread) and G is
+// staged through shared memory by cp.async, double-buffered, so the loads of chunk c+1 fly under the
+// FMAs of chunk c and ~24 warps per SM are resident.  block = 64 column lanes x 2 K halves x 2 row
+// lanes; a chunk is 16 rows x 256 columns of G (16 KB) + 16 rows of A.
+constexpr int T2_ROWS = 16;
+
+template <int K4>   // K padded to 4*K4, K4 even; each half owns K4/2 float4 of every A row
+__global__ void __launch_bounds__(256)
+thin_tn2_kernel(const Gather ga, const float* __restrict__ G, int ldg, float* __restrict__ dW,
+                int lddw, int M, int N, int K, int rows_per_cta) {
+  constexpr int KH4 = K4 / 2;
+  __shared__ float4 Gs[2][T2_ROWS][64];
+  __shared__ float4 As[2][T2_ROWS][K4];
+  __shared__ float4 red[64];
+  const int nl = threadIdx.x & 63, kh = (threadIdx.x >> 6) & 1, rl = threadIdx.x >> 7;
+  const int n = (blockIdx.x * 64 + nl) * 4;
+  const bool n_ok = n < N;
+  float4 acc[4 * KH4];
+#pragma unroll
+  for (int k = 0; k < 4 * KH4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int m0 = blockIdx.y * rows_per_cta;
+  const int m1 = min(M, m0 + rows_per_cta);
+  const int nchunk = (m1 - m0 + T2_ROWS - 1) / T2_ROWS;
+  auto stage = [&](int c) {
+    const int mc = m0 + c * T2_ROWS, buf = c & 1;
+    // G: 16 rows x 64 float4, 4 per thread, zero-filled outside [m1) x [N)
+    for (int i = threadIdx.x; i < T2_ROWS * 64; i += 256) {
+      const int r = i >> 6, q = i & 63;
+      const int col = (blockIdx.x * 64 + q) * 4;
+      const bool ok = mc + r < m1 && col < N;
+      ssb::cp_async_16(ssb::smem_u32(&Gs[buf][r][q]), ok ? G + (int64_t)(mc + r) * ldg + col : G, ok ? 16 : 0);
+    }
+    ssb::cp_async_commit();
+    for (int i = threadIdx.x; i < T2_ROWS * K4; i += 256) {
+      const int r = i / K4, q = i - r * K4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mc + r < m1 && 4 * q < K) {
+        bool valid;
+        const float* src = gather_ptr(ga, mc + r, 4 * q, valid);
+        if (valid) v = ldg4(src);
+      }
+      As[buf][r][q] = v;
+    }
+  };
+  if (nchunk > 0) stage(0);
+  for (int c = 0; c < nchunk; ++c) {
+    ssb::cp_async_wait<0>();
+    __syncthreads();                 // chunk c landed; every thread is done with chunk c-1's buffer
+    if (c + 1 < nchunk) stage(c + 1);
+    const int buf = c & 1;
+#pragma unroll 2
+    for (int r = rl; r < T2_ROWS; r += 2) {      // rows past m1 were staged as zeros
+      const float4 g = Gs[buf][r][nl];
+#pragma unroll
+      for (int q = 0; q < KH4; ++q) {
+        const float4 a = As[buf][r][kh * KH4 + q];
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4& cc = acc[4 * q + j];
+          cc.x = fmaf(av[j], g.x, cc.x); cc.y = fmaf(av[j], g.y, cc.y);
+          cc.z = fmaf(av[j], g.z, cc.z); cc.w = fmaf(av[j], g.w, cc.w);
+        }
+      }
+    }
+  }
+  // combine the 2 row lanes (fixed order), then one vector atomic per (k, 4 columns) and CTA
+#pragma unroll
+  for (int k = 0; k < 4 * KH4; ++k) {
+    const int kk = kh * 4 * KH4 + k;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {      // the two K halves take turns on the 64-entry exchange buffer
+      __syncthreads();
+      if (kh == h && rl == 1) red[nl] = acc[k];
+      __syncthreads();
+      if (kh == h && rl == 0 && n_ok && kk < K) {
+        const float4 o = red[nl];
+        float4 cv = acc[k];
+        cv.x += o.x; cv.y += o.y; cv.z += o.z; cv.w += o.w;
+        atomicAdd(reinterpret_cast<float4*>(dW + (int64_t)kk * lddw + n), cv);
+      }
+    }
+  }
+}
+
+bool thin_tn2_enabled() {   // SSB_THIN_TN2=0: the register-prefetch kernel (A/B)
+  static const bool on = [] {
+    const char* e = getenv("SSB_THIN_TN2");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 int thin_rows_per_cta(int64_t M, int64_t N) {
   const int col_blocks = (int)((N + 255) / 256);
   int row_blocks = (4 * ssb::num_sms() + col_blocks - 1) / col_blocks;
@@ -532,6 +630,15 @@ int ssb_gemm_tn(const ssb_gather_t* A, const float* G, int64_t ldg, float* dW, i
     const int per = thin_rows_per_cta(M, N);
     dim3 tg((unsigned)((N + 255) / 256), (unsigned)((M + per - 1) / per));
     const Gather ga = to_gather(A);
+    if (K > 8 && thin_tn2_enabled()) {
+      switch ((int)((K + 7) / 8) * 2) {   // K4 even
+        case 4: thin_tn2_kernel<4><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
+        case 6: thin_tn2_kernel<6><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
+        default: thin_tn2_kernel<8><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
+      }
+      SSB_LAUNCH_CHECK("thin_tn2");
+      return SSB_OK;
+    }
     switch ((K + 3) / 4 > 4 ? ((K + 7) / 8) * 2 : (int)((K + 3) / 4)) {
       case 1: case 2: thin_tn_kernel<2><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
       case 3: case 4: thin_tn_kernel<4><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
