@@ -414,7 +414,7 @@ thin_tn_kernel(const Gather ga, const float* __restrict__ G, int ldg, float* __r
   }
 }
 
-// Weight gradient of a thin reduction with 8 < K <= 32 (the first convolution: K = 3 taps x 8
+// Weight gradient of a thin reduction, K <= 32 (the first convolution: K = 3 taps x 8
 // channels, dW (24 x 768) reduced over 64 000 rows).  thin_tn_kernel keeps all K x 4 accumulators
 // AND a 16-row register prefetch of G per thread: 217 registers, 8 warps per SM, 190 us at cfg-1 with
 // the warps waiting on their global loads (ncu, r2 session 30: IPC 1.3, long-scoreboard stalls).
@@ -630,8 +630,9 @@ int ssb_gemm_tn(const ssb_gather_t* A, const float* G, int64_t ldg, float* dW, i
     const int per = thin_rows_per_cta(M, N);
     dim3 tg((unsigned)((N + 255) / 256), (unsigned)((M + per - 1) / per));
     const Gather ga = to_gather(A);
-    if (K > 8 && thin_tn2_enabled()) {
+    if (thin_tn2_enabled()) {
       switch ((int)((K + 7) / 8) * 2) {   // K4 even
+        case 2: thin_tn2_kernel<2><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
         case 4: thin_tn2_kernel<4><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
         case 6: thin_tn2_kernel<6><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;
         default: thin_tn2_kernel<8><<<tg, 256, 0, st>>>(ga, G, (int)ldg, dW, (int)lddw, (int)M, (int)N, (int)K, per); break;

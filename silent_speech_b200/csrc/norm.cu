@@ -158,12 +158,13 @@ bn_chunk_stats_kernel(const float* __restrict__ x, int64_t rows, int C,
 // column sums of a tensor held as bf16 split planes (x = hi + lo): 32 column-lanes x 8 columns
 __global__ void __launch_bounds__(256)
 col_partials_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo,
-                           int64_t rows, int C, float* __restrict__ partials /* [nchunks][2][C] */) {
+                           int64_t rows, int C, int rch, int slots,
+                           float* __restrict__ partials /* [nchunks][slots][C] */) {
   __shared__ float red[8][32][9];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = (blockIdx.x * 32 + cl) * 8;
-  const int64_t r0 = (int64_t)blockIdx.y * RCH;
-  const int64_t r1 = min(rows, r0 + RCH);
+  const int64_t r0 = (int64_t)blockIdx.y * rch;
+  const int64_t r1 = min(rows, r0 + rch);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < C) {
     for (int64_t r = r0 + rl; r < r1; r += 8) {
@@ -186,7 +187,7 @@ col_partials_planes_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bflo
       float a = red[0][cl][j];
 #pragma unroll
       for (int i = 1; i < 8; ++i) a += red[i][cl][j];
-      partials[((int64_t)blockIdx.y * 2) * C + c + j] = a;
+      partials[((int64_t)blockIdx.y * slots) * C + c + j] = a;
     }
   }
 }
@@ -223,11 +224,11 @@ __device__ __forceinline__ bool chunk_sums(const float* __restrict__ partials, i
 }
 
 __global__ void __launch_bounds__(32 * FIN_LANES)
-colsum_finalize_kernel(const float* __restrict__ partials, int nchunks, int C,
+colsum_finalize_kernel(const float* __restrict__ partials, int nchunks, int C, int slots,
                                        float* __restrict__ out, int accumulate) {
   const int c = blockIdx.x * 32 + threadIdx.x;
   double s, unused;
-  if (!chunk_sums(partials, nchunks, C, 2, c, s, unused)) return;
+  if (!chunk_sums(partials, nchunks, C, slots, c, s, unused)) return;
   out[c] = (accumulate ? out[c] : 0.f) + (float)s;
 }
 
@@ -725,7 +726,9 @@ extern "C" {
 
 int64_t ssb_col_partials_bytes(int64_t rows, int64_t C) {
   if (rows < 0 || C < 0) return SSB_ERR_ARG;
-  return (int64_t)nchunks_for(rows > 0 ? rows : 1) * 3 * C * 4;   // up to 3 slots per chunk
+  // up to 3 slots per 256-row chunk (BatchNorm), or one slot per 64-row chunk plus the row the
+  // two-value finalize reads past the last one (narrow column sums of split planes)
+  return (int64_t)nchunks_for(rows > 0 ? rows : 1) * 6 * C * 4;
 }
 
 int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumulate,
@@ -739,7 +742,7 @@ int ssb_colsum(const float* x, int64_t rows, int64_t C, float* out, int accumula
   col_partials_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, nullptr, nullptr, nullptr, rows, (int)C,
                                                (int)C, (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials<1>");
-  colsum_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, out,
+  colsum_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, 2, out,
                                                  accumulate);
   SSB_LAUNCH_CHECK("colsum_finalize");
   return SSB_OK;
@@ -755,13 +758,18 @@ int ssb_colsum_planes(const void* planes, int64_t plane_stride, int64_t rows, in
   SSB_REQUIRE(out && workspace && workspace_bytes >= ssb_col_partials_bytes(rows, C),
               "colsum_planes: bad out/workspace");
   cudaStream_t st = (cudaStream_t)stream;
-  const int nch = nchunks_for(rows);
+  // A 768-column tensor has only 3 column blocks: with 256-row chunks 16000 rows give 189 CTAs and the
+  // loads in flight cover a third of the HBM latency-bandwidth product (21 us for 49 MB).  Narrow
+  // tensors use 64-row chunks, one partial slot each (4 x the CTAs).
+  const bool narrow = C <= 1024 && rows >= 2048;
+  const int rch = narrow ? 64 : RCH, slots = narrow ? 1 : 2;
+  const int nch = (int)((rows + rch - 1) / rch);
   dim3 grid((unsigned)((C + 255) / 256), (unsigned)nch);
   const __nv_bfloat16* hi = (const __nv_bfloat16*)planes;
-  col_partials_planes_kernel<<<grid, 256, 0, st>>>(hi, hi + plane_stride, rows, (int)C,
+  col_partials_planes_kernel<<<grid, 256, 0, st>>>(hi, hi + plane_stride, rows, (int)C, rch, slots,
                                                    (float*)workspace);
   SSB_LAUNCH_CHECK("col_partials_planes");
-  colsum_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, out,
+  colsum_finalize_kernel<<<FIN_GRID(C), 0, st>>>((const float*)workspace, nch, (int)C, slots, out,
                                                  accumulate);
   SSB_LAUNCH_CHECK("colsum_finalize");
   return SSB_OK;

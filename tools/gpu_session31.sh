@@ -2,7 +2,7 @@
 # packed FFMA2 in the thin-K kernels: parity tests + per-kernel times in the step
 set -u
 O=gpurun_out
-T=${1:-r2s32}
+T=${1:-r2s33}
 mkdir -p $O
 export PYTHONUNBUFFERED=1
 ( timeout 900 python -m pytest tests/test_ops_gpu.py tests/test_model_gpu.py tests/test_parity_bench_engine_gpu.py -m gpu -q --maxfail=20 ) > $O/${T}_pytest.log 2>&1
