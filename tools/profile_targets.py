@@ -72,6 +72,18 @@ def gemm(n):
             fn()
 
 
+def ln(n):
+    """add + dropout + LayerNorm forward / backward at cfg-1 (16000 x 768, p = 0.2), as the encoder blocks call them
+    (planes-only branch gradient, parameter gradients into sinks)"""
+    M, D = 16000, 768
+    res, br = torch.randn(M, D, device="cuda"), torch.randn(M, D, device="cuda")
+    g, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    dy = torch.randn(M, D, device="cuda")
+    for _ in range(n):
+        y, z, stat = SF._ln_fwd(res, br, g, b, 0.2, 7, 3, 1e-5, True)
+        SF._ln_bwd(dy, z, stat, g, 0.2, 7, 3, (None, None), planes_only=True)
+
+
 def thin(n):
     """first ResBlock at cfg-1 (8-channel EMG in, 768 out, 32 x 4000 samples): the thin-K CUDA-core kernels"""
     from absl import flags
@@ -90,6 +102,6 @@ if __name__ == "__main__":
     what = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     torch.cuda.set_device(0)
-    {"mel": mel, "attn": attn, "dtw": dtw, "ctc": ctc, "gemm": gemm, "thin": thin}[what](n)
+    {"mel": mel, "attn": attn, "dtw": dtw, "ctc": ctc, "gemm": gemm, "thin": thin, "ln": ln}[what](n)
     torch.cuda.synchronize()
     print(what, "done")
