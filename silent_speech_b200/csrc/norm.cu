@@ -604,10 +604,10 @@ add_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ branc
 }
 
 // backward: d_res = dz, d_branch = dz * dropmask * scale; per-CTA partial dgamma/dbeta
-// 32 rows (4 per warp): at 64 the 250 CTAs of a 16000-row tensor filled 0.84 of the 2-CTA-per-SM slots,
-// a third of the SMs ran one CTA, and the latency-bound kernel (ncu, r2 session 34: long-scoreboard
-// stalls, 2.5 TB/s) averaged 13.5 warps per SM
-constexpr int LN_ROWS_PER_CTA = 32;
+// (Tried and measured slower, r2 sessions 35 / 36, 12 launches per step: 32 rows per CTA - more CTAs
+// for the 2-per-SM slots - 756 -> 824 us and a doubled finalize; __launch_bounds__(256, 3) - 80 registers,
+// 328 B of spills - 933 us.  The kernel is latency-bound at 2.5 TB/s with 16 warps per SM.)
+constexpr int LN_ROWS_PER_CTA = 64;
 
 // NV = float4 per lane actually needed (D <= 128 * NV): the register arrays are sized by it, so
 // D = 768 runs with 6-wide state instead of the 8-wide maximum (208 -> ~128 registers, two CTAs
