@@ -606,7 +606,9 @@ add_ln_fwd_kernel(const float* __restrict__ res, const float* __restrict__ branc
 // backward: d_res = dz, d_branch = dz * dropmask * scale; per-CTA partial dgamma/dbeta
 // (Tried and measured slower, r2 sessions 35 / 36, 12 launches per step: 32 rows per CTA - more CTAs
 // for the 2-per-SM slots - 756 -> 824 us and a doubled finalize; __launch_bounds__(256, 3) - 80 registers,
-// 328 B of spills - 933 us.  The kernel is latency-bound at 2.5 TB/s with 16 warps per SM.)
+// 328 B of spills - 933 us; parameter-gradient partials through shared-memory atomics instead of 48
+// accumulator registers, which fits three CTAs per SM without spills - 962 us.  The kernel is
+// latency-bound at 2.5 TB/s with 16 warps per SM, and more resident warps do not help it.)
 constexpr int LN_ROWS_PER_CTA = 64;
 
 // NV = float4 per lane actually needed (D <= 128 * NV): the register arrays are sized by it, so
