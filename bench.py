@@ -404,13 +404,25 @@ def vocoder_side_metric(with_cpu):
     config_v1, random weights): one 600-frame utterance -> 153 600 samples.  Checked against the oracle
     formulation run by stock PyTorch on the same GPU in fp32 (TF32 off), which is also the timed
     stock-torch leg."""
+    import math
     from oracle import vocoder as ov      # checker + baseline legs only
     from silent_speech_b200 import vocoder as sv
-    T, cfg = 600, ov.V1
-    sd = ov.formula_state_dict(cfg)
+    T, cfg = 600, sv.CONFIG_V1
     g = sv.Generator(cfg).to("cuda")
+    # synthetic weights: U(-a, a) with std 1 / sqrt(fan_in) on the trunk, 0.5 / sqrt(fan_in) in the residual
+    # blocks (activations stay O(1) through the stack), seeded; synthetic normalised-mel-like input
+    gen = torch.Generator().manual_seed(1234)
+    sd = {}
+    for name, shp in g.expected_shapes().items():
+        u = torch.rand(shp, generator=gen) * 2 - 1
+        if name.endswith(".bias"):
+            sd[name] = 0.05 * u
+        else:
+            fan_in = (shp[0] * shp[2] / cfg["upsample_rates"][int(name.split(".")[1])]
+                      if name.startswith("ups.") else shp[1] * shp[2])
+            sd[name] = (0.5 if name.startswith("resblocks.") else 1.0) * math.sqrt(3.0 / fan_in) * u
     g.load_state_dict(sd)
-    mel = ov.formula_mel(T).cuda()
+    mel = (1.5 * torch.randn(T, 80, generator=gen)).cuda()
     x = mel.t()[None].contiguous()
     audio = g(x)[0, 0]
     ms = timed(lambda: g(x), 5, 3, 1) / 5
@@ -429,7 +441,7 @@ def vocoder_side_metric(with_cpu):
            "bound": "latency / L2: 77 convolution GEMMs with N = 32 ... 256 output channels"}
     if with_cpu:
         Tc = 100
-        mc = ov.formula_mel(Tc)
+        mc = mel[:Tc].cpu()
         with torch.no_grad():
             ov.generator_forward(sd, mc, cfg)
             t0 = time.perf_counter()

@@ -35,6 +35,11 @@ from . import _lib
 from .functional import _epi, _stream, gemm_tc_kmajor, split_planes
 from ._lib import Scatter, TcOperand
 
+# hifi_gan/config_v1.json (the generator the reference's published vocoder checkpoint uses)
+CONFIG_V1 = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+                 upsample_initial_channel=512, resblock_kernel_sizes=[3, 7, 11],
+                 resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]])
+
 LRELU_SLOPE = 0.1     # hifi_gan/models.py:8
 POST_SLOPE = 0.01     # F.leaky_relu default (models.py:109)
 _f32 = torch.float32
